@@ -1,0 +1,427 @@
+"""CPU oracle for the WavLM / UniSpeech-SAT encoder hot path  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+A functional fp32 restatement (plain PyTorch on CPU) of the reference algorithm in
+`/root/reference/WavLM/WavLM.py` and `/root/reference/WavLM/modules.py` (microsoft/UniSpeech @ 40d3227).
+Only `tests/`, `__graft_entry__.smoke()` and `bench.py`'s CPU-baseline / `--impl reference` legs may import it;
+the product path (`unispeech_b200/`) never does.
+
+Parity status: the reference ships no tests or golden vectors for this path, so the oracle is
+pinned against the reference ITSELF: `tools/make_golden.py` imports the unmodified reference modules in the authoring
+container, loads the deterministic parameters defined below, and commits the outputs under `tests/golden/`;
+`tests/test_oracle_golden.py` checks this restatement against those fixtures.
+
+Every function cites the reference lines it follows.  Parameters are a dict keyed exactly like the reference
+`state_dict`.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+Tensor = torch.Tensor
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# configuration (attribute bag mirroring WavLMConfig, WavLM/WavLM.py:162-217)
+# ----------------------------------------------------------------------------------------------------------------
+def make_config(**kw) -> SimpleNamespace:
+    cfg = dict(
+        extractor_mode="default",
+        encoder_layers=12,
+        encoder_embed_dim=768,
+        encoder_ffn_embed_dim=3072,
+        encoder_attention_heads=12,
+        activation_fn="gelu",
+        layer_norm_first=False,
+        conv_feature_layers="[(512,10,5)] + [(512,3,2)] * 4 + [(512,2,2)] * 2",
+        conv_bias=False,
+        feature_grad_mult=1.0,
+        normalize=False,
+        dropout=0.0,
+        attention_dropout=0.0,
+        activation_dropout=0.0,
+        encoder_layerdrop=0.0,
+        dropout_input=0.0,
+        dropout_features=0.0,
+        mask_length=10,
+        mask_prob=0.65,
+        mask_selection="static",
+        mask_other=0,
+        no_mask_overlap=False,
+        mask_min_space=1,
+        mask_channel_length=10,
+        mask_channel_prob=0.0,
+        mask_channel_selection="static",
+        mask_channel_other=0,
+        no_mask_channel_overlap=False,
+        mask_channel_min_space=1,
+        conv_pos=128,
+        conv_pos_groups=16,
+        relative_position_embedding=True,
+        num_buckets=320,
+        max_distance=800,
+        gru_rel_pos=True,
+    )
+    cfg.update(kw)
+    return SimpleNamespace(**cfg)
+
+
+def base_config(**kw) -> SimpleNamespace:
+    """WavLM-Base: post-LN, GroupNorm extractor (WavLM/README.md model table; cfg of the released checkpoint)."""
+    return make_config(**kw)
+
+
+def large_config(**kw) -> SimpleNamespace:
+    """WavLM-Large: pre-LN, LayerNorm extractor, 24 x 1024 / 4096 / 16 heads."""
+    d = dict(extractor_mode="layer_norm", encoder_layers=24, encoder_embed_dim=1024, encoder_ffn_embed_dim=4096,
+             encoder_attention_heads=16, layer_norm_first=True, normalize=True)
+    d.update(kw)
+    return make_config(**d)
+
+
+def tiny_config(pre_ln: bool = False, **kw) -> SimpleNamespace:
+    """Small shapes with the same structure (head_dim 64), for fixtures that fit in the repo."""
+    d = dict(encoder_layers=2, encoder_embed_dim=128, encoder_ffn_embed_dim=256, encoder_attention_heads=2,
+             conv_feature_layers="[(64,10,5)] + [(64,3,2)] * 4 + [(64,2,2)] * 2",
+             extractor_mode="layer_norm" if pre_ln else "default", layer_norm_first=pre_ln)
+    d.update(kw)
+    return make_config(**d)
+
+
+def conv_layers_of(cfg) -> List[Tuple[int, int, int]]:
+    return eval(cfg.conv_feature_layers)  # same as WavLM/WavLM.py:230
+
+
+def num_frames(L: int, cfg) -> int:
+    """T_out = (T_in - k)//s + 1 per layer, no padding (nn.Conv1d defaults, WavLM/WavLM.py:400-403)."""
+    for (_, k, s) in conv_layers_of(cfg):
+        L = (L - k) // s + 1
+    return L
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# deterministic parameters / inputs (integer hash -> bit-identical everywhere, no RNG state involved)
+# ----------------------------------------------------------------------------------------------------------------
+def hash_uniform(tag: str, shape, lo: float = -1.0, hi: float = 1.0) -> Tensor:
+    n = int(np.prod(shape)) if len(shape) else 1
+    idx = np.arange(n, dtype=np.uint64)
+    key = np.uint64(zlib.crc32(tag.encode()) & 0xFFFFFFFF)
+    x = (idx * np.uint64(2654435761) + key * np.uint64(40503) + np.uint64(12345)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x45D9F3B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    x = (x * np.uint64(0x45D9F3B)) & np.uint64(0xFFFFFFFF)
+    x ^= x >> np.uint64(16)
+    u = x.astype(np.float64) / 4294967296.0
+    v = (lo + (hi - lo) * u).astype(np.float32).reshape(shape)
+    return torch.from_numpy(v.copy())
+
+
+def parameter_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
+    """Key -> shape, exactly the reference state_dict layout (WavLM/WavLM.py:220-269,378-449,507-562)."""
+    D, Fd, H = cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads
+    convs = conv_layers_of(cfg)
+    C = convs[-1][0]
+    sh: Dict[str, Tuple[int, ...]] = {"mask_emb": (D,)}
+    cin = 1
+    for i, (dim, k, _s) in enumerate(convs):
+        sh[f"feature_extractor.conv_layers.{i}.0.weight"] = (dim, cin, k)
+        if cfg.conv_bias:
+            sh[f"feature_extractor.conv_layers.{i}.0.bias"] = (dim,)
+        if cfg.extractor_mode == "layer_norm":
+            sh[f"feature_extractor.conv_layers.{i}.2.1.weight"] = (dim,)
+            sh[f"feature_extractor.conv_layers.{i}.2.1.bias"] = (dim,)
+        elif i == 0:
+            sh[f"feature_extractor.conv_layers.{i}.2.weight"] = (dim,)
+            sh[f"feature_extractor.conv_layers.{i}.2.bias"] = (dim,)
+        cin = dim
+    sh["layer_norm.weight"] = (C,)
+    sh["layer_norm.bias"] = (C,)
+    if C != D:
+        sh["post_extract_proj.weight"] = (D, C)
+        sh["post_extract_proj.bias"] = (D,)
+    sh["encoder.pos_conv.0.bias"] = (D,)
+    sh["encoder.pos_conv.0.weight_g"] = (1, 1, cfg.conv_pos)
+    sh["encoder.pos_conv.0.weight_v"] = (D, D // cfg.conv_pos_groups, cfg.conv_pos)
+    for i in range(cfg.encoder_layers):
+        p = f"encoder.layers.{i}."
+        for n in ("k_proj", "v_proj", "q_proj", "out_proj"):
+            sh[p + f"self_attn.{n}.weight"] = (D, D)
+            sh[p + f"self_attn.{n}.bias"] = (D,)
+        if cfg.gru_rel_pos:
+            sh[p + "self_attn.grep_linear.weight"] = (8, D // H)
+            sh[p + "self_attn.grep_linear.bias"] = (8,)
+            sh[p + "self_attn.grep_a"] = (1, H, 1, 1)
+        if cfg.relative_position_embedding and i == 0:
+            sh[p + "self_attn.relative_attention_bias.weight"] = (cfg.num_buckets, H)
+        sh[p + "self_attn_layer_norm.weight"] = (D,)
+        sh[p + "self_attn_layer_norm.bias"] = (D,)
+        sh[p + "fc1.weight"] = (Fd, D)
+        sh[p + "fc1.bias"] = (Fd,)
+        sh[p + "fc2.weight"] = (D, Fd)
+        sh[p + "fc2.bias"] = (D,)
+        sh[p + "final_layer_norm.weight"] = (D,)
+        sh[p + "final_layer_norm.bias"] = (D,)
+    sh["encoder.layer_norm.weight"] = (D,)
+    sh["encoder.layer_norm.bias"] = (D,)
+    return sh
+
+
+def deterministic_state_dict(cfg, seed: int = 0) -> Dict[str, Tensor]:
+    """Hash-generated parameters with sensible magnitudes (not the reference initialiser; parity only needs the
+    SAME weights on both sides)."""
+    sd: Dict[str, Tensor] = {}
+    for key, shape in parameter_shapes(cfg).items():
+        tag = f"{seed}:{key}"
+        if key.endswith("weight_g"):
+            sd[key] = hash_uniform(tag, shape, 0.5, 1.5)
+        elif key.endswith("grep_a"):
+            sd[key] = hash_uniform(tag, shape, 0.8, 1.2)
+        elif key == "mask_emb":
+            sd[key] = hash_uniform(tag, shape, 0.0, 1.0)
+        elif key.endswith("relative_attention_bias.weight"):
+            sd[key] = hash_uniform(tag, shape, -1.0, 1.0)
+        elif "layer_norm" in key or ".2.weight" in key or ".2.bias" in key or ".2.1." in key:
+            sd[key] = hash_uniform(tag, shape, 0.8, 1.2) if key.endswith("weight") else hash_uniform(tag, shape, -0.1, 0.1)
+        elif key.endswith("bias"):
+            sd[key] = hash_uniform(tag, shape, -0.1, 0.1)
+        else:  # linear / conv weights: uniform with unit-ish gain
+            fan_in = int(np.prod(shape[1:]))
+            a = math.sqrt(3.0 / fan_in) * (1.6 if "feature_extractor" in key else 1.0)
+            sd[key] = hash_uniform(tag, shape, -a, a)
+    return sd
+
+
+def deterministic_waveform(B: int, L: int, seed: int = 0, lengths: Optional[List[int]] = None):
+    """Synthetic 16 kHz batch in [-1,1); padded samples are exactly 0 and flagged in the mask."""
+    wav = hash_uniform(f"wav:{seed}", (B, L))
+    mask = torch.zeros(B, L, dtype=torch.bool)
+    if lengths is not None:
+        for b, n in enumerate(lengths):
+            wav[b, n:] = 0.0
+            mask[b, n:] = True
+    return wav, mask
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# conv feature extractor  (ConvFeatureExtractionModel, WavLM/WavLM.py:378-449 ctor, 485-504 forward)
+# ----------------------------------------------------------------------------------------------------------------
+def conv_feature_extractor(sd: Dict[str, Tensor], source: Tensor, cfg, return_all: bool = False):
+    x = source.unsqueeze(1)  # BxT -> BxCxT, WavLM.py:488
+    outs = []
+    for i, (dim, k, s) in enumerate(conv_layers_of(cfg)):
+        w = sd[f"feature_extractor.conv_layers.{i}.0.weight"]
+        b = sd.get(f"feature_extractor.conv_layers.{i}.0.bias")
+        x = F.conv1d(x, w, b, stride=s)  # WavLM.py:400-403 (no padding)
+        if cfg.extractor_mode == "layer_norm":  # WavLM.py:409-419: TransposeLast, Fp32LayerNorm, TransposeLast
+            x = F.layer_norm(x.transpose(1, 2).float(), (dim,),
+                             sd[f"feature_extractor.conv_layers.{i}.2.1.weight"].float(),
+                             sd[f"feature_extractor.conv_layers.{i}.2.1.bias"].float(), 1e-5).transpose(1, 2)
+        elif i == 0:  # WavLM.py:420-426: Fp32GroupNorm(dim, dim) == per-(b,c) statistics over time
+            x = F.group_norm(x.float(), dim, sd[f"feature_extractor.conv_layers.{i}.2.weight"].float(),
+                             sd[f"feature_extractor.conv_layers.{i}.2.bias"].float(), 1e-5)
+        x = F.gelu(x)  # nn.GELU(): exact erf form
+        outs.append(x)
+    return (x, outs) if return_all else x
+
+
+def frame_padding_mask(padding_mask: Tensor, T: int) -> Tensor:
+    """WavLM.forward_padding_mask, WavLM/WavLM.py:311-321."""
+    extra = padding_mask.size(1) % T
+    if extra > 0:
+        padding_mask = padding_mask[:, :-extra]
+    return padding_mask.view(padding_mask.size(0), T, -1).all(-1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# relative position bias  (MultiheadAttention._relative_positions_bucket / compute_bias, WavLM/modules.py:417-455)
+# ----------------------------------------------------------------------------------------------------------------
+def relative_positions_bucket(relative_positions: Tensor, num_buckets: int, max_distance: int) -> Tensor:
+    nb = num_buckets // 2  # bidirectional
+    buckets = (relative_positions > 0).to(torch.long) * nb
+    rp = torch.abs(relative_positions)
+    max_exact = nb // 2
+    is_small = rp < max_exact
+    large = max_exact + (
+        torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)
+    ).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    return buckets + torch.where(is_small, rp, large)
+
+
+def bucket_lut(T: int, num_buckets: int, max_distance: int) -> Tensor:
+    """bucket(delta) for delta = j - i in [-(T-1), T-1]; index delta + T - 1.  The bias matrix is Toeplitz."""
+    delta = torch.arange(-(T - 1), T, dtype=torch.long)
+    return relative_positions_bucket(delta, num_buckets, max_distance)
+
+
+def compute_bias(T: int, emb_weight: Tensor, num_buckets: int, max_distance: int) -> Tensor:
+    """[H, T, T] position bias exactly as modules.py:445-455 (dense form)."""
+    ctx = torch.arange(T, dtype=torch.long)[:, None]
+    mem = torch.arange(T, dtype=torch.long)[None, :]
+    bucket = relative_positions_bucket(mem - ctx, num_buckets, max_distance)
+    return F.embedding(bucket, emb_weight).permute(2, 0, 1)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# attention  (MultiheadAttention.forward fast path, WavLM/modules.py:457-564)
+# ----------------------------------------------------------------------------------------------------------------
+def gate_values(x_tbc: Tensor, grep_w: Tensor, grep_b: Tensor, grep_a: Tensor, H: int) -> Tensor:
+    """gru_rel_pos gate on the RAW layer input (modules.py:523-533).  Returns [B,H,T,1]."""
+    T, B, D = x_tbc.shape
+    q = x_tbc.transpose(0, 1).view(B, T, H, D // H).permute(0, 2, 1, 3)
+    g = torch.sigmoid(F.linear(q, grep_w, grep_b).view(B, H, T, 2, 4).sum(-1))
+    gate_a, gate_b = g.chunk(2, dim=-1)
+    return gate_a * (gate_b * grep_a - 1.0) + 2.0
+
+
+def self_attention(sd, prefix: str, x_tbc: Tensor, key_padding_mask: Optional[Tensor], position_bias: Optional[Tensor],
+                   cfg) -> Tensor:
+    """softmax((xWq+bq)/sqrt(d) (xWk+bk)^T + gate*bias, -inf at padded keys) (xWv+bv), then out_proj."""
+    T, B, D = x_tbc.shape
+    H = cfg.encoder_attention_heads
+    hd = D // H
+    q = F.linear(x_tbc, sd[prefix + "q_proj.weight"], sd[prefix + "q_proj.bias"]) * (hd ** -0.5)
+    k = F.linear(x_tbc, sd[prefix + "k_proj.weight"], sd[prefix + "k_proj.bias"])
+    v = F.linear(x_tbc, sd[prefix + "v_proj.weight"], sd[prefix + "v_proj.bias"])
+    q = q.contiguous().view(T, B * H, hd).transpose(0, 1)
+    k = k.contiguous().view(T, B * H, hd).transpose(0, 1)
+    v = v.contiguous().view(T, B * H, hd).transpose(0, 1)
+    scores = torch.bmm(q, k.transpose(1, 2))  # [B*H, T, T]
+    if position_bias is not None:
+        bias = position_bias  # [B*H, T, T]
+        if cfg.gru_rel_pos:
+            g = gate_values(x_tbc, sd[prefix + "grep_linear.weight"], sd[prefix + "grep_linear.bias"],
+                            sd[prefix + "grep_a"], H)
+            bias = g.view(B * H, T, 1) * position_bias
+        scores = scores + bias
+    if key_padding_mask is not None:
+        scores = scores.view(B, H, T, T).masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(B * H, T, T)
+    p = torch.softmax(scores, dim=-1)
+    o = torch.bmm(p, v).transpose(0, 1).contiguous().view(T, B, D)
+    return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# encoder layer / stack  (TransformerSentenceEncoderLayer.forward WavLM/WavLM.py:677-742; TransformerEncoder :564-612)
+# ----------------------------------------------------------------------------------------------------------------
+def _ln(x, sd, name):
+    return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
+
+
+def encoder_layer(sd, i: int, x: Tensor, padding_mask, position_bias, cfg) -> Tensor:
+    p = f"encoder.layers.{i}."
+    residual = x
+    if cfg.layer_norm_first:  # WavLM.py:691-714
+        x = _ln(x, sd, p + "self_attn_layer_norm")
+        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg)
+        x = residual + x
+        residual = x
+        x = _ln(x, sd, p + "final_layer_norm")
+        x = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+        x = F.linear(x, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+        x = residual + x
+    else:  # WavLM.py:715-740
+        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg)
+        x = residual + x
+        x = _ln(x, sd, p + "self_attn_layer_norm")
+        residual = x
+        x = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+        x = F.linear(x, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
+        x = residual + x
+        x = _ln(x, sd, p + "final_layer_norm")
+    return x
+
+
+def pos_conv_weight(sd) -> Tensor:
+    """nn.utils.weight_norm(dim=2): w = g * v / ||v|| with the norm over dims (0,1) per tap."""
+    v = sd["encoder.pos_conv.0.weight_v"]
+    g = sd["encoder.pos_conv.0.weight_g"]
+    return g * v / v.norm(2, dim=(0, 1), keepdim=True)
+
+
+def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer: Optional[int] = None):
+    """TransformerEncoder.forward + extract_features (out-of-place restatement of WavLM.py:564-612)."""
+    if padding_mask is not None:
+        x = x.masked_fill(padding_mask.unsqueeze(-1), 0.0)  # x[padding_mask] = 0, :574-575
+    w = pos_conv_weight(sd)
+    x_conv = F.conv1d(x.transpose(1, 2), w, sd["encoder.pos_conv.0.bias"], padding=cfg.conv_pos // 2,
+                      groups=cfg.conv_pos_groups)
+    if cfg.conv_pos % 2 == 0:
+        x_conv = x_conv[:, :, :-1]  # SamePad, modules.py:72-83
+    x = x + F.gelu(x_conv).transpose(1, 2)  # :577-579
+    if not cfg.layer_norm_first:
+        x = _ln(x, sd, "encoder.layer_norm")  # :581-582
+    x = x.transpose(0, 1)  # B x T x C -> T x B x C
+    layer_results = []
+    if tgt_layer is not None:
+        layer_results.append(x)
+    T, B, D = x.shape
+    H = cfg.encoder_attention_heads
+    position_bias = None
+    if cfg.relative_position_embedding:
+        pb = compute_bias(T, sd["encoder.layers.0.self_attn.relative_attention_bias.weight"], cfg.num_buckets,
+                          cfg.max_distance)
+        position_bias = pb.unsqueeze(0).repeat(B, 1, 1, 1).view(B * H, T, T)  # modules.py:504-506
+    r = None
+    for i in range(cfg.encoder_layers):
+        x = encoder_layer(sd, i, x, padding_mask, position_bias, cfg)
+        if tgt_layer is not None:
+            layer_results.append(x)
+        if i == tgt_layer:
+            r = x
+            break
+    if r is not None:
+        x = r
+    x = x.transpose(0, 1)
+    if cfg.layer_norm_first and tgt_layer is None:  # :567-568
+        x = _ln(x, sd, "encoder.layer_norm")
+    return x, layer_results
+
+
+def extract_features(sd, source: Tensor, cfg, padding_mask: Optional[Tensor] = None,
+                     mask_indices: Optional[Tensor] = None, output_layer: Optional[int] = None):
+    """WavLM.extract_features, WavLM/WavLM.py:323-375.  `mask_indices` [B,T] bool replaces the host-RNG
+    compute_mask_indices call of apply_mask (:271-309): masked frames are set to mask_emb."""
+    feats = conv_feature_extractor(sd, source, cfg)  # :333-339 (feature_grad_mult handled by callers)
+    feats = feats.transpose(1, 2)
+    C = feats.shape[-1]
+    feats = F.layer_norm(feats, (C,), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)  # :342
+    if padding_mask is not None:
+        padding_mask = frame_padding_mask(padding_mask, feats.size(1))
+    if "post_extract_proj.weight" in sd:
+        feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
+    x = feats
+    if mask_indices is not None:
+        x = torch.where(mask_indices.unsqueeze(-1), sd["mask_emb"].to(x.dtype), x)  # x[mask_indices] = mask_emb
+    x, layer_results = encoder(sd, x, padding_mask, cfg, None if output_layer is None else output_layer - 1)
+    return {"x": x, "padding_mask": padding_mask, "features": feats, "layer_results": layer_results}
+
+
+def probe_loss(x: Tensor, padding_mask: Optional[Tensor], seed: int = 0) -> Tensor:
+    """Non-degenerate scalar for gradient parity: sum(x * R) over valid frames, R hash-generated."""
+    R = hash_uniform(f"probe:{seed}", tuple(x.shape)).to(x.dtype).to(x.device)
+    if padding_mask is not None:
+        R = R.masked_fill(padding_mask.unsqueeze(-1).to(R.device), 0.0)
+    return (x * R).sum()
+
+
+def forward_flops(L: int, cfg) -> float:
+    """Algorithmic GEMM flops of one forward pass of one utterance (SURVEY.md section 8d formula)."""
+    D, Fd, H = cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads
+    fl, cin, t = 0.0, 1, L
+    for (dim, k, s) in conv_layers_of(cfg):
+        t = (t - k) // s + 1
+        fl += 2.0 * t * dim * cin * k
+        cin = dim
+    T = t
+    fl += 2.0 * T * cin * D
+    fl += 2.0 * T * D * (D // cfg.conv_pos_groups) * cfg.conv_pos
+    fl += cfg.encoder_layers * (8.0 * T * D * D + 4.0 * T * T * D + 4.0 * T * D * Fd + 2.0 * T * H * 64 * 8)
+    return fl

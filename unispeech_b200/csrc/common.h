@@ -1,0 +1,41 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting and launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+namespace b200 {
+
+// thread-local last error string, exposed through b200s_last_error()
+char* last_error_buf();
+void set_last_error(const char* fmt, ...);
+
+#define B200_CHECK_ARG(cond, ...)        \
+  do {                                   \
+    if (!(cond)) {                       \
+      b200::set_last_error(__VA_ARGS__); \
+      return -1;                         \
+    }                                    \
+  } while (0)
+
+#define B200_CHECK_CUDA(expr)                                                                  \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      b200::set_last_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, cudaGetErrorName(_e), \
+                           cudaGetErrorString(_e));                                            \
+      return -2;                                                                               \
+    }                                                                                          \
+  } while (0)
+
+#define B200_CHECK_LAUNCH() B200_CHECK_CUDA(cudaGetLastError())
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }
+
+// sm count of the current device (cached)
+int sm_count();
+
+}  // namespace b200

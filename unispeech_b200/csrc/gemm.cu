@@ -1,0 +1,318 @@
+// Host side of the tcgen05 GEMM family: TMA tensor-map construction, tile mapping and launch.
+#include <stdarg.h>
+
+#include <mutex>
+
+#include "../../include/unispeech_b200.h"
+#include "common.h"
+#include "gemm.cuh"
+
+namespace b200 {
+
+// ------------------------------------------------------------------ error plumbing
+static thread_local char g_err[512] = "";
+char* last_error_buf() { return g_err; }
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct ViewSpec {
+  const void* ptr;
+  long long dims[4];     // elements; dims[0] contiguous
+  long long strides[3];  // elements, for dims 1..3
+  int box[4];
+};
+
+// bf16, 128B swizzle, zero OOB fill.  Returns 0 on success.
+static int make_tmap(CUtensorMap* out, const ViewSpec& v) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    set_last_error("cuTensorMapEncodeTiled entry point not available (no CUDA driver?)");
+    return -3;
+  }
+  cuuint64_t dims[4];
+  cuuint64_t strides[3];
+  cuuint32_t box[4];
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  for (int i = 0; i < 4; ++i) {
+    dims[i] = static_cast<cuuint64_t>(v.dims[i] > 0 ? v.dims[i] : 1);
+    box[i] = static_cast<cuuint32_t>(v.box[i]);
+  }
+  for (int i = 0; i < 3; ++i) {
+    long long s = v.strides[i];
+    if (s <= 0) s = (i == 0 ? v.dims[0] : static_cast<long long>(strides[i - 1] / 2) * v.dims[i]);
+    if (s % 8 != 0) {
+      set_last_error("tensor map stride %lld (dim %d) is not a multiple of 8 elements", s, i + 1);
+      return -1;
+    }
+    strides[i] = static_cast<cuuint64_t>(s) * 2;
+  }
+  if ((reinterpret_cast<uintptr_t>(v.ptr) & 15) != 0) {
+    set_last_error("tensor map base pointer %p is not 16-byte aligned", v.ptr);
+    return -1;
+  }
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_last_error("cuTensorMapEncodeTiled failed (%d): dims {%lld,%lld,%lld,%lld} strides {%lld,%lld,%lld} box {%d,%d,%d,%d}",
+                   static_cast<int>(r), v.dims[0], v.dims[1], v.dims[2], v.dims[3], v.strides[0], v.strides[1],
+                   v.strides[2], v.box[0], v.box[1], v.box[2], v.box[3]);
+    return -3;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------ launch
+template <int BLOCK_N, bool A_MN, bool B_MN>
+static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+  });
+  B200_CHECK_CUDA(attr_err);
+  gemm_bf16_kernel<BLOCK_N, A_MN, B_MN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+static void fill_epilogue(GemmParams& p, const b200s_epilogue* e) {
+  p.bias = nullptr;
+  p.colsum = nullptr;
+  p.out2 = {nullptr, 0, 0};
+  p.aux = {nullptr, 0, 0};
+  p.res1 = {nullptr, 0, 0};
+  p.res2 = {nullptr, 0, 0};
+  if (!e) return;
+  p.bias = e->bias;
+  p.colsum = e->colsum;
+  if (e->colsum) p.flags |= EPI_COLSUM;
+  if (e->gelu) {
+    p.flags |= EPI_GELU;
+    p.out2 = {e->out_pre, e->pre_bs, e->pre_ld};
+  }
+  if (e->dgelu) {
+    p.flags |= EPI_DGELU;
+    p.aux = {const_cast<void*>(e->gelu_aux), e->aux_bs, e->aux_ld};
+  }
+  p.res1 = {const_cast<void*>(e->res1), e->res1_bs, e->res1_ld};
+  p.res2 = {const_cast<void*>(e->res2), e->res2_bs, e->res2_ld};
+}
+
+static int check_epilogue(const b200s_epilogue* e) {
+  if (!e) return 0;
+  B200_CHECK_ARG(!(e->dgelu && !e->gelu_aux), "epilogue: dgelu requires gelu_aux");
+  B200_CHECK_ARG(!(e->gelu && e->dgelu), "epilogue: gelu and dgelu are exclusive");
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200s_version(void) { return 100; }
+const char* b200s_last_error(void) { return b200::last_error_buf(); }
+
+int b200s_check_device(void) {
+  int dev = 0;
+  B200_CHECK_CUDA(cudaGetDevice(&dev));
+  int major = 0, minor = 0;
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+  B200_CHECK_CUDA(cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev));
+  B200_CHECK_ARG(major == 10, "unispeech_b200 needs an sm_100 device (B200); found sm_%d%d", major, minor);
+  return 0;
+}
+
+int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
+                    void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, b200s_stream stream) {
+  B200_CHECK_ARG(a && w && out, "gemm_rows: null pointer");
+  B200_CHECK_ARG(rows > 0 && batches > 0 && K > 0 && N > 0, "gemm_rows: bad sizes");
+  B200_CHECK_ARG(K % 64 == 0, "gemm_rows: K=%d must be a multiple of 64", K);
+  B200_CHECK_ARG(N % 8 == 0, "gemm_rows: N=%d must be a multiple of 8", N);
+  if (check_epilogue(epi)) return -1;
+  const int block_n = (N >= 128) ? 128 : 64;
+
+  CUtensorMap ta, tb;
+  ViewSpec va{a, {K, rows, batches, 1}, {a_rs, batches > 1 ? a_bs : 0, 0}, {64, 128, 1, 1}};
+  if (batches == 1) va.strides[1] = 0;
+  if (make_tmap(&ta, va)) return -3;
+  ViewSpec vb{w, {K, N, 1, 1}, {K, 0, 0}, {64, block_n, 1, 1}};
+  if (make_tmap(&tb, vb)) return -3;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_rows = rows;
+  p.m_tile_stride = 128;
+  p.m_tile_valid = 128;
+  p.m_tiles_per_batch = ceil_div(rows, 128);
+  p.n_total = N;
+  p.n_out_stride = block_n;
+  p.n_tile_valid = block_n;
+  p.k_blocks = K / 64;
+  p.k_blocks_per_batch = 0;
+  p.k_blocks_per_split = p.k_blocks;
+  // A coords: (k0, m0, mb, 0)   B coords: (k0, n_tile*block_n, 0, 0)
+  p.ca[0][4] = 1; p.ca[1][1] = 1; p.ca[2][2] = 1;
+  p.cb[0][4] = 1; p.cb[1][3] = block_n;
+  p.flags = 0;
+  fill_epilogue(p, epi);
+  p.out = {out, out_bs, out_ld};
+  dim3 grid(ceil_div(N, block_n), p.m_tiles_per_batch * batches, 1);
+  B200_CHECK_ARG(grid.y <= 65535, "gemm_rows: too many M tiles (%u)", grid.y);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return block_n == 128 ? launch_gemm<128, false, false>(ta, tb, p, grid, st)
+                        : launch_gemm<64, false, false>(ta, tb, p, grid, st);
+}
+
+int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
+                     int rows, int batches, int N, int K, float* dw, long long dw_ld, b200s_stream stream) {
+  B200_CHECK_ARG(y && x && dw, "gemm_wgrad: null pointer");
+  B200_CHECK_ARG(rows > 0 && batches > 0 && K > 0 && N > 0, "gemm_wgrad: bad sizes");
+  B200_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm_wgrad: N=%d, K=%d must be multiples of 8", N, K);
+  const int block_n = (K >= 128) ? 128 : 64;
+
+  CUtensorMap ta, tb;
+  ViewSpec va{y, {N, rows, batches, 1}, {y_rs, batches > 1 ? y_bs : 0, 0}, {64, 64, 1, 1}};
+  if (make_tmap(&ta, va)) return -3;
+  ViewSpec vb{x, {K, rows, batches, 1}, {x_rs, batches > 1 ? x_bs : 0, 0}, {64, 64, 1, 1}};
+  if (make_tmap(&tb, vb)) return -3;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_rows = N;
+  p.m_tile_stride = 128;
+  p.m_tile_valid = 128;
+  p.m_tiles_per_batch = ceil_div(N, 128);
+  p.n_total = K;
+  p.n_out_stride = block_n;
+  p.n_tile_valid = block_n;
+  p.k_blocks_per_batch = ceil_div(rows, 64);
+  p.k_blocks = p.k_blocks_per_batch * batches;
+  const int tiles = p.m_tiles_per_batch * ceil_div(K, block_n);
+  int splits = ceil_div(2 * sm_count(), tiles);
+  if (splits > p.k_blocks) splits = p.k_blocks;
+  if (splits < 1) splits = 1;
+  p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
+  splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
+  // A coords: (m0 + sub, k0, kbatch, 0)   B coords: (n_tile*block_n + sub, k0, kbatch, 0)
+  p.ca[0][1] = 1; p.ca[0][7] = 1; p.ca[1][4] = 1; p.ca[2][5] = 1;
+  p.cb[0][3] = block_n; p.cb[0][7] = 1; p.cb[1][4] = 1; p.cb[2][5] = 1;
+  p.flags = EPI_OUT_F32 | EPI_ATOMIC;
+  fill_epilogue(p, nullptr);
+  p.out = {dw, 0, dw_ld};
+  dim3 grid(ceil_div(K, block_n), p.m_tiles_per_batch, splits);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return block_n == 128 ? launch_gemm<128, true, true>(ta, tb, p, grid, st)
+                        : launch_gemm<64, true, true>(ta, tb, p, grid, st);
+}
+
+int b200s_posconv_gemm(const void* xpad, long long xpad_bs, int T, int B, int D, int G, int taps, const void* wp,
+                       void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi,
+                       b200s_stream stream) {
+  B200_CHECK_ARG(xpad && wp && out, "posconv_gemm: null pointer");
+  B200_CHECK_ARG(D % G == 0, "posconv_gemm: D %% G != 0");
+  const int Cg = D / G;
+  B200_CHECK_ARG(Cg <= 64 && Cg % 8 == 0, "posconv_gemm: channels per group %d must be <=64 and a multiple of 8", Cg);
+  B200_CHECK_ARG(D % 8 == 0, "posconv_gemm: D must be a multiple of 8");
+  if (check_epilogue(epi)) return -1;
+
+  CUtensorMap ta, tb;
+  ViewSpec va{xpad, {D, taps, T, B}, {D, D, xpad_bs}, {64, 1, 128, 1}};
+  if (make_tmap(&ta, va)) return -3;
+  ViewSpec vb{wp, {taps * 64LL, G * 64LL, 1, 1}, {taps * 64LL, 0, 0}, {64, 64, 1, 1}};
+  if (make_tmap(&tb, vb)) return -3;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_rows = T;
+  p.m_tile_stride = 128;
+  p.m_tile_valid = 128;
+  p.m_tiles_per_batch = ceil_div(T, 128);
+  p.n_total = D;
+  p.n_out_stride = Cg;
+  p.n_tile_valid = Cg;
+  p.k_blocks = taps;
+  p.k_blocks_per_batch = 0;
+  p.k_blocks_per_split = taps;
+  // A coords: (g*Cg, kb, m0, mb)   B coords: (kb*64, g*64, 0, 0)
+  p.ca[0][3] = Cg; p.ca[1][6] = 1; p.ca[2][1] = 1; p.ca[3][2] = 1;
+  p.cb[0][4] = 1; p.cb[1][3] = 64;
+  p.flags = 0;
+  fill_epilogue(p, epi);
+  p.out = {out, out_bs, out_ld};
+  dim3 grid(G, p.m_tiles_per_batch * B, 1);
+  return launch_gemm<64, false, false>(ta, tb, p, grid, static_cast<cudaStream_t>(stream));
+}
+
+int b200s_posconv_wgrad(const void* dy, long long dy_bs, long long dy_rs, const void* xpad, long long xpad_bs, int T,
+                        int B, int D, int G, int taps, float* dwp, b200s_stream stream) {
+  B200_CHECK_ARG(dy && xpad && dwp, "posconv_wgrad: null pointer");
+  B200_CHECK_ARG(D % G == 0, "posconv_wgrad: D %% G != 0");
+  const int Cg = D / G;
+  B200_CHECK_ARG(Cg <= 64 && Cg % 8 == 0, "posconv_wgrad: channels per group %d must be <=64 and a multiple of 8", Cg);
+
+  CUtensorMap ta, tb;
+  ViewSpec va{dy, {D, T, B, 1}, {dy_rs, B > 1 ? dy_bs : 0, 0}, {64, 64, 1, 1}};
+  if (make_tmap(&ta, va)) return -3;
+  ViewSpec vb{xpad, {D, taps, T, B}, {D, D, xpad_bs}, {64, 1, 64, 1}};
+  if (make_tmap(&tb, vb)) return -3;
+
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  p.m_rows = D;
+  p.m_tile_stride = Cg;
+  p.m_tile_valid = Cg;
+  p.m_tiles_per_batch = G;
+  p.n_total = taps * 64;
+  p.n_out_stride = 64;
+  p.n_tile_valid = 64;
+  p.k_blocks_per_batch = ceil_div(T, 64);
+  p.k_blocks = p.k_blocks_per_batch * B;
+  p.k_blocks_per_split = p.k_blocks;
+  // A coords: (m0 + sub, k0, kbatch, 0)   B coords: (m0, tap = n_tile, k0, kbatch)
+  p.ca[0][1] = 1; p.ca[0][7] = 1; p.ca[1][4] = 1; p.ca[2][5] = 1;
+  p.cb[0][1] = 1; p.cb[1][3] = 1; p.cb[2][4] = 1; p.cb[3][5] = 1;
+  p.flags = EPI_OUT_F32 | EPI_ATOMIC;
+  fill_epilogue(p, nullptr);
+  p.out = {dwp, 0, taps * 64LL};
+  dim3 grid(taps, G, 1);
+  return launch_gemm<64, true, true>(ta, tb, p, grid, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,300 @@
+// Generic bf16 tcgen05 GEMM for sm_100a:  D[M,N] (+)= A[M,K] * B[N,K]^T, fp32 accumulation in TMEM.
+//
+// One CTA computes one 128 x BLOCK_N output tile (optionally one K-split of it).  Warp roles:
+//   warp 0 : TMA producer (one elected lane)   global -> 128B-swizzled shared memory ring
+//   warp 1 : TMEM allocator + MMA issuer (one elected lane, tcgen05.mma cta_group::1 kind::f16)
+//   warps 2-5 : epilogue (tcgen05.ld 32x32b, one accumulator row per thread) with a fused
+//               bias / GELU / GELU' / residual / fp32-atomic (split-K) tail.
+// Operands may be K-major (reduction dim contiguous) or MN-major (reduction dim strided; used by the
+// weight-gradient GEMMs), selected per operand.  All the "view" tricks of the WavLM path (strided
+// Conv1d as an overlapping-row view, grouped pos_conv taps, per-batch tiles) are expressed on the host
+// as <=4-D TMA tensor maps plus a small integer matrix that maps tile indices to TMA coordinates.
+#pragma once
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct EpiTensor {
+  void* p;
+  long long bs;  // batch stride (elements)
+  long long ld;  // row stride (elements)
+};
+
+enum : int {
+  EPI_GELU = 1,      // out = gelu(acc + bias); if out2.p: out2 = acc + bias (pre-activation)
+  EPI_DGELU = 2,     // acc *= gelu'(aux)
+  EPI_OUT_F32 = 4,   // out is fp32
+  EPI_ATOMIC = 8,    // fp32 atomicAdd into out (split-K / accumulation)
+  EPI_COLSUM = 16,   // atomically accumulate column sums of the final value into colsum[col] (bias grads)
+};
+
+// variables the coordinate matrices multiply: {1, m0, mb, n_tile, k0, kbatch, kb, sub}
+constexpr int kCoordVars = 8;
+
+struct GemmParams {
+  int m_rows;            // valid rows per batch
+  int m_tiles_per_batch; // ceil over m_tile_stride
+  int m_tile_stride;     // rows between consecutive M tiles (128 normally)
+  int m_tile_valid;      // max valid rows per tile (128 normally; Cg for grouped wgrad)
+  int n_total;           // valid output columns
+  int n_out_stride;      // output column stride per N tile
+  int n_tile_valid;      // max valid columns per tile
+  int k_blocks;          // total number of 64-wide K blocks
+  int k_blocks_per_batch;  // >0: K iterates (batch, row-block); 0: plain
+  int k_blocks_per_split;
+  int ca[4][kCoordVars];
+  int cb[4][kCoordVars];
+  int flags;
+  const float* bias;     // [n] fp32 or null
+  float* colsum;         // [n] fp32 or null (EPI_COLSUM)
+  EpiTensor out, out2, aux, res1, res2;
+};
+
+template <int BLOCK_N>
+struct GemmCfg {
+  static constexpr int kStages = (BLOCK_N <= 64) ? 4 : 3;
+  static constexpr int kABytes = 128 * 128;          // 128 rows x 64 bf16
+  static constexpr int kBBytes = BLOCK_N * 128;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kThreads = 192;
+};
+
+__device__ __forceinline__ int coord_dot(const int* row, const int* v) {
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kCoordVars; ++i) s += row[i] * v[i];
+  return s;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                        const __grid_constant__ CUtensorMap tmB,
+                                                        const __grid_constant__ GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N>;
+  constexpr int kStages = Cfg::kStages;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int n_tile = blockIdx.x;
+  const int mb = blockIdx.y / p.m_tiles_per_batch;
+  const int m0 = (blockIdx.y % p.m_tiles_per_batch) * p.m_tile_stride;
+  const int kb_begin = blockIdx.z * p.k_blocks_per_split;
+  const int kb_end = min(kb_begin + p.k_blocks_per_split, p.k_blocks);
+  if (kb_begin >= kb_end) return;  // uniform per CTA
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t full_bar[kStages];
+  __shared__ uint64_t empty_bar[kStages];
+  __shared__ uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, BLOCK_N);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ TMA producer
+      int v[kCoordVars];
+      v[0] = 1; v[1] = m0; v[2] = mb; v[3] = n_tile;
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        if (p.k_blocks_per_batch > 0) {
+          v[5] = kb / p.k_blocks_per_batch;
+          v[4] = (kb % p.k_blocks_per_batch) * 64;
+        } else {
+          v[5] = 0;
+          v[4] = kb * 64;
+        }
+        v[6] = kb;
+        uint8_t* sa = smem + s * Cfg::kStageBytes;
+        uint8_t* sb = sa + Cfg::kABytes;
+        mbar_expect_tx(&full_bar[s], Cfg::kStageBytes);
+        if constexpr (!A_MN) {
+          v[7] = 0;
+          tma_load_4d(sa, &tmA, &full_bar[s], coord_dot(p.ca[0], v), coord_dot(p.ca[1], v), coord_dot(p.ca[2], v),
+                      coord_dot(p.ca[3], v));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 2; ++i) {
+            v[7] = 64 * i;
+            tma_load_4d(sa + i * 8192, &tmA, &full_bar[s], coord_dot(p.ca[0], v), coord_dot(p.ca[1], v),
+                        coord_dot(p.ca[2], v), coord_dot(p.ca[3], v));
+          }
+        }
+        if constexpr (!B_MN) {
+          v[7] = 0;
+          tma_load_4d(sb, &tmB, &full_bar[s], coord_dot(p.cb[0], v), coord_dot(p.cb[1], v), coord_dot(p.cb[2], v),
+                      coord_dot(p.cb[3], v));
+        } else {
+#pragma unroll
+          for (int i = 0; i < BLOCK_N / 64; ++i) {
+            v[7] = 64 * i;
+            tma_load_4d(sb + i * 8192, &tmB, &full_bar[s], coord_dot(p.cb[0], v), coord_dot(p.cb[1], v),
+                        coord_dot(p.cb[2], v), coord_dot(p.cb[3], v));
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------ MMA issuer
+      constexpr uint32_t idesc = make_idesc_bf16(128, BLOCK_N, A_MN ? 1 : 0, B_MN ? 1 : 0);
+      int it = 0;
+      for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        const int s = it % kStages;
+        const uint32_t ph = (it / kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
+        const uint32_t sb = sa + Cfg::kABytes;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          // K-major: advance 16 elements (32 B) inside the 128B swizzle row; SBO = 8 rows * 128 B.
+          // MN-major: advance 16 K-rows (2048 B); LBO = stride between 64-wide MN atoms (8192 B), SBO = 1024 B.
+          const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+          const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                   : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+          umma_bf16(tmem_base, da, db, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs retire
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    // -------------------------------------------------------------- epilogue
+    const int q = warp & 3;             // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;        // row inside the tile
+    const int m_valid = min(p.m_tile_valid, p.m_rows - m0);
+    const bool row_ok = r < m_valid;
+    const int col_base = n_tile * p.n_out_stride;
+    const int n_valid = min(p.n_tile_valid, p.n_total - col_base);
+    const long long row = static_cast<long long>(m0) + r;
+
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+
+    const int flags = p.flags;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+      if (c0 >= n_valid) break;  // warp-uniform
+      uint32_t acc_u[32];
+      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc_u);
+      tmem_ld_wait();
+      float* acc = reinterpret_cast<float*>(acc_u);
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c0 + j < n_valid) acc[j] += __ldg(p.bias + col_base + c0 + j);
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        const bool ok = row_ok && (c < n_valid);
+        float* a8 = acc + g * 8;
+        if (ok) {
+          const long long col = col_base + c;
+          if (flags & EPI_GELU) {
+            if (p.out2.p != nullptr) {
+              uint4 w;
+              w.x = pack_bf16x2(a8[0], a8[1]); w.y = pack_bf16x2(a8[2], a8[3]);
+              w.z = pack_bf16x2(a8[4], a8[5]); w.w = pack_bf16x2(a8[6], a8[7]);
+              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2.p) + mb * p.out2.bs + row * p.out2.ld + col) = w;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a8[j] = gelu_f(a8[j]);
+          }
+          if (flags & EPI_DGELU) {
+            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux.p) +
+                                                           mb * p.aux.bs + row * p.aux.ld + col);
+            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(wu[j]);
+              a8[2 * j] *= gelu_grad_f(f.x);
+              a8[2 * j + 1] *= gelu_grad_f(f.y);
+            }
+          }
+          if (p.res1.p != nullptr) {
+            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1.p) +
+                                                           mb * p.res1.bs + row * p.res1.ld + col);
+            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(wu[j]);
+              a8[2 * j] += f.x;
+              a8[2 * j + 1] += f.y;
+            }
+          }
+          if (p.res2.p != nullptr) {
+            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res2.p) +
+                                                           mb * p.res2.bs + row * p.res2.ld + col);
+            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 f = unpack_bf16x2(wu[j]);
+              a8[2 * j] += f.x;
+              a8[2 * j + 1] += f.y;
+            }
+          }
+          if (flags & EPI_OUT_F32) {
+            float* o = static_cast<float*>(p.out.p) + mb * p.out.bs + row * p.out.ld + col;
+            if (flags & EPI_ATOMIC) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) atomicAdd(o + j, a8[j]);
+            } else {
+              *reinterpret_cast<float4*>(o) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+              *reinterpret_cast<float4*>(o + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+            }
+          } else {
+            uint4 w;
+            w.x = pack_bf16x2(a8[0], a8[1]); w.y = pack_bf16x2(a8[2], a8[3]);
+            w.z = pack_bf16x2(a8[4], a8[5]); w.w = pack_bf16x2(a8[6], a8[7]);
+            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out.p) + mb * p.out.bs + row * p.out.ld + col) = w;
+          }
+        }
+      }
+      if (flags & EPI_COLSUM) {
+        // column sums of the stored values over this warp's 32 rows: transpose-reduce, then one atomic per column
+        float cv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float t = row_ok ? acc[j] : 0.0f;
+          if (!(flags & EPI_OUT_F32)) t = __bfloat162float(__float2bfloat16_rn(t));
+          cv[j] = t;
+        }
+        const float csum = warp_colsum32(cv, lane);
+        if ((c0 + lane) < n_valid) atomicAdd(p.colsum + col_base + c0 + lane, csum);
+      }
+    }
+  }
+
+  // teardown: everyone done with TMEM before the allocating warp frees it
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
+}  // namespace b200
