@@ -93,6 +93,12 @@ static int make_tmap(CUtensorMap* out, const ViewSpec& v) {
   return 0;
 }
 
+// [B, T, cols] bf16 row-major activations: box = 64 columns x box_rows rows (used by the attention kernels)
+int make_qkv_tmap(CUtensorMap* out, const void* ptr, int T, int B, int cols, int box_rows) {
+  ViewSpec v{ptr, {cols, T, B, 1}, {cols, static_cast<long long>(T) * cols, 0}, {64, box_rows, 1, 1}};
+  return make_tmap(out, v);
+}
+
 // ------------------------------------------------------------------ launch
 template <int BLOCK_N, bool A_MN, bool B_MN>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, dim3 grid,

@@ -1,0 +1,228 @@
+// Parameter preparation kernels: fp32 master parameters in the REFERENCE state_dict layout -> bf16 operands in the layouts
+// the GEMM kernels consume (and the inverse mapping for the fp32 gradients).  All tiny compared with the activations.
+//   * nn.Linear  [N,K]            -> bf16 [N,K] (+ optional row scale, e.g. q * head_dim^-0.5) and its transpose [K,N]
+//   * nn.Conv1d  [Co,Ci,k]        -> forward B operand [Co, k*Ci] (tap-major), per-phase input-gradient operands
+//   * pos_conv   weight_norm(dim=2) [D, D/G, taps] (WavLM/WavLM.py:514-527) -> zero-padded per-group
+//                operands for the forward and the flipped/transposed input-gradient implicit GEMMs; backward of the
+//                weight normalisation.
+#include "../../include/unispeech_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+__global__ void scale_copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i] * scale;
+}
+
+// dst[n*ld + k] = bf16(src[n,k]*scale);  dstT[k*ldT + n] = same, through a 32x32 shared tile
+__global__ void prep_linear_kernel(const float* __restrict__ src, int N, int K, float scale, __nv_bfloat16* __restrict__ dst,
+                                   long long ld, __nv_bfloat16* __restrict__ dstT, long long ldT) {
+  __shared__ float tile[32][33];
+  const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < N && k < K) {
+      v = src[static_cast<long long>(n) * K + k] * scale;
+      if (dst) dst[static_cast<long long>(n) * ld + k] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (dstT) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (n < N && k < K) dstT[static_cast<long long>(k) * ldT + n] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
+// conv forward operand: dst[co, j*Ci + ci] = src[co, ci, j]
+__global__ void prep_conv_fwd_kernel(const float* __restrict__ src, int Co, int Ci, int k, __nv_bfloat16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(Co) * Ci * k;
+  if (i >= n) return;
+  const int ci = i % Ci;
+  const int j = (i / Ci) % k;
+  const int co = i / (static_cast<long long>(Ci) * k);
+  dst[i] = __float2bfloat16_rn(src[(static_cast<long long>(co) * Ci + ci) * k + j]);
+}
+// conv input-gradient operand for phase rho (input row r = s*u + rho):  taps j = rho + s*m, m < nm.
+// dst[ci, mm*Co + co] = src[co, ci, rho + s*(nm-1-mm)]     (A rows are [dY[u-(nm-1)], ..., dY[u]])
+__global__ void prep_conv_dgrad_kernel(const float* __restrict__ src, int Co, int Ci, int k, int s, int rho, int nm,
+                                       __nv_bfloat16* __restrict__ dst) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(Ci) * nm * Co;
+  if (i >= n) return;
+  const int co = i % Co;
+  const int mm = (i / Co) % nm;
+  const int ci = i / (static_cast<long long>(Co) * nm);
+  const int j = rho + s * (nm - 1 - mm);
+  dst[i] = __float2bfloat16_rn(src[(static_cast<long long>(co) * Ci + ci) * k + j]);
+}
+// gradient back to the reference layout: dw[co, ci, j] += dwk[co, j*Ci + ci]
+__global__ void unprep_conv_wgrad_kernel(const float* __restrict__ dwk, int Co, int Ci, int k, float* __restrict__ dw) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(Co) * Ci * k;
+  if (i >= n) return;
+  const int j = i % k;
+  const int ci = (i / k) % Ci;
+  const int co = i / (static_cast<long long>(Ci) * k);
+  dw[i] += dwk[(static_cast<long long>(co) * k + j) * Ci + ci];
+}
+
+// ---- pos_conv weight norm -----------------------------------------------------------------------------------------
+// norm2[j] = sum_{co,ci} v[co,ci,j]^2  (and optionally dot[j] = sum dw*v for the backward)
+__global__ void posconv_tap_reduce_kernel(const float* __restrict__ v, const float* __restrict__ dwp, int D, int Cg, int taps,
+                                          float* __restrict__ norm2, float* __restrict__ dot) {
+  // thread -> tap (coalesced over the contiguous tap axis), blocks stride over (co, ci) rows
+  const int j = threadIdx.x;
+  if (j >= taps) return;
+  const long long rows = static_cast<long long>(D) * Cg;
+  float a = 0.f, d = 0.f;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float x = v[r * taps + j];
+    a += x * x;
+    if (dwp) {
+      const int co = r / Cg, ci = r % Cg;  // co global channel
+      const int g = co / Cg, cog = co % Cg;
+      d += dwp[((static_cast<long long>(g) * Cg + cog) * taps + j) * 64 + ci] * x;
+    }
+  }
+  atomicAdd(norm2 + j, a);
+  if (dwp) atomicAdd(dot + j, d);
+}
+// wp_fwd[(g*64+co), j*64+ci] = w[g*Cg+co, ci, j];   wp_dg[(g*64+ci), j'*64+co] = w[g*Cg+co, ci, taps-1-j']
+// with w = gvec[j] * v / sqrt(norm2[j]); zero padding elsewhere.
+__global__ void posconv_prep_kernel(const float* __restrict__ v, const float* __restrict__ gvec,
+                                    const float* __restrict__ norm2, int G, int Cg, int taps,
+                                    __nv_bfloat16* __restrict__ wp_fwd, __nv_bfloat16* __restrict__ wp_dg) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(G) * 64 * taps * 64;
+  if (i >= n) return;
+  const int c = i % 64;            // inner (ci for fwd)
+  const int j = (i / 64) % taps;
+  const int r = (i / (64LL * taps)) % 64;  // row within group (co for fwd)
+  const int g = i / (64LL * taps * 64);
+  float wf = 0.f, wd = 0.f;
+  if (r < Cg && c < Cg) {
+    // forward: row co=r, col ci=c, tap j
+    wf = v[((static_cast<long long>(g) * Cg + r) * Cg + c) * taps + j] * gvec[j] * rsqrtf(norm2[j]);
+    // dgrad: row ci=r, col co=c, tap jj = taps-1-j
+    const int jj = taps - 1 - j;
+    wd = v[((static_cast<long long>(g) * Cg + c) * Cg + r) * taps + jj] * gvec[jj] * rsqrtf(norm2[jj]);
+  }
+  wp_fwd[i] = __float2bfloat16_rn(wf);
+  wp_dg[i] = __float2bfloat16_rn(wd);
+}
+// backward of weight_norm: dg[j] += dot[j]/norm_j;  dv = g/norm * dw - g*dot/norm^3 * v
+__global__ void posconv_unprep_kernel(const float* __restrict__ v, const float* __restrict__ gvec,
+                                      const float* __restrict__ norm2, const float* __restrict__ dot,
+                                      const float* __restrict__ dwp, int D, int Cg, int taps, float* __restrict__ dv,
+                                      float* __restrict__ dg) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = static_cast<long long>(D) * Cg * taps;
+  if (i < taps) dg[i] += dot[i] * rsqrtf(norm2[i]);
+  if (i >= n) return;
+  const int j = i % taps;
+  const int ci = (i / taps) % Cg;
+  const int co = i / (static_cast<long long>(taps) * Cg);
+  const int g = co / Cg, cog = co % Cg;
+  const float inv = rsqrtf(norm2[j]);
+  const float dw = dwp[((static_cast<long long>(g) * Cg + cog) * taps + j) * 64 + ci];
+  dv[i] += gvec[j] * inv * dw - gvec[j] * dot[j] * inv * inv * inv * v[i];
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200s_scale_copy_f32(const float* src, float* dst, long long n, float scale, b200s_stream stream) {
+  B200_CHECK_ARG(src && dst, "scale_copy_f32: null pointer");
+  if (n == 0) return 0;
+  scale_copy_f32_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, dst, n, scale);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, long long ld, void* dstT, long long ldT,
+                      b200s_stream stream) {
+  B200_CHECK_ARG(src && (dst || dstT), "prep_linear: null pointer");
+  dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
+  prep_linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, N, K, scale, static_cast<__nv_bfloat16*>(dst), ld, static_cast<__nv_bfloat16*>(dstT), ldT);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream) {
+  B200_CHECK_ARG(src && dst, "prep_conv_fwd: null pointer");
+  const long long n = static_cast<long long>(Co) * Ci * k;
+  prep_conv_fwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, Co, Ci, k, static_cast<__nv_bfloat16*>(dst));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rho, void* dst, b200s_stream stream) {
+  B200_CHECK_ARG(src && dst, "prep_conv_dgrad: null pointer");
+  B200_CHECK_ARG(rho >= 0 && rho < s && rho < k, "prep_conv_dgrad: bad phase");
+  const int nm = (k - rho + s - 1) / s;
+  const long long n = static_cast<long long>(Ci) * nm * Co;
+  prep_conv_dgrad_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, Co, Ci, k, s, rho, nm, static_cast<__nv_bfloat16*>(dst));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_unprep_conv_wgrad(const float* dwk, int Co, int Ci, int k, float* dw, b200s_stream stream) {
+  B200_CHECK_ARG(dwk && dw, "unprep_conv_wgrad: null pointer");
+  const long long n = static_cast<long long>(Co) * Ci * k;
+  unprep_conv_wgrad_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dwk, Co, Ci, k, dw);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// norm2: fp32 [taps] workspace (zeroed here)
+int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int G, int taps, float* norm2, void* wp_fwd,
+                       void* wp_dgrad, b200s_stream stream) {
+  B200_CHECK_ARG(weight_v && weight_g && norm2 && wp_fwd && wp_dgrad, "posconv_prep: null pointer");
+  B200_CHECK_ARG(taps <= 1024 && D % G == 0 && D / G <= 64, "posconv_prep: bad sizes");
+  const int Cg = D / G;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float) * taps, st));
+  posconv_tap_reduce_kernel<<<4 * sm_count(), ((taps + 31) / 32) * 32, 0, st>>>(weight_v, nullptr, D, Cg, taps, norm2,
+                                                                               nullptr);
+  B200_CHECK_LAUNCH();
+  const long long n = static_cast<long long>(G) * 64 * taps * 64;
+  posconv_prep_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, st>>>(
+      weight_v, weight_g, norm2, G, Cg, taps, static_cast<__nv_bfloat16*>(wp_fwd),
+      static_cast<__nv_bfloat16*>(wp_dgrad));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// dwp: fp32 [G, Cg, taps, 64] from b200s_posconv_wgrad.  work: fp32 [2*taps] workspace (zeroed here).
+int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const float* dwp, int D, int G, int taps,
+                         float* work, float* dweight_v, float* dweight_g, b200s_stream stream) {
+  B200_CHECK_ARG(weight_v && weight_g && dwp && work && dweight_v && dweight_g, "posconv_unprep: null pointer");
+  const int Cg = D / G;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  B200_CHECK_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * 2 * taps, st));
+  posconv_tap_reduce_kernel<<<4 * sm_count(), ((taps + 31) / 32) * 32, 0, st>>>(weight_v, dwp, D, Cg, taps, work,
+                                                                               work + taps);
+  B200_CHECK_LAUNCH();
+  const long long n = static_cast<long long>(D) * Cg * taps;
+  posconv_unprep_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, st>>>(weight_v, weight_g, work, work + taps,
+                                                                                   dwp, D, Cg, taps, dweight_v, dweight_g);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,618 @@
+// Memory-bound row kernels of the encoder: LayerNorm (+GELU) forward / backward with fused residual-gradient add and
+// parameter-gradient column reductions, bf16 column sums, GELU-derivative multiply, frame masking, gate (gru_rel_pos),
+// relative-position table gather/scatter.  One warp per row, 16-byte vector accesses, warp-shuffle reductions.
+#include <algorithm>
+#include <type_traits>
+
+#include "../../include/unispeech_b200.h"
+#include "common.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+template <int VEC>
+struct VecIO;
+template <>
+struct VecIO<8> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint4 w = *reinterpret_cast<const uint4*>(p);
+    const uint32_t u[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = unpack_bf16x2(u[i]);
+      v[2 * i] = f.x;
+      v[2 * i + 1] = f.y;
+    }
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint4 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    w.z = pack_bf16x2(v[4], v[5]); w.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = w;
+  }
+};
+template <>
+struct VecIO<4> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const uint2 w = *reinterpret_cast<const uint2*>(p);
+    const float2 a = unpack_bf16x2(w.x), b = unpack_bf16x2(w.y);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    uint2 w;
+    w.x = pack_bf16x2(v[0], v[1]); w.y = pack_bf16x2(v[2], v[3]);
+    *reinterpret_cast<uint2*>(p) = w;
+  }
+};
+template <>
+struct VecIO<2> {
+  static __device__ __forceinline__ void load(const __nv_bfloat16* p, float* v) {
+    const float2 a = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p));
+    v[0] = a.x; v[1] = a.y;
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, const float* v) {
+    *reinterpret_cast<uint32_t*>(p) = pack_bf16x2(v[0], v[1]);
+  }
+};
+
+struct RowView {
+  long long bs, rs;
+  int rows_per_batch;
+  __device__ __forceinline__ long long off(long long r) const {
+    return (r / rows_per_batch) * bs + (r % rows_per_batch) * rs;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ LayerNorm forward
+// y = (x - mean) * rstd * gamma + beta  [then exact GELU if gelu != 0]; statistics in fp32 (F.layer_norm,
+// reference: WavLM/WavLM.py:342,559,666,675; Fp32LayerNorm WavLM/modules.py:30-42 for the conv stack)
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     __nv_bfloat16* __restrict__ y, RowView yv,
+                                                     float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                     long long rows, int gelu, float eps) {
+  constexpr int D = 32 * VEC * NCH;
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float g[NCH * VEC], b[NCH * VEC];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      g[i * VEC + j] = gamma[(i * 32 + lane) * VEC + j];
+      b[i * VEC + j] = beta[(i * 32 + lane) * VEC + j];
+    }
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const __nv_bfloat16* xr = x + xv.off(r);
+    float v[NCH * VEC];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) VecIO<VEC>::load(xr + (i * 32 + lane) * VEC, v + i * VEC);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * VEC; ++i) s += v[i];
+    const float mean = warp_sum(s) * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH * VEC; ++i) {
+      const float d = v[i] - mean;
+      q += d * d;
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+#pragma unroll
+    for (int i = 0; i < NCH * VEC; ++i) {
+      float o = (v[i] - mean) * rstd * g[i] + b[i];
+      if (gelu) o = gelu_f(o);
+      v[i] = o;
+    }
+    __nv_bfloat16* yr = y + yv.off(r);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(yr + (i * 32 + lane) * VEC, v + i * VEC);
+    if (lane == 0) {
+      if (mean_out) mean_out[r] = mean;
+      if (rstd_out) rstd_out[r] = rstd;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm backward
+// dz = dy * gelu'(gamma*xhat+beta) if gelu else dy;  dxhat = dz*gamma
+// dx = rstd * (dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) [+ dres];  dgamma += sum_rows dz*xhat; dbeta += sum_rows dz
+// optional colsum += sum_rows dx (as stored, bf16-rounded) -- the bias gradient of the producer of x.
+template <int VEC, int NCH>
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
+                                                     const __nv_bfloat16* __restrict__ x, RowView xv,
+                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                     const __nv_bfloat16* __restrict__ dres, RowView dresv,
+                                                     __nv_bfloat16* __restrict__ dx, RowView dxv,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                     float* __restrict__ colsum, long long rows, int gelu) {
+  constexpr int D = 32 * VEC * NCH;
+  constexpr int N = NCH * VEC;
+  __shared__ float red[8][D];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float g[N], b[N], ag[N], ab[N], ac[N];
+#pragma unroll
+  for (int i = 0; i < NCH; ++i)
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      g[i * VEC + j] = gamma[(i * 32 + lane) * VEC + j];
+      b[i * VEC + j] = gelu ? beta[(i * 32 + lane) * VEC + j] : 0.f;
+    }
+#pragma unroll
+  for (int i = 0; i < N; ++i) ag[i] = ab[i] = ac[i] = 0.f;
+
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    float xh[N], dz[N];
+    const __nv_bfloat16* xr = x + xv.off(r);
+    const __nv_bfloat16* dr = dy + dyv.off(r);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      VecIO<VEC>::load(xr + (i * 32 + lane) * VEC, xh + i * VEC);
+      VecIO<VEC>::load(dr + (i * 32 + lane) * VEC, dz + i * VEC);
+    }
+    const float mean = mean_in[r], rstd = rstd_in[r];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      xh[i] = (xh[i] - mean) * rstd;
+      if (gelu) dz[i] *= gelu_grad_f(g[i] * xh[i] + b[i]);
+      ag[i] += dz[i] * xh[i];
+      ab[i] += dz[i];
+      const float dxh = dz[i] * g[i];
+      dz[i] = dxh;
+      s1 += dxh;
+      s2 += dxh * xh[i];
+    }
+    s1 = warp_sum(s1) * (1.0f / D);
+    s2 = warp_sum(s2) * (1.0f / D);
+    float o[N];
+    if (dres != nullptr) {
+      const __nv_bfloat16* rr = dres + dresv.off(r);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) VecIO<VEC>::load(rr + (i * 32 + lane) * VEC, o + i * VEC);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      o[i] += rstd * (dz[i] - s1 - xh[i] * s2);
+      ac[i] += __bfloat162float(__float2bfloat16_rn(o[i]));
+    }
+    __nv_bfloat16* outr = dx + dxv.off(r);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(outr + (i * 32 + lane) * VEC, o + i * VEC);
+  }
+
+  // block reduction of the per-warp column partials, one quantity at a time through shared memory
+  const int nw = blockDim.x >> 5;
+  auto reduce_to = [&](const float* acc, float* dst) {
+    if (dst == nullptr) return;  // uniform across the block
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NCH; ++i)
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) red[warp][(i * 32 + lane) * VEC + j] = acc[i * VEC + j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float s = 0.f;
+      for (int w = 0; w < nw; ++w) s += red[w][c];
+      atomicAdd(dst + c, s);
+    }
+  };
+  reduce_to(ag, dgamma);
+  reduce_to(ab, dbeta);
+  reduce_to(ac, colsum);
+}
+
+template <typename F>
+static int dispatch_width(int D, F&& f) {
+  switch (D) {
+    case 64: return f(std::integral_constant<int, 2>{}, std::integral_constant<int, 1>{});
+    case 128: return f(std::integral_constant<int, 4>{}, std::integral_constant<int, 1>{});
+    case 256: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 1>{});
+    case 512: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 2>{});
+    case 768: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 3>{});
+    case 1024: return f(std::integral_constant<int, 8>{}, std::integral_constant<int, 4>{});
+    default:
+      set_last_error("row kernels support widths 64/128/256/512/768/1024, got %d", D);
+      return -1;
+  }
+}
+
+static int row_grid(long long rows, int warps_per_block) {
+  long long blocks = ceil_div_ll(rows, warps_per_block);
+  const long long cap = static_cast<long long>(sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+// colsum[c] += sum_rows x[r, c]   (bias gradients); x bf16 [rows, N] with batch/row strides.
+__global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int N,
+                                                     long long rows, float* __restrict__ out) {
+  // block handles a strip of 64 columns (blockIdx.x) and a slice of rows (blockIdx.y); thread -> (row lane, 2 cols)
+  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  const int rl = threadIdx.x >> 5;  // 0..7
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + xv.off(r) + c));
+      a0 += f.x;
+      a1 += f.y;
+    }
+  }
+  __shared__ float red[8][64];
+  red[rl][(threadIdx.x & 31) * 2] = a0;
+  red[rl][(threadIdx.x & 31) * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) atomicAdd(out + cc, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dgelu multiply
+// out = dy * gelu'(pre)  (bf16), optional colsum of the stored values.  Used for the pos_conv backward
+// (x + gelu(conv(x)): WavLM/WavLM.py:577-579) where the product must land in a zero-padded buffer.
+__global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
+                                                        const __nv_bfloat16* __restrict__ pre, RowView prev,
+                                                        __nv_bfloat16* __restrict__ out, RowView outv, int N,
+                                                        long long rows, float* __restrict__ colsum) {
+  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  const int rl = threadIdx.x >> 5;
+  float a0 = 0.f, a1 = 0.f;
+  if (c < N) {
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
+      const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + dyv.off(r) + c));
+      const float2 p = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pre + prev.off(r) + c));
+      const uint32_t w = pack_bf16x2(d.x * gelu_grad_f(p.x), d.y * gelu_grad_f(p.y));
+      *reinterpret_cast<uint32_t*>(out + outv.off(r) + c) = w;
+      const float2 f = unpack_bf16x2(w);
+      a0 += f.x;
+      a1 += f.y;
+    }
+  }
+  if (colsum == nullptr) return;
+  __shared__ float red[8][64];
+  red[rl][(threadIdx.x & 31) * 2] = a0;
+  red[rl][(threadIdx.x & 31) * 2 + 1] = a1;
+  __syncthreads();
+  if (threadIdx.x < 64) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+    const int cc = blockIdx.x * 64 + threadIdx.x;
+    if (cc < N) atomicAdd(colsum + cc, s);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ frame masking
+// x[b,t,:] = 0 where pad[b,t];  = mask_emb where mask[b,t] and not pad   (apply_mask WavLM/WavLM.py:285-286, then
+// x[padding_mask] = 0 WavLM/WavLM.py:574-575).  In place on a [B,T,D] view.
+__global__ void __launch_bounds__(256) frame_mask_fwd_kernel(__nv_bfloat16* __restrict__ x, RowView xv, int D,
+                                                             long long rows, const uint8_t* __restrict__ mask,
+                                                             const uint8_t* __restrict__ pad,
+                                                             const float* __restrict__ mask_emb) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const bool p = pad != nullptr && pad[r] != 0;
+    const bool m = mask != nullptr && mask[r] != 0;
+    if (!p && !m) continue;
+    __nv_bfloat16* xr = x + xv.off(r);
+    for (int c = lane * 2; c < D; c += 64) {
+      const uint32_t w = p ? 0u : pack_bf16x2(mask_emb[c], mask_emb[c + 1]);
+      *reinterpret_cast<uint32_t*>(xr + c) = w;
+    }
+  }
+}
+// backward: d mask_emb += sum over masked & unpadded rows of dx;  dx rows that were overwritten get zero gradient.
+__global__ void __launch_bounds__(256) frame_mask_bwd_kernel(__nv_bfloat16* __restrict__ dx, RowView xv, int D,
+                                                             long long rows, const uint8_t* __restrict__ mask,
+                                                             const uint8_t* __restrict__ pad,
+                                                             float* __restrict__ dmask_emb) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const bool p = pad != nullptr && pad[r] != 0;
+    const bool m = mask != nullptr && mask[r] != 0;
+    if (!p && !m) continue;
+    __nv_bfloat16* xr = dx + xv.off(r);
+    for (int c = lane * 2; c < D; c += 64) {
+      if (!p && dmask_emb != nullptr) {
+        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
+        atomicAdd(dmask_emb + c, f.x);
+        atomicAdd(dmask_emb + c + 1, f.y);
+      }
+      *reinterpret_cast<uint32_t*>(xr + c) = 0u;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ gru_rel_pos gate
+// gate[b,h,t] = ga*(gb*grep_a[h] - 1) + 2, (ga,gb) = sigmoid(sum of the first / last 4 outputs of grep_linear applied to
+// the raw 64-wide head slice of the layer input)  (WavLM/modules.py:523-533).  wa/wb are the pre-summed weight rows.
+__global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int H, int T,
+                                                       long long rows, const float* __restrict__ grep_w,
+                                                       const float* __restrict__ grep_b, const float* __restrict__ grep_a,
+                                                       float* __restrict__ gate) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float wa0 = 0.f, wa1 = 0.f, wb0 = 0.f, wb1 = 0.f, ba = 0.f, bb = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    wa0 += grep_w[o * 64 + lane * 2];
+    wa1 += grep_w[o * 64 + lane * 2 + 1];
+    wb0 += grep_w[(o + 4) * 64 + lane * 2];
+    wb1 += grep_w[(o + 4) * 64 + lane * 2 + 1];
+    ba += grep_b[o];
+    bb += grep_b[o + 4];
+  }
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const __nv_bfloat16* xr = x + xv.off(r);
+    const long long b = r / T, t = r % T;
+    for (int h = 0; h < H; ++h) {
+      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
+      const float sa = warp_sum(f.x * wa0 + f.y * wa1) + ba;
+      const float sb = warp_sum(f.x * wb0 + f.y * wb1) + bb;
+      if (lane == 0) {
+        const float ga = 1.0f / (1.0f + __expf(-sa));
+        const float gb = 1.0f / (1.0f + __expf(-sb));
+        gate[(b * H + h) * T + t] = ga * (gb * grep_a[h] - 1.0f) + 2.0f;
+      }
+    }
+  }
+}
+
+// backward of the gate: dgate[b,h,t] -> dx_gate[b,t,h*64+c] (bf16, written densely: every head slice of every row),
+// dW[o,c], db[o], d grep_a[h].   dW rows 0-3 are identical (= d wa) and rows 4-7 identical (= d wb).
+__global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int H, int T,
+                                                       long long rows, const float* __restrict__ grep_w,
+                                                       const float* __restrict__ grep_b, const float* __restrict__ grep_a,
+                                                       const float* __restrict__ dgate, __nv_bfloat16* __restrict__ dxg,
+                                                       RowView dxv, float* __restrict__ dgrep_w,
+                                                       float* __restrict__ dgrep_b, float* __restrict__ dgrep_a) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  float wa0 = 0.f, wa1 = 0.f, wb0 = 0.f, wb1 = 0.f, ba = 0.f, bb = 0.f;
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    wa0 += grep_w[o * 64 + lane * 2];
+    wa1 += grep_w[o * 64 + lane * 2 + 1];
+    wb0 += grep_w[(o + 4) * 64 + lane * 2];
+    wb1 += grep_w[(o + 4) * 64 + lane * 2 + 1];
+    ba += grep_b[o];
+    bb += grep_b[o + 4];
+  }
+  float dwa0 = 0.f, dwa1 = 0.f, dwb0 = 0.f, dwb1 = 0.f, dba = 0.f, dbb = 0.f;
+  extern __shared__ float dga_smem[];  // [warps][H] partial d grep_a
+  for (int h = lane; h < H; h += 32) dga_smem[warp * H + h] = 0.f;
+  __syncwarp();
+  for (long long r = warp_global; r < rows; r += nwarps) {
+    const __nv_bfloat16* xr = x + xv.off(r);
+    __nv_bfloat16* dr = dxg + dxv.off(r);
+    const long long b = r / T, t = r % T;
+    for (int h = 0; h < H; ++h) {
+      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
+      const float sa = warp_sum(f.x * wa0 + f.y * wa1) + ba;
+      const float sb = warp_sum(f.x * wb0 + f.y * wb1) + bb;
+      const float ga = 1.0f / (1.0f + __expf(-sa));
+      const float gb = 1.0f / (1.0f + __expf(-sb));
+      const float a = grep_a[h];
+      const float dg = dgate[(b * H + h) * T + t];
+      const float dsa = dg * (gb * a - 1.0f) * ga * (1.0f - ga);
+      const float dsb = dg * ga * a * gb * (1.0f - gb);
+      dwa0 += dsa * f.x; dwa1 += dsa * f.y;
+      dwb0 += dsb * f.x; dwb1 += dsb * f.y;
+      if (lane == 0) {
+        dba += dsa;
+        dbb += dsb;
+        dga_smem[warp * H + h] += dg * ga * gb;
+      }
+      *reinterpret_cast<uint32_t*>(dr + h * 64 + lane * 2) = pack_bf16x2(dsa * wa0 + dsb * wb0, dsa * wa1 + dsb * wb1);
+    }
+  }
+  // every one of the 4 rows that were summed receives the same gradient
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    atomicAdd(dgrep_w + o * 64 + lane * 2, dwa0);
+    atomicAdd(dgrep_w + o * 64 + lane * 2 + 1, dwa1);
+    atomicAdd(dgrep_w + (o + 4) * 64 + lane * 2, dwb0);
+    atomicAdd(dgrep_w + (o + 4) * 64 + lane * 2 + 1, dwb1);
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      atomicAdd(dgrep_b + o, dba);
+      atomicAdd(dgrep_b + o + 4, dbb);
+    }
+  }
+  __syncwarp();
+  for (int h = lane; h < H; h += 32) atomicAdd(dgrep_a + h, dga_smem[warp * H + h]);
+}
+
+// ------------------------------------------------------------------------------------------------ relative position table
+// tab[h, i] = E[lut[i], h], i = delta + T - 1  (Toeplitz form of compute_bias, WavLM/modules.py:445-455)
+__global__ void relpos_table_fwd_kernel(const float* __restrict__ emb, const int* __restrict__ lut, int n, int H,
+                                        float* __restrict__ tab) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * H) return;
+  const int h = i / n, d = i % n;
+  tab[i] = emb[lut[d] * H + h];
+}
+__global__ void relpos_table_bwd_kernel(const float* __restrict__ dtab, const int* __restrict__ lut, int n, int H,
+                                        float* __restrict__ demb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * H) return;
+  const int h = i / n, d = i % n;
+  atomicAdd(demb + lut[d] * H + h, dtab[i]);
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                         long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch, int batches,
+                         int D, int gelu, b200s_stream stream) {
+  B200_CHECK_ARG(x && gamma && beta && y, "layer_norm_fwd: null pointer");
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  RowView xv{x_bs, x_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dispatch_width(D, [&](auto vec, auto nch) {
+    ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value><<<row_grid(rows, 8), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(x), xv, gamma, beta, static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows,
+        gelu, 1e-5f);
+    return 0;
+  });
+  if (rc) return rc;
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs, long long x_rs,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta, const void* dres,
+                         long long dres_bs, long long dres_rs, void* dx, long long dx_bs, long long dx_rs, float* dgamma,
+                         float* dbeta, float* colsum, int rows_per_batch, int batches, int D, int gelu,
+                         b200s_stream stream) {
+  B200_CHECK_ARG(dy && x && mean && rstd && gamma && dx, "layer_norm_bwd: null pointer");
+  B200_CHECK_ARG(!gelu || beta, "layer_norm_bwd: gelu mode needs beta");
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  RowView dyv{dy_bs, dy_rs, rows_per_batch}, xv{x_bs, x_rs, rows_per_batch}, rv{dres_bs, dres_rs, rows_per_batch},
+      dxv{dx_bs, dx_rs, rows_per_batch};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  long long blocks = ceil_div_ll(rows, 8 * 4);  // >=4 rows per warp so the column partial sums amortise
+  const long long cap = static_cast<long long>(sm_count()) * 2;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  int rc = dispatch_width(D, [&](auto vec, auto nch) {
+    ln_bwd_kernel<decltype(vec)::value, decltype(nch)::value><<<static_cast<int>(blocks), 256, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(dy), dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
+        static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv, dgamma, dbeta, colsum, rows,
+        gelu);
+    return 0;
+  });
+  if (rc) return rc;
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                 b200s_stream stream) {
+  B200_CHECK_ARG(x && out, "colsum: null pointer");
+  B200_CHECK_ARG(N % 2 == 0, "colsum: N must be even");
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  RowView xv{x_bs, x_rs, rows_per_batch};
+  int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 64), 4LL * sm_count() / std::max(1, ceil_div(N, 64)) + 1));
+  dim3 grid(ceil_div(N, 64), std::max(1, gy));
+  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), xv, N, rows,
+                                                                    out);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs, long long pre_rs,
+                    void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches, int N, float* colsum,
+                    b200s_stream stream) {
+  B200_CHECK_ARG(dy && pre && out, "dgelu_mul: null pointer");
+  B200_CHECK_ARG(N % 2 == 0, "dgelu_mul: N must be even");
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  RowView a{dy_bs, dy_rs, rows_per_batch}, b{pre_bs, pre_rs, rows_per_batch}, c{out_bs, out_rs, rows_per_batch};
+  int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 64), 4LL * sm_count() / std::max(1, ceil_div(N, 64)) + 1));
+  dim3 grid(ceil_div(N, 64), std::max(1, gy));
+  dgelu_mul_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(dy), a, static_cast<const __nv_bfloat16*>(pre), b,
+      static_cast<__nv_bfloat16*>(out), c, N, rows, colsum);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
+                         const uint8_t* pad, const float* mask_emb, b200s_stream stream) {
+  B200_CHECK_ARG(x, "frame_mask_fwd: null pointer");
+  B200_CHECK_ARG(D % 2 == 0, "frame_mask_fwd: D must be even");
+  B200_CHECK_ARG(!mask || mask_emb, "frame_mask_fwd: mask needs mask_emb");
+  if (!mask && !pad) return 0;
+  const long long rows = static_cast<long long>(T) * B;
+  RowView xv{x_bs, x_rs, T};
+  frame_mask_fwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(x), xv, D, rows, mask, pad, mask_emb);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_frame_mask_bwd(void* dx, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
+                         const uint8_t* pad, float* dmask_emb, b200s_stream stream) {
+  B200_CHECK_ARG(dx, "frame_mask_bwd: null pointer");
+  if (!mask && !pad) return 0;
+  const long long rows = static_cast<long long>(T) * B;
+  RowView xv{x_bs, x_rs, T};
+  frame_mask_bwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<__nv_bfloat16*>(dx), xv, D, rows, mask, pad, dmask_emb);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_gate_fwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                   const float* grep_b, const float* grep_a, float* gate, b200s_stream stream) {
+  B200_CHECK_ARG(x && grep_w && grep_b && grep_a && gate, "gate_fwd: null pointer");
+  const long long rows = static_cast<long long>(T) * B;
+  RowView xv{x_bs, x_rs, T};
+  gate_fwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, gate);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                   const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                   long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, b200s_stream stream) {
+  B200_CHECK_ARG(x && grep_w && grep_b && grep_a && dgate && dxg && dgrep_w && dgrep_b && dgrep_a,
+                 "gate_bwd: null pointer");
+  const long long rows = static_cast<long long>(T) * B;
+  RowView xv{x_bs, x_rs, T}, dv{dx_bs, dx_rs, T};
+  long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 8), 2LL * sm_count());
+  if (blocks < 1) blocks = 1;
+  gate_bwd_kernel<<<static_cast<int>(blocks), 256, 8 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, dgate,
+      static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_relpos_table_fwd(const float* emb, const int* lut, int n, int H, float* tab, b200s_stream stream) {
+  B200_CHECK_ARG(emb && lut && tab, "relpos_table_fwd: null pointer");
+  relpos_table_fwd_kernel<<<ceil_div(n * H, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(emb, lut, n, H, tab);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+int b200s_relpos_table_bwd(const float* dtab, const int* lut, int n, int H, float* demb, b200s_stream stream) {
+  B200_CHECK_ARG(dtab && lut && demb, "relpos_table_bwd: null pointer");
+  relpos_table_bwd_kernel<<<ceil_div(n * H, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dtab, lut, n, H, demb);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+}  // extern "C"
