@@ -1,0 +1,280 @@
+"""Headline benchmark: WavLM forward+backward throughput in audio-seconds/second (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--model base|large] [--impl ours|reference]
+
+N=1 workload = BASELINE.json configs[1]: WavLM-Base, batch 16 x 15 s synthetic 16 kHz waveform per GPU, masking on, fwd + bwd of the
+whole encoder through the public API (`WavLM.extract_features` + probe loss + `backward()`), bf16 kernels, dropout 0.
+N>1 (launched with torch.distributed.run): same per-GPU batch (weak scaling), plus ONE NCCL allreduce of the flat fp32
+gradient buffer per step.  Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks.
+Inputs are far larger than L2 (the first conv activation alone is 786 MB), so no explicit L2 flush is needed.
+
+`--impl reference` times the CPU oracle (the restatement of the reference's PyTorch path, pinned to the reference by golden
+fixtures) on the host cores with all threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+SR = 16000
+
+
+def model_config(name: str):
+    from oracle import wavlm_oracle as O
+    if name == "base":
+        return O.base_config(), 16, 15
+    if name == "large":
+        return O.large_config(), 8, 20
+    if name == "tiny":
+        return O.tiny_config(), 4, 2
+    raise ValueError(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_step(cfg, B, secs, steps, threads):
+    """One bounded CPU sample: oracle fwd+bwd on B x secs of audio, all host threads.  Returns audio-s/s and seconds."""
+    from oracle import wavlm_oracle as O
+    torch.set_num_threads(threads)
+    sd = {k: v.clone().requires_grad_(True) for k, v in O.deterministic_state_dict(cfg).items()}
+    wav, _ = O.deterministic_waveform(B, secs * SR, seed=3)
+    pm = torch.zeros(B, secs * SR, dtype=torch.bool)
+    T = O.num_frames(secs * SR, cfg)
+    mi = O.hash_uniform("benchmask", (B, T)) > 0.3
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        res = O.extract_features(sd, wav, cfg, padding_mask=pm, mask_indices=mi)
+        loss = O.probe_loss(res["x"], res["padding_mask"], seed=2)
+        loss.backward()
+        for v in sd.values():
+            v.grad = None
+        times.append(time.perf_counter() - t0)
+    best = sorted(times)[len(times) // 2]
+    return B * secs / best, best
+
+
+def run_reference(args):
+    cfg, B, secs = model_config(args.model)
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    cb, csecs = (2, secs) if args.model != "tiny" else (B, secs)
+    steps = max(1, min(args.steps, 3))
+    for _ in range(min(args.warmup, 1)):
+        cpu_step(cfg, cb, csecs, 1, threads)
+    value, step_s = cpu_step(cfg, cb, csecs, steps, threads)
+    line = {
+        "impl": "reference", "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"WavLM-{args.model} fwd+bwd, oracle (CPU restatement of the reference PyTorch path), "
+                               f"bounded sample {cb} x {csecs} s per step"},
+        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                         "sample": f"{cb} x {csecs} s, {steps} step(s), median"},
+        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    from oracle import wavlm_oracle as O  # parameter / input generators and the CPU baseline only
+    from unispeech_b200 import _lib, ops
+    from unispeech_b200.wavlm import WavLM, WavLMConfig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    cfg, B, secs = model_config(args.model)
+    L_ = secs * SR
+    T = O.num_frames(L_, cfg)
+    model = WavLM(WavLMConfig(vars(cfg)))
+    model.load_state_dict(O.deterministic_state_dict(cfg))
+    model = model.to(dev).train()
+
+    gen = torch.Generator().manual_seed(1337 + rank)
+    wav_host = torch.randn(B, L_, generator=gen).pin_memory()
+    wav_host = torch.nn.functional.layer_norm(wav_host, (L_,)) if cfg.normalize else wav_host
+    wav_host = wav_host.pin_memory()
+    pad_host = torch.zeros(B, L_, dtype=torch.bool)  # the reference always passes an (all-False) mask in training (S14)
+    wav_dev = wav_host.to(dev)
+    R = torch.randn(B, T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(e2e: bool):
+        model.grad_buffer().zero_() if model._engine is not None and model._engine.flat is not None else None
+        wav = wav_host.to(dev, non_blocking=True) if e2e else wav_dev
+        x, _ = model.extract_features(wav, padding_mask=pad_host, mask=True)
+        loss = (x.float() * R).sum()
+        loss.backward()
+        if world > 1:
+            dist.all_reduce(model.grad_buffer(), op=dist.ReduceOp.AVG)
+        if e2e:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def timed(n_steps: int, e2e: bool):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n_steps):
+            step(e2e)
+        ev1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lc0 = _lib.load().b200s_launch_count
+    lc0.restype = __import__("ctypes").c_longlong
+    n0 = lc0()
+    ms = timed(args.steps, False)
+    launches = lc0() - n0
+    clocks = sampler.stop() if rank == 0 else None
+    for _ in range(2):
+        step(True)
+    ms_e2e = timed(args.steps, True)
+
+    audio_s = world * B * secs * args.steps
+    value = audio_s / (ms * 1e-3)
+    e2e_value = audio_s / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel family (tcgen05 GEMM): per-op CUDA-event timing in one extra profiled step
+    roofline, breakdown = None, None
+    if rank == 0 and not args.no_profile:
+        prof = ops.Profiler()
+        ops.set_profiler(prof)
+        step(False)
+        torch.cuda.synchronize()
+        ops.set_profiler(None)
+        breakdown = prof.summary()
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        gemm_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
+        gemm_flops = sum(v["flops"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
+                    "traffic": None, "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
+
+    cpu_baseline = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cb = 2 if args.model != "tiny" else B
+        v, s = cpu_step(cfg, cb, secs, 1, threads)
+        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
+                        "sample": f"oracle fwd+bwd fp32, {cb} x {secs} s, 1 step ({s:.1f} s)"}
+
+    if rank == 0:
+        fwd_flops = O.forward_flops(L_, cfg)
+        line = {
+            "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": f"WavLM-{args.model} fwd+bwd, batch {B} x {secs} s per GPU, 16 kHz synthetic, mask_prob "
+                                   f"{cfg.mask_prob}, dropout 0, all-False padding mask", "global_batch": world * B,
+                       "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)",
+                       "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "model_tflops": 3 * fwd_flops * world * B * args.steps / (ms * 1e-3) / 1e12,
+        }
+        if breakdown is not None:
+            line["breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,16 +1,18 @@
 /*
  * unispeech_b200 -- C ABI of the B200-native WavLM / UniSpeech-SAT encoder hot path.
  *
- * Every entry point enqueues hand-written sm_100a kernels on the given CUDA stream and returns
- * without synchronising.  All pointers are DEVICE pointers owned by the caller (PyTorch tensors);
- * the library never allocates or frees caller memory on the hot path.
- * Return value: 0 on success, negative on error (message via b200s_last_error(), thread-local).
- * There is no CPU fallback: on a device that is not compute capability 10.x every call fails.
+ * Every entry point enqueues hand-written sm_100a kernels on the given CUDA stream and returns without
+ * synchronising.  All pointers are DEVICE pointers owned by the caller (PyTorch tensors); the library never
+ * allocates or frees caller memory on the hot path.  Return value: 0 on success, negative on error (message via
+ * b200s_last_error(), thread-local).  There is no CPU fallback: on a device that is not compute capability 10.x
+ * b200s_check_device() fails and so does every kernel launch.
  *
- * The reference (microsoft/UniSpeech) has no FFI for this path: it is plain PyTorch module code.
- * Each function below cites the reference lines whose library calls (cuDNN conv, cuBLAS GEMM,
- * F.multi_head_attention_forward, F.layer_norm, F.group_norm, F.gelu) it replaces.
- * Activations are bf16, accumulation fp32, parameters/gradients fp32 masters.
+ * The reference (microsoft/UniSpeech) has no FFI for this path: it is plain PyTorch module code.  Each function
+ * below cites the reference lines whose library calls (cuDNN conv, cuBLAS GEMM, F.multi_head_attention_forward,
+ * F.layer_norm, F.group_norm, F.gelu, autograd) it replaces.  Paths are relative to /root/reference.
+ * Conventions: activations bf16, accumulation fp32, parameters / gradients fp32 masters in the reference
+ * state_dict layout.  "bs" = batch stride, "rs"/"ld" = row stride, always in ELEMENTS.  Gradient outputs marked
+ * (+=) are accumulated with fp32 atomics: the caller zeroes them once per optimisation step.
  */
 #ifndef UNISPEECH_B200_H_
 #define UNISPEECH_B200_H_
@@ -28,12 +30,13 @@ int b200s_version(void);
 const char* b200s_last_error(void);
 /* 0 if the current device can run the kernels (sm_100), negative otherwise */
 int b200s_check_device(void);
+/* number of kernels launched by this library so far (bench.py reports the per-step count) */
+long long b200s_launch_count(void);
 
-/* ---- fused GEMM epilogue description (all tensors optional unless noted) ---------------------
- * value = acc (+ bias[col]);  if gelu: out_pre <- value (optional), value = gelu(value)
+/* ---- fused GEMM epilogue description (all tensors optional) ------------------------------------------------
+ * value = acc (+ bias[col]);  if gelu: out_pre <- value (optional), value = gelu_erf(value)
  *         if dgelu: value *= gelu'(gelu_aux[row,col]);  value += res1 + res2;  out <- value
- * bs = batch stride, ld = row stride, in elements.  colsum (fp32[N]) accumulates column sums of
- * the stored values (bias gradients). */
+ * colsum (fp32[N], +=) accumulates column sums of the stored values (bias gradients). */
 typedef struct {
   const float* bias;
   const void* res1; long long res1_bs, res1_ld;
@@ -45,37 +48,126 @@ typedef struct {
   int dgelu;
 } b200s_epilogue;
 
-/* out[b, r, 0:N] = epilogue( A[b, r, 0:K] . W[N,K]^T ),  bf16 in / bf16 out, fp32 accumulate.
- * A rows live at a + b*a_bs + r*a_rs (elements) and may OVERLAP (a_rs < K): this is how the strided
- * Conv1d layers of ConvFeatureExtractionModel (WavLM/WavLM.py:400-403,485-504) become GEMMs on a
- * channels-last [B,T,C] activation (row = k*C window, row stride = stride*C).  Also used for every
- * nn.Linear forward / input-gradient (q,k,v,out_proj: WavLM/modules.py:540-563; fc1/fc2:
- * WavLM/WavLM.py:706-739; post_extract_proj: WavLM/WavLM.py:347-348). */
+/* ============================ tcgen05 GEMM family (csrc/gemm.cuh, gemm.cu) ============================ */
+
+/* out[b, r, 0:N] = epilogue( A[b, r, 0:K] . W[N,K]^T ),  bf16 in / bf16 out, fp32 accumulate in TMEM.
+ * A rows live at a + b*a_bs + r*a_rs and may OVERLAP (a_rs < K): this is how the strided Conv1d layers 1-6 of
+ * ConvFeatureExtractionModel (WavLM/WavLM.py:400-403,485-504) and their input gradients become GEMMs on
+ * channels-last [B,T,C] activations (row = k*C window, row stride = stride*C).  Also every nn.Linear forward /
+ * input-gradient: q,k,v,out_proj (WavLM/modules.py:540-563), fc1/fc2 (WavLM/WavLM.py:706-739),
+ * post_extract_proj (WavLM/WavLM.py:347-348).  K % 64 == 0, N % 8 == 0. */
 int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K,
                     const void* w, int N, void* out, long long out_bs, long long out_ld,
                     const b200s_epilogue* epi, b200s_stream stream);
 
-/* dW[n, k] += sum_{b,r} Y[b,r,n] * X[b,r,k]   (fp32 atomic accumulation into dw, row stride dw_ld).
- * Weight gradient of the GEMMs above (autograd of nn.Linear / nn.Conv1d in the reference).
- * X rows may overlap like A above (conv im2col view).  N and K are multiples of 8. */
+/* dW[n, k] (+=) sum_{b,r} Y[b,r,n] * X[b,r,k]   (fp32, row stride dw_ld): the weight gradient of the GEMMs above
+ * (autograd of nn.Linear / nn.Conv1d).  Both operands are read MN-major by tcgen05.mma; X rows may overlap
+ * (conv im2col view).  Split-K over (batch, row) blocks.  N % 8 == 0, K % 8 == 0. */
 int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs,
                      long long x_rs, int rows, int batches, int N, int K, float* dw, long long dw_ld,
                      b200s_stream stream);
 
-/* Grouped positional convolution as an implicit GEMM (TransformerEncoder.pos_conv,
- * WavLM/WavLM.py:514-527,577-579; SamePad WavLM/modules.py:72-83).
+/* Grouped positional convolution as an implicit GEMM (TransformerEncoder.pos_conv, WavLM/WavLM.py:514-527,577-579;
+ * SamePad WavLM/modules.py:72-83), also used for its input gradient with flipped/transposed taps:
  *   out[b,t,g*Cg+n] = epilogue( sum_{j<taps} sum_{c<Cg} xpad[b, t+j, g*Cg+c] * wp[g*64+n, j*64+c] )
- * xpad: [B, Tpad, D] bf16 with row stride D (zero rows around the T valid frames; the caller offsets
- * the pointer so that tap j of output frame t reads row t+j);  wp: [G*64, taps*64] bf16, zero padded. */
+ * xpad: [B, Tpad, D] bf16 (row stride D) with zero rows around the T valid frames, pointer offset so that tap j of
+ * output frame t reads row t+j;  wp: [G*64, taps*64] bf16 zero padded (b200s_posconv_prep). Cg = D/G <= 64. */
 int b200s_posconv_gemm(const void* xpad, long long xpad_bs, int T, int B, int D, int G, int taps,
                        const void* wp, void* out, long long out_bs, long long out_ld,
                        const b200s_epilogue* epi, b200s_stream stream);
 
-/* dWp[g*Cg+n... ] : dwp[g, n, j, c] += sum_{b,t} dy[b,t,g*Cg+n] * xpad[b,t+j,g*Cg+c]
- * dwp: fp32 [G, Cg, taps, 64] (c padded to 64; columns >= Cg hold garbage-free zeros are NOT guaranteed:
- * only c < Cg is meaningful). */
+/* dwp[g, n, j, c] (+=) sum_{b,t} dy[b,t,g*Cg+n] * xpad[b,t+j,g*Cg+c];  dwp fp32 [G, Cg, taps, 64], only c < Cg is
+ * meaningful. */
 int b200s_posconv_wgrad(const void* dy, long long dy_bs, long long dy_rs, const void* xpad, long long xpad_bs,
                         int T, int B, int D, int G, int taps, float* dwp, b200s_stream stream);
+
+/* ============================ attention (csrc/attn_fwd.cu, attn_bwd.cu) ============================ */
+
+/* out[b,t,h*64+d] = sum_j softmax_j(scale q_i.k_j + gate[b,h,i]*tab[h,j-i+T-1], -inf at padded keys) v_j
+ * Replaces compute_bias + gate multiply + F.multi_head_attention_forward (WavLM/modules.py:417-455,504-563); the
+ * [B*H,T,T] bias is never materialised (it is Toeplitz).  qkv: bf16 [B,T,3D] fused projection output; gate: fp32
+ * [B,H,T] or NULL (=1); tab: fp32 [H,2T-1] or NULL (no bias); key_pad: uint8 [B,T] or NULL; out: bf16 [B,T,D];
+ * lse: fp32 [B,H,T] log2-domain log-sum-exp (saved for backward).  head_dim = 64, T <= 4096. */
+int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out,
+                   float* lse, int B, int T, int H, float scale, b200s_stream stream);
+
+/* Backward of b200s_attn_fwd (autograd of the same lines).  delta: fp32 [B,H,T] workspace; dqkv: bf16 [B,T,3D];
+ * dgate: fp32 [B,H,T] (written); dtab: fp32 [H,2T-1] (+=, shared by all layers: WavLM/WavLM.py:549,594-599). */
+int b200s_attn_bwd(const void* qkv, const void* out, const void* dout, const float* gate, const float* tab,
+                   const uint8_t* key_pad, const float* lse, float* delta, void* dqkv, float* dgate, float* dtab,
+                   int B, int T, int H, float scale, b200s_stream stream);
+
+/* ============================ row kernels (csrc/rowops.cu) ============================ */
+
+/* y = LayerNorm(x) * gamma + beta [then exact GELU]; saves mean / rstd (fp32 [rows]).  nn.LayerNorm / Fp32LayerNorm
+ * (WavLM/WavLM.py:342,559,666,675; WavLM/modules.py:30-42) and the LN+GELU of the layer_norm extractor
+ * (WavLM/WavLM.py:409-419).  D in {64,128,256,512,768,1024}. */
+int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta,
+                         void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch,
+                         int batches, int D, int gelu, b200s_stream stream);
+
+/* dx = LN-backward(dy) [+ dres];  dgamma, dbeta (+=);  colsum (+=) = column sums of dx (bias gradient of x's producer). */
+int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs,
+                         long long x_rs, const float* mean, const float* rstd, const float* gamma,
+                         const float* beta, const void* dres, long long dres_bs, long long dres_rs, void* dx,
+                         long long dx_bs, long long dx_rs, float* dgamma, float* dbeta, float* colsum,
+                         int rows_per_batch, int batches, int D, int gelu, b200s_stream stream);
+
+/* out[c] (+=) sum_rows x[r,c]  -- nn.Linear bias gradients */
+int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                 b200s_stream stream);
+
+/* out = dy * gelu'(pre); colsum (+=) optional.  Backward of x + gelu(pos_conv(x)) (WavLM/WavLM.py:577-579) and of the
+ * last conv layer's GELU. */
+int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs,
+                    long long pre_rs, void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches,
+                    int N, float* colsum, b200s_stream stream);
+
+/* x[b,t,:] = mask_emb where mask[b,t]; = 0 where pad[b,t]   (apply_mask WavLM/WavLM.py:285-286; x[padding_mask]=0 :574-575) */
+int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
+                         const uint8_t* pad, const float* mask_emb, b200s_stream stream);
+int b200s_frame_mask_bwd(void* dx, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
+                         const uint8_t* pad, float* dmask_emb, b200s_stream stream);
+
+/* gate[b,h,t] of gru_rel_pos from the RAW layer input (WavLM/modules.py:523-533) and its backward */
+int b200s_gate_fwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                   const float* grep_b, const float* grep_a, float* gate, b200s_stream stream);
+int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                   const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                   long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, b200s_stream stream);
+
+/* tab[h, i] = emb[lut[i], h]  (Toeplitz form of compute_bias, WavLM/modules.py:445-455) and the scatter-add backward */
+int b200s_relpos_table_fwd(const float* emb, const int* lut, int n, int H, float* tab, b200s_stream stream);
+int b200s_relpos_table_bwd(const float* dtab, const int* lut, int n, int H, float* demb, b200s_stream stream);
+
+/* ============================ conv layer 0 (csrc/conv0.cu) ============================ */
+
+/* Conv1d(1,C,k,stride s, no bias) + GroupNorm(C,C) (mode 0) or LayerNorm over channels (mode 1) + GELU on the raw
+ * waveform (WavLM/WavLM.py:400-426).  wav fp32 [B,L]; w fp32 [C,1,k]; out bf16 channels-last.  stats: fp64 [B,C,2]
+ * (mode 0);  fmean/frstd: fp32 [B,T] (mode 1).  C in {64, 512}. */
+int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w,
+                    const float* gamma, const float* beta, int mode, double* stats, float* fmean, float* frstd,
+                    void* out, long long out_bs, b200s_stream stream);
+int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w,
+                    const float* gamma, const float* beta, int mode, const double* stats, float* bstats,
+                    const float* fmean, const float* frstd, const void* da, long long da_bs, float* dw,
+                    float* dgamma, float* dbeta, b200s_stream stream);
+
+/* ============================ parameter preparation (csrc/prep.cu) ============================ */
+
+int b200s_scale_copy_f32(const float* src, float* dst, long long n, float scale, b200s_stream stream);
+/* fp32 [N,K] -> bf16 dst[n*ld+k] and/or its transpose dstT[k*ldT+n] */
+int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, long long ld, void* dstT,
+                      long long ldT, b200s_stream stream);
+/* nn.Conv1d weight [Co,Ci,k] -> forward operand [Co, k*Ci] / per-phase input-gradient operand / gradient un-layout */
+int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream);
+int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rho, void* dst, b200s_stream stream);
+int b200s_unprep_conv_wgrad(const float* dwk, int Co, int Ci, int k, float* dw, b200s_stream stream);
+/* weight_norm(dim=2) of pos_conv (WavLM/WavLM.py:526) -> padded per-group operands; and its backward */
+int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int G, int taps, float* norm2,
+                       void* wp_fwd, void* wp_dgrad, b200s_stream stream);
+int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const float* dwp, int D, int G, int taps,
+                         float* work, float* dweight_v, float* dweight_g, b200s_stream stream);
 
 #ifdef __cplusplus
 }

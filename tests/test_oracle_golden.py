@@ -24,6 +24,7 @@ CASES = {
 
 def test_all_fixtures_are_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
+    names.remove("mask_indices")  # span-sampler fixture, covered by tests/test_api_cpu.py
     assert names == sorted(CASES)
 
 

@@ -30,7 +30,13 @@ void set_last_error(const char* fmt, ...);
     }                                                                                          \
   } while (0)
 
-#define B200_CHECK_LAUNCH() B200_CHECK_CUDA(cudaGetLastError())
+// number of kernels this library has launched (read through b200s_launch_count(); bench.py reports it)
+extern long long g_launch_count;
+#define B200_CHECK_LAUNCH()              \
+  do {                                   \
+    ++b200::g_launch_count;              \
+    B200_CHECK_CUDA(cudaGetLastError()); \
+  } while (0)
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline long long ceil_div_ll(long long a, long long b) { return (a + b - 1) / b; }

@@ -10,6 +10,7 @@
 namespace b200 {
 
 // ------------------------------------------------------------------ error plumbing
+long long g_launch_count = 0;
 static thread_local char g_err[512] = "";
 char* last_error_buf() { return g_err; }
 void set_last_error(const char* fmt, ...) {
@@ -153,6 +154,7 @@ using namespace b200;
 extern "C" {
 
 int b200s_version(void) { return 100; }
+long long b200s_launch_count(void) { return b200::g_launch_count; }
 const char* b200s_last_error(void) { return b200::last_error_buf(); }
 
 int b200s_check_device(void) {

@@ -1,0 +1,545 @@
+"""Host-side orchestration of the WavLM hot path over the C-ABI kernels (forward and backward).
+
+Everything numerical runs in the hand-written sm_100a kernels (`ops.*`); this file only owns buffers, parameter
+preparation, the order of launches and the autograd glue.  PyTorch is used for device memory and streams.
+
+Layouts
+  * activations: bf16, channels-last / batch-major `[B, T, C]` (the reference's `T x B x C` tensors are views of these);
+  * conv stack gradients: `[B, Tg, C]` with `lead` zero rows in front (so the input-gradient GEMM can read row u-1);
+  * pos_conv input / its output gradient: `[B, T+128, D]` with 64 zero rows on each side (taps become a TMA dimension);
+  * parameters: fp32 masters in the reference state_dict layout; bf16 GEMM operands are re-derived by `prepare()`;
+  * gradients: one flat fp32 buffer, `param.grad` are views into it (q/k/v projections adjacent so the fused [3D,D]
+    weight gradient is a single GEMM); the data-parallel allreduce runs on the flat buffer.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+BF = torch.bfloat16
+
+
+def _even(n: int) -> int:
+    return n + (n & 1)
+
+
+def relative_positions_bucket_lut(T: int, num_buckets: int, max_distance: int) -> torch.Tensor:
+    """bucket(delta) for delta in [-(T-1), T-1] (index delta+T-1).  Host integer/fp32 glue computed with the same torch
+    CPU ops as the reference `_relative_positions_bucket` (WavLM/modules.py:417-443), which also runs on the host."""
+    rp = torch.arange(-(T - 1), T, dtype=torch.long)
+    nb = num_buckets // 2
+    buckets = (rp > 0).to(torch.long) * nb
+    rp = torch.abs(rp)
+    max_exact = nb // 2
+    is_small = rp < max_exact
+    large = max_exact + (torch.log(rp.float() / max_exact) / math.log(max_distance / max_exact) * (nb - max_exact)).to(torch.long)
+    large = torch.min(large, torch.full_like(large, nb - 1))
+    return (buckets + torch.where(is_small, rp, large)).to(torch.int32)
+
+
+class FlatGrads:
+    """One flat fp32 gradient buffer; every parameter's `.grad` is a view into it."""
+
+    def __init__(self, groups: List[List[torch.nn.Parameter]], device):
+        self.params: List[torch.nn.Parameter] = [p for g in groups for p in g]
+        total, self.offsets = 0, {}
+        for p in self.params:
+            self.offsets[id(p)] = total
+            total += (p.numel() + 3) // 4 * 4  # keep every view 16-byte aligned
+        self.flat = torch.zeros(total, dtype=torch.float32, device=device)
+        self.views = {id(p): self.flat[self.offsets[id(p)]: self.offsets[id(p)] + p.numel()].view_as(p) for p in self.params}
+
+    def view(self, p) -> torch.Tensor:
+        return self.views[id(p)]
+
+    def attach(self):
+        """Make every trainable p.grad the flat view.  A parameter whose grad was reset to None (optimizer.zero_grad) gets a
+        zeroed view: autograd semantics are 'accumulate into .grad', and the kernels accumulate with atomics."""
+        need_zero = any(p.requires_grad and p.grad is None for p in self.params)
+        if need_zero:
+            self.flat.zero_()
+        for p in self.params:
+            if not p.requires_grad:
+                continue
+            v = self.views[id(p)]
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                if p.grad is not None:
+                    v.copy_(p.grad)
+                p.grad = v
+
+
+class ConvGeom:
+    """Frame counts and buffer geometry of the strided conv stack (WavLM/WavLM.py:378-449)."""
+
+    def __init__(self, conv_layers, L_: int):
+        self.layers = conv_layers
+        self.T = []
+        t = L_
+        for (_, k, s) in conv_layers:
+            t = (t - k) // s + 1
+            self.T.append(t)
+        assert self.T[-1] >= 1, "waveform too short for the conv stack"
+        self.Tp = [_even(t) for t in self.T]                       # activation rows per batch (even)
+        self.lead, self.Tg = [], []                                # gradient buffers
+        for i, (_, k, s) in enumerate(conv_layers):
+            lead = (k + s - 1) // s - 1
+            self.lead.append(lead)
+            t_in = L_ if i == 0 else self.T[i - 1]
+            self.Tg.append(_even((t_in + s - 1) // s + lead + 1))
+
+
+class Engine:
+    def __init__(self, model):
+        self.m = model
+        self.cfg = model.cfg
+        self.dev = None
+        self.prepared_version = None
+        self.lut_cache: Dict[int, torch.Tensor] = {}
+        self.flat: Optional[FlatGrads] = None
+
+    # ------------------------------------------------------------------------------------------------ setup
+    def _ensure_device(self, device):
+        if self.dev == device:
+            return
+        L.check_device()
+        self.dev = device
+        m, cfg = self.m, self.cfg
+        D, Fd, H = cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads
+        convs = m.conv_cfg
+        C = convs[-1][0]
+        assert all(c[0] == C for c in convs), "conv stack must have a constant channel count"
+        assert D == H * 64, "head_dim must be 64"
+        assert m.post_extract_proj is not None, "encoder_embed_dim must differ from the conv dim (projection layer)"
+        e = lambda *s: torch.empty(*s, dtype=BF, device=device)
+        self.wf, self.wd = {}, {}
+        for i, (_, k, s) in enumerate(convs):
+            if i == 0:
+                continue
+            self.wf[i] = e(C, k * C)
+            self.wd[i] = [e(C, ((k - rho + s - 1) // s) * C) for rho in range(min(s, k))]
+        self.wp, self.wpT = e(D, C), e(C, D)
+        G, taps = cfg.conv_pos_groups, cfg.conv_pos
+        self.pc_fwd, self.pc_dg = e(G, 64, taps, 64), e(G, 64, taps, 64)
+        self.pc_norm2 = torch.zeros(taps, dtype=torch.float32, device=device)
+        self.lw = []
+        for _ in m.encoder.layers:
+            self.lw.append(dict(qkv=e(3 * D, D), qkvT=e(D, 3 * D), bqkv=torch.empty(3 * D, dtype=torch.float32, device=device),
+                                o=e(D, D), oT=e(D, D), w1=e(Fd, D), w1T=e(D, Fd), w2=e(D, Fd), w2T=e(Fd, D)))
+        # flat gradient buffer, q/k/v adjacent per layer
+        groups = []
+        for lyr in m.encoder.layers:
+            a = lyr.self_attn
+            groups.append([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
+            groups.append([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias])
+        seen = {id(p) for g in groups for p in g}
+        groups.append([p for p in m.parameters() if id(p) not in seen])
+        self.flat = FlatGrads(groups, device)
+
+    def _param_version(self):
+        return tuple(p._version for p in self.m.parameters())
+
+    def prepare(self, force=False):
+        """fp32 masters -> bf16 GEMM operands (transposes, tap-major conv layouts, weight-normed pos_conv, fused qkv)."""
+        ver = self._param_version()
+        if not force and ver == self.prepared_version:
+            return
+        m, cfg = self.m, self.cfg
+        D, Fd = cfg.encoder_embed_dim, cfg.encoder_ffn_embed_dim
+        convs = m.conv_cfg
+        C = convs[-1][0]
+        for i, (_, k, s) in enumerate(convs):
+            if i == 0:
+                continue
+            w = m.feature_extractor.conv_layers[i][0].weight
+            ops.prep_conv_fwd(w, C, C, k, self.wf[i])
+            for rho in range(min(s, k)):
+                ops.prep_conv_dgrad(w, C, C, k, s, rho, self.wd[i][rho])
+        ops.prep_linear(m.post_extract_proj.weight, D, C, 1.0, self.wp, C, self.wpT, D)
+        pc = m.encoder.pos_conv[0]
+        ops.posconv_prep(pc.weight_v, pc.weight_g, D, cfg.conv_pos_groups, cfg.conv_pos, self.pc_norm2, self.pc_fwd, self.pc_dg)
+        for lyr, w in zip(m.encoder.layers, self.lw):
+            a = lyr.self_attn
+            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                ops.prep_linear(proj.weight, D, D, 1.0, w["qkv"][j * D:], D, w["qkvT"][:, j * D:], 3 * D)
+                ops.scale_copy_f32(proj.bias, w["bqkv"][j * D:], D, 1.0)
+            ops.prep_linear(a.out_proj.weight, D, D, 1.0, w["o"], D, w["oT"], D)
+            ops.prep_linear(lyr.fc1.weight, Fd, D, 1.0, w["w1"], D, w["w1T"], Fd)
+            ops.prep_linear(lyr.fc2.weight, D, Fd, 1.0, w["w2"], Fd, w["w2T"], D)
+        self.prepared_version = ver
+
+    def lut(self, T: int) -> torch.Tensor:
+        if T not in self.lut_cache:
+            self.lut_cache[T] = relative_positions_bucket_lut(T, self.cfg.num_buckets, self.cfg.max_distance).to(self.dev)
+        return self.lut_cache[T]
+
+    def g(self, p):  # gradient view of a parameter
+        return self.flat.view(p)
+
+    # ------------------------------------------------------------------------------------------------ conv stack
+    def conv_forward(self, wav: torch.Tensor, save: bool):
+        """ConvFeatureExtractionModel.forward (WavLM/WavLM.py:485-504) -> channels-last features [B, Tp, C] (valid rows T)."""
+        m, cfg = self.m, self.cfg
+        convs = m.conv_cfg
+        B, L_ = wav.shape
+        geo = ConvGeom(convs, L_)
+        C = convs[0][0]
+        ln_mode = cfg.extractor_mode == "layer_norm"
+        dev = wav.device
+        st = dict(geo=geo, wav=wav, a=[], y=[], mean=[], rstd=[])
+        blk0 = m.feature_extractor.conv_layers[0]
+        _, k0, s0 = convs[0]
+        a0 = torch.empty(B, geo.Tp[0], C, dtype=BF, device=dev)
+        norm0 = blk0[2][1] if ln_mode else blk0[2]
+        if ln_mode:
+            fmean = torch.empty(B, geo.T[0], dtype=torch.float32, device=dev)
+            frstd = torch.empty(B, geo.T[0], dtype=torch.float32, device=dev)
+            ops.conv0_fwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 1, None, fmean, frstd,
+                          a0, geo.Tp[0] * C)
+            st["stats0"] = (fmean, frstd)
+        else:
+            stats = torch.empty(B, C, 2, dtype=torch.float64, device=dev)
+            ops.conv0_fwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 0, stats, None, None,
+                          a0, geo.Tp[0] * C)
+            st["stats0"] = stats
+        st["a"].append(a0)
+        st["y"].append(None)
+        st["mean"].append(None)
+        st["rstd"].append(None)
+        for i in range(1, len(convs)):
+            _, k, s = convs[i]
+            Ti, Tpi = geo.T[i], geo.Tp[i]
+            a_prev = st["a"][i - 1]
+            out = torch.empty(B, Tpi, C, dtype=BF, device=dev)
+            if ln_mode:
+                y = torch.empty(B, Tpi, C, dtype=BF, device=dev)
+                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, y, Tpi * C, C, None)
+                ln = m.feature_extractor.conv_layers[i][2][1]
+                mean = torch.empty(B * Ti, dtype=torch.float32, device=dev)
+                rstd = torch.empty(B * Ti, dtype=torch.float32, device=dev)
+                ops.layer_norm_fwd(y, Tpi * C, C, ln.weight, ln.bias, out, Tpi * C, C, mean, rstd, Ti, B, C, gelu=True)
+                st["y"].append(y); st["mean"].append(mean); st["rstd"].append(rstd)
+            else:
+                y = torch.empty(B, Tpi, C, dtype=BF, device=dev) if save else None
+                epi = L.make_epilogue(gelu=True, out_pre=y, pre_bs=Tpi * C, pre_ld=C)
+                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, out, Tpi * C, C, epi)
+                st["y"].append(y); st["mean"].append(None); st["rstd"].append(None)
+            st["a"].append(out)
+            if not save:
+                st["a"][i - 1] = None if i - 1 > 0 else st["a"][0]
+        return st
+
+    def conv_backward(self, st, dfeat: torch.Tensor):
+        """dfeat: gradient w.r.t. the extractor output a[-1] (bf16 [B, Tp, C] layout).  Accumulates all conv-stack
+        parameter gradients; the waveform gets none."""
+        m, cfg = self.m, self.cfg
+        convs = m.conv_cfg
+        geo: ConvGeom = st["geo"]
+        wav = st["wav"]
+        B, L_ = wav.shape
+        C = convs[0][0]
+        dev = wav.device
+        ln_mode = cfg.extractor_mode == "layer_norm"
+        n = len(convs)
+        dA = dfeat  # gradient w.r.t. a[i], no-lead layout [B, Tp_i, C]
+        gpad = None
+        for i in range(n - 1, 0, -1):
+            _, k, s = convs[i]
+            Ti, Tpi, lead, Tg = geo.T[i], geo.Tp[i], geo.lead[i], geo.Tg[i]
+            # ---- dY_i (gradient w.r.t. the conv output of layer i) in lead layout
+            if gpad is None:
+                gpad = torch.zeros(B, Tg, C, dtype=BF, device=dev)
+                gv = gpad[:, lead:]
+                if ln_mode:
+                    ln = m.feature_extractor.conv_layers[i][2][1]
+                    ops.layer_norm_bwd(dA, Tpi * C, C, st["y"][i], Tpi * C, C, st["mean"][i], st["rstd"][i], ln.weight,
+                                       ln.bias, None, 0, 0, gv, Tg * C, C, self.g(ln.weight), self.g(ln.bias), None, Ti, B, C,
+                                       gelu=True)
+                else:
+                    ops.dgelu_mul(dA, Tpi * C, C, st["y"][i], Tpi * C, C, gv, Tg * C, C, Ti, B, C, None)
+            gv = gpad[:, lead:]
+            # ---- weight gradient: dW[co, (j,ci)] = sum dY[b,t,co] * a_{i-1}[b, s*t + j, ci]
+            a_prev = st["a"][i - 1]
+            dwk = torch.zeros(C, k * C, dtype=torch.float32, device=dev)
+            ops.gemm_wgrad(gv, Tg * C, C, a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, C, k * C, dwk, k * C)
+            w = m.feature_extractor.conv_layers[i][0].weight
+            ops.unprep_conv_wgrad(dwk, C, C, k, self.g(w))
+            # ---- input gradient, one GEMM per phase rho of the stride
+            T_in, Tp_in = geo.T[i - 1], geo.Tp[i - 1]
+            fuse_dgelu = (not ln_mode) and (i - 1 >= 1)
+            if fuse_dgelu or (ln_mode and i - 1 >= 1):
+                lead_p, Tg_p = geo.lead[i - 1], geo.Tg[i - 1]
+                gnext = torch.zeros(B, Tg_p, C, dtype=BF, device=dev)
+            if fuse_dgelu:
+                dst, dst_bs, dst_off = gnext, Tg_p * C, lead_p * C
+            else:
+                dAp = torch.zeros(B, Tp_in, C, dtype=BF, device=dev)
+                dst, dst_bs, dst_off = dAp, Tp_in * C, 0
+            for rho in range(min(s, k)):
+                nm = (k - rho + s - 1) // s
+                n_u = (T_in - rho + s - 1) // s
+                if n_u <= 0:
+                    continue
+                a_view = gpad.view(-1)[(lead - (nm - 1)) * C:]
+                epi = None
+                if fuse_dgelu:
+                    y_prev = st["y"][i - 1]
+                    epi = L.make_epilogue(dgelu=True, gelu_aux=y_prev.view(-1)[rho * C:], aux_bs=Tp_in * C, aux_ld=s * C)
+                ops.gemm_rows(a_view, Tg * C, C, n_u, B, nm * C, self.wd[i][rho], C, dst.view(-1)[dst_off + rho * C:], dst_bs,
+                              s * C, epi)
+            if fuse_dgelu:
+                gpad = gnext
+                dA = None
+            elif ln_mode and i - 1 >= 1:
+                ln = m.feature_extractor.conv_layers[i - 1][2][1]
+                ops.layer_norm_bwd(dAp, Tp_in * C, C, st["y"][i - 1], Tp_in * C, C, st["mean"][i - 1], st["rstd"][i - 1],
+                                   ln.weight, ln.bias, None, 0, 0, gnext[:, lead_p:], Tg_p * C, C, self.g(ln.weight),
+                                   self.g(ln.bias), None, T_in, B, C, gelu=True)
+                gpad = gnext
+                dA = None
+            else:
+                dA = dAp  # gradient w.r.t. a[0]
+        # ---- layer 0
+        blk0 = m.feature_extractor.conv_layers[0]
+        _, k0, s0 = convs[0]
+        norm0 = blk0[2][1] if ln_mode else blk0[2]
+        if n == 1:
+            dA = dfeat
+        if ln_mode:
+            fmean, frstd = st["stats0"]
+            ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 1, None, None, fmean,
+                          frstd, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias))
+        else:
+            bstats = torch.empty(B, C, 2, dtype=torch.float32, device=dev)
+            ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 0, st["stats0"], bstats,
+                          None, None, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias))
+
+    # ------------------------------------------------------------------------------------------------ LN + proj + mask
+    def project_forward(self, feats, T, mask_u8, pad_u8, save, want_features):
+        """transpose -> LayerNorm(C) -> post_extract_proj -> mask_emb / zero padded frames (WavLM/WavLM.py:341-357,574-575).
+        Writes into the zero-padded pos_conv input buffer."""
+        m, cfg = self.m, self.cfg
+        B, Tp, C = feats.shape
+        D = cfg.encoder_embed_dim
+        dev = feats.device
+        half = cfg.conv_pos // 2
+        fn = torch.empty(B, T, C, dtype=BF, device=dev)
+        mean = torch.empty(B * T, dtype=torch.float32, device=dev)
+        rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
+        ops.layer_norm_fwd(feats, Tp * C, C, m.layer_norm.weight, m.layer_norm.bias, fn, T * C, C, mean, rstd, T, B, C)
+        Tpad = T + cfg.conv_pos
+        xpad = torch.zeros(B, Tpad, D, dtype=BF, device=dev)
+        xv = xpad[:, half:]
+        epi = L.make_epilogue(bias=m.post_extract_proj.bias)
+        ops.gemm_rows(fn, T * C, C, T, B, C, self.wp, D, xv, Tpad * D, D, epi)
+        features = xv[:, :T].clone() if want_features else None
+        ops.frame_mask_fwd(xv, Tpad * D, D, T, B, D, mask_u8, pad_u8, m.mask_emb)
+        return dict(fn=fn, mean=mean, rstd=rstd, xpad=xpad, feats=feats if save else None, features=features)
+
+    def project_backward(self, st, dxm, T, mask_u8, pad_u8):
+        """dxm: gradient w.r.t. the masked projection output, bf16 [B,T,D] (modified in place). Returns d(features) [B,Tp,C]."""
+        m, cfg = self.m, self.cfg
+        B = dxm.shape[0]
+        D = cfg.encoder_embed_dim
+        feats = st["feats"]
+        Tp, C = feats.shape[1], feats.shape[2]
+        dev = dxm.device
+        ops.frame_mask_bwd(dxm, T * D, D, T, B, D, mask_u8, pad_u8, self.g(m.mask_emb))
+        ops.colsum(dxm, T * D, D, T, B, D, self.g(m.post_extract_proj.bias))
+        ops.gemm_wgrad(dxm, T * D, D, st["fn"], T * C, C, T, B, D, C, self.g(m.post_extract_proj.weight), C)
+        dfn = torch.empty(B, T, C, dtype=BF, device=dev)
+        ops.gemm_rows(dxm, T * D, D, T, B, D, self.wpT, C, dfn, T * C, C, None)
+        dfeat = torch.zeros(B, Tp, C, dtype=BF, device=dev)
+        ops.layer_norm_bwd(dfn, T * C, C, feats, Tp * C, C, st["mean"], st["rstd"], m.layer_norm.weight, m.layer_norm.bias,
+                           None, 0, 0, dfeat, Tp * C, C, self.g(m.layer_norm.weight), self.g(m.layer_norm.bias), None, T, B, C)
+        return dfeat
+
+    # ------------------------------------------------------------------------------------------------ pos_conv stage
+    def posconv_forward(self, xpad, T, save):
+        """x + gelu(pos_conv(x)) [-> encoder.layer_norm for post-LN models]  (WavLM/WavLM.py:577-582)."""
+        m, cfg = self.m, self.cfg
+        B, Tpad, D = xpad.shape
+        dev = xpad.device
+        G, taps, half = cfg.conv_pos_groups, cfg.conv_pos, cfg.conv_pos // 2
+        xs = torch.empty(B, T, D, dtype=BF, device=dev)
+        pre = torch.empty(B, T, D, dtype=BF, device=dev) if save else None
+        pc = m.encoder.pos_conv[0]
+        epi = L.make_epilogue(bias=pc.bias, gelu=True, out_pre=pre, pre_bs=T * D, pre_ld=D, res1=xpad[:, half:],
+                              res1_bs=Tpad * D, res1_ld=D)
+        ops.posconv_gemm(xpad, Tpad * D, T, B, D, G, taps, self.pc_fwd, xs, T * D, D, epi)
+        st = dict(xpad=xpad, pre=pre, xs=xs)
+        if not cfg.layer_norm_first:
+            x0 = torch.empty(B, T, D, dtype=BF, device=dev)
+            mean = torch.empty(B * T, dtype=torch.float32, device=dev)
+            rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
+            ln = m.encoder.layer_norm
+            ops.layer_norm_fwd(xs, T * D, D, ln.weight, ln.bias, x0, T * D, D, mean, rstd, T, B, D)
+            st.update(mean=mean, rstd=rstd)
+            return x0, st
+        return xs, st
+
+    def posconv_backward(self, st, dx0, T):
+        m, cfg = self.m, self.cfg
+        xpad = st["xpad"]
+        B, Tpad, D = xpad.shape
+        dev = xpad.device
+        G, taps, half = cfg.conv_pos_groups, cfg.conv_pos, cfg.conv_pos // 2
+        Cg = D // G
+        if not cfg.layer_norm_first:
+            ln = m.encoder.layer_norm
+            dxs = torch.empty(B, T, D, dtype=BF, device=dev)
+            ops.layer_norm_bwd(dx0, T * D, D, st["xs"], T * D, D, st["mean"], st["rstd"], ln.weight, ln.bias, None, 0, 0, dxs,
+                               T * D, D, self.g(ln.weight), self.g(ln.bias), None, T, B, D)
+        else:
+            dxs = dx0
+        pc = m.encoder.pos_conv[0]
+        dpre = torch.zeros(B, Tpad, D, dtype=BF, device=dev)
+        ops.dgelu_mul(dxs, T * D, D, st["pre"], T * D, D, dpre[:, half:], Tpad * D, D, T, B, D, self.g(pc.bias))
+        dwp = torch.zeros(G, Cg, taps, 64, dtype=torch.float32, device=dev)
+        ops.posconv_wgrad(dpre[:, half:], Tpad * D, D, xpad, Tpad * D, T, B, D, G, taps, dwp)
+        work = torch.empty(2 * taps, dtype=torch.float32, device=dev)
+        ops.posconv_unprep(pc.weight_v, pc.weight_g, dwp, D, G, taps, work, self.g(pc.weight_v), self.g(pc.weight_g))
+        # input gradient: correlation with the flipped, transposed taps; frame t reads dpre rows t-63 .. t+64
+        dxm = torch.empty(B, T, D, dtype=BF, device=dev)
+        epi = L.make_epilogue(res1=dxs, res1_bs=T * D, res1_ld=D)
+        ops.posconv_gemm(dpre.view(-1)[D:], Tpad * D, T, B, D, G, taps, self.pc_dg, dxm, T * D, D, epi)
+        return dxm
+
+    # ------------------------------------------------------------------------------------------------ transformer layer
+    def layer_forward(self, idx: int, x: torch.Tensor, pad_u8, tab, save: bool):
+        """TransformerSentenceEncoderLayer.forward (WavLM/WavLM.py:677-742) + MultiheadAttention fast path
+        (WavLM/modules.py:457-564) on x: bf16 [B,T,D]."""
+        m, cfg = self.m, self.cfg
+        lyr = m.encoder.layers[idx]
+        a = lyr.self_attn
+        w = self.lw[idx]
+        B, T, D = x.shape
+        M = B * T
+        Fd, H = cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads
+        dev = x.device
+        e = lambda *s: torch.empty(*s, dtype=BF, device=dev)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        pre_ln = cfg.layer_norm_first
+        st = dict(x=x)
+        if pre_ln:
+            xn, st["mean1"], st["rstd1"] = e(B, T, D), f(M), f(M)
+            ln = lyr.self_attn_layer_norm
+            ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, xn, T * D, D, st["mean1"], st["rstd1"], T, B, D)
+            st["xn"] = xn
+        else:
+            xn = x
+        qkv = e(B, T, 3 * D)
+        ops.gemm_rows(xn, 0, D, M, 1, D, w["qkv"], 3 * D, qkv, 0, 3 * D, L.make_epilogue(bias=w["bqkv"]))
+        gate = None
+        if tab is not None and cfg.gru_rel_pos:
+            gate = f(B, H, T)
+            ops.gate_fwd(xn, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, gate)
+        ao, lse = e(B, T, D), f(B, H, T)
+        ops.attn_fwd(qkv, gate, tab, pad_u8, ao, lse, B, T, H, 64 ** -0.5)
+        y1 = e(B, T, D)
+        ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias, res1=x, res1_ld=D))
+        if pre_ln:
+            x1 = y1
+            x1n, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
+            ln = lyr.final_layer_norm
+            ops.layer_norm_fwd(x1, T * D, D, ln.weight, ln.bias, x1n, T * D, D, st["mean2"], st["rstd2"], T, B, D)
+            ffn_in = x1n
+        else:
+            x1, st["mean1"], st["rstd1"] = e(B, T, D), f(M), f(M)
+            ln = lyr.self_attn_layer_norm
+            ops.layer_norm_fwd(y1, T * D, D, ln.weight, ln.bias, x1, T * D, D, st["mean1"], st["rstd1"], T, B, D)
+            ffn_in = x1
+        hg = e(B, T, Fd)
+        hp = e(B, T, Fd) if save else None
+        ops.gemm_rows(ffn_in, 0, D, M, 1, D, w["w1"], Fd, hg, 0, Fd,
+                      L.make_epilogue(bias=lyr.fc1.bias, gelu=True, out_pre=hp, pre_ld=Fd))
+        y2 = e(B, T, D)
+        ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias, res1=x1, res1_ld=D))
+        if pre_ln:
+            out = y2
+        else:
+            out, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
+            ln = lyr.final_layer_norm
+            ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
+        if save:
+            st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8)
+        return out, (st if save else None)
+
+    def layer_backward(self, idx: int, st, dout: torch.Tensor, dtab):
+        m, cfg = self.m, self.cfg
+        lyr = m.encoder.layers[idx]
+        a = lyr.self_attn
+        w = self.lw[idx]
+        x = st["x"]
+        B, T, D = x.shape
+        M = B * T
+        Fd, H = cfg.encoder_ffn_embed_dim, cfg.encoder_attention_heads
+        dev = x.device
+        e = lambda *s: torch.empty(*s, dtype=BF, device=dev)
+        f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        g = self.g
+        pre_ln = cfg.layer_norm_first
+        tab, pad = st["tab"], st["pad"]
+        # ---------------- FFN block
+        if pre_ln:
+            dy2 = dout                                           # x2 = x1 + fc2(...)
+            ops.colsum(dy2, T * D, D, T, B, D, g(lyr.fc2.bias))
+        else:
+            dy2 = e(B, T, D)
+            ln = lyr.final_layer_norm
+            ops.layer_norm_bwd(dout, T * D, D, st["y2"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, None, 0, 0,
+                               dy2, T * D, D, g(ln.weight), g(ln.bias), g(lyr.fc2.bias), T, B, D)
+        ops.gemm_wgrad(dy2, 0, D, st["hg"], 0, Fd, M, 1, D, Fd, g(lyr.fc2.weight), Fd)
+        dhp = e(B, T, Fd)
+        ops.gemm_rows(dy2, 0, D, M, 1, D, w["w2T"], Fd, dhp, 0, Fd,
+                      L.make_epilogue(dgelu=True, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias)))
+        ops.gemm_wgrad(dhp, 0, Fd, st["ffn_in"], 0, D, M, 1, Fd, D, g(lyr.fc1.weight), D)
+        dx1 = e(B, T, D)
+        if pre_ln:
+            dffn_in = e(B, T, D)
+            ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dffn_in, 0, D, None)
+            ln = lyr.final_layer_norm
+            ops.layer_norm_bwd(dffn_in, T * D, D, st["x1"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, dy2, T * D, D,
+                               dx1, T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
+            dy1 = dx1                                            # x1 = x + out_proj(attn)
+            ops.colsum(dy1, T * D, D, T, B, D, g(a.out_proj.bias))
+        else:
+            ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dx1, 0, D, L.make_epilogue(res1=dy2, res1_ld=D))
+            dy1 = e(B, T, D)
+            ln = lyr.self_attn_layer_norm
+            ops.layer_norm_bwd(dx1, T * D, D, st["y1"], T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, None, 0, 0,
+                               dy1, T * D, D, g(ln.weight), g(ln.bias), g(a.out_proj.bias), T, B, D)
+        # ---------------- attention block
+        ops.gemm_wgrad(dy1, 0, D, st["ao"], 0, D, M, 1, D, D, g(a.out_proj.weight), D)
+        dao = e(B, T, D)
+        ops.gemm_rows(dy1, 0, D, M, 1, D, w["oT"], D, dao, 0, D, None)
+        dqkv = e(B, T, 3 * D)
+        delta = f(B, H, T)
+        gate = st["gate"]
+        dgate = f(B, H, T) if tab is not None else None
+        ops.attn_bwd(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, dqkv, dgate, dtab if tab is not None else None,
+                     B, T, H, 64 ** -0.5)
+        ops.colsum(dqkv, 0, 3 * D, M, 1, 3 * D, g(a.q_proj.bias).view(-1))  # q,k,v bias grads are adjacent in the flat buffer
+        attn_in = st["xn"] if pre_ln else x
+        dxg = None
+        if gate is not None:
+            dxg = e(B, T, D)
+            ops.gate_bwd(attn_in, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, dgate, dxg, T * D, D,
+                         g(a.grep_linear.weight), g(a.grep_linear.bias), g(a.grep_a))
+        ops.gemm_wgrad(dqkv, 0, 3 * D, attn_in, 0, D, M, 1, 3 * D, D, g(a.q_proj.weight), D)
+        dx = e(B, T, D)
+        if pre_ln:
+            dxn = e(B, T, D)
+            ops.gemm_rows(dqkv, 0, 3 * D, M, 1, 3 * D, w["qkvT"], D, dxn, 0, D,
+                          L.make_epilogue(res1=dxg, res1_ld=D) if dxg is not None else None)
+            ln = lyr.self_attn_layer_norm
+            ops.layer_norm_bwd(dxn, T * D, D, x, T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, dy1, T * D, D, dx,
+                               T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
+        else:
+            ops.gemm_rows(dqkv, 0, 3 * D, M, 1, 3 * D, w["qkvT"], D, dx, 0, D,
+                          L.make_epilogue(res1=dy1, res1_ld=D, res2=dxg, res2_ld=D))
+        return dx

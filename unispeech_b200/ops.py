@@ -21,128 +21,165 @@ def _s():
     return L.stream_ptr()
 
 
+class Profiler:
+    """Per-op CUDA-event timing of one step (bench.py): every C-ABI call is bracketed by events on the launch stream."""
+
+    def __init__(self):
+        self.records = []
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for name, flops, e0, e1 in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["flops"] += flops
+            d["calls"] += 1
+        return out
+
+
+_profiler: Optional[Profiler] = None
+
+
+def set_profiler(p: Optional[Profiler]):
+    global _profiler
+    _profiler = p
+
+
+def _call(name, *args, flops=0.0):
+    if _profiler is None:
+        return L.call(name, *args)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    L.call(name, *args)
+    e1.record()
+    _profiler.records.append((name[len("b200s_"):], flops, e0, e1))
+
+
 # ------------------------------------------------------------------------------------------------- GEMM family
 def gemm_rows(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi: Optional[L.Epilogue] = None):
-    L.call("b200s_gemm_rows", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
-           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s())
+    _call("b200s_gemm_rows", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
+           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s(),
+          flops=2.0 * rows * batches * K * N)
 
 
 def gemm_wgrad(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld):
-    L.call("b200s_gemm_wgrad", L.ptr(y), L.ll(y_bs), L.ll(y_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows),
-           i32(batches), i32(N), i32(K), L.ptr(dw), L.ll(dw_ld), _s())
+    _call("b200s_gemm_wgrad", L.ptr(y), L.ll(y_bs), L.ll(y_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows),
+           i32(batches), i32(N), i32(K), L.ptr(dw), L.ll(dw_ld), _s(), flops=2.0 * rows * batches * K * N)
 
 
 def posconv_gemm(xpad, xpad_bs, T, B, D, G, taps, wp, out, out_bs, out_ld, epi=None):
-    L.call("b200s_posconv_gemm", L.ptr(xpad), L.ll(xpad_bs), i32(T), i32(B), i32(D), i32(G), i32(taps), L.ptr(wp),
-           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s())
+    _call("b200s_posconv_gemm", L.ptr(xpad), L.ll(xpad_bs), i32(T), i32(B), i32(D), i32(G), i32(taps), L.ptr(wp),
+           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s(),
+          flops=2.0 * T * B * D * (D // G) * taps)
 
 
 def posconv_wgrad(dy, dy_bs, dy_rs, xpad, xpad_bs, T, B, D, G, taps, dwp):
-    L.call("b200s_posconv_wgrad", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(xpad), L.ll(xpad_bs), i32(T), i32(B),
-           i32(D), i32(G), i32(taps), L.ptr(dwp), _s())
+    _call("b200s_posconv_wgrad", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(xpad), L.ll(xpad_bs), i32(T), i32(B),
+           i32(D), i32(G), i32(taps), L.ptr(dwp), _s(), flops=2.0 * T * B * D * (D // G) * taps)
 
 
 # ------------------------------------------------------------------------------------------------- row kernels
 def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu=False):
-    L.call("b200s_layer_norm_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
+    _call("b200s_layer_norm_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
            L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s())
 
 
 def layer_norm_bwd(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
                    dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu=False):
-    L.call("b200s_layer_norm_bwd", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean),
+    _call("b200s_layer_norm_bwd", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean),
            L.ptr(rstd), L.ptr(gamma), L.ptr(beta), L.ptr(dres), L.ll(dres_bs), L.ll(dres_rs), L.ptr(dx), L.ll(dx_bs),
            L.ll(dx_rs), L.ptr(dgamma), L.ptr(dbeta), L.ptr(colsum), i32(rows_per_batch), i32(batches), i32(D),
            i32(1 if gelu else 0), _s())
 
 
 def colsum(x, x_bs, x_rs, rows_per_batch, batches, N, out):
-    L.call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())
+    _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())
 
 
 def dgelu_mul(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum_out=None):
-    L.call("b200s_dgelu_mul", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(pre), L.ll(pre_bs), L.ll(pre_rs), L.ptr(out),
+    _call("b200s_dgelu_mul", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(pre), L.ll(pre_bs), L.ll(pre_rs), L.ptr(out),
            L.ll(out_bs), L.ll(out_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(colsum_out), _s())
 
 
 def frame_mask_fwd(x, x_bs, x_rs, T, B, D, mask, pad, mask_emb):
-    L.call("b200s_frame_mask_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(D), L.ptr(mask), L.ptr(pad),
+    _call("b200s_frame_mask_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(D), L.ptr(mask), L.ptr(pad),
            L.ptr(mask_emb), _s())
 
 
 def frame_mask_bwd(dx, x_bs, x_rs, T, B, D, mask, pad, dmask_emb):
-    L.call("b200s_frame_mask_bwd", L.ptr(dx), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(D), L.ptr(mask), L.ptr(pad),
+    _call("b200s_frame_mask_bwd", L.ptr(dx), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(D), L.ptr(mask), L.ptr(pad),
            L.ptr(dmask_emb), _s())
 
 
 def gate_fwd(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, gate):
-    L.call("b200s_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b),
+    _call("b200s_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b),
            L.ptr(grep_a), L.ptr(gate), _s())
 
 
 def gate_bwd(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, dgate, dxg, dx_bs, dx_rs, dgrep_w, dgrep_b, dgrep_a):
-    L.call("b200s_gate_bwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b),
+    _call("b200s_gate_bwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b),
            L.ptr(grep_a), L.ptr(dgate), L.ptr(dxg), L.ll(dx_bs), L.ll(dx_rs), L.ptr(dgrep_w), L.ptr(dgrep_b),
            L.ptr(dgrep_a), _s())
 
 
 def relpos_table_fwd(emb, lut, n, H, tab):
-    L.call("b200s_relpos_table_fwd", L.ptr(emb), L.ptr(lut), i32(n), i32(H), L.ptr(tab), _s())
+    _call("b200s_relpos_table_fwd", L.ptr(emb), L.ptr(lut), i32(n), i32(H), L.ptr(tab), _s())
 
 
 def relpos_table_bwd(dtab, lut, n, H, demb):
-    L.call("b200s_relpos_table_bwd", L.ptr(dtab), L.ptr(lut), i32(n), i32(H), L.ptr(demb), _s())
+    _call("b200s_relpos_table_bwd", L.ptr(dtab), L.ptr(lut), i32(n), i32(H), L.ptr(demb), _s())
 
 
 # ------------------------------------------------------------------------------------------------- conv layer 0
 def conv0_fwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, fmean, frstd, out, out_bs):
-    L.call("b200s_conv0_fwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
+    _call("b200s_conv0_fwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
            L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(fmean), L.ptr(frstd), L.ptr(out), L.ll(out_bs), _s())
 
 
 def conv0_bwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, da, da_bs, dw, dgamma, dbeta):
-    L.call("b200s_conv0_bwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
+    _call("b200s_conv0_bwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
            L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(bstats), L.ptr(fmean), L.ptr(frstd), L.ptr(da), L.ll(da_bs),
            L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), _s())
 
 
 # ------------------------------------------------------------------------------------------------- parameter prep
 def scale_copy_f32(src, dst, n, scale=1.0):
-    L.call("b200s_scale_copy_f32", L.ptr(src), L.ptr(dst), L.ll(n), f32(scale), _s())
+    _call("b200s_scale_copy_f32", L.ptr(src), L.ptr(dst), L.ll(n), f32(scale), _s())
 
 
 def prep_linear(src, N, K, scale, dst, ld, dstT, ldT):
-    L.call("b200s_prep_linear", L.ptr(src), i32(N), i32(K), f32(scale), L.ptr(dst), L.ll(ld), L.ptr(dstT), L.ll(ldT), _s())
+    _call("b200s_prep_linear", L.ptr(src), i32(N), i32(K), f32(scale), L.ptr(dst), L.ll(ld), L.ptr(dstT), L.ll(ldT), _s())
 
 
 def prep_conv_fwd(src, Co, Ci, k, dst):
-    L.call("b200s_prep_conv_fwd", L.ptr(src), i32(Co), i32(Ci), i32(k), L.ptr(dst), _s())
+    _call("b200s_prep_conv_fwd", L.ptr(src), i32(Co), i32(Ci), i32(k), L.ptr(dst), _s())
 
 
 def prep_conv_dgrad(src, Co, Ci, k, s, rho, dst):
-    L.call("b200s_prep_conv_dgrad", L.ptr(src), i32(Co), i32(Ci), i32(k), i32(s), i32(rho), L.ptr(dst), _s())
+    _call("b200s_prep_conv_dgrad", L.ptr(src), i32(Co), i32(Ci), i32(k), i32(s), i32(rho), L.ptr(dst), _s())
 
 
 def unprep_conv_wgrad(dwk, Co, Ci, k, dw):
-    L.call("b200s_unprep_conv_wgrad", L.ptr(dwk), i32(Co), i32(Ci), i32(k), L.ptr(dw), _s())
+    _call("b200s_unprep_conv_wgrad", L.ptr(dwk), i32(Co), i32(Ci), i32(k), L.ptr(dw), _s())
 
 
 def posconv_prep(weight_v, weight_g, D, G, taps, norm2, wp_fwd, wp_dgrad):
-    L.call("b200s_posconv_prep", L.ptr(weight_v), L.ptr(weight_g), i32(D), i32(G), i32(taps), L.ptr(norm2),
+    _call("b200s_posconv_prep", L.ptr(weight_v), L.ptr(weight_g), i32(D), i32(G), i32(taps), L.ptr(norm2),
            L.ptr(wp_fwd), L.ptr(wp_dgrad), _s())
 
 
 def posconv_unprep(weight_v, weight_g, dwp, D, G, taps, work, dweight_v, dweight_g):
-    L.call("b200s_posconv_unprep", L.ptr(weight_v), L.ptr(weight_g), L.ptr(dwp), i32(D), i32(G), i32(taps),
+    _call("b200s_posconv_unprep", L.ptr(weight_v), L.ptr(weight_g), L.ptr(dwp), i32(D), i32(G), i32(taps),
            L.ptr(work), L.ptr(dweight_v), L.ptr(dweight_g), _s())
 
 
 # ------------------------------------------------------------------------------------------------- attention
 def attn_fwd(qkv, gate, tab, key_pad, out, lse, B, T, H, scale):
-    L.call("b200s_attn_fwd", L.ptr(qkv), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(out), L.ptr(lse), i32(B), i32(T),
+    _call("b200s_attn_fwd", L.ptr(qkv), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(out), L.ptr(lse), i32(B), i32(T),
            i32(H), f32(scale), _s())
 
 
 def attn_bwd(qkv, out, dout, gate, tab, key_pad, lse, delta, dqkv, dgate, dtab, B, T, H, scale):
-    L.call("b200s_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
+    _call("b200s_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
            L.ptr(delta), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
