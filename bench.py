@@ -144,6 +144,7 @@ def main():
     import torch.distributed as dist
     from oracle import wavlm_oracle as O  # parameter / input generators and the CPU baseline only
     from unispeech_b200 import _lib, ops
+    from unispeech_b200.parallel import all_reduce_grads
     from unispeech_b200.wavlm import WavLM, WavLMConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,7 +179,7 @@ def main():
         loss = (x.float() * R).sum()
         loss.backward()
         if world > 1:
-            dist.all_reduce(model.grad_buffer(), op=dist.ReduceOp.AVG)
+            all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
         if e2e:
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
