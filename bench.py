@@ -136,6 +136,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="run the step as one CUDA graph launch")
+    ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -172,8 +174,10 @@ def main():
     R = torch.randn(B, T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
     loss_host = torch.zeros(1).pin_memory()
 
-    def step(e2e: bool):
-        model.grad_buffer().zero_() if model._engine is not None and model._engine.flat is not None else None
+    def eager_step(e2e: bool):
+        if model._engine is not None and model._engine.flat is not None:
+            model.grad_buffer().zero_()
+            model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
         wav = wav_host.to(dev, non_blocking=True) if e2e else wav_dev
         x, _ = model.extract_features(wav, padding_mask=pad_host, mask=True)
         loss = (x.float() * R).sum()
@@ -183,6 +187,52 @@ def main():
         if e2e:
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
+
+    # ---- CUDA-graph mode: the whole step (zero grads, operand prep, forward, loss, backward) is one graph launch; the host
+    # only samples the span mask (numpy, as the reference does) and uploads it into a static buffer before each replay.
+    graph_state = {}
+
+    def build_graph():
+        wav_static = wav_dev.clone()
+        pad_static = torch.zeros(B, L_, dtype=torch.bool, device=dev)
+        mask_static = torch.zeros(B, T, dtype=torch.bool, device=dev)
+        mask_pinned = [torch.zeros(B, T, dtype=torch.bool).pin_memory() for _ in range(8)]  # ring: copies are async
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):  # warm-up on the capture stream (allocator pools, cudaFuncSetAttribute, lazy init)
+                model.grad_buffer().zero_()
+                x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
+                (x.float() * R).sum().backward()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        model._engine.prepared_version = None
+        with torch.cuda.graph(g):
+            model.grad_buffer().zero_()
+            x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
+            loss = (x.float() * R).sum()
+            loss.backward()
+        graph_state.update(g=g, wav=wav_static, mask=mask_static, mask_pinned=mask_pinned, loss=loss, n=0)
+
+    def graph_step(e2e: bool):
+        gs = graph_state
+        if e2e:
+            gs["wav"].copy_(wav_host, non_blocking=True)
+        mi = model.apply_mask(B, T, None)  # host span sampler, numpy RNG (no padding in this workload)
+        buf = gs["mask_pinned"][gs["n"] % len(gs["mask_pinned"])]
+        gs["n"] += 1
+        buf.copy_(mi)
+        gs["mask"].copy_(buf, non_blocking=True)
+        gs["g"].replay()
+        if world > 1:
+            all_reduce_grads(model.grad_buffer())
+        if e2e:
+            loss_host.copy_(gs["loss"].detach().reshape(1), non_blocking=True)
+        return gs["loss"]
+
+    def step(e2e: bool):
+        return graph_step(e2e) if graph_state else eager_step(e2e)
 
     def timed(n_steps: int, e2e: bool):
         if world > 1:
@@ -206,6 +256,18 @@ def main():
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
+    if args.graph:
+        build_graph()
+        for _ in range(2):
+            step(False)
+        torch.cuda.synchronize()
+    if args.ncu_step:
+        # exactly one warmed-up step between cudaProfilerStart/Stop: run under `ncu --profile-from-start off ...`
+        torch.cuda.profiler.start()
+        step(False)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -228,7 +290,7 @@ def main():
     if rank == 0 and not args.no_profile:
         prof = ops.Profiler()
         ops.set_profiler(prof)
-        step(False)
+        eager_step(False)
         torch.cuda.synchronize()
         ops.set_profiler(None)
         breakdown = prof.summary()
@@ -262,7 +324,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"WavLM-{args.model} fwd+bwd, batch {B} x {secs} s per GPU, 16 kHz synthetic, mask_prob "
                                    f"{cfg.mask_prob}, dropout 0, all-False padding mask", "global_batch": world * B,
-                       "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)",
+                       "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", "cuda_graph": bool(args.graph),
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

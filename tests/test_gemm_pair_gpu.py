@@ -1,0 +1,96 @@
+"""GPU parity tests of the persistent CTA-pair (cta_group::2, 256x256 tiles) GEMM kernel against PyTorch fp32 references.
+Shapes are chosen large enough that b200s_gemm_rows / b200s_gemm_wgrad dispatch to the pair kernel, with ragged tails."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,K,N", [(3000, 768, 768), (2048, 512, 256), (11984, 768, 2304), (4100, 3072, 768), (2500, 256, 520)])
+def test_pair_gemm_rows(cuda_device, M, K, N):
+    from unispeech_b200 import _lib as L
+    from unispeech_b200 import ops
+    torch.manual_seed(M)
+    dev = cuda_device
+    a = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) / K ** 0.5)
+    bias = torch.randn(N, device=dev)
+    r1 = bf(torch.randn(M, N, device=dev))
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    pre = torch.empty_like(out)
+    epi = L.make_epilogue(bias=bias, gelu=True, out_pre=pre, pre_ld=N, res1=r1, res1_ld=N)
+    ops.gemm_rows(a, 0, K, M, 1, K, w, N, out, 0, N, epi)
+    torch.cuda.synchronize()
+    acc = a.float() @ w.float().t() + bias
+    assert (pre.float() - acc).abs().max().item() < 0.05
+    assert (out.float() - (F.gelu(acc) + r1.float())).abs().max().item() < 0.06
+    # dgelu + two residuals + column sums
+    aux = bf(torch.randn(M, N, device=dev))
+    r2 = bf(torch.randn(M, N, device=dev))
+    out2 = torch.empty_like(out)
+    colsum = torch.zeros(N, device=dev)
+    epi = L.make_epilogue(bias=bias, dgelu=True, gelu_aux=aux, aux_ld=N, res1=r1, res1_ld=N, res2=r2, res2_ld=N, colsum=colsum)
+    ops.gemm_rows(a, 0, K, M, 1, K, w, N, out2, 0, N, epi)
+    torch.cuda.synchronize()
+    x = aux.float().requires_grad_(True)
+    g = torch.autograd.grad(F.gelu(x).sum(), x)[0]
+    ref2 = acc * g + r1.float() + r2.float()
+    assert (out2.float() - ref2).abs().max().item() < 0.08
+    assert (colsum - out2.float().sum(0)).abs().max().item() < 0.02 * max(1.0, out2.float().sum(0).abs().max().item())
+
+
+@pytest.mark.parametrize("C_,k,s,T,B", [(512, 3, 2, 9001, 2), (512, 2, 2, 3000, 3)])
+def test_pair_conv_view(cuda_device, C_, k, s, T, B):
+    from unispeech_b200 import ops
+    torch.manual_seed(T)
+    dev = cuda_device
+    Tpad = T + (T % 2)
+    x = torch.zeros(B, Tpad, C_, device=dev, dtype=torch.bfloat16)
+    x[:, :T] = bf(torch.randn(B, T, C_, device=dev))
+    w = bf(torch.randn(C_, C_, k, device=dev) / (C_ * k) ** 0.5)
+    wk = w.permute(0, 2, 1).contiguous().view(C_, k * C_)
+    T_out = (T - k) // s + 1
+    out = torch.empty(B, T_out, C_, device=dev, dtype=torch.bfloat16)
+    ops.gemm_rows(x, Tpad * C_, s * C_, T_out, B, k * C_, wk, C_, out, T_out * C_, C_, None)
+    torch.cuda.synchronize()
+    ref = F.conv1d(x[:, :T].float().transpose(1, 2), w.float(), stride=s).transpose(1, 2)
+    assert (out.float() - ref).abs().max().item() < 0.04
+
+
+@pytest.mark.parametrize("rows,B,N,K", [(3000, 1, 768, 512), (2000, 2, 256, 1536), (11984, 1, 2304, 768), (1500, 3, 520, 264)])
+def test_pair_wgrad(cuda_device, rows, B, N, K):
+    from unispeech_b200 import ops
+    torch.manual_seed(rows)
+    dev = cuda_device
+    y = bf(torch.randn(B, rows, N, device=dev))
+    x = bf(torch.randn(B, rows, K, device=dev))
+    dw = torch.zeros(N, K, device=dev)
+    ops.gemm_wgrad(y, rows * N, N, x, rows * K, K, rows, B, N, K, dw, K)
+    torch.cuda.synchronize()
+    ref = torch.einsum("brn,brk->nk", y.float(), x.float())
+    err = (dw - ref).abs().max().item()
+    assert err < 1e-2 * max(1.0, ref.abs().max().item()), err
+
+
+def test_pair_wgrad_conv_view(cuda_device):
+    from unispeech_b200 import ops
+    torch.manual_seed(4)
+    dev = cuda_device
+    C_, k, s, T, B = 512, 3, 2, 4001, 2
+    Tpad = T + (T % 2)
+    x = torch.zeros(B, Tpad, C_, device=dev, dtype=torch.bfloat16)
+    x[:, :T] = bf(torch.randn(B, T, C_, device=dev))
+    T_out = (T - k) // s + 1
+    dy = bf(torch.randn(B, T_out, C_, device=dev))
+    dw = torch.zeros(C_, k * C_, device=dev)
+    ops.gemm_wgrad(dy, T_out * C_, C_, x, Tpad * C_, s * C_, T_out, B, C_, k * C_, dw, k * C_)
+    torch.cuda.synchronize()
+    w = torch.zeros(C_, C_, k, device=dev, requires_grad=True)
+    (F.conv1d(x[:, :T].float().transpose(1, 2), w, stride=s) * dy.float().transpose(1, 2)).sum().backward()
+    ref = w.grad.permute(0, 2, 1).reshape(C_, k * C_)
+    assert (dw - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())

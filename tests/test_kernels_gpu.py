@@ -142,7 +142,7 @@ def test_conv0_fwd_bwd(cuda_device, Cc, mode):
     beta = torch.randn(Cc, device=dev) * 0.1
     Tp = T + (T % 2)
     out = torch.zeros(B, Tp, Cc, device=dev, dtype=torch.bfloat16)
-    stats = torch.zeros(B, Cc, 2, device=dev, dtype=torch.float64)
+    stats = torch.zeros(B * Cc * 2 + B * 128, device=dev, dtype=torch.float64)
     fmean = torch.zeros(B, T, device=dev)
     frstd = torch.zeros(B, T, device=dev)
     ops.conv0_fwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, fmean, frstd, out, Tp * Cc)
@@ -160,7 +160,7 @@ def test_conv0_fwd_bwd(cuda_device, Cc, mode):
     dap = torch.zeros(B, Tp, Cc, device=dev, dtype=torch.bfloat16)
     dap[:, :T] = da
     dw, dg, db = torch.zeros_like(w), torch.zeros_like(gamma), torch.zeros_like(beta)
-    bstats = torch.zeros(B, Cc, 2, device=dev)
+    bstats = torch.zeros(B, Cc, 12, device=dev)
     ops.conv0_bwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, dap, Tp * Cc, dw, dg, db)
     torch.cuda.synchronize()
     for got, want, name in ((dw, wr.grad, "dw"), (dg, gr.grad, "dgamma"), (db, br.grad, "dbeta")):

@@ -1,14 +1,17 @@
 // Flash-style attention forward with the WavLM gated relative-position bias, tcgen05 + TMEM + TMA (sm_100a).
 //
-// One CTA = 128 query rows of one (batch, head).  Thread r owns query row r (TMEM lane r): the row maximum / sum of the
-// online softmax are thread-local, no shuffles.  Per key tile n (128 keys):
-//   S_n  = Q K_n^T           tcgen05.mma 128x128x64  -> TMEM (double buffered, issued one tile ahead)
+// One CTA = 256 query rows of one (batch, head): two warpgroups (WG) of 128 threads, each owning one 128-row query tile,
+// plus one TMA producer warp.  Thread r of a WG owns query row r (TMEM lane r): the row maximum / sum of the online softmax
+// are thread-local, no shuffles.  The two WGs share every K/V tile (one TMA load feeds both) and ping-pong on the tensor
+// core: while one WG runs its softmax on the CUDA cores, the other WG's S = Q K^T and O = P V MMAs run.
+// Per WG and key tile n (128 keys):
+//   S_n  = Q K_n^T           tcgen05.mma 128x128x64  -> TMEM
 //   p    = exp2(S*scale*log2e + gate_i*log2e*tab[j-i] + keymask - m)   (two passes over TMEM: max, then exp)
 //   P_n -> shared memory in the K-major SWIZZLE_128B operand layout (bf16)
 //   O_n  = P_n V_n           tcgen05.mma 128x64x128, V_n read as an MN-major operand straight from the TMA tile
-//   O_reg = O_reg*alpha + O_{n-1}   (registers; the rescale never touches TMEM, and is deferred by one tile so the PV
-//                                    MMA of tile n overlaps the softmax of tile n+1)
-// K/V tiles stream through a 2-stage TMA ring; thread 0 is both the TMA producer and the MMA issuer.
+//   O_reg = O_reg*alpha + O_{n-1}   (registers; the rescale never touches TMEM and is deferred by one tile, so the PV MMA
+//                                    of tile n overlaps the softmax of tile n+1)
+// K/V stages are released by tcgen05.commit arrivals of BOTH WGs' issuing threads (mbarrier count 2).
 #include "../../include/unispeech_b200.h"
 #include "attn_common.cuh"
 #include "common.h"
@@ -20,14 +23,23 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 
-constexpr int kFwdQ = 0, kFwdK = 16384, kFwdV = 49152, kFwdP = 81920, kFwdTab = 147456;
+constexpr int kFwdQ = 0;                   // 2 x 16 KB (one Q tile per warpgroup)
+constexpr int kFwdK = 32768;               // 2 stages x 16 KB
+constexpr int kFwdV = 65536;               // 2 stages x 16 KB
+constexpr int kFwdP = 98304;               // 2 x 32 KB (one P tile per warpgroup)
+constexpr int kFwdTab = 163840;            // fp32 bias-table slice, key mask, tile flags
+constexpr int kFwdThreads = 288;           // 2 warpgroups + 1 producer warp
 
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm,
-                                                          const __grid_constant__ AttnParams p) {
+__global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm,
+                                                                 const __grid_constant__ AttnParams p) {
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int q0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
+  const int wg = warp >> 2;  // 0, 1 = softmax warpgroups; 2 = producer warp
+  const int q0 = blockIdx.x * 2 * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
 
   extern __shared__ uint8_t smem_raw[];
@@ -36,11 +48,11 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
   uint8_t* sK = smem + kFwdK;
   uint8_t* sV = smem + kFwdV;
   uint8_t* sP = smem + kFwdP;
-  float* tab_s = reinterpret_cast<float*>(smem + kFwdTab);
-  float* kbias = tab_s + (N + 1) * kAttnTile;
+  float* tab_s = reinterpret_cast<float*>(smem + kFwdTab);  // [(N+2)*128]: index j - r + 255, r = row inside the 256-row block
+  float* kbias = tab_s + (N + 2) * kAttnTile;                // [N*128]
   int* tile_flags = reinterpret_cast<int*>(kbias + N * kAttnTile);
 
-  __shared__ uint64_t q_full, k_full[2], v_full[2], s_full[2], o_full[2];
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], o_full[2];
   __shared__ uint32_t tmem_base_s;
 
   if (tid == 0) {
@@ -49,191 +61,205 @@ __global__ void __launch_bounds__(128, 1) attn_fwd_kernel(const __grid_constant_
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&s_full[i], 1);
+      mbar_init(&k_empty[i], 2);  // one tcgen05.commit arrival per warpgroup
+      mbar_init(&v_empty[i], 2);
+      mbar_init(&s_full[i], 1);   // index = warpgroup
       mbar_init(&o_full[i], 1);
     }
     fence_mbar_init();
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
-  if (HAS_BIAS) load_tab_slice(tab_s, p.tab, h, T, q0, N);
+  if (HAS_BIAS) {
+    const int len = (N + 2) * kAttnTile;
+    const int base = (T - 1) - (q0 + 2 * kAttnTile - 1);
+    for (int i = tid; i < len; i += blockDim.x) {
+      const int gi = i + base;
+      tab_s[i] = (gi >= 0 && gi < 2 * T - 1) ? p.tab[static_cast<long long>(h) * (2 * T - 1) + gi] : 0.f;
+    }
+  }
   load_key_mask(kbias, tile_flags, p.key_pad, b, T, N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-  constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
 
-  auto issue_s = [&](int n) {  // S_n = Q K_n^T into TMEM S[n&1]
-    const uint32_t a = smem_u32(sQ), bb = smem_u32(sK + (n & 1) * 16384);
-#pragma unroll
-    for (int k = 0; k < 4; ++k)
-      umma_bf16(tmem + (n & 1) * 128, make_smem_desc_sw128(a + k * 32, 16, 1024),
-                make_smem_desc_sw128(bb + k * 32, 16, 1024), idesc_s, k > 0 ? 1u : 0u);
-    umma_commit(&s_full[n & 1]);
-  };
-
-  if (tid == 0) {
-    mbar_expect_tx(&q_full, 16384);
-    tma_load_4d(sQ, &tm, &q_full, h * kHeadDim, q0, b, 0);
-    for (int s = 0; s < 2 && s < N; ++s) {
-      mbar_expect_tx(&k_full[s], 16384);
-      tma_load_4d(sK + s * 16384, &tm, &k_full[s], D + h * kHeadDim, s * kAttnTile, b, 0);
-      mbar_expect_tx(&v_full[s], 16384);
-      tma_load_4d(sV + s * 16384, &tm, &v_full[s], 2 * D + h * kHeadDim, s * kAttnTile, b, 0);
-    }
-    mbar_wait(&q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    issue_s(0);
-  }
-  __syncwarp();
-
-  const int r = tid;                 // query row inside the tile == TMEM lane
-  const bool row_valid = (q0 + r) < T;
-  float gl = 0.f;
-  if (HAS_BIAS) {
-    const float g = (p.gate != nullptr && row_valid) ? p.gate[(static_cast<long long>(b) * p.H + h) * T + q0 + r] : 1.0f;
-    gl = g * kLog2e;
-  }
-  const float sc = p.scale * kLog2e;
-  const float* tabrow = tab_s + (kAttnTile - 1 - r);
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-
-  float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-  float o[kHeadDim];
-#pragma unroll
-  for (int i = 0; i < kHeadDim; ++i) o[i] = 0.f;
-
-  auto accumulate_o = [&](int n_prev) {
-    uint32_t t0[32], t1[32];
-    const uint32_t col = 256 + (n_prev & 1) * 64;
-    tmem_ld_32x32b_x32(tmem + lane_addr + col, t0);
-    tmem_ld_32x32b_x32(tmem + lane_addr + col + 32, t1);
-    tmem_ld_wait();
-#pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      o[i] = o[i] * alpha_prev + __uint_as_float(t0[i]);
-      o[32 + i] = o[32 + i] * alpha_prev + __uint_as_float(t1[i]);
-    }
-  };
-
-  for (int n = 0; n < N; ++n) {
-    const int buf = n & 1;
-    const uint32_t ph = (n >> 1) & 1;
-    const int k0 = n * kAttnTile;
-    mbar_wait(&s_full[buf], ph);
-    tc_fence_after();
-    if (tid == 0) {
-      if (n + 2 < N) {  // K stage `buf` is free: S_n has consumed it
-        mbar_expect_tx(&k_full[buf], 16384);
-        tma_load_4d(sK + buf * 16384, &tm, &k_full[buf], D + h * kHeadDim, (n + 2) * kAttnTile, b, 0);
+  if (wg == 2) {
+    // ------------------------------------------------------------------ TMA producer warp
+    if ((tid & 31) == 0) {
+      mbar_expect_tx(&q_full, 32768);
+      tma_load_4d(sQ, &tm, &q_full, h * kHeadDim, q0, b, 0);
+      tma_load_4d(sQ + 16384, &tm, &q_full, h * kHeadDim, q0 + kAttnTile, b, 0);
+      for (int n = 0; n < N; ++n) {
+        const int s = n & 1;
+        const uint32_t ph = (n >> 1) & 1;
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_expect_tx(&k_full[s], 16384);
+        tma_load_4d(sK + s * 16384, &tm, &k_full[s], D + h * kHeadDim, n * kAttnTile, b, 0);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_expect_tx(&v_full[s], 16384);
+        tma_load_4d(sV + s * 16384, &tm, &v_full[s], 2 * D + h * kHeadDim, n * kAttnTile, b, 0);
       }
-      if (n + 1 < N) {
-        mbar_wait(&k_full[buf ^ 1], ((n + 1) >> 1) & 1);
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / MMA-issuing warpgroups
+    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+    const int r = tid & 127;                 // row inside this warpgroup's tile == TMEM lane
+    const int r256 = wg * kAttnTile + r;     // row inside the CTA's 256-row block
+    const bool issuer = (r == 0);
+    const bool row_valid = (q0 + r256) < T;
+    const uint32_t tmem_s = tmem + wg * 256;        // S: 128 columns
+    const uint32_t tmem_o = tmem + wg * 256 + 128;  // O tile: 64 columns
+    uint8_t* sQw = sQ + wg * 16384;
+    uint8_t* sPw = sP + wg * 32768;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+
+    auto issue_s = [&](int n) {  // S_n = Q K_n^T, then release the K stage once the MMAs retire
+      const uint32_t a = smem_u32(sQw), bb = smem_u32(sK + (n & 1) * 16384);
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        umma_bf16(tmem_s, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw128(bb + k * 32, 16, 1024), idesc_s,
+                  k > 0 ? 1u : 0u);
+      umma_commit(&s_full[wg]);
+      umma_commit(&k_empty[n & 1]);
+    };
+
+    if (issuer) {
+      mbar_wait(&q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      issue_s(0);
+    }
+    __syncwarp();
+
+    float gl = 0.f;
+    if (HAS_BIAS) {
+      const float g = (p.gate != nullptr && row_valid) ? p.gate[(static_cast<long long>(b) * p.H + h) * T + q0 + r256] : 1.0f;
+      gl = g * kLog2e;
+    }
+    const float sc = p.scale * kLog2e;
+    const float* tabrow = tab_s + (2 * kAttnTile - 1 - r256);
+
+    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
+    float o[kHeadDim];
+#pragma unroll
+    for (int i = 0; i < kHeadDim; ++i) o[i] = 0.f;
+
+    auto accumulate_o = [&]() {
+      uint32_t t0[32], t1[32];
+      tmem_ld_32x32b_x32(tmem_o + lane_addr, t0);
+      tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, t1);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        o[i] = o[i] * alpha_prev + __uint_as_float(t0[i]);
+        o[32 + i] = o[32 + i] * alpha_prev + __uint_as_float(t1[i]);
+      }
+    };
+
+    for (int n = 0; n < N; ++n) {
+      const int k0 = n * kAttnTile;
+      mbar_wait(&s_full[wg], n & 1);
+      tc_fence_after();
+      const bool msk = tile_flags[n] != 0;
+      const uint32_t s_addr = tmem_s + lane_addr;
+      // ---- pass 1: row maximum of this tile
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+        uint32_t su[32];
+        tmem_ld_32x32b_x32(s_addr + c0, su);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(su[j]) * sc;
+          if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
+          if (msk) x += kbias[k0 + c0 + j];
+          mx = fmaxf(mx, x);
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+      const float alpha_cur = fast_exp2(m_run - m_use);
+      // ---- the PV MMA of the previous tile has long finished: fold its result in (this also frees the P buffer and O tile)
+      if (n >= 1) {
+        mbar_wait(&o_full[wg], (n - 1) & 1);
         tc_fence_after();
-        issue_s(n + 1);
+        accumulate_o();
       }
-    }
-    __syncwarp();
-
-    const bool msk = tile_flags[n] != 0;
-    const uint32_t s_addr = tmem + lane_addr + buf * 128;
-    // ---- pass 1: row maximum of this tile
-    float mx = -INFINITY;
+      // ---- pass 2: probabilities, row sum, bf16 P tile into shared memory (operand layout)
+      float lsum = 0.f;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
-      uint32_t su[32];
-      tmem_ld_32x32b_x32(s_addr + c0, su);
-      tmem_ld_wait();
+      for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+        uint32_t su[32];
+        tmem_ld_32x32b_x32(s_addr + c0, su);
+        tmem_ld_wait();
+        float pv[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(su[j]) * sc;
-        if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-        if (msk) x += kbias[k0 + c0 + j];
-        mx = fmaxf(mx, x);
-      }
-    }
-    const float m_new = fmaxf(m_run, mx);
-    const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha_cur = fast_exp2(m_run - m_use);
-    // ---- pass 2: probabilities, row sum, bf16 P tile into shared memory (operand layout)
-    float lsum = 0.f;
-    uint8_t* ptile = sP + buf * 32768;
-#pragma unroll 1
-    for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
-      uint32_t su[32];
-      tmem_ld_32x32b_x32(s_addr + c0, su);
-      tmem_ld_wait();
-      float pv[32];
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(su[j]) * sc;
+          if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
+          if (msk) x += kbias[k0 + c0 + j];
+          const float e = fast_exp2(x - m_use);
+          pv[j] = e;
+          lsum += e;
+        }
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float x = __uint_as_float(su[j]) * sc;
-        if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-        if (msk) x += kbias[k0 + c0 + j];
-        const float e = fast_exp2(x - m_use);
-        pv[j] = e;
-        lsum += e;
+        for (int g = 0; g < 4; ++g) {
+          uint4 w;
+          w.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
+          w.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+          w.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
+          w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+          store_sw128_chunk(sPw, r, (c0 >> 3) + g, w);
+        }
       }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        uint4 w;
-        w.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-        w.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-        w.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-        w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-        store_sw128_chunk(ptile, r, (c0 >> 3) + g, w);
-      }
-    }
-    l_run = l_run * alpha_cur + lsum;
-    m_run = m_new;
+      l_run = l_run * alpha_cur + lsum;
+      m_run = m_new;
+      alpha_prev = alpha_cur;
 
-    fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-      mbar_wait(&v_full[buf], ph);
-      tc_fence_after();
-      const uint32_t a = smem_u32(ptile), bb = smem_u32(sV + buf * 16384);
+      fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      tc_fence_before();
+      named_bar_sync(1 + wg, kAttnTile);  // this warpgroup only: P complete, S and O tile fully read
+      if (issuer) {
+        tc_fence_after();
+        mbar_wait(&v_full[n & 1], (n >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a = smem_u32(sPw), bb = smem_u32(sV + (n & 1) * 16384);
 #pragma unroll
-      for (int k = 0; k < 8; ++k)
-        umma_bf16(tmem + 256 + buf * 64, make_smem_desc_sw128(a + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                  make_smem_desc_sw128(bb + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
-      umma_commit(&o_full[buf]);
-    }
-    __syncwarp();
-    if (n >= 1) {
-      mbar_wait(&o_full[buf ^ 1], ((n - 1) >> 1) & 1);
-      tc_fence_after();
-      if (tid == 0 && n + 1 < N) {  // V stage of tile n-1 is free
-        mbar_expect_tx(&v_full[buf ^ 1], 16384);
-        tma_load_4d(sV + (buf ^ 1) * 16384, &tm, &v_full[buf ^ 1], 2 * D + h * kHeadDim, (n + 1) * kAttnTile, b, 0);
+        for (int k = 0; k < 8; ++k)
+          umma_bf16(tmem_o, make_smem_desc_sw128(a + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(bb + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
+        umma_commit(&o_full[wg]);
+        umma_commit(&v_empty[n & 1]);
+        if (n + 1 < N) {
+          mbar_wait(&k_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+          tc_fence_after();
+          issue_s(n + 1);
+        }
       }
       __syncwarp();
-      accumulate_o(n - 1);
     }
-    alpha_prev = alpha_cur;
-  }
-  mbar_wait(&o_full[(N - 1) & 1], ((N - 1) >> 1) & 1);
-  tc_fence_after();
-  accumulate_o(N - 1);
+    mbar_wait(&o_full[wg], (N - 1) & 1);
+    tc_fence_after();
+    accumulate_o();
 
-  if (row_valid) {
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * T + q0 + r) * D + h * kHeadDim;
+    if (row_valid) {
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * T + q0 + r256) * D + h * kHeadDim;
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      uint4 w;
-      w.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
-      w.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-      w.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
-      w.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
-      *reinterpret_cast<uint4*>(dst + g * 8) = w;
+      for (int g = 0; g < 8; ++g) {
+        uint4 w;
+        w.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
+        w.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
+        w.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
+        w.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        *reinterpret_cast<uint4*>(dst + g * 8) = w;
+      }
+      if (p.lse != nullptr)
+        p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + r256] = (l_run > 0.f) ? (m_run + log2f(l_run)) : INFINITY;
     }
-    if (p.lse != nullptr)
-      p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + r] = (l_run > 0.f) ? (m_run + log2f(l_run)) : INFINITY;
   }
 
   tc_fence_before();
@@ -270,16 +296,16 @@ int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const u
   p.gate = gate; p.tab = tab; p.key_pad = key_pad;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
-  const int smem = kFwdTab + sizeof(float) * ((p.n_tiles + 1) * kAttnTile + p.n_tiles * kAttnTile) +
+  const int smem = kFwdTab + sizeof(float) * ((p.n_tiles + 2) * kAttnTile + p.n_tiles * kAttnTile) +
                    sizeof(int) * p.n_tiles + 1024;
-  dim3 grid(p.n_tiles, H, B);
+  dim3 grid(ceil_div(T, 2 * kAttnTile), H, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tab != nullptr) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<true><<<grid, 128, smem, st>>>(tm, p);
+    attn_fwd_kernel<true><<<grid, kFwdThreads, smem, st>>>(tm, p);
   } else {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<false><<<grid, 128, smem, st>>>(tm, p);
+    attn_fwd_kernel<false><<<grid, kFwdThreads, smem, st>>>(tm, p);
   }
   B200_CHECK_LAUNCH();
   return 0;

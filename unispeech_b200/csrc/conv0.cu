@@ -348,6 +348,12 @@ __global__ void __launch_bounds__(256) conv0_bwd_dw_kernel(const float* __restri
   }
 }
 
+int conv0_gn_stats_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, double* stats,
+                          cudaStream_t st);
+int conv0_gn_bwd_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
+                        const float* beta, const double* stats, float* bstats, const void* da, long long da_bs, float* dw,
+                        float* dgamma, float* dbeta, cudaStream_t st);
+
 static int conv0_grid_x(int T) {
   int gx = std::min(ceil_div(T, 8 * 4), std::max(1, 4 * sm_count()));
   return std::max(gx, 1);
@@ -371,7 +377,7 @@ using namespace b200;
 
 extern "C" {
 
-// Forward.  mode 0: GroupNorm(C,C) (stats: fp64 [B,C,2] workspace, zeroed by this call); mode 1: LayerNorm over channels
+// Forward.  mode 0: GroupNorm(C,C) (stats: fp64 [B*C*2 + B*128] workspace: per-(b,c) sums + waveform autocorrelation); mode 1: LayerNorm over channels
 // (fmean/frstd: fp32 [B,T] outputs).  wav fp32 [B,L]; w fp32 [C,1,k]; out bf16 [B, out_bs/C rows, C].
 int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
                     const float* beta, int mode, double* stats, float* fmean, float* frstd, void* out, long long out_bs,
@@ -384,11 +390,8 @@ int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, i
   DISPATCH_C(C, {
     const size_t sm_w = sizeof(float) * kMaxTaps * kC, sm_red = sizeof(float) * 8 * kC;
     if (mode == 0) {
-      B200_CHECK_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * 2 * B * kC, st));
-      B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_gn_stats_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(sm_w + sm_red)));
-      conv0_gn_stats_kernel<kC><<<grid, 256, sm_w + sm_red, st>>>(wav, L, T, k, s, w, stats);
-      B200_CHECK_LAUNCH();
+      (void)sm_red;
+      if (int rc = conv0_gn_stats_launch(wav, L, B, T, kC, k, s, w, stats, st)) return rc;  // analytic, from the autocorrelation
       conv0_fwd_kernel<kC, 0><<<grid, 256, sm_w, st>>>(wav, L, T, k, s, w, gamma, beta, stats, nullptr, nullptr,
                                                       static_cast<__nv_bfloat16*>(out), out_bs);
     } else {
@@ -401,7 +404,7 @@ int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, i
 }
 
 // Backward: da = gradient w.r.t. the layer output (after norm + GELU), bf16 [B, rows, C].  Accumulates dw [C,1,k], dgamma,
-// dbeta (fp32 atomics).  bstats: fp32 [B,C,2] workspace (mode 0, zeroed here).  The waveform receives no gradient.
+// dbeta (fp32 atomics).  bstats: fp32 [B,C,12] workspace (mode 0, zeroed here).  The waveform receives no gradient.
 int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
                     const float* beta, int mode, const double* stats, float* bstats, const float* fmean,
                     const float* frstd, const void* da, long long da_bs, float* dw, float* dgamma, float* dbeta,
@@ -416,19 +419,9 @@ int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, i
     const size_t sm = sizeof(float) * (kMaxTaps + 8) * kC;
     constexpr int JT = 5;
     if (mode == 0) {
-      B200_CHECK_CUDA(cudaMemsetAsync(bstats, 0, sizeof(float) * 2 * B * kC, st));
-      B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_gn_bwd_stats_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(sm)));
-      conv0_gn_bwd_stats_kernel<kC><<<grid, 256, sm, st>>>(wav, L, T, k, s, w, gamma, beta, stats, dap, da_bs, bstats,
-                                                          dgamma, dbeta);
-      B200_CHECK_LAUNCH();
-      B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_dw_kernel<kC, 0, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(sm)));
-      for (int j0 = 0; j0 < k; j0 += JT) {
-        conv0_bwd_dw_kernel<kC, 0, JT><<<grid, 256, sm, st>>>(wav, L, T, k, s, w, gamma, beta, stats, bstats, nullptr,
-                                                             nullptr, dap, da_bs, j0, dw, dgamma, dbeta);
-        B200_CHECK_LAUNCH();
-      }
+      (void)grid;
+      if (int rc = conv0_gn_bwd_launch(wav, L, B, T, kC, k, s, w, gamma, beta, stats, bstats, da, da_bs, dw, dgamma, dbeta, st))
+        return rc;
     } else {
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_dw_kernel<kC, 1, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(sm)));

@@ -1,11 +1,14 @@
 // Host side of the tcgen05 GEMM family: TMA tensor-map construction, tile mapping and launch.
 #include <stdarg.h>
+#include <stdlib.h>
 
+#include <algorithm>
 #include <mutex>
 
 #include "../../include/unispeech_b200.h"
 #include "common.h"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 
 namespace b200 {
 
@@ -117,6 +120,47 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
   return 0;
 }
 
+// persistent CTA-pair kernel (gemm2.cuh): cluster (2,1,1), one pair per two SMs
+template <bool A_MN, bool B_MN>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg;
+  static std::once_flag once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(once, [] {
+    attr_err = cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    Cfg::kSmemBytes);
+  });
+  B200_CHECK_CUDA(attr_err);
+  const int items = p.tiles_total * p.splits;
+  const int pairs = std::max(1, std::min(items, sm_count() / 2));
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN>, ta, tb, p));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// 0/1 switch for the CTA-pair kernel (B200S_GEMM_PAIR=0 forces the single-CTA kernel; used by the A/B micro-benchmarks)
+static bool pair_kernel_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_GEMM_PAIR");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
+
 static void fill_epilogue(GemmParams& p, const b200s_epilogue* e) {
   p.bias = nullptr;
   p.colsum = nullptr;
@@ -174,12 +218,41 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   B200_CHECK_ARG(K % 64 == 0, "gemm_rows: K=%d must be a multiple of 64", K);
   B200_CHECK_ARG(N % 8 == 0, "gemm_rows: N=%d must be a multiple of 8", N);
   if (check_epilogue(epi)) return -1;
-  const int block_n = (N >= 128) ? 128 : 64;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
 
   CUtensorMap ta, tb;
   ViewSpec va{a, {K, rows, batches, 1}, {a_rs, batches > 1 ? a_bs : 0, 0}, {64, 128, 1, 1}};
   if (batches == 1) va.strides[1] = 0;
   if (make_tmap(&ta, va)) return -3;
+
+  if (pair_kernel_enabled() && N >= 256 && rows >= 256 && static_cast<long long>(rows) * batches >= 2048) {
+    // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows
+    ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, 128, 1, 1}};
+    if (make_tmap(&tb, vb2)) return -3;
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.m_rows = rows;
+    p.m_tile_stride = 256;
+    p.m_tile_valid = 256;
+    p.m_tiles_per_batch = ceil_div(rows, 256);
+    p.n_total = N;
+    p.n_out_stride = 256;
+    p.n_tile_valid = 256;
+    p.n_tiles = ceil_div(N, 256);
+    p.tiles_total = p.m_tiles_per_batch * batches * p.n_tiles;
+    p.splits = 1;
+    p.k_blocks = K / 64;
+    p.k_blocks_per_batch = 0;
+    p.k_blocks_per_split = p.k_blocks;
+    // A coords: (k0, m0 [+128*rank, added by the kernel], mb, 0)   B coords: (k0, n_tile*256 + sub(=128*rank), 0, 0)
+    p.ca[0][4] = 1; p.ca[1][1] = 1; p.ca[2][2] = 1;
+    p.cb[0][4] = 1; p.cb[1][3] = 256; p.cb[1][7] = 1;
+    p.flags = 0;
+    fill_epilogue(p, epi);
+    p.out = {out, out_bs, out_ld};
+    return launch_gemm_pair<false, false>(ta, tb, p, st);
+  }
+  const int block_n = (N >= 128) ? 128 : 64;
   ViewSpec vb{w, {K, N, 1, 1}, {K, 0, 0}, {64, block_n, 1, 1}};
   if (make_tmap(&tb, vb)) return -3;
 
@@ -203,7 +276,6 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   p.out = {out, out_bs, out_ld};
   dim3 grid(ceil_div(N, block_n), p.m_tiles_per_batch * batches, 1);
   B200_CHECK_ARG(grid.y <= 65535, "gemm_rows: too many M tiles (%u)", grid.y);
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
   return block_n == 128 ? launch_gemm<128, false, false>(ta, tb, p, grid, st)
                         : launch_gemm<64, false, false>(ta, tb, p, grid, st);
 }
@@ -220,6 +292,36 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
   if (make_tmap(&ta, va)) return -3;
   ViewSpec vb{x, {K, rows, batches, 1}, {x_rs, batches > 1 ? x_bs : 0, 0}, {64, 64, 1, 1}};
   if (make_tmap(&tb, vb)) return -3;
+
+  if (pair_kernel_enabled() && N >= 256 && K >= 256 && static_cast<long long>(rows) * batches >= 1024) {
+    // persistent CTA-pair kernel, both operands MN-major; work items = (K split, tile)
+    GemmParams p;
+    memset(&p, 0, sizeof(p));
+    p.m_rows = N;
+    p.m_tile_stride = 256;
+    p.m_tile_valid = 256;
+    p.m_tiles_per_batch = ceil_div(N, 256);
+    p.n_total = K;
+    p.n_out_stride = 256;
+    p.n_tile_valid = 256;
+    p.n_tiles = ceil_div(K, 256);
+    p.tiles_total = p.m_tiles_per_batch * p.n_tiles;
+    p.k_blocks_per_batch = ceil_div(rows, 64);
+    p.k_blocks = p.k_blocks_per_batch * batches;
+    const int pairs = std::max(1, sm_count() / 2);
+    // about one work item per CTA pair: the fp32 reduction epilogue of a split is the expensive part, the main loop is cheap
+    int splits = std::max(1, pairs / p.tiles_total);
+    if (splits > p.k_blocks) splits = p.k_blocks;
+    p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
+    p.splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
+    // A coords: (m0 [+128*rank] + sub, k0, kbatch, 0)   B coords: (n_tile*256 + sub (=128*rank + 64*i), k0, kbatch, 0)
+    p.ca[0][1] = 1; p.ca[0][7] = 1; p.ca[1][4] = 1; p.ca[2][5] = 1;
+    p.cb[0][3] = 256; p.cb[0][7] = 1; p.cb[1][4] = 1; p.cb[2][5] = 1;
+    p.flags = EPI_OUT_F32 | (p.splits > 1 ? EPI_ATOMIC : EPI_ACCUM);
+    fill_epilogue(p, nullptr);
+    p.out = {dw, 0, dw_ld};
+    return launch_gemm_pair<true, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
+  }
 
   GemmParams p;
   memset(&p, 0, sizeof(p));

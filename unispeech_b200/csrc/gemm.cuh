@@ -26,6 +26,7 @@ enum : int {
   EPI_OUT_F32 = 4,   // out is fp32
   EPI_ATOMIC = 8,    // fp32 atomicAdd into out (split-K / accumulation)
   EPI_COLSUM = 16,   // atomically accumulate column sums of the final value into colsum[col] (bias grads)
+  EPI_ACCUM = 32,    // fp32 out += value, non-atomic (single writer per element: split-K disabled)
 };
 
 // variables the coordinate matrices multiply: {1, m0, mb, n_tile, k0, kbatch, kb, sub}
@@ -48,6 +49,8 @@ struct GemmParams {
   const float* bias;     // [n] fp32 or null
   float* colsum;         // [n] fp32 or null (EPI_COLSUM)
   EpiTensor out, out2, aux, res1, res2;
+  // persistent CTA-pair kernel only (gemm2.cuh): work items = (split, m_tile, n_tile), n fastest
+  int n_tiles, tiles_total, splits;
 };
 
 template <int BLOCK_N>
@@ -65,6 +68,128 @@ __device__ __forceinline__ int coord_dot(const int* row, const int* v) {
 #pragma unroll
   for (int i = 0; i < kCoordVars; ++i) s += row[i] * v[i];
   return s;
+}
+
+// Per-thread row pointers of the epilogue tensors (computed once per tile: the epilogue is issue-bound -- one warp per
+// scheduler -- so every instruction removed from the per-element path is wall-clock time).
+struct EpiRow {
+  __nv_bfloat16* out_bf;
+  float* out_f32;
+  __nv_bfloat16* out2;
+  const __nv_bfloat16* aux;
+  const __nv_bfloat16* res1;
+  const __nv_bfloat16* res2;
+};
+__device__ __forceinline__ EpiRow make_epi_row(const GemmParams& p, int mb, long long row) {
+  EpiRow e;
+  e.out_bf = static_cast<__nv_bfloat16*>(p.out.p) + mb * p.out.bs + row * p.out.ld;
+  e.out_f32 = static_cast<float*>(p.out.p) + mb * p.out.bs + row * p.out.ld;
+  e.out2 = p.out2.p ? static_cast<__nv_bfloat16*>(p.out2.p) + mb * p.out2.bs + row * p.out2.ld : nullptr;
+  e.aux = p.aux.p ? static_cast<const __nv_bfloat16*>(p.aux.p) + mb * p.aux.bs + row * p.aux.ld : nullptr;
+  e.res1 = p.res1.p ? static_cast<const __nv_bfloat16*>(p.res1.p) + mb * p.res1.bs + row * p.res1.ld : nullptr;
+  e.res2 = p.res2.p ? static_cast<const __nv_bfloat16*>(p.res2.p) + mb * p.res2.bs + row * p.res2.ld : nullptr;
+  return e;
+}
+__device__ __forceinline__ void add_bf16x8(float* a8, const __nv_bfloat16* src) {
+  const uint4 w = *reinterpret_cast<const uint4*>(src);
+  const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = unpack_bf16x2(wu[j]);
+    a8[2 * j] += f.x;
+    a8[2 * j + 1] += f.y;
+  }
+}
+__device__ __forceinline__ uint4 pack_bf16x8(const float* a8) {
+  uint4 w;
+  w.x = pack_bf16x2(a8[0], a8[1]); w.y = pack_bf16x2(a8[2], a8[3]);
+  w.z = pack_bf16x2(a8[4], a8[5]); w.w = pack_bf16x2(a8[6], a8[7]);
+  return w;
+}
+
+// One 32-column chunk of the fused epilogue for this thread's accumulator row (taddr = TMEM address of the chunk).
+__device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const EpiRow& e, uint32_t taddr, int c0, int n_valid,
+                                                 int col_base, bool row_ok, int lane) {
+  const int flags = p.flags;
+  uint32_t acc_u[32];
+  tmem_ld_32x32b_x32(taddr, acc_u);
+  tmem_ld_wait();
+  float* acc = reinterpret_cast<float*>(acc_u);
+  const bool full = (c0 + 32 <= n_valid);  // warp-uniform
+  if (p.bias != nullptr) {
+    const float* bp = p.bias + col_base + c0;
+    if (full) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(bp) + j);
+        acc[4 * j] += b4.x; acc[4 * j + 1] += b4.y; acc[4 * j + 2] += b4.z; acc[4 * j + 3] += b4.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (c0 + j < n_valid) acc[j] += __ldg(bp + j);
+    }
+  }
+  if (row_ok) {
+    const int col0 = col_base + c0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      if (!full && (c0 + g * 8 >= n_valid)) break;
+      const int col = col0 + g * 8;
+      float* a8 = acc + g * 8;
+      if (flags & EPI_GELU) {
+        if (e.out2 != nullptr) *reinterpret_cast<uint4*>(e.out2 + col) = pack_bf16x8(a8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a8[j] = gelu_f(a8[j]);
+      }
+      if (flags & EPI_DGELU) {
+        const uint4 w = *reinterpret_cast<const uint4*>(e.aux + col);
+        const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float2 f = unpack_bf16x2(wu[j]);
+          a8[2 * j] *= gelu_grad_f(f.x);
+          a8[2 * j + 1] *= gelu_grad_f(f.y);
+        }
+      }
+      if (e.res1 != nullptr) add_bf16x8(a8, e.res1 + col);
+      if (e.res2 != nullptr) add_bf16x8(a8, e.res2 + col);
+      if (flags & EPI_OUT_F32) {
+        float* o = e.out_f32 + col;
+        if (flags & EPI_ATOMIC) {
+          // 128-bit vector reductions (REDG.E.ADD.F32x4): the split-K epilogue is bound by LSU issue, not bytes
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(a8[0]), "f"(a8[1]), "f"(a8[2]), "f"(a8[3])
+                       : "memory");
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4), "f"(a8[4]), "f"(a8[5]), "f"(a8[6]),
+                       "f"(a8[7])
+                       : "memory");
+        } else if (flags & EPI_ACCUM) {
+          float4 o0 = *reinterpret_cast<float4*>(o), o1 = *reinterpret_cast<float4*>(o + 4);
+          o0.x += a8[0]; o0.y += a8[1]; o0.z += a8[2]; o0.w += a8[3];
+          o1.x += a8[4]; o1.y += a8[5]; o1.z += a8[6]; o1.w += a8[7];
+          *reinterpret_cast<float4*>(o) = o0;
+          *reinterpret_cast<float4*>(o + 4) = o1;
+        } else {
+          *reinterpret_cast<float4*>(o) = make_float4(a8[0], a8[1], a8[2], a8[3]);
+          *reinterpret_cast<float4*>(o + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
+        }
+      } else {
+        *reinterpret_cast<uint4*>(e.out_bf + col) = pack_bf16x8(a8);
+      }
+    }
+  }
+  if (flags & EPI_COLSUM) {
+    // column sums of the stored values over this warp's 32 rows: transpose-reduce, then one atomic per column
+    float cv[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      float t = row_ok ? acc[j] : 0.0f;
+      if (!(flags & EPI_OUT_F32)) t = __bfloat162float(__float2bfloat16_rn(t));
+      cv[j] = t;
+    }
+    const float csum = warp_colsum32(cv, lane);
+    if ((c0 + lane) < n_valid) atomicAdd(p.colsum + col_base + c0 + lane, csum);
+  }
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN>
@@ -190,101 +315,14 @@ __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ 
     const int n_valid = min(p.n_tile_valid, p.n_total - col_base);
     const long long row = static_cast<long long>(m0) + r;
 
+    const EpiRow erow = make_epi_row(p, mb, row);
     mbar_wait(&tmem_full_bar, 0);
     tc_fence_after();
 
-    const int flags = p.flags;
 #pragma unroll 1
     for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
       if (c0 >= n_valid) break;  // warp-uniform
-      uint32_t acc_u[32];
-      tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, acc_u);
-      tmem_ld_wait();
-      float* acc = reinterpret_cast<float*>(acc_u);
-      if (p.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c0 + j < n_valid) acc[j] += __ldg(p.bias + col_base + c0 + j);
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        const int c = c0 + g * 8;
-        const bool ok = row_ok && (c < n_valid);
-        float* a8 = acc + g * 8;
-        if (ok) {
-          const long long col = col_base + c;
-          if (flags & EPI_GELU) {
-            if (p.out2.p != nullptr) {
-              uint4 w;
-              w.x = pack_bf16x2(a8[0], a8[1]); w.y = pack_bf16x2(a8[2], a8[3]);
-              w.z = pack_bf16x2(a8[4], a8[5]); w.w = pack_bf16x2(a8[6], a8[7]);
-              *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out2.p) + mb * p.out2.bs + row * p.out2.ld + col) = w;
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a8[j] = gelu_f(a8[j]);
-          }
-          if (flags & EPI_DGELU) {
-            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.aux.p) +
-                                                           mb * p.aux.bs + row * p.aux.ld + col);
-            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(wu[j]);
-              a8[2 * j] *= gelu_grad_f(f.x);
-              a8[2 * j + 1] *= gelu_grad_f(f.y);
-            }
-          }
-          if (p.res1.p != nullptr) {
-            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res1.p) +
-                                                           mb * p.res1.bs + row * p.res1.ld + col);
-            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(wu[j]);
-              a8[2 * j] += f.x;
-              a8[2 * j + 1] += f.y;
-            }
-          }
-          if (p.res2.p != nullptr) {
-            const uint4 w = *reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(p.res2.p) +
-                                                           mb * p.res2.bs + row * p.res2.ld + col);
-            const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float2 f = unpack_bf16x2(wu[j]);
-              a8[2 * j] += f.x;
-              a8[2 * j + 1] += f.y;
-            }
-          }
-          if (flags & EPI_OUT_F32) {
-            float* o = static_cast<float*>(p.out.p) + mb * p.out.bs + row * p.out.ld + col;
-            if (flags & EPI_ATOMIC) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) atomicAdd(o + j, a8[j]);
-            } else {
-              *reinterpret_cast<float4*>(o) = make_float4(a8[0], a8[1], a8[2], a8[3]);
-              *reinterpret_cast<float4*>(o + 4) = make_float4(a8[4], a8[5], a8[6], a8[7]);
-            }
-          } else {
-            uint4 w;
-            w.x = pack_bf16x2(a8[0], a8[1]); w.y = pack_bf16x2(a8[2], a8[3]);
-            w.z = pack_bf16x2(a8[4], a8[5]); w.w = pack_bf16x2(a8[6], a8[7]);
-            *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(p.out.p) + mb * p.out.bs + row * p.out.ld + col) = w;
-          }
-        }
-      }
-      if (flags & EPI_COLSUM) {
-        // column sums of the stored values over this warp's 32 rows: transpose-reduce, then one atomic per column
-        float cv[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float t = row_ok ? acc[j] : 0.0f;
-          if (!(flags & EPI_OUT_F32)) t = __bfloat162float(__float2bfloat16_rn(t));
-          cv[j] = t;
-        }
-        const float csum = warp_colsum32(cv, lane);
-        if ((c0 + lane) < n_valid) atomicAdd(p.colsum + col_base + c0 + lane, csum);
-      }
+      epilogue_chunk32(p, erow, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, c0, n_valid, col_base, row_ok, lane);
     }
   }
 

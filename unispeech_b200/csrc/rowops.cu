@@ -238,28 +238,32 @@ static int row_grid(long long rows, int warps_per_block) {
 // colsum[c] += sum_rows x[r, c]   (bias gradients); x bf16 [rows, N] with batch/row strides.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int N,
                                                      long long rows, float* __restrict__ out) {
-  // block handles a strip of 64 columns (blockIdx.x) and a slice of rows (blockIdx.y); thread -> (row lane, 2 cols)
-  const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
+  // block: a strip of 256 columns (32 lanes x 8 columns, 16-byte loads) x 8 row lanes; rows strided over blockIdx.y
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 256 + lane * 8;
   const int rl = threadIdx.x >> 5;  // 0..7
-  float a0 = 0.f, a1 = 0.f;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
   if (c < N) {
-    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
-      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(x + xv.off(r) + c));
-      a0 += f.x;
-      a1 += f.y;
+    const long long step = static_cast<long long>(gridDim.y) * 8;
+#pragma unroll 4
+    for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += step) {
+      float v[8];
+      VecIO<8>::load(x + xv.off(r) + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] += v[i];
     }
   }
-  __shared__ float red[8][64];
-  red[rl][(threadIdx.x & 31) * 2] = a0;
-  red[rl][(threadIdx.x & 31) * 2 + 1] = a1;
-  __syncthreads();
-  if (threadIdx.x < 64) {
-    float s = 0.f;
+  __shared__ float red[8][256];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
-    const int cc = blockIdx.x * 64 + threadIdx.x;
-    if (cc < N) atomicAdd(out + cc, s);
-  }
+  for (int i = 0; i < 8; ++i) red[rl][lane * 8 + i] = a[i];
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w][threadIdx.x];
+  const int cc = blockIdx.x * 256 + threadIdx.x;
+  if (cc < N) atomicAdd(out + cc, s);
 }
 
 // ------------------------------------------------------------------------------------------------ dgelu multiply
@@ -428,23 +432,37 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
       *reinterpret_cast<uint32_t*>(dr + h * 64 + lane * 2) = pack_bf16x2(dsa * wa0 + dsb * wb0, dsa * wa1 + dsb * wb1);
     }
   }
-  // every one of the 4 rows that were summed receives the same gradient
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    atomicAdd(dgrep_w + o * 64 + lane * 2, dwa0);
-    atomicAdd(dgrep_w + o * 64 + lane * 2 + 1, dwa1);
-    atomicAdd(dgrep_w + (o + 4) * 64 + lane * 2, dwb0);
-    atomicAdd(dgrep_w + (o + 4) * 64 + lane * 2 + 1, dwb1);
-  }
+  // block-level reduction first (one set of global atomics per block, not per warp: all blocks hit the same 1 KB)
+  __shared__ float red_w[8][130];
+  red_w[warp][lane * 2] = dwa0;
+  red_w[warp][lane * 2 + 1] = dwa1;
+  red_w[warp][64 + lane * 2] = dwb0;
+  red_w[warp][64 + lane * 2 + 1] = dwb1;
   if (lane == 0) {
+    red_w[warp][128] = dba;
+    red_w[warp][129] = dbb;
+  }
+  __syncthreads();
+  const int nw = blockDim.x >> 5;
+  if (threadIdx.x < 130) {
+    float s = 0.f;
+    for (int w8 = 0; w8 < nw; ++w8) s += red_w[w8][threadIdx.x];
+    // every one of the 4 rows that were summed receives the same gradient
+    if (threadIdx.x < 128) {
+      const int half = threadIdx.x >> 6, c = threadIdx.x & 63;
 #pragma unroll
-    for (int o = 0; o < 4; ++o) {
-      atomicAdd(dgrep_b + o, dba);
-      atomicAdd(dgrep_b + o + 4, dbb);
+      for (int o = 0; o < 4; ++o) atomicAdd(dgrep_w + (o + 4 * half) * 64 + c, s);
+    } else {
+      const int half = threadIdx.x - 128;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) atomicAdd(dgrep_b + o + 4 * half, s);
     }
   }
-  __syncwarp();
-  for (int h = lane; h < H; h += 32) atomicAdd(dgrep_a + h, dga_smem[warp * H + h]);
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float s = 0.f;
+    for (int w8 = 0; w8 < nw; ++w8) s += dga_smem[w8 * H + h];
+    atomicAdd(dgrep_a + h, s);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ relative position table
@@ -520,12 +538,13 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
 int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
                  b200s_stream stream) {
   B200_CHECK_ARG(x && out, "colsum: null pointer");
-  B200_CHECK_ARG(N % 2 == 0, "colsum: N must be even");
+  B200_CHECK_ARG(N % 8 == 0, "colsum: N must be a multiple of 8");
   const long long rows = static_cast<long long>(rows_per_batch) * batches;
   if (rows == 0) return 0;
   RowView xv{x_bs, x_rs, rows_per_batch};
-  int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 64), 4LL * sm_count() / std::max(1, ceil_div(N, 64)) + 1));
-  dim3 grid(ceil_div(N, 64), std::max(1, gy));
+  const int gx = ceil_div(N, 256);
+  int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 32), std::max(1, 4 * sm_count() / gx)));
+  dim3 grid(gx, std::max(1, gy));
   colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), xv, N, rows,
                                                                     out);
   B200_CHECK_LAUNCH();

@@ -202,7 +202,7 @@ class Engine:
                           a0, geo.Tp[0] * C)
             st["stats0"] = (fmean, frstd)
         else:
-            stats = torch.empty(B, C, 2, dtype=torch.float64, device=dev)
+            stats = torch.empty(B * C * 2 + B * 128, dtype=torch.float64, device=dev)  # per-(b,c) sums + autocorrelation
             ops.conv0_fwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 0, stats, None, None,
                           a0, geo.Tp[0] * C)
             st["stats0"] = stats
@@ -314,7 +314,7 @@ class Engine:
             ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 1, None, None, fmean,
                           frstd, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias))
         else:
-            bstats = torch.empty(B, C, 2, dtype=torch.float32, device=dev)
+            bstats = torch.empty(B, C, 12, dtype=torch.float32, device=dev)
             ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 0, st["stats0"], bstats,
                           None, None, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias))
 
