@@ -203,7 +203,8 @@ def main():
             for _ in range(2):  # warm-up on the capture stream (allocator pools, cudaFuncSetAttribute, lazy init)
                 model.grad_buffer().zero_()
                 x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
-                (x.float() * R).sum().backward()
+                with torch.autograd.set_multithreading_enabled(False):
+                    (x.float() * R).sum().backward()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
@@ -212,7 +213,8 @@ def main():
             model.grad_buffer().zero_()
             x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
             loss = (x.float() * R).sum()
-            loss.backward()
+            with torch.autograd.set_multithreading_enabled(False):  # backward in the capturing thread
+                loss.backward()
         graph_state.update(g=g, wav=wav_static, mask=mask_static, mask_pinned=mask_pinned, loss=loss, n=0)
 
     def graph_step(e2e: bool):

@@ -159,6 +159,9 @@ int b200s_scale_copy_f32(const float* src, float* dst, long long n, float scale,
 /* fp32 [N,K] -> bf16 dst[n*ld+k] and/or its transpose dstT[k*ldT+n] */
 int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, long long ld, void* dstT,
                       long long ldT, b200s_stream stream);
+/* all nn.Linear operands of the model in ONE launch: descs = device array of n_descs 56-byte records
+ * {const float* src; bf16* dst; bf16* dstT; int64 ld, ldT; int32 N, K, tile_begin, tiles_k} (32x32 tiles, prefix-summed) */
+int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b200s_stream stream);
 /* nn.Conv1d weight [Co,Ci,k] -> forward operand [Co, k*Ci] / per-phase input-gradient operand / gradient un-layout */
 int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream);
 int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rho, void* dst, b200s_stream stream);

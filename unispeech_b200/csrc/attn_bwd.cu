@@ -45,7 +45,7 @@ constexpr int kKvK = 0, kKvV = 16384, kKvQ = 32768, kKvDO = 65536, kKvPT = 98304
               kKvTab = 167936;
 
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+__global__ void __launch_bounds__(256, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                               const __grid_constant__ CUtensorMap tm_do,
                                                               const __grid_constant__ AttnParams p) {
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -89,6 +89,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
     }
   }
   auto load_colvec = [&](int qi) {
+    if (tid >= kAttnTile) return;  // one loader per query column
     const int i = qi * kAttnTile + tid;
     float4 v;
     if (i < T) {
@@ -145,14 +146,17 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
   }
   __syncwarp();
 
-  const int r = tid;  // key row inside the tile
+  // two threads per key row: warpgroup `half` handles query columns [64*half, 64*half+64) of every tile (two warps per
+  // scheduler hide the latency of this issue-bound phase; the MMAs, TMEM and shared-memory layout are unchanged)
+  const int r = tid & (kAttnTile - 1);  // key row inside the tile
+  const int half = tid >> 7;
   const int key = k0 + r;
   const bool key_valid = key < T;
   const bool key_masked = !key_valid || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + key] != 0);
   const float kb = key_masked ? -INFINITY : 0.f;
   const float sc = p.scale * kLog2e;
   const float* tabrow = tab_s + r + N * kAttnTile - 1;
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
 
   for (int qi = 0; qi < N; ++qi) {
     const int st = qi & 1;
@@ -164,7 +168,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
     __syncwarp();
     const float4* cv = colvec + st * kAttnTile;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+    for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
       uint32_t su[32], du[32];
       tmem_ld_32x32b_x32(tmem + lane_addr + c0, su);
       tmem_ld_32x32b_x32(tmem + lane_addr + 128 + c0, du);
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dkv_kernel(const __grid_const
   {
     uint32_t t0[32], t1[32];
 #pragma unroll 1
-    for (int which = 0; which < 2; ++which) {  // 0: dV (cols 256..), 1: dK (cols 320..)
+    for (int which = half; which <= half; ++which) {  // warpgroup 0 writes dV (cols 256..), warpgroup 1 dK (cols 320..)
       const uint32_t col = 256 + which * 64;
       tmem_ld_32x32b_x32(tmem + lane_addr + col, t0);
       tmem_ld_32x32b_x32(tmem + lane_addr + col + 32, t1);
@@ -269,7 +273,7 @@ constexpr int kWStride = 130;  // bf16 elements per staged row (65 words: confli
 constexpr int kDqTab = kDqW + 128 * kWStride * 2 + 64;  // 164416, 16B aligned
 
 template <bool HAS_BIAS>
-__global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv,
+__global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                              const __grid_constant__ CUtensorMap tm_do,
                                                              const __grid_constant__ AttnParams p) {
   const int tid = threadIdx.x, warp = tid >> 5;
@@ -349,7 +353,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
   }
   __syncwarp();
 
-  const int r = tid;
+  const int r = tid & (kAttnTile - 1);  // two threads per query row, see the dK/dV kernel
+  const int half = tid >> 7;
   const bool row_valid = (q0 + r) < T;
   const long long ridx = (static_cast<long long>(b) * p.H + h) * T + q0 + r;
   const float lse2 = row_valid ? p.lse[ridx] : INFINITY;
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
   const float gl = g * kLog2e;
   const float sc = p.scale * kLog2e;
   const float* tabrow = tab_s + (kAttnTile - 1 - r);
-  const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+  const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
   float dgate_acc = 0.f;
   uint32_t* wrow = reinterpret_cast<uint32_t*>(sW) + r * (kWStride / 2);
 
@@ -373,7 +378,7 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
     __syncwarp();
     const bool msk = tile_flags[n] != 0;
 #pragma unroll 1
-    for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+    for (int c0 = half * 64; c0 < half * 64 + 64; c0 += 32) {
       uint32_t su[32], du[32];
       tmem_ld_32x32b_x32(tmem + lane_addr + c0, su);
       tmem_ld_32x32b_x32(tmem + lane_addr + 128 + c0, du);
@@ -430,10 +435,10 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
     __syncwarp();
     if (HAS_BIAS) {
       // diagonal sums of the staged tile: thread d sums W[rr][(rr+d) & 127]; columns wrap once, giving two diagonals
-      const int d = tid;
+      const int d = r;
       float acc_pos = 0.f, acc_neg = 0.f;
 #pragma unroll 8
-      for (int rr = 0; rr < kAttnTile; ++rr) {
+      for (int rr = half * 64; rr < half * 64 + 64; ++rr) {
         const int c = (rr + d) & (kAttnTile - 1);
         const float v = __bfloat162float(sW[rr * kWStride + c]);
         if (rr + d < kAttnTile) acc_pos += v; else acc_neg += v;
@@ -446,12 +451,15 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
   mbar_wait(&acc_done, 0);
   tc_fence_after();
   {
-    uint32_t t0[32], t1[32];
-    tmem_ld_32x32b_x32(tmem + lane_addr + 256, t0);
-    tmem_ld_32x32b_x32(tmem + lane_addr + 288, t1);
+    uint32_t t0[32];
+    tmem_ld_32x32b_x32(tmem + lane_addr + 256 + half * 32, t0);  // each warpgroup writes 32 of the 64 dQ columns
     tmem_ld_wait();
+    __shared__ float dgate_x[kAttnTile];
+    if (HAS_BIAS && half == 1) dgate_x[r] = dgate_acc;
+    __syncthreads();
+    if (HAS_BIAS && half == 0) dgate_acc += dgate_x[r];
     if (row_valid) {
-      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + q0 + r) * (3 * D) + h * kHeadDim;
+      __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + q0 + r) * (3 * D) + h * kHeadDim + half * 32;
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
         uint4 w;
@@ -460,13 +468,8 @@ __global__ void __launch_bounds__(128, 1) attn_bwd_dq_kernel(const __grid_consta
         w.z = pack_bf16x2(__uint_as_float(t0[gq * 8 + 4]), __uint_as_float(t0[gq * 8 + 5]));
         w.w = pack_bf16x2(__uint_as_float(t0[gq * 8 + 6]), __uint_as_float(t0[gq * 8 + 7]));
         *reinterpret_cast<uint4*>(dst + gq * 8) = w;
-        w.x = pack_bf16x2(__uint_as_float(t1[gq * 8 + 0]), __uint_as_float(t1[gq * 8 + 1]));
-        w.y = pack_bf16x2(__uint_as_float(t1[gq * 8 + 2]), __uint_as_float(t1[gq * 8 + 3]));
-        w.z = pack_bf16x2(__uint_as_float(t1[gq * 8 + 4]), __uint_as_float(t1[gq * 8 + 5]));
-        w.w = pack_bf16x2(__uint_as_float(t1[gq * 8 + 6]), __uint_as_float(t1[gq * 8 + 7]));
-        *reinterpret_cast<uint4*>(dst + 32 + gq * 8) = w;
       }
-      if (HAS_BIAS && p.dgate != nullptr) p.dgate[ridx] = dgate_acc;
+      if (HAS_BIAS && half == 0 && p.dgate != nullptr) p.dgate[ridx] = dgate_acc;
     }
   }
   if (HAS_BIAS && p.dtab != nullptr) {
@@ -531,16 +534,16 @@ int b200s_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   const int smem_dq = kDqTab + sizeof(float) * ((N + 1) * kAttnTile * 2 + N * kAttnTile) + sizeof(int) * N + 1024;
   if (tab != nullptr) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    attn_bwd_dkv_kernel<true><<<grid, 128, smem_kv, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_dkv_kernel<true><<<grid, 256, smem_kv, st>>>(tm_qkv, tm_do, p);
     B200_CHECK_LAUNCH();
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
-    attn_bwd_dq_kernel<true><<<grid, 128, smem_dq, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_dq_kernel<true><<<grid, 256, smem_dq, st>>>(tm_qkv, tm_do, p);
   } else {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    attn_bwd_dkv_kernel<false><<<grid, 128, smem_kv, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_dkv_kernel<false><<<grid, 256, smem_kv, st>>>(tm_qkv, tm_do, p);
     B200_CHECK_LAUNCH();
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
-    attn_bwd_dq_kernel<false><<<grid, 128, smem_dq, st>>>(tm_qkv, tm_do, p);
+    attn_bwd_dq_kernel<false><<<grid, 256, smem_dq, st>>>(tm_qkv, tm_do, p);
   }
   B200_CHECK_LAUNCH();
   return 0;

@@ -39,6 +39,46 @@ __global__ void prep_linear_kernel(const float* __restrict__ src, int N, int K, 
   }
 }
 
+// Batched variant: ONE launch prepares every nn.Linear operand of the model (descriptor table in device memory, built once;
+// the master parameters never move).  Block -> (descriptor, 32x32 tile) by binary search over the tile prefix sums.
+struct PrepLinearDesc {
+  const float* src;
+  __nv_bfloat16* dst;
+  __nv_bfloat16* dstT;
+  long long ld, ldT;
+  int N, K;
+  int tile_begin;  // first global tile index of this descriptor
+  int tiles_k;     // ceil(K / 32)
+};
+__global__ void prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ descs, int n_descs) {
+  __shared__ float tile[32][33];
+  int lo = 0, hi = n_descs - 1;
+  const int t = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (descs[mid].tile_begin <= t) lo = mid; else hi = mid - 1;
+  }
+  const PrepLinearDesc d = descs[lo];
+  const int lt = t - d.tile_begin;
+  const int n0 = (lt / d.tiles_k) * 32, k0 = (lt % d.tiles_k) * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int n = n0 + i, k = k0 + threadIdx.x;
+    float v = 0.f;
+    if (n < d.N && k < d.K) {
+      v = d.src[static_cast<long long>(n) * d.K + k];
+      if (d.dst) d.dst[static_cast<long long>(n) * d.ld + k] = __float2bfloat16_rn(v);
+    }
+    tile[i][threadIdx.x] = v;
+  }
+  __syncthreads();
+  if (d.dstT) {
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+      const int k = k0 + i, n = n0 + threadIdx.x;
+      if (n < d.N && k < d.K) d.dstT[static_cast<long long>(k) * d.ldT + n] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    }
+  }
+}
+
 // conv forward operand: dst[co, j*Ci + ci] = src[co, ci, j]
 __global__ void prep_conv_fwd_kernel(const float* __restrict__ src, int Co, int Ci, int k, __nv_bfloat16* __restrict__ dst) {
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -156,6 +196,17 @@ int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, lo
   dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
   prep_linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
       src, N, K, scale, static_cast<__nv_bfloat16*>(dst), ld, static_cast<__nv_bfloat16*>(dstT), ldT);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// descs: DEVICE array of n_descs records {const float* src; bf16* dst; bf16* dstT; int64 ld, ldT; int32 N, K, tile_begin,
+// tiles_k} (48 bytes each, tile_begin = prefix sum of ceil(N/32)*ceil(K/32)); total_tiles = sum of all tiles.
+int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b200s_stream stream) {
+  B200_CHECK_ARG(descs && n_descs > 0 && total_tiles > 0, "prep_linear_batched: bad arguments");
+  static_assert(sizeof(PrepLinearDesc) == 56, "descriptor layout is part of the ABI");
+  prep_linear_batched_kernel<<<total_tiles, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const PrepLinearDesc*>(descs), n_descs);
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -369,6 +369,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __re
   for (long long r = warp_global; r < rows; r += nwarps) {
     const __nv_bfloat16* xr = x + xv.off(r);
     const long long b = r / T, t = r % T;
+#pragma unroll 4
     for (int h = 0; h < H; ++h) {
       const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
       const float sa = warp_sum(f.x * wa0 + f.y * wa1) + ba;
@@ -412,6 +413,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     const __nv_bfloat16* xr = x + xv.off(r);
     __nv_bfloat16* dr = dxg + dxv.off(r);
     const long long b = r / T, t = r % T;
+#pragma unroll 4
     for (int h = 0; h < H; ++h) {
       const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
       const float sa = warp_sum(f.x * wa0 + f.y * wa1) + ba;
@@ -612,7 +614,7 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
                  "gate_bwd: null pointer");
   const long long rows = static_cast<long long>(T) * B;
   RowView xv{x_bs, x_rs, T}, dv{dx_bs, dx_rs, T};
-  long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 8), 2LL * sm_count());
+  long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 2), 4LL * sm_count());
   if (blocks < 1) blocks = 1;
   gate_bwd_kernel<<<static_cast<int>(blocks), 256, 8 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
       static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, dgate,

@@ -127,9 +127,36 @@ class Engine:
         self.pc_fwd, self.pc_dg = e(G, 64, taps, 64), e(G, 64, taps, 64)
         self.pc_norm2 = torch.zeros(taps, dtype=torch.float32, device=device)
         self.lw = []
-        for _ in m.encoder.layers:
-            self.lw.append(dict(qkv=e(3 * D, D), qkvT=e(D, 3 * D), bqkv=torch.empty(3 * D, dtype=torch.float32, device=device),
+        for lyr in m.encoder.layers:
+            # q/k/v masters become views of ONE fused [3D, D] / [3D] fp32 tensor (same values, same state_dict keys): the fused
+            # projection operand is then a single prep call and the fused bias needs no copy at all
+            a = lyr.self_attn
+            fw = torch.cat([a.q_proj.weight.data, a.k_proj.weight.data, a.v_proj.weight.data], 0).contiguous()
+            fb = torch.cat([a.q_proj.bias.data, a.k_proj.bias.data, a.v_proj.bias.data], 0).contiguous()
+            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
+                proj.weight.data = fw[j * D:(j + 1) * D]
+                proj.bias.data = fb[j * D:(j + 1) * D]
+            self.lw.append(dict(qkv=e(3 * D, D), qkvT=e(D, 3 * D), bqkv=fb, wqkv_master=fw,
                                 o=e(D, D), oT=e(D, D), w1=e(Fd, D), w1T=e(D, Fd), w2=e(D, Fd), w2T=e(Fd, D)))
+        # descriptor table for the one-launch nn.Linear operand preparation (b200s_prep_linear_batched)
+        import struct
+        recs, tiles = [], 0
+
+        def add(src, N, K, dst, ld, dstT, ldT):
+            nonlocal tiles
+            tk = (K + 31) // 32
+            recs.append(struct.pack("<QQQqqiiii", src.data_ptr(), dst.data_ptr(), dstT.data_ptr(), ld, ldT, N, K, tiles, tk))
+            tiles += ((N + 31) // 32) * tk
+
+        add(m.post_extract_proj.weight.data, D, C, self.wp, C, self.wpT, D)
+        for lyr, w in zip(m.encoder.layers, self.lw):
+            add(w["wqkv_master"], 3 * D, D, w["qkv"], D, w["qkvT"], 3 * D)
+            add(lyr.self_attn.out_proj.weight.data, D, D, w["o"], D, w["oT"], D)
+            add(lyr.fc1.weight.data, Fd, D, w["w1"], D, w["w1T"], Fd)
+            add(lyr.fc2.weight.data, D, Fd, w["w2"], Fd, w["w2T"], D)
+        self.prep_descs = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(device)
+        self.prep_n, self.prep_tiles = len(recs), tiles
+        self.prep_ptrs = [(lyr.self_attn.k_proj.weight, w["wqkv_master"]) for lyr, w in zip(m.encoder.layers, self.lw)]
         # flat gradient buffer, q/k/v adjacent per layer
         groups = []
         for lyr in m.encoder.layers:
@@ -159,17 +186,13 @@ class Engine:
             ops.prep_conv_fwd(w, C, C, k, self.wf[i])
             for rho in range(min(s, k)):
                 ops.prep_conv_dgrad(w, C, C, k, s, rho, self.wd[i][rho])
-        ops.prep_linear(m.post_extract_proj.weight, D, C, 1.0, self.wp, C, self.wpT, D)
         pc = m.encoder.pos_conv[0]
         ops.posconv_prep(pc.weight_v, pc.weight_g, D, cfg.conv_pos_groups, cfg.conv_pos, self.pc_norm2, self.pc_fwd, self.pc_dg)
-        for lyr, w in zip(m.encoder.layers, self.lw):
-            a = lyr.self_attn
-            for j, proj in enumerate((a.q_proj, a.k_proj, a.v_proj)):
-                ops.prep_linear(proj.weight, D, D, 1.0, w["qkv"][j * D:], D, w["qkvT"][:, j * D:], 3 * D)
-                ops.scale_copy_f32(proj.bias, w["bqkv"][j * D:], D, 1.0)
-            ops.prep_linear(a.out_proj.weight, D, D, 1.0, w["o"], D, w["oT"], D)
-            ops.prep_linear(lyr.fc1.weight, Fd, D, 1.0, w["w1"], D, w["w1T"], Fd)
-            ops.prep_linear(lyr.fc2.weight, D, Fd, 1.0, w["w2"], Fd, w["w2T"], D)
+        for kw, fw in self.prep_ptrs:  # the descriptor table holds raw master pointers: they must not have moved
+            if kw.data_ptr() != fw.data_ptr() + 4 * D * D:
+                raise RuntimeError("model parameters were re-allocated after the first GPU forward (e.g. .to()/.cuda()); "
+                                   "move the model to its device before the first call")
+        ops.prep_linear_batched(self.prep_descs, self.prep_n, self.prep_tiles)  # every nn.Linear operand, one launch
         self.prepared_version = ver
 
     def lut(self, T: int) -> torch.Tensor:

@@ -152,6 +152,10 @@ def prep_linear(src, N, K, scale, dst, ld, dstT, ldT):
     _call("b200s_prep_linear", L.ptr(src), i32(N), i32(K), f32(scale), L.ptr(dst), L.ll(ld), L.ptr(dstT), L.ll(ldT), _s())
 
 
+def prep_linear_batched(descs, n_descs, total_tiles):
+    _call("b200s_prep_linear_batched", L.ptr(descs), i32(n_descs), i32(total_tiles), _s())
+
+
 def prep_conv_fwd(src, Co, Ci, k, dst):
     _call("b200s_prep_conv_fwd", L.ptr(src), i32(Co), i32(Ci), i32(k), L.ptr(dst), _s())
 

@@ -84,15 +84,27 @@ def _check_supported(cfg):
 # ----------------------------------------------------------------------------------------------------------------
 # autograd glue: each Function runs the kernels of one stage and stashes what its backward needs
 # ----------------------------------------------------------------------------------------------------------------
+def _on_forward_stream(bwd):
+    """Run a Function's backward on the stream its forward ran on (explicitly: the kernels are launched through ctypes on
+    `torch.cuda.current_stream()`, and the autograd worker thread must not fall back to the legacy default stream -- this is
+    what makes side-stream execution and CUDA-graph capture of the whole step legal)."""
+    def wrapped(ctx, *grads):
+        with torch.cuda.stream(ctx.fwd_stream):
+            return bwd(ctx, *grads)
+    return wrapped
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, anchor, eng: Engine, wav):
+        ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0])
         st = eng.conv_forward(wav, save)
         ctx.eng, ctx.st = eng, (st if save else None)
         return st["a"][-1], st
 
     @staticmethod
+    @_on_forward_stream
     def backward(ctx, dfeat, _unused=None):
         ctx.eng.conv_backward(ctx.st, dfeat.contiguous())
         ctx.st = None
@@ -102,6 +114,7 @@ class _ConvFn(torch.autograd.Function):
 class _ProjFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, anchor, eng: Engine, T, mask_u8, pad_u8, want_features):
+        ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         st = eng.project_forward(feats, T, mask_u8, pad_u8, save, want_features)
         ctx.eng, ctx.st, ctx.T, ctx.mask, ctx.pad = eng, st, T, mask_u8, pad_u8
@@ -111,6 +124,7 @@ class _ProjFn(torch.autograd.Function):
         return xv, st["features"]
 
     @staticmethod
+    @_on_forward_stream
     def backward(ctx, dxv, _dfeatures):
         mult = ctx.eng.cfg.feature_grad_mult
         dfeat = ctx.eng.project_backward(ctx.st, dxv.contiguous(), ctx.T, ctx.mask, ctx.pad)
@@ -123,12 +137,14 @@ class _ProjFn(torch.autograd.Function):
 class _StemFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, xv, anchor, eng: Engine, xpad, T):
+        ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         x0, st = eng.posconv_forward(xpad, T, save)
         ctx.eng, ctx.st, ctx.T = eng, st, T
         return x0
 
     @staticmethod
+    @_on_forward_stream
     def backward(ctx, dx0):
         dxm = ctx.eng.posconv_backward(ctx.st, dx0.contiguous(), ctx.T)
         ctx.st = None
@@ -138,6 +154,7 @@ class _StemFn(torch.autograd.Function):
 class _LayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, anchor, eng: Engine, idx, pad_u8, bias_state):
+        ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         tab = bias_state["tab"] if bias_state is not None else None
         out, st = eng.layer_forward(idx, x, pad_u8, tab, save)
@@ -150,6 +167,7 @@ class _LayerFn(torch.autograd.Function):
         return out
 
     @staticmethod
+    @_on_forward_stream
     def backward(ctx, dout):
         eng, bs = ctx.eng, ctx.bias_state
         dtab = bs["dtab"] if bs is not None else None
@@ -167,6 +185,7 @@ class _LayerFn(torch.autograd.Function):
 class _LNFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, eng: Engine, ln):
+        ctx.fwd_stream = torch.cuda.current_stream()
         from . import ops
         B, T, D = x.shape
         y = torch.empty_like(x)
@@ -177,6 +196,7 @@ class _LNFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_on_forward_stream
     def backward(ctx, dy):
         from . import ops
         x, ln, eng = ctx.x, ctx.ln, ctx.eng
