@@ -121,13 +121,13 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 // persistent CTA-pair kernel (gemm2.cuh): cluster (2,1,1), one pair per two SMs
-template <bool A_MN, bool B_MN>
+template <bool A_MN, bool B_MN, int KIND>
 static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<KIND>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    attr_err = cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     Cfg::kSmemBytes);
   });
   B200_CHECK_CUDA(attr_err);
@@ -146,7 +146,7 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN>, ta, tb, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND>, ta, tb, p));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -182,6 +182,20 @@ static void fill_epilogue(GemmParams& p, const b200s_epilogue* e) {
   }
   p.res1 = {const_cast<void*>(e->res1), e->res1_bs, e->res1_ld};
   p.res2 = {const_cast<void*>(e->res2), e->res2_bs, e->res2_ld};
+  // compacted input list of the pair kernel's staged epilogue
+  if (e->dgelu) p.in[p.n_in++] = p.aux;
+  if (e->res1) p.in[p.n_in++] = p.res1;
+  if (e->res2) p.in[p.n_in++] = p.res2;
+}
+
+// all row strides / batch strides / base pointers of the bf16 epilogue tensors 16-byte aligned (the staged epilogue moves
+// 16-byte chunks); otherwise the single-CTA kernel (element-wise tail) is used
+static bool epilogue_aligned(const GemmParams& p) {
+  auto ok = [](const EpiTensor& t) {
+    return t.p == nullptr || ((reinterpret_cast<uintptr_t>(t.p) & 15) == 0 && t.ld % 8 == 0 && t.bs % 8 == 0);
+  };
+  return ok(p.out) && ok(p.out2) && ok(p.aux) && ok(p.res1) && ok(p.res2) &&
+         (p.bias == nullptr || (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0);
 }
 
 static int check_epilogue(const b200s_epilogue* e) {
@@ -225,12 +239,15 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   if (batches == 1) va.strides[1] = 0;
   if (make_tmap(&ta, va)) return -3;
 
-  if (pair_kernel_enabled() && N >= 256 && rows >= 256 && static_cast<long long>(rows) * batches >= 2048) {
+  GemmParams p;
+  memset(&p, 0, sizeof(p));
+  fill_epilogue(p, epi);
+  p.out = {out, out_bs, out_ld};
+  const bool pair_epi_ok = epilogue_aligned(p) && !((p.flags & EPI_GELU) && p.n_in > 1);
+  if (pair_kernel_enabled() && pair_epi_ok && N >= 256 && rows >= 256 && static_cast<long long>(rows) * batches >= 2048) {
     // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows
     ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, 128, 1, 1}};
     if (make_tmap(&tb, vb2)) return -3;
-    GemmParams p;
-    memset(&p, 0, sizeof(p));
     p.m_rows = rows;
     p.m_tile_stride = 256;
     p.m_tile_valid = 256;
@@ -247,17 +264,14 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
     // A coords: (k0, m0 [+128*rank, added by the kernel], mb, 0)   B coords: (k0, n_tile*256 + sub(=128*rank), 0, 0)
     p.ca[0][4] = 1; p.ca[1][1] = 1; p.ca[2][2] = 1;
     p.cb[0][4] = 1; p.cb[1][3] = 256; p.cb[1][7] = 1;
-    p.flags = 0;
-    fill_epilogue(p, epi);
-    p.out = {out, out_bs, out_ld};
-    return launch_gemm_pair<false, false>(ta, tb, p, st);
+    if (p.flags & EPI_GELU) return launch_gemm_pair<false, false, EK_GELU>(ta, tb, p, st);
+    if (p.flags & EPI_DGELU) return launch_gemm_pair<false, false, EK_DGELU>(ta, tb, p, st);
+    return launch_gemm_pair<false, false, EK_LINEAR>(ta, tb, p, st);
   }
   const int block_n = (N >= 128) ? 128 : 64;
   ViewSpec vb{w, {K, N, 1, 1}, {K, 0, 0}, {64, block_n, 1, 1}};
   if (make_tmap(&tb, vb)) return -3;
 
-  GemmParams p;
-  memset(&p, 0, sizeof(p));
   p.m_rows = rows;
   p.m_tile_stride = 128;
   p.m_tile_valid = 128;
@@ -271,9 +285,6 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   // A coords: (k0, m0, mb, 0)   B coords: (k0, n_tile*block_n, 0, 0)
   p.ca[0][4] = 1; p.ca[1][1] = 1; p.ca[2][2] = 1;
   p.cb[0][4] = 1; p.cb[1][3] = block_n;
-  p.flags = 0;
-  fill_epilogue(p, epi);
-  p.out = {out, out_bs, out_ld};
   dim3 grid(ceil_div(N, block_n), p.m_tiles_per_batch * batches, 1);
   B200_CHECK_ARG(grid.y <= 65535, "gemm_rows: too many M tiles (%u)", grid.y);
   return block_n == 128 ? launch_gemm<128, false, false>(ta, tb, p, grid, st)
@@ -320,7 +331,7 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
     p.flags = EPI_OUT_F32 | (p.splits > 1 ? EPI_ATOMIC : EPI_ACCUM);
     fill_epilogue(p, nullptr);
     p.out = {dw, 0, dw_ld};
-    return launch_gemm_pair<true, true>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    return launch_gemm_pair<true, true, EK_F32>(ta, tb, p, static_cast<cudaStream_t>(stream));
   }
 
   GemmParams p;

@@ -51,6 +51,10 @@ struct GemmParams {
   EpiTensor out, out2, aux, res1, res2;
   // persistent CTA-pair kernel only (gemm2.cuh): work items = (split, m_tile, n_tile), n fastest
   int n_tiles, tiles_total, splits;
+  // bf16 epilogue inputs in application order, compacted on the host: in[0] is the GELU' argument when EPI_DGELU is set,
+  // the others are added (res1, res2)
+  EpiTensor in[3];
+  int n_in;
 };
 
 template <int BLOCK_N>

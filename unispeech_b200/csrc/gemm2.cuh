@@ -17,21 +17,124 @@
 
 namespace b200 {
 
+// Epilogue kinds of the pair kernel (compile-time: keeps each instantiation's code small -- the fused tail used to be one
+// 58 KB body that thrashed the instruction cache).
+enum : int {
+  EK_LINEAR = 0,  // bf16 out = acc (+bias) (+in0) (+in1) (+in2)
+  EK_GELU = 1,    // bf16 out2 = acc + bias (optional); out = gelu(acc + bias) (+inputs)
+  EK_DGELU = 2,   // bf16 out = (acc (+bias)) * gelu'(in0) (+in1) (+in2), optional column sums
+  EK_F32 = 3,     // fp32 out (+)= acc: vector reductions (split-K) or read-modify-write (single writer)
+};
+
+template <int KIND>
 struct Gemm2Cfg {
-  static constexpr int kStages = 6;
+  // bf16 kinds: 4 operand stages + two 4 KB staging buffers per epilogue warp (input prefetch + coalesced output);
+  // fp32 kind (weight gradients): 6 stages + one 4 KB staging buffer per epilogue warp.
+  static constexpr int kStages = (KIND == EK_F32) ? 6 : 4;
   static constexpr int kABytes = 128 * 128;  // 128 rows x 64 bf16 per CTA
   static constexpr int kBBytes = 128 * 128;  // this CTA's half (128 N rows) of the 256-wide B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024;
+  static constexpr int kEpiWarps = 8;
+  static constexpr int kStageBufBytes = 4096;                       // 32 rows x 128 B, 16-byte chunks XOR-swizzled by row & 7
+  static constexpr int kStageBufs = (KIND == EK_F32) ? 1 : 2;
+  static constexpr int kStagingBytes = kEpiWarps * kStageBufs * kStageBufBytes;
+  static constexpr int kBiasBytes = (KIND == EK_F32) ? 0 : kEpiWarps * 128 * 4;  // 128 fp32 bias values per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
   static constexpr int kTileM = 256, kTileN = 256;
+  static_assert(kSmemBytes + 256 <= 232448, "pair GEMM exceeds the 227 KB shared-memory limit");
 };
 
-template <bool A_MN, bool B_MN>
+// ---------------------------------------------------------------- staged (coalesced) epilogue helpers
+// A warp's staging buffer holds 32 rows x 128 bytes (64 bf16 or 32 fp32 columns).  Byte offset of 16-byte chunk c of row r:
+// r*128 + ((c ^ (r & 7)) << 4) -- conflict-free both for "one row per lane" accesses (compute side) and for "8 lanes per row"
+// accesses (global-memory side: a warp instruction then covers 4 full 128-byte lines instead of 32 partial sectors).
+__device__ __forceinline__ uint32_t stg_off(int row, int chunk) {
+  return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// Where one epilogue warp works for one tile: 32 accumulator rows x 128 columns.
+struct EpiTile {
+  int mb;          // batch index of the tile
+  long long row0;  // first row (within the batch) of this warp's 32 rows
+  int rows_valid;  // 0..32
+  int col0;        // first global output column of this warp's 128 columns
+  int cols_valid;  // 0..128 (multiple of 8)
+};
+
+// Start the asynchronous, coalesced copy of one 32-row x 64-column bf16 block of an epilogue input into a staging buffer.
+__device__ __noinline__ void stage_input_async(const EpiTensor t, const EpiTile et, int cc, uint32_t buf, int lane) {
+  const int chunk = lane & 7;
+  const int colc = cc * 64 + chunk * 8;
+  if (colc >= et.cols_valid) return;
+  const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(t.p) + et.mb * t.bs + et.row0 * t.ld + et.col0 + colc;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    if (row < et.rows_valid) cp_async16(buf + stg_off(row, chunk), base + row * t.ld);
+  }
+}
+
+// Coalesced store of a staged 32 x 64 bf16 block (rows beyond rows_valid / columns beyond cols_valid are skipped).
+__device__ __noinline__ void flush_bf16(const EpiTensor t, const EpiTile et, int cc, uint32_t buf, int lane) {
+  const int chunk = lane & 7;
+  const int colc = cc * 64 + chunk * 8;
+  __nv_bfloat16* base = static_cast<__nv_bfloat16*>(t.p) + et.mb * t.bs + et.row0 * t.ld + et.col0 + colc;
+  const bool col_ok = colc < et.cols_valid;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const uint4 v = lds128(buf + stg_off(row, chunk));
+    if (col_ok && row < et.rows_valid) *reinterpret_cast<uint4*>(base + row * t.ld) = v;
+  }
+}
+
+// This lane's row of a staged bf16 block: acc[j] (op)= staged[lane][j], j = 0..63
+template <bool MUL_DGELU>
+__device__ __forceinline__ void consume_row(float* acc, uint32_t buf, int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const uint4 w = lds128(buf + stg_off(lane, g));
+    const uint32_t wu[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_bf16x2(wu[j]);
+      if (MUL_DGELU) {
+        acc[g * 8 + 2 * j] *= gelu_grad_f(f.x);
+        acc[g * 8 + 2 * j + 1] *= gelu_grad_f(f.y);
+      } else {
+        acc[g * 8 + 2 * j] += f.x;
+        acc[g * 8 + 2 * j + 1] += f.y;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void stage_row_bf16(const float* acc, uint32_t buf, int lane) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) sts128(buf + stg_off(lane, g), pack_bf16x8(acc + g * 8));
+}
+
+template <bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ GemmParams p) {
-  using Cfg = Gemm2Cfg;
+  using Cfg = Gemm2Cfg<KIND>;
   constexpr int kStages = Cfg::kStages;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -85,53 +188,61 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------------------ TMA producer (both CTAs)
+      // TMA coordinates are affine in (m0, mb, n_tile, k0, kbatch, kb, sub): the per-tile part is evaluated once per tile, the
+      // per-K-block part is three multiply-adds per coordinate (this single thread must stay well ahead of the tensor core).
       int v[kCoordVars];
-      v[0] = 1;
       int it = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
         int mb, m0, n_tile, kb_begin, kb_end;
         decode(item, mb, m0, n_tile, kb_begin, kb_end);
-        v[1] = m0 + 128 * static_cast<int>(rank);
-        v[2] = mb;
-        v[3] = n_tile;
+        if (kb_begin >= kb_end) continue;
+        v[0] = 1; v[1] = m0 + 128 * static_cast<int>(rank); v[2] = mb; v[3] = n_tile;
+        v[4] = 0; v[5] = 0; v[6] = 0; v[7] = 0;
+        int ta[4], tb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          ta[i] = coord_dot(p.ca[i], v);
+          tb[i] = coord_dot(p.cb[i], v) + p.cb[i][7] * 128 * static_cast<int>(rank);
+        }
+        int kbatch = 0, kin = kb_begin;  // kb = kbatch * k_blocks_per_batch + kin
+        if (p.k_blocks_per_batch > 0) {
+          kbatch = kb_begin / p.k_blocks_per_batch;
+          kin = kb_begin - kbatch * p.k_blocks_per_batch;
+        }
         for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (p.k_blocks_per_batch > 0) {
-            v[5] = kb / p.k_blocks_per_batch;
-            v[4] = (kb % p.k_blocks_per_batch) * 64;
-          } else {
-            v[5] = 0;
-            v[4] = kb * 64;
+          int ka[4], kbv[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            ka[i] = ta[i] + p.ca[i][4] * (kin * 64) + p.ca[i][5] * kbatch + p.ca[i][6] * kb;
+            kbv[i] = tb[i] + p.cb[i][4] * (kin * 64) + p.cb[i][5] * kbatch + p.cb[i][6] * kb;
           }
-          v[6] = kb;
+          mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);  // bytes of both CTAs
           if constexpr (!A_MN) {
-            v[7] = 0;
-            tma_load_4d_2cta(sa, &tmA, &full_bar[s], coord_dot(p.ca[0], v), coord_dot(p.ca[1], v), coord_dot(p.ca[2], v),
-                             coord_dot(p.ca[3], v));
+            tma_load_4d_2cta(sa, &tmA, &full_bar[s], ka[0], ka[1], ka[2], ka[3]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              v[7] = 64 * i;
-              tma_load_4d_2cta(sa + i * 8192, &tmA, &full_bar[s], coord_dot(p.ca[0], v), coord_dot(p.ca[1], v),
-                               coord_dot(p.ca[2], v), coord_dot(p.ca[3], v));
-            }
+            for (int i = 0; i < 2; ++i)
+              tma_load_4d_2cta(sa + i * 8192, &tmA, &full_bar[s], ka[0] + p.ca[0][7] * 64 * i, ka[1] + p.ca[1][7] * 64 * i,
+                               ka[2] + p.ca[2][7] * 64 * i, ka[3] + p.ca[3][7] * 64 * i);
           }
           if constexpr (!B_MN) {
-            v[7] = 128 * static_cast<int>(rank);
-            tma_load_4d_2cta(sb, &tmB, &full_bar[s], coord_dot(p.cb[0], v), coord_dot(p.cb[1], v), coord_dot(p.cb[2], v),
-                             coord_dot(p.cb[3], v));
+            tma_load_4d_2cta(sb, &tmB, &full_bar[s], kbv[0], kbv[1], kbv[2], kbv[3]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              v[7] = 128 * static_cast<int>(rank) + 64 * i;
-              tma_load_4d_2cta(sb + i * 8192, &tmB, &full_bar[s], coord_dot(p.cb[0], v), coord_dot(p.cb[1], v),
-                               coord_dot(p.cb[2], v), coord_dot(p.cb[3], v));
-            }
+            for (int i = 0; i < 2; ++i)
+              tma_load_4d_2cta(sb + i * 8192, &tmB, &full_bar[s], kbv[0] + p.cb[0][7] * 64 * i, kbv[1] + p.cb[1][7] * 64 * i,
+                               kbv[2] + p.cb[2][7] * 64 * i, kbv[3] + p.cb[3][7] * 64 * i);
+          }
+          if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) {
+            kin = 0;
+            ++kbatch;
+          } else if (p.k_blocks_per_batch == 0) {
+            ++kin;
           }
         }
       }
@@ -174,37 +285,212 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
     }
   } else {
     // -------------------------------------------------------------- epilogue (both CTAs, 128 rows each)
-    // 8 epilogue warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair splits the 256
-    // accumulator columns in halves.  Two warps per scheduler roughly double the issue rate of this issue-bound phase.
+    // 8 epilogue warps: two per TMEM lane quadrant (a warp may only touch lanes 32*(warp%4)..+31); the pair of warps splits
+    // the 256 accumulator columns in halves, each half is processed as two 64-column chunks.  All global traffic of the
+    // epilogue goes through the warp's swizzled staging buffers so that it is line-coalesced (see stg_off).
     const int q = warp & 3;
     const int half = (warp - 2) >> 2;
-    const int r = q * 32 + lane;
-    int local = 0;
-    for (int item = pair; item < n_items; item += n_pairs) {
+    const int ew = warp - 2;
+    const uint32_t stg0 = smem_u32(smem + kStages * Cfg::kStageBytes + ew * Cfg::kStageBufs * Cfg::kStageBufBytes);
+    float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes) + ew * 128;
+    const int n_in = (KIND == EK_F32) ? 0 : p.n_in;
+
+    // next non-empty work item of this pair at or after `item` (n_items if none)
+    auto next_item = [&](int item) {
+      for (; item < n_items; item += n_pairs) {
+        int mb, m0, n_tile, kb_begin, kb_end;
+        decode(item, mb, m0, n_tile, kb_begin, kb_end);
+        if (kb_begin < kb_end) break;
+      }
+      return item;
+    };
+    auto tile_of = [&](int item) {
       int mb, m0, n_tile, kb_begin, kb_end;
       decode(item, mb, m0, n_tile, kb_begin, kb_end);
-      if (kb_begin >= kb_end) continue;
-      const int a = local & 1;
-      const int m0c = m0 + 128 * static_cast<int>(rank);
-      const int m_valid = min(128, min(p.m_tile_valid, p.m_rows - m0) - 128 * static_cast<int>(rank));
-      const bool row_ok = r < m_valid;
+      EpiTile et;
+      et.mb = mb;
+      const int m_valid = min(p.m_tile_valid, p.m_rows - m0) - 128 * static_cast<int>(rank) - q * 32;
+      et.rows_valid = max(0, min(32, m_valid));
+      et.row0 = static_cast<long long>(m0) + 128 * static_cast<int>(rank) + q * 32;
       const int col_base = n_tile * p.n_out_stride;
-      const int n_valid = min(p.n_tile_valid, p.n_total - col_base);
-      const long long row = static_cast<long long>(m0c) + r;
-      const EpiRow erow = make_epi_row(p, mb, row);
+      const int n_valid = min(p.n_tile_valid, p.n_total - col_base) - half * 128;
+      et.cols_valid = max(0, min(128, n_valid));
+      et.col0 = col_base + half * 128;
+      return et;
+    };
+    // Input staging protocol.  `early` (exactly one input, no pre-activation output): the input of sequence element
+    // (tile, chunk) #seq lives in buffer seq & 1 and the output is staged through the same buffer once the input is consumed, so
+    // the prefetch of #seq+1 into the other buffer is issued at the start of #seq and is fully hidden.  Otherwise: input 0 ->
+    // buffer 0, input 1 -> buffer 1, output through buffer 0, pre-activation (EK_GELU, <= 1 input) through buffer 1, and the
+    // next prefetch is issued after the output has been flushed.
+    const bool early = (KIND != EK_GELU) && (n_in == 1);
+    auto prefetch = [&](const EpiTile& t, int cc, int seq) {
+      if (early) {
+        stage_input_async(p.in[0], t, cc, stg0 + (seq & 1) * Cfg::kStageBufBytes, lane);
+      } else {
+        stage_input_async(p.in[0], t, cc, stg0, lane);
+        if (n_in >= 2) stage_input_async(p.in[1], t, cc, stg0 + Cfg::kStageBufBytes, lane);
+      }
+      cp_async_commit();
+    };
+
+    int item = next_item(pair);
+    int local = 0;
+    EpiTile et = tile_of(item < n_items ? item : 0);
+    if (n_in >= 1 && item < n_items) prefetch(et, 0, 0);
+    while (item < n_items) {
+      const int item_next = next_item(item + n_pairs);
+      const EpiTile et_next = tile_of(item_next < n_items ? item_next : 0);
+      const int a = local & 1;
+      if (KIND != EK_F32 && p.bias != nullptr) {  // this warp's 128 bias values -> shared memory (one coalesced load)
+        const int c = lane * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c < et.cols_valid) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + et.col0 + c));
+        __syncwarp();
+        *reinterpret_cast<float4*>(bias_s + c) = b4;
+        __syncwarp();
+      }
       mbar_wait(&tmem_full_bar[a], (local >> 1) & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c0 = half * 128; c0 < half * 128 + 128; c0 += 32) {
-        if (c0 >= n_valid) break;
-        epilogue_chunk32(p, erow, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + c0, c0, n_valid, col_base,
-                         row_ok, lane);
+      for (int cc = 0; cc < 2; ++cc) {
+        const int seq = 2 * local + cc;
+        const bool chunk_live = cc * 64 < et.cols_valid;  // warp-uniform
+        // ---- accumulators of this lane's row: 64 fp32 columns
+        float acc[64];
+        {
+          const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + a * 256 + half * 128 + cc * 64;
+          tmem_ld_32x32b_x32(taddr, reinterpret_cast<uint32_t*>(acc));
+          tmem_ld_32x32b_x32(taddr + 32, reinterpret_cast<uint32_t*>(acc) + 32);
+        }
+        const bool have_next = (cc == 0) || (item_next < n_items);   // is there a sequence element #seq+1?
+        const EpiTile et_pf = (cc == 0) ? et : et_next;
+        if (early) {  // the next sequence element's input goes into the other buffer right away
+          if (have_next) prefetch(et_pf, cc ^ 1, seq + 1);
+          else cp_async_commit();
+        }
+        tmem_ld_wait();
+        if (cc == 1) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp early
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
+        }
+        if constexpr (KIND == EK_F32) {
+          // ---- fp32 (+)= acc, two 32-column passes through the staging buffer
+          if (chunk_live) {
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {
+                const float* a4 = acc + h2 * 32 + g * 4;
+                uint4 w;
+                w.x = __float_as_uint(a4[0]); w.y = __float_as_uint(a4[1]);
+                w.z = __float_as_uint(a4[2]); w.w = __float_as_uint(a4[3]);
+                sts128(stg0 + stg_off(lane, g), w);
+              }
+              __syncwarp();
+              const int chunk = lane & 7;
+              const int colc = cc * 64 + h2 * 32 + chunk * 4;
+              float* base = static_cast<float*>(p.out.p) + et.mb * p.out.bs + et.row0 * p.out.ld + et.col0 + colc;
+              const bool col_ok = colc < et.cols_valid;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int row = i * 4 + (lane >> 3);
+                const uint4 w = lds128(stg0 + stg_off(row, chunk));
+                if (col_ok && row < et.rows_valid) {
+                  float* o = base + row * p.out.ld;
+                  if (p.flags & EPI_ATOMIC) {
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(__uint_as_float(w.x)),
+                                 "f"(__uint_as_float(w.y)), "f"(__uint_as_float(w.z)), "f"(__uint_as_float(w.w))
+                                 : "memory");
+                  } else {
+                    float4 o4 = *reinterpret_cast<float4*>(o);
+                    o4.x += __uint_as_float(w.x); o4.y += __uint_as_float(w.y);
+                    o4.z += __uint_as_float(w.z); o4.w += __uint_as_float(w.w);
+                    *reinterpret_cast<float4*>(o) = o4;
+                  }
+                }
+              }
+              __syncwarp();
+            }
+          }
+        } else {
+          const uint32_t buf_a = stg0 + (early ? (seq & 1) * Cfg::kStageBufBytes : 0);
+          const uint32_t buf_b = stg0 + Cfg::kStageBufBytes;
+          if (chunk_live) {
+            if (p.bias != nullptr) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bias_s + cc * 64 + j * 4);
+                acc[4 * j] += b4.x; acc[4 * j + 1] += b4.y; acc[4 * j + 2] += b4.z; acc[4 * j + 3] += b4.w;
+              }
+            }
+            if constexpr (KIND == EK_GELU) {
+              if (p.out2.p != nullptr) {  // pre-activation, saved for the backward pass (buffer 1 is free: n_in <= 1)
+                stage_row_bf16(acc, buf_b, lane);
+                __syncwarp();
+                flush_bf16(p.out2, et, cc, buf_b, lane);
+                __syncwarp();
+              }
+#pragma unroll
+              for (int j = 0; j < 64; ++j) acc[j] = gelu_f(acc[j]);
+            }
+          }
+          // ---- inputs (prefetched with cp.async): wait, make them visible to the whole warp, consume row-wise
+          if (n_in >= 1) {
+            if (early) cp_async_wait<1>(); else cp_async_wait<0>();
+            __syncwarp();
+            if constexpr (KIND == EK_DGELU) {
+              if (chunk_live) consume_row<true>(acc, buf_a, lane);
+            }
+#pragma unroll 1
+            for (int k = (KIND == EK_DGELU) ? 1 : 0; k < n_in; ++k) {
+              if (k >= 2) {  // rare third input: synchronous round through buffer 1
+                __syncwarp();
+                stage_input_async(p.in[2], et, cc, buf_b, lane);
+                cp_async_commit();
+                cp_async_wait<0>();
+                __syncwarp();
+              }
+              if (chunk_live) consume_row<false>(acc, k == 0 ? buf_a : buf_b, lane);
+            }
+            __syncwarp();  // every lane is done reading the input buffers: they may be overwritten
+          }
+          if (chunk_live) {
+            stage_row_bf16(acc, buf_a, lane);
+            __syncwarp();
+            flush_bf16(p.out, et, cc, buf_a, lane);
+            if (p.flags & EPI_COLSUM) {
+              // column sums of the stored (bf16-rounded) values from the staged tile: lane l owns columns 2l, 2l+1 of the chunk
+              float s0 = 0.f, s1 = 0.f;
+              const int chunk = lane >> 2, within = (lane & 3) * 4;
+#pragma unroll 4
+              for (int row = 0; row < et.rows_valid; ++row) {
+                uint32_t w;
+                asm volatile("ld.shared.b32 %0, [%1];" : "=r"(w) : "r"(buf_a + stg_off(row, chunk) + within) : "memory");
+                const float2 f = unpack_bf16x2(w);
+                s0 += f.x;
+                s1 += f.y;
+              }
+              const int c = cc * 64 + 2 * lane;
+              if (c < et.cols_valid) {
+                atomicAdd(p.colsum + et.col0 + c, s0);
+                atomicAdd(p.colsum + et.col0 + c + 1, s1);
+              }
+            }
+            __syncwarp();
+          }
+          if (n_in >= 1 && !early) {  // late mode: the buffers are free only now
+            if (have_next) prefetch(et_pf, cc ^ 1, seq + 1);
+            else cp_async_commit();
+          }
+        }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);  // tell the leader's MMA warp this accumulator is free
+      item = item_next;
+      et = et_next;
       ++local;
     }
+    cp_async_wait<0>();
   }
 
   tc_fence_before();
