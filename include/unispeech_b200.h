@@ -97,6 +97,13 @@ int b200s_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
                    const uint8_t* key_pad, const float* lse, float* delta, void* dqkv, float* dgate, float* dtab,
                    int B, int T, int H, float scale, b200s_stream stream);
 
+/* Same contract as b200s_attn_bwd, computed by ONE fused tensor-core kernel (csrc/attn_bwd2.cu: probabilities recomputed
+ * once, dK/dV accumulated in TMEM, dQ reduced across key tiles in fp32).  dq_acc: fp32 [B,T,D] workspace that must be ZERO
+ * on entry and is zero again on return.  T <= 2048. */
+int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, const float* gate, const float* tab,
+                         const uint8_t* key_pad, const float* lse, float* delta, float* dq_acc, void* dqkv,
+                         float* dgate, float* dtab, int B, int T, int H, float scale, b200s_stream stream);
+
 /* ============================ row kernels (csrc/rowops.cu) ============================ */
 
 /* y = LayerNorm(x) * gamma + beta [then exact GELU]; saves mean / rstd (fp32 [rows]).  nn.LayerNorm / Fp32LayerNorm

@@ -284,9 +284,11 @@ def test_attn_fwd(cuda_device, B, T, H, bias, padded):
     assert err < 0.03, err
 
 
+@pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("B,T,H,bias,padded", [(2, 100, 2, True, True), (1, 128, 2, True, False), (2, 333, 3, True, True),
-                                               (1, 520, 4, True, False), (2, 257, 2, False, True)])
-def test_attn_bwd(cuda_device, B, T, H, bias, padded):
+                                               (1, 520, 4, True, False), (2, 257, 2, False, True), (1, 749, 3, True, False),
+                                               (2, 1499, 1, True, True)])
+def test_attn_bwd(cuda_device, B, T, H, bias, padded, fused):
     from unispeech_b200 import ops
     dev = cuda_device
     torch.manual_seed(T + 1)
@@ -308,7 +310,15 @@ def test_attn_bwd(cuda_device, B, T, H, bias, padded):
     dqkv = torch.zeros(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
     dgate = torch.zeros(B, H, T, device=dev) if bias else None
     dtab = torch.zeros(H, 2 * T - 1, device=dev) if bias else None
-    ops.attn_bwd(qkv, out, dout, gate, tab, pad, lse, delta, dqkv, dgate, dtab, B, T, H, 0.125)
+    if fused:
+        dq_acc = torch.zeros(B, T, D, device=dev)
+        if bias:
+            dgate.fill_(7.0)  # the fused path must overwrite, not accumulate into, d gate
+        ops.attn_bwd_fused(qkv, out, dout, gate, tab, pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, 0.125)
+        torch.cuda.synchronize()
+        assert dq_acc.abs().max().item() == 0.0  # workspace handed back clean
+    else:
+        ops.attn_bwd(qkv, out, dout, gate, tab, pad, lse, delta, dqkv, dgate, dtab, B, T, H, 0.125)
     torch.cuda.synchronize()
     qr = qkv.float().requires_grad_(True)
     gr = gate.clone().requires_grad_(True) if bias else None

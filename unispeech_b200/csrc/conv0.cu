@@ -353,6 +353,9 @@ int conv0_gn_stats_launch(const float* wav, long long L, int B, int T, int C, in
 int conv0_gn_bwd_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
                         const float* beta, const double* stats, float* bstats, const void* da, long long da_bs, float* dw,
                         float* dgamma, float* dbeta, cudaStream_t st);
+int conv0_gn_fwd_apply_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w,
+                              const float* gamma, const float* beta, const double* stats, void* out, long long out_bs,
+                              cudaStream_t st);
 
 static int conv0_grid_x(int T) {
   int gx = std::min(ceil_div(T, 8 * 4), std::max(1, 4 * sm_count()));
@@ -392,8 +395,7 @@ int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, i
     if (mode == 0) {
       (void)sm_red;
       if (int rc = conv0_gn_stats_launch(wav, L, B, T, kC, k, s, w, stats, st)) return rc;  // analytic, from the autocorrelation
-      conv0_fwd_kernel<kC, 0><<<grid, 256, sm_w, st>>>(wav, L, T, k, s, w, gamma, beta, stats, nullptr, nullptr,
-                                                      static_cast<__nv_bfloat16*>(out), out_bs);
+      return conv0_gn_fwd_apply_launch(wav, L, B, T, kC, k, s, w, gamma, beta, stats, out, out_bs, st);
     } else {
       conv0_fwd_kernel<kC, 1><<<grid, 256, sm_w, st>>>(wav, L, T, k, s, w, gamma, beta, nullptr, fmean, frstd,
                                                       static_cast<__nv_bfloat16*>(out), out_bs);

@@ -22,6 +22,7 @@ namespace b200 {
 constexpr int kGnTaps = 10;                 // fast path: kernel size <= 10 (every WavLM / UniSpeech config uses 10)
 constexpr int kAc = kGnTaps + kGnTaps * kGnTaps;  // X1[10] + A[10][10] per utterance (fp64), stored with stride 128
 constexpr int kAcStride = 128;
+constexpr int kFrTile = 64;  // frames staged per shared-memory tile (apply / backward pass kernels)
 
 // ---------------------------------------------------------------------------------------------- waveform autocorrelation
 __global__ void __launch_bounds__(256) conv0_autocorr_kernel(const float* __restrict__ wav, long long L, int T, int k, int s,
@@ -97,9 +98,65 @@ __global__ void conv0_gn_stats_finalize_kernel(const float* __restrict__ w, cons
   stats[static_cast<long long>(i) * 2 + 1] = s2;
 }
 
-// ---------------------------------------------------------------------------------------------- backward pass
-constexpr int kFrTile = 64;  // frames staged per shared-memory tile
+// ---------------------------------------------------------------------------------------------- forward apply pass
+// out[b,t,c] = gelu(gamma_c * (conv[b,t,c] - mean_bc) * rstd_bc + beta_c), written bf16 channels-last.  Thread <-> 2 adjacent
+// channels with the ten taps in registers, GroupNorm folded INTO the taps (w' = gamma*rstd*w, b' = beta - gamma*rstd*mean), so
+// an output element costs 10 FMA + GELU; the waveform window of each frame is broadcast from shared memory (three 16-byte
+// loads per frame) and every warp store covers one full 128-byte line of a frame row.
+template <int C>
+__global__ void __launch_bounds__(C / 2) conv0_gn_fwd_apply_kernel(const float* __restrict__ wav, long long L, int T, int k,
+                                                                   int s, const float* __restrict__ w,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   const double* __restrict__ stats, int t_chunk,
+                                                                   __nv_bfloat16* __restrict__ out, long long out_bs) {
+  __shared__ __align__(16) float xs[kFrTile][12];
+  const int b = blockIdx.y;
+  const int t_begin = blockIdx.x * t_chunk;
+  const int t_end = min(T, t_begin + t_chunk);
+  const int c0 = threadIdx.x * 2;
+  const float* x = wav + static_cast<long long>(b) * L;
+  float wr[2][kGnTaps], bias[2];
+#pragma unroll
+  for (int ch = 0; ch < 2; ++ch) {
+    const double m = stats[(static_cast<long long>(b) * C + c0 + ch) * 2] / T;
+    const double var = stats[(static_cast<long long>(b) * C + c0 + ch) * 2 + 1] / T - m * m;
+    const float rstd = static_cast<float>(1.0 / sqrt((var > 0 ? var : 0) + 1e-5));
+    const float a = gamma[c0 + ch] * rstd;
+#pragma unroll
+    for (int j = 0; j < kGnTaps; ++j) wr[ch][j] = (j < k) ? a * w[(c0 + ch) * k + j] : 0.f;
+    bias[ch] = beta[c0 + ch] - a * static_cast<float>(m);
+  }
+  __nv_bfloat16* out_b = out + b * out_bs + c0;
+  for (int t0 = t_begin; t0 < t_end; t0 += kFrTile) {
+    const int nf = min(kFrTile, t_end - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kFrTile * 12; i += blockDim.x) {
+      const int f = i / 12, j = i % 12;
+      const long long p = static_cast<long long>(t0 + f) * s + j;
+      xs[f][j] = (f < nf && j < k && p < L) ? x[p] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int f = 0; f < nf; ++f) {
+      const float4 w0 = *reinterpret_cast<const float4*>(&xs[f][0]);
+      const float4 w1 = *reinterpret_cast<const float4*>(&xs[f][4]);
+      const float4 w2 = *reinterpret_cast<const float4*>(&xs[f][8]);
+      const float win[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+      float z[2];
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        float acc = bias[ch];
+#pragma unroll
+        for (int j = 0; j < kGnTaps; ++j) acc = fmaf(wr[ch][j], win[j], acc);
+        z[ch] = gelu_f(acc);
+      }
+      *reinterpret_cast<uint32_t*>(out_b + static_cast<long long>(t0 + f) * C) = pack_bf16x2(z[0], z[1]);
+    }
+  }
+}
 
+// ---------------------------------------------------------------------------------------------- backward pass
 template <int C>
 __global__ void __launch_bounds__(C / 2) conv0_gn_bwd_pass_kernel(const float* __restrict__ wav, long long L, int T, int k,
                                                                   int s, const float* __restrict__ w,
@@ -214,6 +271,27 @@ int conv0_gn_stats_launch(const float* wav, long long L, int B, int T, int C, in
   conv0_autocorr_kernel<<<grid, 256, 0, st>>>(wav, L, T, k, s, acorr);
   B200_CHECK_LAUNCH();
   conv0_gn_stats_finalize_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(w, acorr, B, C, k, stats);
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int conv0_gn_fwd_apply_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w,
+                              const float* gamma, const float* beta, const double* stats, void* out, long long out_bs,
+                              cudaStream_t st) {
+  B200_CHECK_ARG(k <= kGnTaps, "conv0 GroupNorm path supports kernel size <= %d (got %d)", kGnTaps, k);
+  int chunks = std::max(1, (8 * sm_count()) / std::max(1, B));
+  int t_chunk = ceil_div(ceil_div(T, chunks), kFrTile) * kFrTile;
+  chunks = ceil_div(T, t_chunk);
+  dim3 grid(chunks, B);
+  __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
+  if (C == 512) {
+    conv0_gn_fwd_apply_kernel<512><<<grid, 256, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs);
+  } else if (C == 64) {
+    conv0_gn_fwd_apply_kernel<64><<<grid, 32, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs);
+  } else {
+    set_last_error("conv0: channel count %d not supported (64 / 512)", C);
+    return -1;
+  }
   B200_CHECK_LAUNCH();
   return 0;
 }

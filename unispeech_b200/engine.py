@@ -544,8 +544,16 @@ class Engine:
         delta = f(B, H, T)
         gate = st["gate"]
         dgate = f(B, H, T) if tab is not None else None
-        ops.attn_bwd(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, dqkv, dgate, dtab if tab is not None else None,
-                     B, T, H, 64 ** -0.5)
+        if T <= 2048:
+            key = (B, T, D)
+            if getattr(self, "_dq_acc_key", None) != key:  # fp32 dQ accumulator: zero on entry, re-zeroed by the kernel
+                self._dq_acc = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
+                self._dq_acc_key = key
+            ops.attn_bwd_fused(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, self._dq_acc, dqkv, dgate,
+                               dtab if tab is not None else None, B, T, H, 64 ** -0.5)
+        else:
+            ops.attn_bwd(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, dqkv, dgate,
+                         dtab if tab is not None else None, B, T, H, 64 ** -0.5)
         ops.colsum(dqkv, 0, 3 * D, M, 1, 3 * D, g(a.q_proj.bias).view(-1))  # q,k,v bias grads are adjacent in the flat buffer
         attn_in = st["xn"] if pre_ln else x
         dxg = None

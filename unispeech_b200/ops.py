@@ -187,3 +187,8 @@ def attn_fwd(qkv, gate, tab, key_pad, out, lse, B, T, H, scale):
 def attn_bwd(qkv, out, dout, gate, tab, key_pad, lse, delta, dqkv, dgate, dtab, B, T, H, scale):
     _call("b200s_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
            L.ptr(delta), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
+
+
+def attn_bwd_fused(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale):
+    _call("b200s_attn_bwd_fused", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
+           L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
