@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dkv_kernel(const __grid_const
   const int T = p.T, D = p.D, N = p.n_tiles;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
   uint8_t* sK = smem + kKvK;
   uint8_t* sV = smem + kKvV;
   uint8_t* sQ = smem + kKvQ;    // 2 stages
@@ -281,7 +281,7 @@ __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const __grid_consta
   const int T = p.T, D = p.D, N = p.n_tiles;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
   uint8_t* sQ = smem + kDqQ;
   uint8_t* sDO = smem + kDqDO;
   uint8_t* sK = smem + kDqK;  // 2 stages

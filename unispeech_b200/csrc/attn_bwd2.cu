@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   const int NH = 2 * N;  // half tiles
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
   uint8_t* sK = smem + kFK;
   uint8_t* sV = smem + kFV;
   uint8_t* sQ = smem + kFQ;
@@ -268,11 +268,6 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       uint32_t su[32], du[32];
       tmem_ld_32x32b_x32(tmem + lane_addr + hf * 128 + ch * 32, su);
       tmem_ld_32x32b_x32(tmem + lane_addr + hf * 128 + 64 + ch * 32, du);
-      if (hh >= 1) {
-        // all threads have staged half tile hh-1 (needed by its diagonal sums; also orders the double-buffered staging)
-        mbar_wait(&ready[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
-        if (HAS_BIAS) diag_sums(hh - 1);
-      }
       if (hf == 1 && qi >= 1) flush_dq(qi - 1);  // dQ of the previous query tile finished a whole phase ago
       tmem_ld_wait();
       const float4* cv = colvec + (qi & 1) * kAttnTile + hf * 64 + ch * 32;
@@ -306,7 +301,13 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
         const float csum = warp_colsum32(dgc, lane);
         atomicAdd(&dgate_s[i0 + lane], csum);
       }
-      if (hh >= 1) {  // MMAs that read the P^T / dS^T blocks (and, in order, everything issued before them) have retired
+      if (hh >= 1) {
+        // Every thread has staged half tile hh-1 (needed by its diagonal sums; the same wait orders the reuse of the double-
+        // buffered staging tile and of the colvec buffers).  Waiting HERE, a whole phase after the arrivals, means the warps
+        // never run in lock step: a warp may be up to one phase ahead of the slowest one.
+        mbar_wait(&ready[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
+        if (HAS_BIAS) diag_sums(hh - 1);
+        // MMAs that read the P^T / dS^T blocks (and, in order, everything issued before them) have retired
         mbar_wait(&mma_done[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
       }
 #pragma unroll

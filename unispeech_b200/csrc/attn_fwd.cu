@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
   const int T = p.T, D = p.D, N = p.n_tiles;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
   uint8_t* sQ = smem + kFwdQ;
   uint8_t* sK = smem + kFwdK;
   uint8_t* sV = smem + kFwdV;

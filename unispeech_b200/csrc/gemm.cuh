@@ -213,7 +213,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ 
   if (kb_begin >= kb_end) return;  // uniform per CTA
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
   __shared__ uint64_t full_bar[kStages];
   __shared__ uint64_t empty_bar[kStages];
   __shared__ uint64_t tmem_full_bar;

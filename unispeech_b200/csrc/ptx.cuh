@@ -241,27 +241,40 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 // exact (erf) GELU and its derivative, fp32 (reference: torch.nn.functional.gelu default, WavLM/modules.py:140-141)
-// erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution): 1 MUFU.RCP + 1 MUFU.EX2 + 7 FMA-class
-// instead of libdevice erff's ~25 instructions -- the GELU epilogues are issue-bound, not accuracy-bound.
-// e2 = exp(-x^2/2) is returned because GELU' needs the same exponential.
-__device__ __forceinline__ float gelu_cdf(float x, float& e2) {
+// erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below bf16 resolution) on the raw SFU instructions:
+// 1 MUFU.RCP + 1 MUFU.EX2 + ~12 FMA-pipe instructions (libdevice erff is ~25, __fdividef/__expf add range fix-ups that this
+// argument range never needs) -- the GELU epilogues and the conv0 passes are issue-bound, not accuracy-bound.
+//   h(x) = 0.5 * erfc(|x| / sqrt 2) = Phi(-|x|);   gelu(x) = max(x, 0) - |x| h;   gelu'(x) = Phi(x) + x phi(x)
+__device__ __forceinline__ float mufu_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float mufu_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// returns h = Phi(-|x|); e2 = exp(-x^2/2)
+__device__ __forceinline__ float gelu_half_erfc(float x, float& e2) {
   const float ax = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  e2 = __expf(-ax * ax);
-  const float half_erfc = 0.5f * poly * t * e2;     // 0.5 * erfc(|x|/sqrt2)
-  return x >= 0.f ? 1.0f - half_erfc : half_erfc;  // Phi(x)
+  const float t = mufu_rcp(fmaf(0.3275911f, ax, 1.0f));
+  float poly = fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f);
+  poly = fmaf(poly, t, 0.5f * 1.421413741f);
+  poly = fmaf(poly, t, 0.5f * -0.284496736f);
+  poly = fmaf(poly, t, 0.5f * 0.254829592f);
+  e2 = mufu_ex2(ax * (ax * -1.4426950408889634f));  // exp(-ax^2)
+  return poly * t * e2;
 }
 __device__ __forceinline__ float gelu_f(float x) {
   float e2;
-  return x * gelu_cdf(x, e2);
+  const float h = gelu_half_erfc(x, e2);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float e2;
-  const float cdf = gelu_cdf(x, e2);
+  const float h = gelu_half_erfc(x, e2);
+  const float cdf = x >= 0.f ? 1.0f - h : h;
   return fmaf(x * 0.39894228040143268f, e2, cdf);
 }
 
