@@ -109,7 +109,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    cb, csecs = (2, secs) if args.model != "tiny" else (B, secs)
+    cb, csecs = (1, secs) if args.model != "tiny" else (B, secs)
     steps = max(1, min(args.steps, 3))
     for _ in range(min(args.warmup, 1)):
         cpu_step(cfg, cb, csecs, 1, threads)
@@ -136,7 +136,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="run the step as one CUDA graph launch")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -188,53 +187,8 @@ def main():
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
 
-    # ---- CUDA-graph mode: the whole step (zero grads, operand prep, forward, loss, backward) is one graph launch; the host
-    # only samples the span mask (numpy, as the reference does) and uploads it into a static buffer before each replay.
-    graph_state = {}
-
-    def build_graph():
-        wav_static = wav_dev.clone()
-        pad_static = torch.zeros(B, L_, dtype=torch.bool, device=dev)
-        mask_static = torch.zeros(B, T, dtype=torch.bool, device=dev)
-        mask_pinned = [torch.zeros(B, T, dtype=torch.bool).pin_memory() for _ in range(8)]  # ring: copies are async
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):  # warm-up on the capture stream (allocator pools, cudaFuncSetAttribute, lazy init)
-                model.grad_buffer().zero_()
-                x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
-                with torch.autograd.set_multithreading_enabled(False):
-                    (x.float() * R).sum().backward()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        model._engine.prepared_version = None
-        with torch.cuda.graph(g):
-            model.grad_buffer().zero_()
-            x, _ = model.extract_features(wav_static, padding_mask=pad_static, mask=True, mask_indices=mask_static)
-            loss = (x.float() * R).sum()
-            with torch.autograd.set_multithreading_enabled(False):  # backward in the capturing thread
-                loss.backward()
-        graph_state.update(g=g, wav=wav_static, mask=mask_static, mask_pinned=mask_pinned, loss=loss, n=0)
-
-    def graph_step(e2e: bool):
-        gs = graph_state
-        if e2e:
-            gs["wav"].copy_(wav_host, non_blocking=True)
-        mi = model.apply_mask(B, T, None)  # host span sampler, numpy RNG (no padding in this workload)
-        buf = gs["mask_pinned"][gs["n"] % len(gs["mask_pinned"])]
-        gs["n"] += 1
-        buf.copy_(mi)
-        gs["mask"].copy_(buf, non_blocking=True)
-        gs["g"].replay()
-        if world > 1:
-            all_reduce_grads(model.grad_buffer())
-        if e2e:
-            loss_host.copy_(gs["loss"].detach().reshape(1), non_blocking=True)
-        return gs["loss"]
-
     def step(e2e: bool):
-        return graph_step(e2e) if graph_state else eager_step(e2e)
+        return eager_step(e2e)
 
     def timed(n_steps: int, e2e: bool):
         if world > 1:
@@ -258,11 +212,6 @@ def main():
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
-    if args.graph:
-        build_graph()
-        for _ in range(2):
-            step(False)
-        torch.cuda.synchronize()
     if args.ncu_step:
         # exactly one warmed-up step between cudaProfilerStart/Stop: run under `ncu --profile-from-start off ...`
         torch.cuda.profiler.start()
@@ -305,15 +254,25 @@ def main():
         gemm_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
         gemm_flops = sum(v["flops"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (all tcgen05 GEMM launches of one step)", "achieved": achieved,
-                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+        n_gemm = sum(v["calls"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the same launches from the committed ncu capture of one step (profiles/, same workload)
+            tj = json.load(open(os.path.join(ROOT, "profiles", f"gemm_traffic_{args.model}.json")))
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+        except Exception:
+            pass
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_pair_kernel / gemm_bf16_kernel (all tcgen05 GEMM launches of one step, "
+                                                 "per-launch averages)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1400",
-                    "traffic": None, "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
+                    "flop_per_launch": gemm_flops / max(n_gemm, 1), "launches_per_step": n_gemm,
+                    "us_per_launch": gemm_ms * 1e3 / max(n_gemm, 1), "traffic": traffic, "traffic_source": traffic_src,
+                    "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cb = 2 if args.model != "tiny" else B
+        cb = 1 if args.model != "tiny" else B
         v, s = cpu_step(cfg, cb, secs, 1, threads)
         cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                         "sample": f"oracle fwd+bwd fp32, {cb} x {secs} s, 1 step ({s:.1f} s)"}
@@ -326,7 +285,7 @@ def main():
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": f"WavLM-{args.model} fwd+bwd, batch {B} x {secs} s per GPU, 16 kHz synthetic, mask_prob "
                                    f"{cfg.mask_prob}, dropout 0, all-False padding mask", "global_batch": world * B,
-                       "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", "cuda_graph": bool(args.graph),
+                       "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", 
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},

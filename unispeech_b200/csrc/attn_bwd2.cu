@@ -46,7 +46,11 @@ constexpr int kWStride2 = 66;      // bf16 per staged row (33 words: conflict-fr
 constexpr int kFWBytes = 128 * kWStride2 * 2;   // 16896
 constexpr int kFVec = kFW + 2 * kFWBytes;        // 197632: colvec [2][128] float4
 constexpr int kFTab = kFVec + 2 * 128 * 16;      // 201728: tab_s[(N+1)*128], dtab_acc[(N+1)*128], dgate_s[N*128]
-constexpr int kFThreads = 384;  // 2 CUDA-core warpgroups + 1 producer warpgroup (only its first lane works)
+constexpr int kNC = 4;                        // threads per key row: each handles kCW query columns of a 64-wide half tile
+constexpr int kCW = 64 / kNC;                 // 16
+constexpr int kCudaThreads = 128 * kNC;       // 16 CUDA-core warps: four per scheduler hide the TMEM / SFU / LDS latencies
+constexpr int kFThreads = kCudaThreads + 128; // + 1 producer warpgroup (only its first lane works)
+constexpr int kProdWarp = kCudaThreads / 32;
 
 }  // namespace
 
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_free[i], 1);
       mbar_init(&st_full[i], 1);
-      mbar_init(&ready[i], 256);
+      mbar_init(&ready[i], kCudaThreads);
       mbar_init(&mma_done[i], 1);
     }
     mbar_init(&dq_full, 1);
@@ -131,10 +135,10 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   // TMEM columns: S^T/dP^T stage s at s*128 (S^T) and s*128+64 (dP^T); dV 256; dK 320; dQ 384
   constexpr uint32_t kColDV = 256, kColDK = 320, kColDQ = 384;
 
-  if (warp >= 8) {
-    // registers are granted per warpgroup: the producer group keeps 40 per thread and the CUDA-core groups take the rest
+  if (warp >= kProdWarp) {
+    // registers are granted per warpgroup (96 per thread at launch): the producer group keeps 40, the CUDA-core groups get 104
     asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
-    if (warp == 8 && lane == 0) {
+    if (warp == kProdWarp && lane == 0) {
       // ================================================================== TMA producer + MMA issuer
       constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);   // K-major A (K/V), K-major B (Q/dO half tile)
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);  // K-major A (P^T/dS^T), MN-major B (dO/Q)
@@ -216,9 +220,9 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     }
   } else {
     // ==================================================================== CUDA-core warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
     const int r = tid & (kAttnTile - 1);  // key row inside the tile == TMEM lane
-    const int ch = tid >> 7;              // which 32 query columns of the 64-wide half tile
+    const int ch = tid >> 7;              // which kCW query columns of the 64-wide half tile
     const int key = k0 + r;
     const bool key_valid = key < T;
     const bool key_masked = !key_valid || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + key] != 0);
@@ -231,14 +235,14 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     auto flush_dq = [&](int qi) {
       mbar_wait(&dq_full, qi & 1);
       tc_fence_after();
-      uint32_t t0[32];
-      tmem_ld_32x32b_x32(tmem + lane_addr + kColDQ + ch * 32, t0);
+      uint32_t t0[kCW];
+      tmem_ld_32x32b_x16(tmem + lane_addr + kColDQ + ch * kCW, t0);
       tmem_ld_wait();
       const int q = qi * kAttnTile + r;  // TMEM lane = query row of the dQ accumulator
       if (q < T) {
-        float* dst = dq_acc + (static_cast<long long>(b) * T + q) * D + h * kHeadDim + ch * 32;
+        float* dst = dq_acc + (static_cast<long long>(b) * T + q) * D + h * kHeadDim + ch * kCW;
 #pragma unroll
-        for (int g = 0; g < 8; ++g)
+        for (int g = 0; g < kCW / 4; ++g)
           asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(t0[g * 4 + 0])),
                        "f"(__uint_as_float(t0[g * 4 + 1])), "f"(__uint_as_float(t0[g * 4 + 2])),
                        "f"(__uint_as_float(t0[g * 4 + 3]))
@@ -246,35 +250,43 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       }
     };
     // diagonal sums of the staged gate*dS^T tile of half tile hh (thread: diagonal d = r, query columns 32*ch..)
+    // Element (key row rr, local query c) of the staged tile belongs to diagonal rr - c; thread (d = r, ch) walks
+    // rr = (d + c) & 127 over its kCW columns: the wrap point is a per-thread constant, so every load is base + immediate.
+    const int diag_w0 = kAttnTile - r - ch * kCW;  // columns e >= diag_w0 (e = c - ch*kCW) are on the wrapped diagonal
+    const uint32_t diag_base = static_cast<uint32_t>(r * kWStride2 + ch * kCW * (kWStride2 + 1)) * 2u;
     auto diag_sums = [&](int hh) {
-      const __nv_bfloat16* W = reinterpret_cast<const __nv_bfloat16*>(smem + kFW + (hh & 1) * kFWBytes);
-      float acc_pos = 0.f, acc_neg = 0.f;
-#pragma unroll 8
-      for (int c = ch * 32; c < ch * 32 + 32; ++c) {
-        const int rr = (r + c) & (kAttnTile - 1);
-        const float v = __bfloat162float(W[rr * kWStride2 + c]);
-        if (r + c < kAttnTile) acc_pos += v; else acc_neg += v;
+      const uint32_t w_nowrap = smem_u32(smem + kFW + (hh & 1) * kFWBytes) + diag_base;
+      const uint32_t w_wrap = w_nowrap - static_cast<uint32_t>(kAttnTile * kWStride2 * 2);
+      float acc_all = 0.f, acc_pos = 0.f;
+#pragma unroll
+      for (int e = 0; e < kCW; ++e) {
+        const bool wrapped = e >= diag_w0;
+        uint32_t v16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v16) : "r"((wrapped ? w_wrap : w_nowrap) + e * (kWStride2 + 1) * 2));
+        const float v = __uint_as_float(v16 << 16);
+        acc_all += v;
+        if (!wrapped) acc_pos += v;
       }
       const int l_pos = r + N * kAttnTile - 1 - (hh >> 1) * kAttnTile - (hh & 1) * 64;
       atomicAdd(&dtab_acc[l_pos], acc_pos);
-      if (r + ch * 32 + 31 >= kAttnTile) atomicAdd(&dtab_acc[l_pos - kAttnTile], acc_neg);
+      if (diag_w0 < kCW) atomicAdd(&dtab_acc[l_pos - kAttnTile], acc_all - acc_pos);
     };
 
     for (int hh = 0; hh < NH; ++hh) {
       const int qi = hh >> 1, hf = hh & 1;
-      const int i0 = qi * kAttnTile + hf * 64 + ch * 32;  // first global query of this thread's 32 columns
+      const int i0 = qi * kAttnTile + hf * 64 + ch * kCW;  // first global query of this thread's columns
       mbar_wait(&st_full[hf], qi & 1);
       tc_fence_after();
-      uint32_t su[32], du[32];
-      tmem_ld_32x32b_x32(tmem + lane_addr + hf * 128 + ch * 32, su);
-      tmem_ld_32x32b_x32(tmem + lane_addr + hf * 128 + 64 + ch * 32, du);
+      uint32_t su[kCW], du[kCW];
+      tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + ch * kCW, su);
+      tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + 64 + ch * kCW, du);
       if (hf == 1 && qi >= 1) flush_dq(qi - 1);  // dQ of the previous query tile finished a whole phase ago
       tmem_ld_wait();
-      const float4* cv = colvec + (qi & 1) * kAttnTile + hf * 64 + ch * 32;
-      uint32_t pw[16], dw[16], ww[16];
-      float dgc[32];
+      const float4* cv = colvec + (qi & 1) * kAttnTile + hf * 64 + ch * kCW;
+      uint32_t pw[kCW / 2], dw[kCW / 2], ww[kCW / 2];
+      float dgc[kCW];
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
+      for (int j = 0; j < kCW; j += 2) {
         float pr2[2], ds2[2], w2[2];
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
@@ -297,9 +309,9 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
         ww[j >> 1] = pack_bf16x2(w2[0], w2[1]);
       }
       if (HAS_BIAS) {
-        // d gate: sum over the 32 key rows of this warp for each of its 32 query columns, then one shared atomic per column
-        const float csum = warp_colsum32(dgc, lane);
-        atomicAdd(&dgate_s[i0 + lane], csum);
+        // d gate: sum over the 32 key rows of this warp for each of its query columns, then one shared atomic per column
+        const float csum = warp_colsum16(dgc, lane);
+        if ((lane & 1) == 0) atomicAdd(&dgate_s[i0 + (lane >> 1)], csum);
       }
       if (hh >= 1) {
         // Every thread has staged half tile hh-1 (needed by its diagonal sums; the same wait orders the reuse of the double-
@@ -311,14 +323,14 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
         mbar_wait(&mma_done[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
       }
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        store_sw128_chunk(sPT, r, hf * 8 + ch * 4 + g, make_uint4(pw[g * 4], pw[g * 4 + 1], pw[g * 4 + 2], pw[g * 4 + 3]));
-        store_sw128_chunk(sDST, r, hf * 8 + ch * 4 + g, make_uint4(dw[g * 4], dw[g * 4 + 1], dw[g * 4 + 2], dw[g * 4 + 3]));
+      for (int g = 0; g < kCW / 8; ++g) {
+        store_sw128_chunk(sPT, r, hf * 8 + ch * (kCW / 8) + g, make_uint4(pw[g * 4], pw[g * 4 + 1], pw[g * 4 + 2], pw[g * 4 + 3]));
+        store_sw128_chunk(sDST, r, hf * 8 + ch * (kCW / 8) + g, make_uint4(dw[g * 4], dw[g * 4 + 1], dw[g * 4 + 2], dw[g * 4 + 3]));
       }
       if (HAS_BIAS) {
-        uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + kFW + (hh & 1) * kFWBytes) + r * (kWStride2 / 2) + ch * 16;
+        uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + kFW + (hh & 1) * kFWBytes) + r * (kWStride2 / 2) + ch * (kCW / 2);
 #pragma unroll
-        for (int j = 0; j < 16; ++j) wrow[j] = ww[j];
+        for (int j = 0; j < kCW / 2; ++j) wrow[j] = ww[j];
       }
       if (hf == 0 && qi + 1 < N && tid < kAttnTile) load_colvec(qi + 1);  // other buffer: last read in query tile qi-1
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -332,13 +344,14 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     mbar_wait(&acc_done, 0);
     tc_fence_after();
     {
-      uint32_t t0[32], t1[32];
-      const uint32_t col = (ch == 0) ? kColDV : kColDK;  // warps 0-3 write dV, warps 4-7 dK
+      // 128 key rows x (64 dV + 64 dK) columns over 512 threads: ch 0,1 -> dV columns 32*(ch&1).., ch 2,3 -> dK
+      uint32_t t0[32];
+      const uint32_t col = ((ch < kNC / 2) ? kColDV : kColDK) + (ch & (kNC / 2 - 1)) * (128 / kNC);
       tmem_ld_32x32b_x32(tmem + lane_addr + col, t0);
-      tmem_ld_32x32b_x32(tmem + lane_addr + col + 32, t1);
       tmem_ld_wait();
       if (key_valid) {
-        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + key) * (3 * D) + (ch == 0 ? 2 * D : D) + h * kHeadDim;
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + key) * (3 * D) + ((ch < kNC / 2) ? 2 * D : D) +
+                             h * kHeadDim + (ch & (kNC / 2 - 1)) * (128 / kNC);
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           uint4 w;
@@ -347,11 +360,6 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
           w.z = pack_bf16x2(__uint_as_float(t0[g * 8 + 4]), __uint_as_float(t0[g * 8 + 5]));
           w.w = pack_bf16x2(__uint_as_float(t0[g * 8 + 6]), __uint_as_float(t0[g * 8 + 7]));
           *reinterpret_cast<uint4*>(dst + g * 8) = w;
-          w.x = pack_bf16x2(__uint_as_float(t1[g * 8 + 0]), __uint_as_float(t1[g * 8 + 1]));
-          w.y = pack_bf16x2(__uint_as_float(t1[g * 8 + 2]), __uint_as_float(t1[g * 8 + 3]));
-          w.z = pack_bf16x2(__uint_as_float(t1[g * 8 + 4]), __uint_as_float(t1[g * 8 + 5]));
-          w.w = pack_bf16x2(__uint_as_float(t1[g * 8 + 6]), __uint_as_float(t1[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + 32 + g * 8) = w;
         }
       }
     }

@@ -335,4 +335,41 @@ __device__ __forceinline__ float warp_colsum32(const float (&v)[32], int lane) {
   return keep + __shfl_xor_sync(0xffffffffu, send, 1);
 }
 
+// Same for a 16-column register tile: 16 shuffles; on return lanes 2c and 2c+1 both hold the sum of column c.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+  float a[8], b[4], c[2];
+  {
+    const bool up = (lane & 16) != 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float send = up ? v[i] : v[i + 8];
+      const float keep = up ? v[i + 8] : v[i];
+      a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+  }
+  {
+    const bool up = (lane & 8) != 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float send = up ? a[i] : a[i + 4];
+      const float keep = up ? a[i + 4] : a[i];
+      b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+  }
+  {
+    const bool up = (lane & 4) != 0;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float send = up ? b[i] : b[i + 2];
+      const float keep = up ? b[i + 2] : b[i];
+      c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+  }
+  const bool up = (lane & 2) != 0;
+  const float send = up ? c[0] : c[1];
+  const float keep = up ? c[1] : c[0];
+  const float d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
 }  // namespace b200

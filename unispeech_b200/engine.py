@@ -28,6 +28,17 @@ def _even(n: int) -> int:
     return n + (n & 1)
 
 
+def _grad_rows(B: int, Tg: int, C: int, lead: int, valid: int, device) -> torch.Tensor:
+    """Gradient buffer [B, Tg, C] (bf16) in `lead` layout: rows [lead, lead + valid) are fully written by the producing
+    kernel, so only the zero rows the input-gradient GEMM reads around them are cleared (not the whole buffer)."""
+    g = torch.empty(B, Tg, C, dtype=BF, device=device)
+    if lead > 0:
+        g[:, :lead].zero_()
+    if lead + valid < Tg:
+        g[:, lead + valid:].zero_()
+    return g
+
+
 def relative_positions_bucket_lut(T: int, num_buckets: int, max_distance: int) -> torch.Tensor:
     """bucket(delta) for delta in [-(T-1), T-1] (index delta+T-1).  Host integer/fp32 glue computed with the same torch
     CPU ops as the reference `_relative_positions_bucket` (WavLM/modules.py:417-443), which also runs on the host."""
@@ -275,7 +286,7 @@ class Engine:
             Ti, Tpi, lead, Tg = geo.T[i], geo.Tp[i], geo.lead[i], geo.Tg[i]
             # ---- dY_i (gradient w.r.t. the conv output of layer i) in lead layout
             if gpad is None:
-                gpad = torch.zeros(B, Tg, C, dtype=BF, device=dev)
+                gpad = _grad_rows(B, Tg, C, lead, Ti, dev)
                 gv = gpad[:, lead:]
                 if ln_mode:
                     ln = m.feature_extractor.conv_layers[i][2][1]
@@ -296,11 +307,11 @@ class Engine:
             fuse_dgelu = (not ln_mode) and (i - 1 >= 1)
             if fuse_dgelu or (ln_mode and i - 1 >= 1):
                 lead_p, Tg_p = geo.lead[i - 1], geo.Tg[i - 1]
-                gnext = torch.zeros(B, Tg_p, C, dtype=BF, device=dev)
+                gnext = _grad_rows(B, Tg_p, C, lead_p, T_in, dev)
             if fuse_dgelu:
                 dst, dst_bs, dst_off = gnext, Tg_p * C, lead_p * C
             else:
-                dAp = torch.zeros(B, Tp_in, C, dtype=BF, device=dev)
+                dAp = torch.empty(B, Tp_in, C, dtype=BF, device=dev)  # rows < T_in are written by the phase GEMMs; the pad row is never read
                 dst, dst_bs, dst_off = dAp, Tp_in * C, 0
             for rho in range(min(s, k)):
                 nm = (k - rho + s - 1) // s
@@ -376,7 +387,7 @@ class Engine:
         ops.gemm_wgrad(dxm, T * D, D, st["fn"], T * C, C, T, B, D, C, self.g(m.post_extract_proj.weight), C)
         dfn = torch.empty(B, T, C, dtype=BF, device=dev)
         ops.gemm_rows(dxm, T * D, D, T, B, D, self.wpT, C, dfn, T * C, C, None)
-        dfeat = torch.zeros(B, Tp, C, dtype=BF, device=dev)
+        dfeat = torch.empty(B, Tp, C, dtype=BF, device=dev)  # rows < T written below; the pad row is never read
         ops.layer_norm_bwd(dfn, T * C, C, feats, Tp * C, C, st["mean"], st["rstd"], m.layer_norm.weight, m.layer_norm.bias,
                            None, 0, 0, dfeat, Tp * C, C, self.g(m.layer_norm.weight), self.g(m.layer_norm.bias), None, T, B, C)
         return dfeat
