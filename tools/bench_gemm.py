@@ -57,7 +57,7 @@ def main():
         cases.append((name + "_wgrad", "convw", T_out, 16, k * 512, 512))
     print(f"{'case':14s} {'ms':>8s} {'TFLOP/s':>9s} {'frac':>6s}")
     for name, kind, rows, batches, K, N in cases:
-        if args.only and args.only != name:
+        if args.only and name not in args.only.split(','):
             continue
         flops = 2.0 * rows * batches * K * N
         if kind == "rows":

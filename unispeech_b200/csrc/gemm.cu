@@ -161,7 +161,17 @@ static bool pair_kernel_enabled() {
   return v == 1;
 }
 
+static int gemm_debug_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_GEMM_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
 static void fill_epilogue(GemmParams& p, const b200s_epilogue* e) {
+  p.debug = gemm_debug_flags();
   p.bias = nullptr;
   p.colsum = nullptr;
   p.out2 = {nullptr, 0, 0};

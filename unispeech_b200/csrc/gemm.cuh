@@ -55,6 +55,7 @@ struct GemmParams {
   // the others are added (res1, res2)
   EpiTensor in[3];
   int n_in;
+  int debug;  // diagnostics only (B200S_GEMM_DEBUG): 1 = no epilogue global traffic, 2 = no MMAs, 4 = no TMA loads
 };
 
 template <int BLOCK_N>

@@ -221,6 +221,12 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
+          if (p.debug & 4) {  // diagnostics: barriers flow, no loads
+            if (rank == 0) mbar_arrive(&full_bar[s]);
+            if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) { kin = 0; ++kbatch; }
+            else if (p.k_blocks_per_batch == 0) ++kin;
+            continue;
+          }
           if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);  // bytes of both CTAs
           if constexpr (!A_MN) {
             tma_load_4d_2cta(sa, &tmA, &full_bar[s], ka[0], ka[1], ka[2], ka[3]);
@@ -268,13 +274,15 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
           const uint32_t sb = sa + Cfg::kABytes;
+          if (!(p.debug & 2)) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sa + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
-                                     : make_smem_desc_sw128(sb + k * 32, 16, 1024);
-            umma_bf16_2cta(tmem_acc, da, db, idesc, (first && k == 0) ? 0u : 1u);
+            for (int k = 0; k < 4; ++k) {
+              const uint64_t da = A_MN ? make_smem_desc_sw128(sa + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(sa + k * 32, 16, 1024);
+              const uint64_t db = B_MN ? make_smem_desc_sw128(sb + k * 2048, 8192, 1024)
+                                       : make_smem_desc_sw128(sb + k * 32, 16, 1024);
+              umma_bf16_2cta(tmem_acc, da, db, idesc, (first && k == 0) ? 0u : 1u);
+            }
           }
           first = false;
           umma_commit_2cta(&empty_bar[s], 0x3);  // frees the stage in both CTAs
@@ -355,7 +363,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
 #pragma unroll 1
       for (int cc = 0; cc < 2; ++cc) {
         const int seq = 2 * local + cc;
-        const bool chunk_live = cc * 64 < et.cols_valid;  // warp-uniform
+        const bool chunk_live = (cc * 64 < et.cols_valid) && !(p.debug & 1);  // warp-uniform
         // ---- accumulators of this lane's row: 64 fp32 columns
         float acc[64];
         {
