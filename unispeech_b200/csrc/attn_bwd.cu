@@ -26,6 +26,7 @@ __device__ __forceinline__ float fast_exp2_b(float x) {
 __global__ void __launch_bounds__(256) attn_delta_kernel(const __nv_bfloat16* __restrict__ o,
                                                          const __nv_bfloat16* __restrict__ dout, int B, int T, int H,
                                                          float* __restrict__ delta) {
+  pdl_grid_sync();
   // one warp per (b,t): lane handles 2 columns of each head
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -48,6 +49,7 @@ template <bool HAS_BIAS>
 __global__ void __launch_bounds__(256, 1) attn_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                               const __grid_constant__ CUtensorMap tm_do,
                                                               const __grid_constant__ AttnParams p) {
+  pdl_grid_sync();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int k0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
@@ -276,6 +278,7 @@ template <bool HAS_BIAS>
 __global__ void __launch_bounds__(256, 1) attn_bwd_dq_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                              const __grid_constant__ CUtensorMap tm_do,
                                                              const __grid_constant__ AttnParams p) {
+  pdl_grid_sync();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int q0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
@@ -509,8 +512,8 @@ int b200s_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   const int D = H * kHeadDim;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = static_cast<long long>(B) * T;
-  attn_delta_kernel<<<static_cast<unsigned>(ceil_div_ll(rows * 32, 256)), 256, 0, st>>>(
-      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), B, T, H, delta);
+  B200_CHECK_CUDA(launch_pdl(attn_delta_kernel, dim3(static_cast<unsigned>(ceil_div_ll(rows * 32, 256))), dim3(256), 0, st, 
+      static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), B, T, H, delta));
   B200_CHECK_LAUNCH();
 
   CUtensorMap tm_qkv, tm_do;
@@ -534,16 +537,16 @@ int b200s_attn_bwd(const void* qkv, const void* out, const void* dout, const flo
   const int smem_dq = kDqTab + sizeof(float) * ((N + 1) * kAttnTile * 2 + N * kAttnTile) + sizeof(int) * N + 1024;
   if (tab != nullptr) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    attn_bwd_dkv_kernel<true><<<grid, 256, smem_kv, st>>>(tm_qkv, tm_do, p);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel<true>, dim3(grid), dim3(256), smem_kv, st, tm_qkv, tm_do, p));
     B200_CHECK_LAUNCH();
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
-    attn_bwd_dq_kernel<true><<<grid, 256, smem_dq, st>>>(tm_qkv, tm_do, p);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel<true>, dim3(grid), dim3(256), smem_dq, st, tm_qkv, tm_do, p));
   } else {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dkv_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_kv));
-    attn_bwd_dkv_kernel<false><<<grid, 256, smem_kv, st>>>(tm_qkv, tm_do, p);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_dkv_kernel<false>, dim3(grid), dim3(256), smem_kv, st, tm_qkv, tm_do, p));
     B200_CHECK_LAUNCH();
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_dq_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_dq));
-    attn_bwd_dq_kernel<false><<<grid, 256, smem_dq, st>>>(tm_qkv, tm_do, p);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_dq_kernel<false>, dim3(grid), dim3(256), smem_dq, st, tm_qkv, tm_do, p));
   }
   B200_CHECK_LAUNCH();
   return 0;

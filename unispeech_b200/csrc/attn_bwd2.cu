@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap tm_do,
                                                                       const __grid_constant__ AttnParams p,
                                                                       float* __restrict__ dq_acc) {
+  pdl_grid_sync();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
@@ -391,6 +392,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
 __global__ void __launch_bounds__(256) attn_delta2_kernel(const __nv_bfloat16* __restrict__ o,
                                                           const __nv_bfloat16* __restrict__ dout, int B, int T, int H,
                                                           float* __restrict__ delta, float* __restrict__ dgate) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long row = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   if (row >= static_cast<long long>(B) * T) return;
@@ -410,6 +412,7 @@ __global__ void __launch_bounds__(256) attn_delta2_kernel(const __nv_bfloat16* _
 // dq_acc (fp32 [B*T, D]) -> bf16 into the q columns of dqkv [B*T, 3D]; the accumulator is cleared for the next layer.
 __global__ void __launch_bounds__(256) attn_dq_convert_kernel(float* __restrict__ dq_acc, __nv_bfloat16* __restrict__ dqkv,
                                                               long long rows, int D) {
+  pdl_grid_sync();
   const int vec_per_row = D / 8;
   const long long n = rows * vec_per_row;
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n;
@@ -446,9 +449,9 @@ int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, con
   const int D = H * kHeadDim;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long rows = static_cast<long long>(B) * T;
-  attn_delta2_kernel<<<static_cast<unsigned>(ceil_div_ll(rows * 32, 256)), 256, 0, st>>>(
+  B200_CHECK_CUDA(launch_pdl(attn_delta2_kernel, dim3(static_cast<unsigned>(ceil_div_ll(rows * 32, 256))), dim3(256), 0, st, 
       static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(dout), B, T, H, delta,
-      tab != nullptr ? dgate : nullptr);
+      tab != nullptr ? dgate : nullptr));
   B200_CHECK_LAUNCH();
 
   CUtensorMap tm_qkv, tm_do;
@@ -472,15 +475,15 @@ int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, con
   dim3 grid(N, H, B);
   if (tab != nullptr) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_bwd_fused_kernel<true><<<grid, kFThreads, smem, st>>>(tm_qkv, tm_do, p, dq_acc);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_fused_kernel<true>, dim3(grid), dim3(kFThreads), smem, st, tm_qkv, tm_do, p, dq_acc));
   } else {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_bwd_fused_kernel<false><<<grid, kFThreads, smem, st>>>(tm_qkv, tm_do, p, dq_acc);
+    B200_CHECK_CUDA(launch_pdl(attn_bwd_fused_kernel<false>, dim3(grid), dim3(kFThreads), smem, st, tm_qkv, tm_do, p, dq_acc));
   }
   B200_CHECK_LAUNCH();
   const long long nvec = rows * (D / 8);
   const int blocks = static_cast<int>(std::min<long long>(ceil_div_ll(nvec, 256), 148 * 16));
-  attn_dq_convert_kernel<<<blocks, 256, 0, st>>>(dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, D);
+  B200_CHECK_CUDA(launch_pdl(attn_dq_convert_kernel, dim3(blocks), dim3(256), 0, st, dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, D));
   B200_CHECK_LAUNCH();
   return 0;
 }

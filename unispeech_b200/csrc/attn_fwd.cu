@@ -37,6 +37,7 @@ constexpr int kFwdThreads = 288;           // 2 warpgroups + 1 producer warp
 template <bool HAS_BIAS>
 __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm,
                                                                  const __grid_constant__ AttnParams p) {
+  pdl_grid_sync();
   const int tid = threadIdx.x, warp = tid >> 5;
   const int wg = warp >> 2;  // 0, 1 = softmax warpgroups; 2 = producer warp
   const int q0 = blockIdx.x * 2 * kAttnTile, h = blockIdx.y, b = blockIdx.z;
@@ -302,10 +303,10 @@ int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const u
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tab != nullptr) {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<true><<<grid, kFwdThreads, smem, st>>>(tm, p);
+    B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kFwdThreads), smem, st, tm, p));
   } else {
     B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attn_fwd_kernel<false><<<grid, kFwdThreads, smem, st>>>(tm, p);
+    B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kFwdThreads), smem, st, tm, p));
   }
   B200_CHECK_LAUNCH();
   return 0;

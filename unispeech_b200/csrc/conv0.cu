@@ -113,6 +113,7 @@ template <int C>
 __global__ void __launch_bounds__(256) conv0_gn_stats_kernel(const float* __restrict__ wav, long long L, int T, int k,
                                                              int s, const float* __restrict__ w,
                                                              double* __restrict__ stats) {
+  pdl_grid_sync();
   using M = LaneMap<C>;
   extern __shared__ float smem[];
   float* w_s = smem;            // [k][C]
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(256) conv0_fwd_kernel(const float* __restrict_
                                                         const double* __restrict__ stats, float* __restrict__ fmean,
                                                         float* __restrict__ frstd, __nv_bfloat16* __restrict__ out,
                                                         long long out_bs) {
+  pdl_grid_sync();
   using M = LaneMap<C>;
   extern __shared__ float smem[];
   float* w_s = smem;
@@ -218,6 +220,7 @@ __global__ void __launch_bounds__(256) conv0_gn_bwd_stats_kernel(const float* __
                                                                  const __nv_bfloat16* __restrict__ da, long long da_bs,
                                                                  float* __restrict__ bstats, float* __restrict__ dgamma,
                                                                  float* __restrict__ dbeta) {
+  pdl_grid_sync();
   using M = LaneMap<C>;
   extern __shared__ float smem[];
   float* w_s = smem;
@@ -271,6 +274,7 @@ __global__ void __launch_bounds__(256) conv0_bwd_dw_kernel(const float* __restri
                                                            const __nv_bfloat16* __restrict__ da, long long da_bs, int j0,
                                                            float* __restrict__ dw, float* __restrict__ dgamma,
                                                            float* __restrict__ dbeta) {
+  pdl_grid_sync();
   using M = LaneMap<C>;
   extern __shared__ float smem[];
   float* w_s = smem;
@@ -397,8 +401,8 @@ int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, i
       if (int rc = conv0_gn_stats_launch(wav, L, B, T, kC, k, s, w, stats, st)) return rc;  // analytic, from the autocorrelation
       return conv0_gn_fwd_apply_launch(wav, L, B, T, kC, k, s, w, gamma, beta, stats, out, out_bs, st);
     } else {
-      conv0_fwd_kernel<kC, 1><<<grid, 256, sm_w, st>>>(wav, L, T, k, s, w, gamma, beta, nullptr, fmean, frstd,
-                                                      static_cast<__nv_bfloat16*>(out), out_bs);
+      B200_CHECK_CUDA(launch_pdl(conv0_fwd_kernel<kC, 1>, dim3(grid), dim3(256), sm_w, st, wav, L, T, k, s, w, gamma, beta, nullptr, fmean, frstd,
+                                                      static_cast<__nv_bfloat16*>(out), out_bs));
     }
     B200_CHECK_LAUNCH();
   })
@@ -428,8 +432,8 @@ int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, i
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_dw_kernel<kC, 1, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(sm)));
       for (int j0 = 0; j0 < k; j0 += JT) {
-        conv0_bwd_dw_kernel<kC, 1, JT><<<grid, 256, sm, st>>>(wav, L, T, k, s, w, gamma, beta, nullptr, nullptr, fmean,
-                                                             frstd, dap, da_bs, j0, dw, dgamma, dbeta);
+        B200_CHECK_CUDA(launch_pdl(conv0_bwd_dw_kernel<kC, 1, JT>, dim3(grid), dim3(256), sm, st, wav, L, T, k, s, w, gamma, beta, nullptr, nullptr, fmean,
+                                                             frstd, dap, da_bs, j0, dw, dgamma, dbeta));
         B200_CHECK_LAUNCH();
       }
     }

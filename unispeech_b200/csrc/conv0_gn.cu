@@ -27,6 +27,7 @@ constexpr int kFrTile = 64;  // frames staged per shared-memory tile (apply / ba
 // ---------------------------------------------------------------------------------------------- waveform autocorrelation
 __global__ void __launch_bounds__(256) conv0_autocorr_kernel(const float* __restrict__ wav, long long L, int T, int k, int s,
                                                              double* __restrict__ acorr) {
+  pdl_grid_sync();
   const int b = blockIdx.y;
   const float* x = wav + static_cast<long long>(b) * L;
   float x1[kGnTaps], a[kGnTaps * (kGnTaps + 1) / 2];
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(256) conv0_autocorr_kernel(const float* __rest
 // stats[b][c] = {sum_t conv, sum_t conv^2}
 __global__ void conv0_gn_stats_finalize_kernel(const float* __restrict__ w, const double* __restrict__ acorr, int B, int C,
                                                int k, double* __restrict__ stats) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i % C;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(C / 2) conv0_gn_fwd_apply_kernel(const float* 
                                                                    const float* __restrict__ beta,
                                                                    const double* __restrict__ stats, int t_chunk,
                                                                    __nv_bfloat16* __restrict__ out, long long out_bs) {
+  pdl_grid_sync();
   __shared__ __align__(16) float xs[kFrTile][12];
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * t_chunk;
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(C / 2) conv0_gn_bwd_pass_kernel(const float* _
                                                                   const double* __restrict__ stats,
                                                                   const __nv_bfloat16* __restrict__ da, long long da_bs,
                                                                   int t_chunk, float* __restrict__ bstats) {
+  pdl_grid_sync();
   __shared__ __align__(16) float xs[kFrTile][12];
   const int b = blockIdx.y;
   const int t_begin = blockIdx.x * t_chunk;
@@ -235,6 +239,7 @@ __global__ void conv0_gn_bwd_finalize_kernel(const float* __restrict__ w, const 
                                              const double* __restrict__ stats, const double* __restrict__ acorr,
                                              const float* __restrict__ bstats, int B, int C, int k, int T,
                                              float* __restrict__ dw, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= C * k) return;
   const int c = i / k, j = i % k;
@@ -268,9 +273,9 @@ int conv0_gn_stats_launch(const float* wav, long long L, int B, int T, int C, in
   double* acorr = stats + static_cast<long long>(B) * C * 2;  // caller allocates B*C*2 + B*128 doubles
   B200_CHECK_CUDA(cudaMemsetAsync(acorr, 0, sizeof(double) * B * kAcStride, st));
   dim3 grid(std::max(1, std::min(ceil_div(T, 256 * 8), 64)), B);
-  conv0_autocorr_kernel<<<grid, 256, 0, st>>>(wav, L, T, k, s, acorr);
+  B200_CHECK_CUDA(launch_pdl(conv0_autocorr_kernel, dim3(grid), dim3(256), 0, st, wav, L, T, k, s, acorr));
   B200_CHECK_LAUNCH();
-  conv0_gn_stats_finalize_kernel<<<ceil_div(B * C, 128), 128, 0, st>>>(w, acorr, B, C, k, stats);
+  B200_CHECK_CUDA(launch_pdl(conv0_gn_stats_finalize_kernel, dim3(ceil_div(B * C, 128)), dim3(128), 0, st, w, acorr, B, C, k, stats));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -285,9 +290,9 @@ int conv0_gn_fwd_apply_launch(const float* wav, long long L, int B, int T, int C
   dim3 grid(chunks, B);
   __nv_bfloat16* o = static_cast<__nv_bfloat16*>(out);
   if (C == 512) {
-    conv0_gn_fwd_apply_kernel<512><<<grid, 256, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs);
+    B200_CHECK_CUDA(launch_pdl(conv0_gn_fwd_apply_kernel<512>, dim3(grid), dim3(256), 0, st, wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs));
   } else if (C == 64) {
-    conv0_gn_fwd_apply_kernel<64><<<grid, 32, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs);
+    B200_CHECK_CUDA(launch_pdl(conv0_gn_fwd_apply_kernel<64>, dim3(grid), dim3(32), 0, st, wav, L, T, k, s, w, gamma, beta, stats, t_chunk, o, out_bs));
   } else {
     set_last_error("conv0: channel count %d not supported (64 / 512)", C);
     return -1;
@@ -309,16 +314,16 @@ int conv0_gn_bwd_launch(const float* wav, long long L, int B, int T, int C, int 
   const __nv_bfloat16* dap = static_cast<const __nv_bfloat16*>(da);
   const double* acorr = stats + static_cast<long long>(B) * C * 2;
   if (C == 512) {
-    conv0_gn_bwd_pass_kernel<512><<<grid, 256, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, dap, da_bs, t_chunk, bstats);
+    B200_CHECK_CUDA(launch_pdl(conv0_gn_bwd_pass_kernel<512>, dim3(grid), dim3(256), 0, st, wav, L, T, k, s, w, gamma, beta, stats, dap, da_bs, t_chunk, bstats));
   } else if (C == 64) {
-    conv0_gn_bwd_pass_kernel<64><<<grid, 32, 0, st>>>(wav, L, T, k, s, w, gamma, beta, stats, dap, da_bs, t_chunk, bstats);
+    B200_CHECK_CUDA(launch_pdl(conv0_gn_bwd_pass_kernel<64>, dim3(grid), dim3(32), 0, st, wav, L, T, k, s, w, gamma, beta, stats, dap, da_bs, t_chunk, bstats));
   } else {
     set_last_error("conv0: channel count %d not supported (64 / 512)", C);
     return -1;
   }
   B200_CHECK_LAUNCH();
-  conv0_gn_bwd_finalize_kernel<<<ceil_div(C * k, 128), 128, 0, st>>>(w, gamma, stats, acorr, bstats, B, C, k, T, dw, dgamma,
-                                                                    dbeta);
+  B200_CHECK_CUDA(launch_pdl(conv0_gn_bwd_finalize_kernel, dim3(ceil_div(C * k, 128)), dim3(128), 0, st, w, gamma, stats, acorr, bstats, B, C, k, T, dw, dgamma,
+                                                                    dbeta));
   B200_CHECK_LAUNCH();
   return 0;
 }

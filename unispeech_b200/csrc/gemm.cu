@@ -22,6 +22,14 @@ void set_last_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
+}
 int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -115,7 +123,7 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
   });
   B200_CHECK_CUDA(attr_err);
-  gemm_bf16_kernel<BLOCK_N, A_MN, B_MN><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(ta, tb, p);
+  B200_CHECK_CUDA(launch_pdl(gemm_bf16_kernel<BLOCK_N, A_MN, B_MN>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, stream, ta, tb, p));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -139,13 +147,15 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
   cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = pdl_enabled() ? 2 : 1;
   B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND>, ta, tb, p));
   B200_CHECK_LAUNCH();
   return 0;

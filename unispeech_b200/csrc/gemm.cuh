@@ -201,6 +201,7 @@ template <int BLOCK_N, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA,
                                                         const __grid_constant__ CUtensorMap tmB,
                                                         const __grid_constant__ GemmParams p) {
+  pdl_launch_dependents();
   using Cfg = GemmCfg<BLOCK_N>;
   constexpr int kStages = Cfg::kStages;
 
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // prologue overlapped the previous kernel's tail; global memory is touched only from here on
 
   if (warp == 0) {
     if (lane == 0) {

@@ -134,6 +134,7 @@ template <bool A_MN, bool B_MN, int KIND>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ GemmParams p) {
+  pdl_launch_dependents();  // the next kernel's CTAs may start their prologue as soon as SMs free up
   using Cfg = Gemm2Cfg<KIND>;
   constexpr int kStages = Cfg::kStages;
   const int warp = threadIdx.x >> 5;
@@ -172,6 +173,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   cluster_sync_all();  // barriers of BOTH CTAs initialised (and TMEM allocated) before any remote arrive / multicast
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
   // item -> (split, m tile, n tile) and its K-block range; identical in every role of both CTAs
   auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end) {

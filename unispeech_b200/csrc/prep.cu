@@ -12,6 +12,7 @@
 namespace b200 {
 
 __global__ void scale_copy_f32_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n, float scale) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i] * scale;
 }
@@ -19,6 +20,7 @@ __global__ void scale_copy_f32_kernel(const float* __restrict__ src, float* __re
 // dst[n*ld + k] = bf16(src[n,k]*scale);  dstT[k*ldT + n] = same, through a 32x32 shared tile
 __global__ void prep_linear_kernel(const float* __restrict__ src, int N, int K, float scale, __nv_bfloat16* __restrict__ dst,
                                    long long ld, __nv_bfloat16* __restrict__ dstT, long long ldT) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   const int n0 = blockIdx.y * 32, k0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -51,6 +53,7 @@ struct PrepLinearDesc {
   int tiles_k;     // ceil(K / 32)
 };
 __global__ void prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ descs, int n_descs) {
+  pdl_grid_sync();
   __shared__ float tile[32][33];
   int lo = 0, hi = n_descs - 1;
   const int t = blockIdx.x;
@@ -81,6 +84,7 @@ __global__ void prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ de
 
 // conv forward operand: dst[co, j*Ci + ci] = src[co, ci, j]
 __global__ void prep_conv_fwd_kernel(const float* __restrict__ src, int Co, int Ci, int k, __nv_bfloat16* __restrict__ dst) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(Co) * Ci * k;
   if (i >= n) return;
@@ -93,6 +97,7 @@ __global__ void prep_conv_fwd_kernel(const float* __restrict__ src, int Co, int 
 // dst[ci, mm*Co + co] = src[co, ci, rho + s*(nm-1-mm)]     (A rows are [dY[u-(nm-1)], ..., dY[u]])
 __global__ void prep_conv_dgrad_kernel(const float* __restrict__ src, int Co, int Ci, int k, int s, int rho, int nm,
                                        __nv_bfloat16* __restrict__ dst) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(Ci) * nm * Co;
   if (i >= n) return;
@@ -104,6 +109,7 @@ __global__ void prep_conv_dgrad_kernel(const float* __restrict__ src, int Co, in
 }
 // gradient back to the reference layout: dw[co, ci, j] += dwk[co, j*Ci + ci]
 __global__ void unprep_conv_wgrad_kernel(const float* __restrict__ dwk, int Co, int Ci, int k, float* __restrict__ dw) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(Co) * Ci * k;
   if (i >= n) return;
@@ -117,6 +123,7 @@ __global__ void unprep_conv_wgrad_kernel(const float* __restrict__ dwk, int Co, 
 // norm2[j] = sum_{co,ci} v[co,ci,j]^2  (and optionally dot[j] = sum dw*v for the backward)
 __global__ void posconv_tap_reduce_kernel(const float* __restrict__ v, const float* __restrict__ dwp, int D, int Cg, int taps,
                                           float* __restrict__ norm2, float* __restrict__ dot) {
+  pdl_grid_sync();
   // thread -> tap (coalesced over the contiguous tap axis), blocks stride over (co, ci) rows
   const int j = threadIdx.x;
   if (j >= taps) return;
@@ -139,6 +146,7 @@ __global__ void posconv_tap_reduce_kernel(const float* __restrict__ v, const flo
 __global__ void posconv_prep_kernel(const float* __restrict__ v, const float* __restrict__ gvec,
                                     const float* __restrict__ norm2, int G, int Cg, int taps,
                                     __nv_bfloat16* __restrict__ wp_fwd, __nv_bfloat16* __restrict__ wp_dg) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(G) * 64 * taps * 64;
   if (i >= n) return;
@@ -162,6 +170,7 @@ __global__ void posconv_unprep_kernel(const float* __restrict__ v, const float* 
                                       const float* __restrict__ norm2, const float* __restrict__ dot,
                                       const float* __restrict__ dwp, int D, int Cg, int taps, float* __restrict__ dv,
                                       float* __restrict__ dg) {
+  pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(D) * Cg * taps;
   if (i < taps) dg[i] += dot[i] * rsqrtf(norm2[i]);
@@ -184,8 +193,8 @@ extern "C" {
 int b200s_scale_copy_f32(const float* src, float* dst, long long n, float scale, b200s_stream stream) {
   B200_CHECK_ARG(src && dst, "scale_copy_f32: null pointer");
   if (n == 0) return 0;
-  scale_copy_f32_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, dst, n, scale);
+  B200_CHECK_CUDA(launch_pdl(scale_copy_f32_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      src, dst, n, scale));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -194,8 +203,8 @@ int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, lo
                       b200s_stream stream) {
   B200_CHECK_ARG(src && (dst || dstT), "prep_linear: null pointer");
   dim3 grid(ceil_div(K, 32), ceil_div(N, 32)), block(32, 8);
-  prep_linear_kernel<<<grid, block, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, N, K, scale, static_cast<__nv_bfloat16*>(dst), ld, static_cast<__nv_bfloat16*>(dstT), ldT);
+  B200_CHECK_CUDA(launch_pdl(prep_linear_kernel, dim3(grid), dim3(block), 0, static_cast<cudaStream_t>(stream), 
+      src, N, K, scale, static_cast<__nv_bfloat16*>(dst), ld, static_cast<__nv_bfloat16*>(dstT), ldT));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -205,8 +214,8 @@ int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, lo
 int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b200s_stream stream) {
   B200_CHECK_ARG(descs && n_descs > 0 && total_tiles > 0, "prep_linear_batched: bad arguments");
   static_assert(sizeof(PrepLinearDesc) == 56, "descriptor layout is part of the ABI");
-  prep_linear_batched_kernel<<<total_tiles, dim3(32, 8), 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const PrepLinearDesc*>(descs), n_descs);
+  B200_CHECK_CUDA(launch_pdl(prep_linear_batched_kernel, dim3(total_tiles), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const PrepLinearDesc*>(descs), n_descs));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -214,8 +223,8 @@ int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b
 int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream) {
   B200_CHECK_ARG(src && dst, "prep_conv_fwd: null pointer");
   const long long n = static_cast<long long>(Co) * Ci * k;
-  prep_conv_fwd_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, Co, Ci, k, static_cast<__nv_bfloat16*>(dst));
+  B200_CHECK_CUDA(launch_pdl(prep_conv_fwd_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      src, Co, Ci, k, static_cast<__nv_bfloat16*>(dst)));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -225,8 +234,8 @@ int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rh
   B200_CHECK_ARG(rho >= 0 && rho < s && rho < k, "prep_conv_dgrad: bad phase");
   const int nm = (k - rho + s - 1) / s;
   const long long n = static_cast<long long>(Ci) * nm * Co;
-  prep_conv_dgrad_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      src, Co, Ci, k, s, rho, nm, static_cast<__nv_bfloat16*>(dst));
+  B200_CHECK_CUDA(launch_pdl(prep_conv_dgrad_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      src, Co, Ci, k, s, rho, nm, static_cast<__nv_bfloat16*>(dst)));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -234,8 +243,8 @@ int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rh
 int b200s_unprep_conv_wgrad(const float* dwk, int Co, int Ci, int k, float* dw, b200s_stream stream) {
   B200_CHECK_ARG(dwk && dw, "unprep_conv_wgrad: null pointer");
   const long long n = static_cast<long long>(Co) * Ci * k;
-  unprep_conv_wgrad_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      dwk, Co, Ci, k, dw);
+  B200_CHECK_CUDA(launch_pdl(unprep_conv_wgrad_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      dwk, Co, Ci, k, dw));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -248,13 +257,13 @@ int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int 
   const int Cg = D / G;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   B200_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float) * taps, st));
-  posconv_tap_reduce_kernel<<<4 * sm_count(), ((taps + 31) / 32) * 32, 0, st>>>(weight_v, nullptr, D, Cg, taps, norm2,
-                                                                               nullptr);
+  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v, nullptr, D, Cg, taps, norm2,
+                                                                               nullptr));
   B200_CHECK_LAUNCH();
   const long long n = static_cast<long long>(G) * 64 * taps * 64;
-  posconv_prep_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, st>>>(
+  B200_CHECK_CUDA(launch_pdl(posconv_prep_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, st, 
       weight_v, weight_g, norm2, G, Cg, taps, static_cast<__nv_bfloat16*>(wp_fwd),
-      static_cast<__nv_bfloat16*>(wp_dgrad));
+      static_cast<__nv_bfloat16*>(wp_dgrad)));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -266,12 +275,12 @@ int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const flo
   const int Cg = D / G;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   B200_CHECK_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * 2 * taps, st));
-  posconv_tap_reduce_kernel<<<4 * sm_count(), ((taps + 31) / 32) * 32, 0, st>>>(weight_v, dwp, D, Cg, taps, work,
-                                                                               work + taps);
+  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v, dwp, D, Cg, taps, work,
+                                                                               work + taps));
   B200_CHECK_LAUNCH();
   const long long n = static_cast<long long>(D) * Cg * taps;
-  posconv_unprep_kernel<<<static_cast<unsigned>(ceil_div_ll(n, 256)), 256, 0, st>>>(weight_v, weight_g, work, work + taps,
-                                                                                   dwp, D, Cg, taps, dweight_v, dweight_g);
+  B200_CHECK_CUDA(launch_pdl(posconv_unprep_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, st, weight_v, weight_g, work, work + taps,
+                                                                                   dwp, D, Cg, taps, dweight_v, dweight_g));
   B200_CHECK_LAUNCH();
   return 0;
 }

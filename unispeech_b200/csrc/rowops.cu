@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
                                                      __nv_bfloat16* __restrict__ y, RowView yv,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                      long long rows, int gelu, float eps) {
+  pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -129,6 +130,7 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
                                                      __nv_bfloat16* __restrict__ dx, RowView dxv,
                                                      float* __restrict__ dgamma, float* __restrict__ dbeta,
                                                      float* __restrict__ colsum, long long rows, int gelu) {
+  pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
   constexpr int N = NCH * VEC;
   __shared__ float red[8][D];
@@ -238,6 +240,7 @@ static int row_grid(long long rows, int warps_per_block) {
 // colsum[c] += sum_rows x[r, c]   (bias gradients); x bf16 [rows, N] with batch/row strides.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int N,
                                                      long long rows, float* __restrict__ out) {
+  pdl_grid_sync();
   // block: a strip of 256 columns (32 lanes x 8 columns, 16-byte loads) x 8 row lanes; rows strided over blockIdx.y
   const int lane = threadIdx.x & 31;
   const int c = blockIdx.x * 256 + lane * 8;
@@ -273,6 +276,7 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ pre, RowView prev,
                                                         __nv_bfloat16* __restrict__ out, RowView outv, int N,
                                                         long long rows, float* __restrict__ colsum) {
+  pdl_grid_sync();
   const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
   const int rl = threadIdx.x >> 5;
   float a0 = 0.f, a1 = 0.f;
@@ -308,6 +312,7 @@ __global__ void __launch_bounds__(256) frame_mask_fwd_kernel(__nv_bfloat16* __re
                                                              long long rows, const uint8_t* __restrict__ mask,
                                                              const uint8_t* __restrict__ pad,
                                                              const float* __restrict__ mask_emb) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -327,21 +332,42 @@ __global__ void __launch_bounds__(256) frame_mask_bwd_kernel(__nv_bfloat16* __re
                                                              long long rows, const uint8_t* __restrict__ mask,
                                                              const uint8_t* __restrict__ pad,
                                                              float* __restrict__ dmask_emb) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  // per-warp register partials of d mask_emb (lane owns columns lane*2 + 64*i): one atomic per column per warp at the end
+  // instead of one per masked row (65 % of the rows hit the same D addresses)
+  constexpr int kMaxIter = 32;  // D <= 2048
+  float acc[kMaxIter][2];
+#pragma unroll
+  for (int i = 0; i < kMaxIter; ++i) acc[i][0] = acc[i][1] = 0.f;
   for (long long r = warp_global; r < rows; r += nwarps) {
     const bool p = pad != nullptr && pad[r] != 0;
     const bool m = mask != nullptr && mask[r] != 0;
     if (!p && !m) continue;
     __nv_bfloat16* xr = dx + xv.off(r);
-    for (int c = lane * 2; c < D; c += 64) {
-      if (!p && dmask_emb != nullptr) {
-        const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
-        atomicAdd(dmask_emb + c, f.x);
-        atomicAdd(dmask_emb + c + 1, f.y);
+#pragma unroll
+    for (int i = 0; i < kMaxIter; ++i) {
+      const int c = lane * 2 + 64 * i;
+      if (c < D) {
+        if (!p) {
+          const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + c));
+          acc[i][0] += f.x;
+          acc[i][1] += f.y;
+        }
+        *reinterpret_cast<uint32_t*>(xr + c) = 0u;
       }
-      *reinterpret_cast<uint32_t*>(xr + c) = 0u;
+    }
+  }
+  if (dmask_emb != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kMaxIter; ++i) {
+      const int c = lane * 2 + 64 * i;
+      if (c < D && (acc[i][0] != 0.f || acc[i][1] != 0.f)) {
+        atomicAdd(dmask_emb + c, acc[i][0]);
+        atomicAdd(dmask_emb + c + 1, acc[i][1]);
+      }
     }
   }
 }
@@ -353,6 +379,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __re
                                                        long long rows, const float* __restrict__ grep_w,
                                                        const float* __restrict__ grep_b, const float* __restrict__ grep_a,
                                                        float* __restrict__ gate) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
@@ -391,6 +418,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ dgate, __nv_bfloat16* __restrict__ dxg,
                                                        RowView dxv, float* __restrict__ dgrep_w,
                                                        float* __restrict__ dgrep_b, float* __restrict__ dgrep_a) {
+  pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -471,6 +499,7 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
 // tab[h, i] = E[lut[i], h], i = delta + T - 1  (Toeplitz form of compute_bias, WavLM/modules.py:445-455)
 __global__ void relpos_table_fwd_kernel(const float* __restrict__ emb, const int* __restrict__ lut, int n, int H,
                                         float* __restrict__ tab) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * H) return;
   const int h = i / n, d = i % n;
@@ -478,6 +507,7 @@ __global__ void relpos_table_fwd_kernel(const float* __restrict__ emb, const int
 }
 __global__ void relpos_table_bwd_kernel(const float* __restrict__ dtab, const int* __restrict__ lut, int n, int H,
                                         float* __restrict__ demb) {
+  pdl_grid_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n * H) return;
   const int h = i / n, d = i % n;
@@ -499,9 +529,9 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
   RowView xv{x_bs, x_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
-    ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value><<<row_grid(rows, 8), 256, 0, st>>>(
+    B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value>, dim3(row_grid(rows, 8)), dim3(256), 0, st, 
         static_cast<const __nv_bfloat16*>(x), xv, gamma, beta, static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows,
-        gelu, 1e-5f);
+        gelu, 1e-5f));
     return 0;
   });
   if (rc) return rc;
@@ -526,10 +556,10 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
-    ln_bwd_kernel<decltype(vec)::value, decltype(nch)::value><<<static_cast<int>(blocks), 256, 0, st>>>(
+    B200_CHECK_CUDA(launch_pdl(ln_bwd_kernel<decltype(vec)::value, decltype(nch)::value>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, 
         static_cast<const __nv_bfloat16*>(dy), dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
         static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv, dgamma, dbeta, colsum, rows,
-        gelu);
+        gelu));
     return 0;
   });
   if (rc) return rc;
@@ -547,8 +577,8 @@ int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_bat
   const int gx = ceil_div(N, 256);
   int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 32), std::max(1, 4 * sm_count() / gx)));
   dim3 grid(gx, std::max(1, gy));
-  colsum_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<const __nv_bfloat16*>(x), xv, N, rows,
-                                                                    out);
+  B200_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), xv, N, rows,
+                                                                    out));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -563,9 +593,9 @@ int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void
   RowView a{dy_bs, dy_rs, rows_per_batch}, b{pre_bs, pre_rs, rows_per_batch}, c{out_bs, out_rs, rows_per_batch};
   int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 64), 4LL * sm_count() / std::max(1, ceil_div(N, 64)) + 1));
   dim3 grid(ceil_div(N, 64), std::max(1, gy));
-  dgelu_mul_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  B200_CHECK_CUDA(launch_pdl(dgelu_mul_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), a, static_cast<const __nv_bfloat16*>(pre), b,
-      static_cast<__nv_bfloat16*>(out), c, N, rows, colsum);
+      static_cast<__nv_bfloat16*>(out), c, N, rows, colsum));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -578,8 +608,8 @@ int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, 
   if (!mask && !pad) return 0;
   const long long rows = static_cast<long long>(T) * B;
   RowView xv{x_bs, x_rs, T};
-  frame_mask_fwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(x), xv, D, rows, mask, pad, mask_emb);
+  B200_CHECK_CUDA(launch_pdl(frame_mask_fwd_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<__nv_bfloat16*>(x), xv, D, rows, mask, pad, mask_emb));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -587,11 +617,12 @@ int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, 
 int b200s_frame_mask_bwd(void* dx, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
                          const uint8_t* pad, float* dmask_emb, b200s_stream stream) {
   B200_CHECK_ARG(dx, "frame_mask_bwd: null pointer");
+  B200_CHECK_ARG(D <= 2048 && D % 2 == 0, "frame_mask_bwd: D=%d must be even and <= 2048", D);
   if (!mask && !pad) return 0;
   const long long rows = static_cast<long long>(T) * B;
   RowView xv{x_bs, x_rs, T};
-  frame_mask_bwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<__nv_bfloat16*>(dx), xv, D, rows, mask, pad, dmask_emb);
+  B200_CHECK_CUDA(launch_pdl(frame_mask_bwd_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<__nv_bfloat16*>(dx), xv, D, rows, mask, pad, dmask_emb));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -601,8 +632,8 @@ int b200s_gate_fwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   B200_CHECK_ARG(x && grep_w && grep_b && grep_a && gate, "gate_fwd: null pointer");
   const long long rows = static_cast<long long>(T) * B;
   RowView xv{x_bs, x_rs, T};
-  gate_fwd_kernel<<<row_grid(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, gate);
+  B200_CHECK_CUDA(launch_pdl(gate_fwd_kernel, dim3(row_grid(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 
+      static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, gate));
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -616,22 +647,22 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   RowView xv{x_bs, x_rs, T}, dv{dx_bs, dx_rs, T};
   long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 2), 4LL * sm_count());
   if (blocks < 1) blocks = 1;
-  gate_bwd_kernel<<<static_cast<int>(blocks), 256, 8 * H * sizeof(float), static_cast<cudaStream_t>(stream)>>>(
+  B200_CHECK_CUDA(launch_pdl(gate_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 8 * H * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, dgate,
-      static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a);
+      static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a));
   B200_CHECK_LAUNCH();
   return 0;
 }
 
 int b200s_relpos_table_fwd(const float* emb, const int* lut, int n, int H, float* tab, b200s_stream stream) {
   B200_CHECK_ARG(emb && lut && tab, "relpos_table_fwd: null pointer");
-  relpos_table_fwd_kernel<<<ceil_div(n * H, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(emb, lut, n, H, tab);
+  B200_CHECK_CUDA(launch_pdl(relpos_table_fwd_kernel, dim3(ceil_div(n * H, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), emb, lut, n, H, tab));
   B200_CHECK_LAUNCH();
   return 0;
 }
 int b200s_relpos_table_bwd(const float* dtab, const int* lut, int n, int H, float* demb, b200s_stream stream) {
   B200_CHECK_ARG(dtab && lut && demb, "relpos_table_bwd: null pointer");
-  relpos_table_bwd_kernel<<<ceil_div(n * H, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(dtab, lut, n, H, demb);
+  B200_CHECK_CUDA(launch_pdl(relpos_table_bwd_kernel, dim3(ceil_div(n * H, 256)), dim3(256), 0, static_cast<cudaStream_t>(stream), dtab, lut, n, H, demb));
   B200_CHECK_LAUNCH();
   return 0;
 }
