@@ -199,7 +199,7 @@ def main():
     R = torch.randn(B, T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
     loss_host = torch.zeros(1).pin_memory()
 
-    def eager_step(e2e: bool):
+    def eager_step(e2e: bool, collective: bool = True):
         if model._engine is not None and model._engine.flat is not None:
             model.grad_buffer().zero_()
             model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
@@ -207,7 +207,7 @@ def main():
         x, _ = model.extract_features(wav, padding_mask=pad_host, mask=True)
         loss = (x.float() * R).sum()
         loss.backward()
-        if world > 1:
+        if world > 1 and collective:
             all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
         if e2e:
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
@@ -267,7 +267,7 @@ def main():
     if rank == 0 and not args.no_profile:
         prof = ops.Profiler()
         ops.set_profiler(prof)
-        eager_step(False)
+        eager_step(False, collective=False)  # rank 0 only: no collective in this extra, per-op-timed step
         torch.cuda.synchronize()
         ops.set_profiler(None)
         breakdown = prof.summary()
@@ -324,6 +324,7 @@ def main():
             line["breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
         print(json.dumps(line))
     if world > 1:
+        dist.barrier()  # the other ranks wait here while rank 0 finishes its profiled step and the CPU baseline
         dist.destroy_process_group()
 
 

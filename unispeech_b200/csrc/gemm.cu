@@ -129,36 +129,82 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 }
 
 // persistent CTA-pair kernel (gemm2.cuh): cluster (2,1,1), one pair per two SMs
-template <bool A_MN, bool B_MN, int KIND>
-static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+// how many CTA pairs share (multicast) the B operand: 2 when B200S_GEMM_CLUSTER4=1 and the problem has >= 2 M tiles
+static int cluster_pairs_for(int m_tiles_total) {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_GEMM_CLUSTER4");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return (v == 1 && m_tiles_total >= 2) ? 2 : 1;
+}
+
+// opt the kernel into its shared-memory size (once) and report how many clusters can be resident at once (a 4-CTA cluster
+// does not fit every GPC remainder, so fewer than sm_count / 4 are)
+template <bool A_MN, bool B_MN, int KIND, int NPAIR>
+static cudaError_t pair_kernel_setup(int* units) {
   using Cfg = Gemm2Cfg<KIND>;
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
+  static int max_units = 0;
   std::call_once(once, [] {
-    attr_err = cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    Cfg::kSmemBytes);
+    attr_err = cudaFuncSetAttribute(gemm_bf16_pair_kernel<A_MN, B_MN, KIND, NPAIR>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
+    max_units = sm_count() / (2 * NPAIR);
+    if (attr_err == cudaSuccess && NPAIR > 1) {
+      cudaLaunchConfig_t q;
+      memset(&q, 0, sizeof(q));
+      q.gridDim = dim3(2 * NPAIR * max_units, 1, 1);
+      q.blockDim = dim3(Cfg::kThreads, 1, 1);
+      q.dynamicSmemBytes = Cfg::kSmemBytes;
+      cudaLaunchAttribute qa[1];
+      qa[0].id = cudaLaunchAttributeClusterDimension;
+      qa[0].val.clusterDim.x = 2 * NPAIR;
+      qa[0].val.clusterDim.y = 1;
+      qa[0].val.clusterDim.z = 1;
+      q.attrs = qa;
+      q.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_bf16_pair_kernel<A_MN, B_MN, KIND, NPAIR>, &q) == cudaSuccess && n > 0)
+        max_units = std::min(max_units, n);
+    }
   });
-  B200_CHECK_CUDA(attr_err);
-  const int items = p.tiles_total * p.splits;
-  const int pairs = std::max(1, std::min(items, sm_count() / 2));
+  *units = max_units;
+  return attr_err;
+}
+
+template <bool A_MN, bool B_MN, int KIND, int NPAIR>
+static int launch_gemm_pair_n(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<KIND>;
+  int max_units = 0;
+  B200_CHECK_CUDA((pair_kernel_setup<A_MN, B_MN, KIND, NPAIR>(&max_units)));
+  const int m_tiles_total = p.tiles_total / p.n_tiles;
+  const int items = ceil_div(m_tiles_total, NPAIR) * p.n_tiles * p.splits;
+  const int pairs = std::max(1, std::min(items, max_units));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(2 * pairs, 1, 1);
+  cfg.gridDim = dim3(2 * NPAIR * pairs, 1, 1);
   cfg.blockDim = dim3(Cfg::kThreads, 1, 1);
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = stream;
   cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = 2 * NPAIR;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND>, ta, tb, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND, NPAIR>, ta, tb, p));
   B200_CHECK_LAUNCH();
   return 0;
+}
+template <bool A_MN, bool B_MN, int KIND>
+static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, int npair,
+                            cudaStream_t stream) {
+  return npair == 2 ? launch_gemm_pair_n<A_MN, B_MN, KIND, 2>(ta, tb, p, stream)
+                    : launch_gemm_pair_n<A_MN, B_MN, KIND, 1>(ta, tb, p, stream);
 }
 
 // 0/1 switch for the CTA-pair kernel (B200S_GEMM_PAIR=0 forces the single-CTA kernel; used by the A/B micro-benchmarks)
@@ -265,8 +311,10 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   p.out = {out, out_bs, out_ld};
   const bool pair_epi_ok = epilogue_aligned(p) && !((p.flags & EPI_GELU) && p.n_in > 1);
   if (pair_kernel_enabled() && pair_epi_ok && N >= 256 && rows >= 256 && static_cast<long long>(rows) * batches >= 2048) {
-    // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows
-    ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, 128, 1, 1}};
+    // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows (loaded as one box,
+    // or as 64-row quarters multicast between two pairs)
+    const int npair = cluster_pairs_for(ceil_div(rows, 256) * batches);
+    ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, npair == 2 ? 64 : 128, 1, 1}};
     if (make_tmap(&tb, vb2)) return -3;
     p.m_rows = rows;
     p.m_tile_stride = 256;
@@ -284,9 +332,9 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
     // A coords: (k0, m0 [+128*rank, added by the kernel], mb, 0)   B coords: (k0, n_tile*256 + sub(=128*rank), 0, 0)
     p.ca[0][4] = 1; p.ca[1][1] = 1; p.ca[2][2] = 1;
     p.cb[0][4] = 1; p.cb[1][3] = 256; p.cb[1][7] = 1;
-    if (p.flags & EPI_GELU) return launch_gemm_pair<false, false, EK_GELU>(ta, tb, p, st);
-    if (p.flags & EPI_DGELU) return launch_gemm_pair<false, false, EK_DGELU>(ta, tb, p, st);
-    return launch_gemm_pair<false, false, EK_LINEAR>(ta, tb, p, st);
+    if (p.flags & EPI_GELU) return launch_gemm_pair<false, false, EK_GELU>(ta, tb, p, npair, st);
+    if (p.flags & EPI_DGELU) return launch_gemm_pair<false, false, EK_DGELU>(ta, tb, p, npair, st);
+    return launch_gemm_pair<false, false, EK_LINEAR>(ta, tb, p, npair, st);
   }
   const int block_n = (N >= 128) ? 128 : 64;
   ViewSpec vb{w, {K, N, 1, 1}, {K, 0, 0}, {64, block_n, 1, 1}};
@@ -339,9 +387,14 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
     p.tiles_total = p.m_tiles_per_batch * p.n_tiles;
     p.k_blocks_per_batch = ceil_div(rows, 64);
     p.k_blocks = p.k_blocks_per_batch * batches;
-    const int pairs = std::max(1, sm_count() / 2);
-    // about one work item per CTA pair: the fp32 reduction epilogue of a split is the expensive part, the main loop is cheap
-    int splits = std::max(1, pairs / p.tiles_total);
+    // multicast pays only when the M (output-feature) tile count pairs up without much waste
+    const int npair = (p.m_tiles_per_batch % 2 == 0 || p.m_tiles_per_batch >= 8) ? cluster_pairs_for(p.m_tiles_per_batch) : 1;
+    int units = 0;
+    if (npair == 2) B200_CHECK_CUDA((pair_kernel_setup<true, true, EK_F32, 2>(&units)));
+    else B200_CHECK_CUDA((pair_kernel_setup<true, true, EK_F32, 1>(&units)));
+    // about one work item per cluster: the fp32 reduction epilogue of a split is the expensive part, the main loop is cheap
+    const int pairs = std::max(1, units);
+    int splits = std::max(1, pairs / (ceil_div(p.m_tiles_per_batch, npair) * p.n_tiles));
     if (splits > p.k_blocks) splits = p.k_blocks;
     p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
     p.splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
@@ -351,7 +404,7 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
     p.flags = EPI_OUT_F32 | (p.splits > 1 ? EPI_ATOMIC : EPI_ACCUM);
     fill_epilogue(p, nullptr);
     p.out = {dw, 0, dw_ld};
-    return launch_gemm_pair<true, true, EK_F32>(ta, tb, p, static_cast<cudaStream_t>(stream));
+    return launch_gemm_pair<true, true, EK_F32>(ta, tb, p, npair, static_cast<cudaStream_t>(stream));
   }
 
   GemmParams p;

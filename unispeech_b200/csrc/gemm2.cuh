@@ -130,7 +130,11 @@ __device__ __forceinline__ void stage_row_bf16(const float* acc, uint32_t buf, i
   for (int g = 0; g < 8; ++g) sts128(buf + stg_off(lane, g), pack_bf16x8(acc + g * 8));
 }
 
-template <bool A_MN, bool B_MN, int KIND>
+// NPAIR = 1: cluster = one CTA pair.  NPAIR = 2: cluster = two CTA pairs working on M-adjacent tiles of the SAME N tile; every
+// CTA loads one quarter of the B tile (64 of its 256 rows) and TMA-multicasts it to the CTA of the same rank in the other
+// pair, so the B operand crosses the L2 -> SM fabric once per cluster instead of once per pair.  The kernel is bound by that
+// fabric (about 6.9 KB/clk chip-wide, measured: the loads alone take longer than the MMAs), not by the tensor pipe.
+template <bool A_MN, bool B_MN, int KIND, int NPAIR>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
                                                                 const __grid_constant__ GemmParams p) {
@@ -139,10 +143,15 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   constexpr int kStages = Cfg::kStages;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();      // 0 = leader
-  const int pair = blockIdx.x >> 1;
-  const int n_pairs = gridDim.x >> 1;
-  const int n_items = p.tiles_total * p.splits;
+  const uint32_t crank = cluster_ctarank();     // rank inside the cluster
+  const uint32_t rank = crank & 1u;             // rank inside the CTA pair, 0 = leader (issues the MMAs)
+  const int cp = static_cast<int>(crank >> 1);  // pair index inside the cluster
+  const int pair = blockIdx.x / (2 * NPAIR);    // work unit (cluster) index
+  const int n_pairs = gridDim.x / (2 * NPAIR);
+  const int m_tiles_total = p.tiles_total / p.n_tiles;
+  const int sup_tiles = ((m_tiles_total + NPAIR - 1) / NPAIR) * p.n_tiles;  // work items per K split
+  const int n_items = sup_tiles * p.splits;
+  constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << (2 * NPAIR)) - 1u);
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
@@ -158,7 +167,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], NPAIR);  // one tcgen05.commit arrival per pair that reads (a multicast copy of) the stage
     }
 #pragma unroll
     for (int a = 0; a < 2; ++a) {
@@ -175,12 +184,15 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
-  // item -> (split, m tile, n tile) and its K-block range; identical in every role of both CTAs
-  auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end) {
-    const int split = item / p.tiles_total;
-    const int tile = item % p.tiles_total;
+  // item -> (split, m tile of THIS pair, n tile) and its K-block range; identical in every role of the pair's CTAs.
+  // `active` is false for the second pair of a cluster when the M tile count is odd: it still loads and multicasts its part
+  // of B and keeps the stage barriers flowing, but issues no MMA and has no epilogue.
+  auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end, bool& active) {
+    const int split = item / sup_tiles;
+    const int tile = item % sup_tiles;
     n_tile = tile % p.n_tiles;
-    const int mt = tile / p.n_tiles;
+    const int mt = (tile / p.n_tiles) * NPAIR + cp;
+    active = mt < m_tiles_total;
     mb = mt / p.m_tiles_per_batch;
     m0 = (mt % p.m_tiles_per_batch) * p.m_tile_stride;
     kb_begin = split * p.k_blocks_per_split;
@@ -196,16 +208,21 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
       int it = 0;
       for (int item = pair; item < n_items; item += n_pairs) {
         int mb, m0, n_tile, kb_begin, kb_end;
-        decode(item, mb, m0, n_tile, kb_begin, kb_end);
+        bool active;
+        decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
         if (kb_begin >= kb_end) continue;
         v[0] = 1; v[1] = m0 + 128 * static_cast<int>(rank); v[2] = mb; v[3] = n_tile;
         v[4] = 0; v[5] = 0; v[6] = 0; v[7] = 0;
         int ta[4], tb[4];
+        // B rows of this CTA: its half of the 256-row tile (NPAIR = 1) or its quarter (NPAIR = 2, multicast to the other pair)
+        const int b_sub = 128 * static_cast<int>(rank) + (NPAIR == 2 ? 64 * cp : 0);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           ta[i] = coord_dot(p.ca[i], v);
-          tb[i] = coord_dot(p.cb[i], v) + p.cb[i][7] * 128 * static_cast<int>(rank);
+          tb[i] = coord_dot(p.cb[i], v) + p.cb[i][7] * b_sub;
         }
+        const uint32_t tx_bytes = (active ? 2 * Cfg::kABytes : 0) + 2 * Cfg::kBBytes;
+        const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
         int kbatch = 0, kin = kb_begin;  // kb = kbatch * k_blocks_per_batch + kin
         if (p.k_blocks_per_batch > 0) {
           kbatch = kb_begin / p.k_blocks_per_batch;
@@ -223,28 +240,36 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * Cfg::kStageBytes;
           uint8_t* sb = sa + Cfg::kABytes;
-          if (p.debug & 4) {  // diagnostics: barriers flow, no loads
+          if (NPAIR == 1 && (p.debug & 4)) {  // diagnostics: barriers flow, no loads
             if (rank == 0) mbar_arrive(&full_bar[s]);
             if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) { kin = 0; ++kbatch; }
             else if (p.k_blocks_per_batch == 0) ++kin;
             continue;
           }
-          if (rank == 0) mbar_expect_tx(&full_bar[s], 2 * Cfg::kStageBytes);  // bytes of both CTAs
-          if constexpr (!A_MN) {
-            tma_load_4d_2cta(sa, &tmA, &full_bar[s], ka[0], ka[1], ka[2], ka[3]);
-          } else {
+          if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);  // bytes landing in both CTAs of this pair
+          if (active) {
+            if constexpr (!A_MN) {
+              tma_load_4d_2cta(sa, &tmA, &full_bar[s], ka[0], ka[1], ka[2], ka[3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-              tma_load_4d_2cta(sa + i * 8192, &tmA, &full_bar[s], ka[0] + p.ca[0][7] * 64 * i, ka[1] + p.ca[1][7] * 64 * i,
-                               ka[2] + p.ca[2][7] * 64 * i, ka[3] + p.ca[3][7] * 64 * i);
+              for (int i = 0; i < 2; ++i)
+                tma_load_4d_2cta(sa + i * 8192, &tmA, &full_bar[s], ka[0] + p.ca[0][7] * 64 * i, ka[1] + p.ca[1][7] * 64 * i,
+                                 ka[2] + p.ca[2][7] * 64 * i, ka[3] + p.ca[3][7] * 64 * i);
+            }
           }
-          if constexpr (!B_MN) {
-            tma_load_4d_2cta(sb, &tmB, &full_bar[s], kbv[0], kbv[1], kbv[2], kbv[3]);
-          } else {
+          if constexpr (NPAIR == 1) {
+            if constexpr (!B_MN) {
+              tma_load_4d_2cta(sb, &tmB, &full_bar[s], kbv[0], kbv[1], kbv[2], kbv[3]);
+            } else {
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
-              tma_load_4d_2cta(sb + i * 8192, &tmB, &full_bar[s], kbv[0] + p.cb[0][7] * 64 * i, kbv[1] + p.cb[1][7] * 64 * i,
-                               kbv[2] + p.cb[2][7] * 64 * i, kbv[3] + p.cb[3][7] * 64 * i);
+              for (int i = 0; i < 2; ++i)
+                tma_load_4d_2cta(sb + i * 8192, &tmB, &full_bar[s], kbv[0] + p.cb[0][7] * 64 * i, kbv[1] + p.cb[1][7] * 64 * i,
+                                 kbv[2] + p.cb[2][7] * 64 * i, kbv[3] + p.cb[3][7] * 64 * i);
+            }
+          } else {
+            // one 64-row quarter of the B tile (8 KB: box 64 x 64 in both majornesses), delivered to this CTA and to the CTA
+            // of the same pair rank in the other pair; each destination signals its own pair leader's full barrier
+            tma_load_4d_2cta_mc(sb + cp * 8192, &tmB, &full_bar[s], kbv[0], kbv[1], kbv[2], kbv[3], mc_mask);
           }
           if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) {
             kin = 0;
@@ -262,8 +287,16 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
       int it = 0, local = 0;  // `local` counts the non-empty items this pair has processed (accumulator stage = local & 1)
       for (int item = pair; item < n_items; item += n_pairs) {
         int mb, m0, n_tile, kb_begin, kb_end;
-        decode(item, mb, m0, n_tile, kb_begin, kb_end);
+        bool active;
+        decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
         if (kb_begin >= kb_end) continue;
+        if (!active) {  // nothing to compute: just hand the stages (which received the multicast B parts) back
+          for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+            mbar_wait(&full_bar[it % kStages], (it / kStages) & 1);
+            umma_commit_2cta(&empty_bar[it % kStages], kAllCtas);
+          }
+          continue;
+        }
         const int a = local & 1;
         mbar_wait(&tmem_empty_bar[a], ((local >> 1) & 1) ^ 1);  // both CTAs' epilogues drained this accumulator
         tc_fence_after();
@@ -287,9 +320,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             }
           }
           first = false;
-          umma_commit_2cta(&empty_bar[s], 0x3);  // frees the stage in both CTAs
+          umma_commit_2cta(&empty_bar[s], kAllCtas);  // frees the stage in every CTA that writes into it
         }
-        umma_commit_2cta(&tmem_full_bar[a], 0x3);
+        umma_commit_2cta(&tmem_full_bar[a], static_cast<uint16_t>(0x3u << (2 * cp)));
         ++local;
       }
     }
@@ -309,14 +342,16 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
     auto next_item = [&](int item) {
       for (; item < n_items; item += n_pairs) {
         int mb, m0, n_tile, kb_begin, kb_end;
-        decode(item, mb, m0, n_tile, kb_begin, kb_end);
-        if (kb_begin < kb_end) break;
+        bool active;
+        decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
+        if (kb_begin < kb_end && active) break;
       }
       return item;
     };
     auto tile_of = [&](int item) {
       int mb, m0, n_tile, kb_begin, kb_end;
-      decode(item, mb, m0, n_tile, kb_begin, kb_end);
+      bool active;
+      decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
       EpiTile et;
       et.mb = mb;
       const int m_valid = min(p.m_tile_valid, p.m_rows - m0) - 128 * static_cast<int>(rank) - q * 32;
@@ -383,7 +418,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         if (cc == 1) {  // all TMEM reads of this tile are done: hand the accumulator back to the MMA warp early
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], 0);
+          if (lane == 0) mbar_arrive_remote(&tmem_empty_bar[a], crank & ~1u);  // this pair's leader
         }
         if constexpr (KIND == EK_F32) {
           // ---- fp32 (+)= acc, two 32-column passes through the staging buffer
