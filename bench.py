@@ -258,6 +258,15 @@ def main():
         step(True)
     ms_e2e = timed(args.steps, True)
 
+    # host cost of enqueueing one step (launch queue empty at the start, two steps timed without synchronising): if this
+    # approaches ms_per_step the run is launch-bound, not GPU-bound
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(2):
+        step(False)
+    host_ms = (time.perf_counter() - t0) * 1e3 / 2
+    torch.cuda.synchronize()
+
     audio_s = world * B * secs * args.steps
     value = audio_s / (ms * 1e-3)
     e2e_value = audio_s / (ms_e2e * 1e-3)
@@ -316,7 +325,7 @@ def main():
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "model_tflops": 3 * fwd_flops * world * B * args.steps / (ms * 1e-3) / 1e12,
         }

@@ -94,3 +94,34 @@ def test_pair_wgrad_conv_view(cuda_device):
     (F.conv1d(x[:, :T].float().transpose(1, 2), w, stride=s) * dy.float().transpose(1, 2)).sum().backward()
     ref = w.grad.permute(0, 2, 1).reshape(C_, k * C_)
     assert (dw - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
+
+
+def test_pair_gemm_cluster4_multicast(cuda_device, monkeypatch):
+    """Experimental NPAIR=2 path (two CTA pairs per cluster, B quarters TMA-multicast between them): same results."""
+    from unispeech_b200 import _lib as L
+    from unispeech_b200 import ops
+    monkeypatch.setenv("B200S_GEMM_CLUSTER4", "1")
+    torch.manual_seed(11)
+    dev = cuda_device
+    M, K, N = 2900, 512, 768  # 12 M tiles (last one ragged), 3 N tiles
+    a = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) / K ** 0.5)
+    bias = torch.randn(N, device=dev)
+    r1 = bf(torch.randn(M, N, device=dev))
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm_rows(a, 0, K, M, 1, K, w, N, out, 0, N, L.make_epilogue(bias=bias, res1=r1, res1_ld=N))
+    torch.cuda.synchronize()
+    ref = a.float() @ w.float().t() + bias + r1.float()
+    assert (out.float() - ref).abs().max().item() < 0.06
+    # odd number of M tiles (the second pair of the last cluster is inactive) + weight gradient with an even M tile count
+    M2 = 2300
+    out2 = torch.empty(M2, N, device=dev, dtype=torch.bfloat16)
+    ops.gemm_rows(a[:M2], 0, K, M2, 1, K, w, N, out2, 0, N, L.make_epilogue(bias=bias))
+    y = bf(torch.randn(3000, 512, device=dev))
+    x = bf(torch.randn(3000, 768, device=dev))
+    dw = torch.zeros(512, 768, device=dev)
+    ops.gemm_wgrad(y, 0, 512, x, 0, 768, 3000, 1, 512, 768, dw, 768)
+    torch.cuda.synchronize()
+    assert (out2.float() - (a[:M2].float() @ w.float().t() + bias)).abs().max().item() < 0.06
+    refw = y.float().t() @ x.float()
+    assert (dw - refw).abs().max().item() < 1e-2 * max(1.0, refw.abs().max().item())

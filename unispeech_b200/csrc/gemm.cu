@@ -130,13 +130,11 @@ static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmP
 
 // persistent CTA-pair kernel (gemm2.cuh): cluster (2,1,1), one pair per two SMs
 // how many CTA pairs share (multicast) the B operand: 2 when B200S_GEMM_CLUSTER4=1 and the problem has >= 2 M tiles
+// (experimental, off by default: measured SLOWER than independent pairs on B200 -- a 4-CTA cluster only gets 132 of the 148
+// SMs and the multicast does not raise the L2 -> SM throughput at this cluster size; kept for the A/B numbers in DESIGN.md)
 static int cluster_pairs_for(int m_tiles_total) {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("B200S_GEMM_CLUSTER4");
-    v = (e && e[0] == '1') ? 1 : 0;
-  }
-  return (v == 1 && m_tiles_total >= 2) ? 2 : 1;
+  const char* e = getenv("B200S_GEMM_CLUSTER4");
+  return (e && e[0] == '1' && m_tiles_total >= 2) ? 2 : 1;
 }
 
 // opt the kernel into its shared-memory size (once) and report how many clusters can be resident at once (a 4-CTA cluster
