@@ -113,6 +113,13 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
                          void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch,
                          int batches, int D, int gelu, b200s_stream stream);
 
+/* LayerNorm forward fused with the gru_rel_pos gate of the attention that consumes y (b200s_gate_fwd semantics on the stored
+ * bf16 y): saves one pass over y per layer.  D = H * 64; gate: fp32 [B, H, T]; rows = B * T with the usual views. */
+int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta,
+                              void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                              const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                              b200s_stream stream);
+
 /* dx = LN-backward(dy) [+ dres];  dgamma, dbeta (+=);  colsum (+=) = column sums of dx (bias gradient of x's producer). */
 int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs,
                          long long x_rs, const float* mean, const float* rstd, const float* gamma,

@@ -96,6 +96,31 @@ def test_colsum_dgelu_mask(cuda_device):
     assert torch.equal(dy[keep], dy0[keep]) and dy[~keep].abs().max().item() == 0
 
 
+@pytest.mark.parametrize("H", [4, 12, 16])
+def test_layer_norm_gate_fwd(cuda_device, H):
+    """LayerNorm fused with the gate of the consuming attention == layer_norm_fwd followed by gate_fwd on the stored output."""
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(100 + H)
+    B, T, D = 3, 77, H * 64
+    x = bf(torch.randn(B, T, D, device=dev) * 2 + 0.3)
+    gamma, beta = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev) * 0.1
+    gw = torch.randn(8, 64, device=dev) * 0.2
+    gb = torch.randn(8, device=dev) * 0.1
+    ga = torch.rand(1, H, 1, 1, device=dev) + 0.5
+    y1, y2 = torch.empty_like(x), torch.empty_like(x)
+    m1, r1, m2, r2 = (torch.empty(B * T, device=dev) for _ in range(4))
+    g1, g2 = torch.empty(B, H, T, device=dev), torch.empty(B, H, T, device=dev)
+    ops.layer_norm_fwd(x, T * D, D, gamma, beta, y1, T * D, D, m1, r1, T, B, D)
+    ops.gate_fwd(y1, T * D, D, T, B, H, gw, gb, ga, g1)
+    ops.layer_norm_gate_fwd(x, T * D, D, gamma, beta, y2, T * D, D, m2, r2, T, B, D, gw, gb, ga, H, g2)
+    torch.cuda.synchronize()
+    ref = F.layer_norm(x.float(), (D,), gamma, beta)
+    assert (y1.float() - ref).abs().max().item() < 0.03
+    assert torch.equal(y1, y2) and torch.equal(m1, m2) and torch.equal(r1, r2)
+    assert (g1 - g2).abs().max().item() < 1e-5
+
+
 @pytest.mark.parametrize("H", [2, 12])
 def test_gate_fwd_bwd(cuda_device, H):
     from unispeech_b200 import ops

@@ -171,9 +171,25 @@ static cudaError_t pair_kernel_setup(int* units) {
   return attr_err;
 }
 
+// output tensor maps of the staged epilogue: one SWIZZLE_128B box = 32 rows x 64 bf16 columns of [batches][rows][N]
+static int make_out_tmap(CUtensorMap* tm, const EpiTensor& t, int N, int rows, int batches) {
+  ViewSpec v{t.p, {N, rows, batches, 1}, {t.ld, batches > 1 ? t.bs : 0, 0}, {64, 32, 1, 1}};
+  return make_tmap(tm, v);
+}
+
 template <bool A_MN, bool B_MN, int KIND, int NPAIR>
 static int launch_gemm_pair_n(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<KIND>;
+  CUtensorMap to, to2;
+  if (KIND != EK_F32) {
+    const int batches = p.tiles_total / (p.m_tiles_per_batch * p.n_tiles);
+    if (make_out_tmap(&to, p.out, p.n_total, p.m_rows, batches)) return -3;
+    to2 = to;
+    if (p.out2.p != nullptr && make_out_tmap(&to2, p.out2, p.n_total, p.m_rows, batches)) return -3;
+  } else {
+    to = ta;  // unused by the fp32 kind
+    to2 = ta;
+  }
   int max_units = 0;
   B200_CHECK_CUDA((pair_kernel_setup<A_MN, B_MN, KIND, NPAIR>(&max_units)));
   const int m_tiles_total = p.tiles_total / p.n_tiles;
@@ -194,7 +210,7 @@ static int launch_gemm_pair_n(const CUtensorMap& ta, const CUtensorMap& tb, cons
   attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = pdl_enabled() ? 2 : 1;
-  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND, NPAIR>, ta, tb, p));
+  B200_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_bf16_pair_kernel<A_MN, B_MN, KIND, NPAIR>, ta, tb, to, to2, p));
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -137,6 +137,8 @@ __device__ __forceinline__ void stage_row_bf16(const float* acc, uint32_t buf, i
 template <bool A_MN, bool B_MN, int KIND, int NPAIR>
 __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmB,
+                                                                const __grid_constant__ CUtensorMap tmO,
+                                                                const __grid_constant__ CUtensorMap tmO2,
                                                                 const __grid_constant__ GemmParams p) {
   pdl_launch_dependents();  // the next kernel's CTAs may start their prologue as soon as SMs free up
   using Cfg = Gemm2Cfg<KIND>;
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (KIND != EK_F32) tma_prefetch_desc(&tmO);
 #pragma unroll
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -411,6 +414,8 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         const bool have_next = (cc == 0) || (item_next < n_items);   // is there a sequence element #seq+1?
         const EpiTile et_pf = (cc == 0) ? et : et_next;
         if (early) {  // the next sequence element's input goes into the other buffer right away
+          if (lane == 0) bulk_wait_read0();  // ... once the TMA store that still reads that buffer has drained it
+          __syncwarp();
           if (have_next) prefetch(et_pf, cc ^ 1, seq + 1);
           else cp_async_commit();
         }
@@ -472,10 +477,15 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             }
             if constexpr (KIND == EK_GELU) {
               if (p.out2.p != nullptr) {  // pre-activation, saved for the backward pass (buffer 1 is free: n_in <= 1)
+                if (lane == 0) bulk_wait_read0();
+                __syncwarp();
                 stage_row_bf16(acc, buf_b, lane);
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
-                flush_bf16(p.out2, et, cc, buf_b, lane);
-                __syncwarp();
+                if (lane == 0) {
+                  tma_store_4d(&tmO2, buf_b, et.col0 + cc * 64, static_cast<int>(et.row0), et.mb, 0);
+                  bulk_commit();
+                }
               }
 #pragma unroll
               for (int j = 0; j < 64; ++j) acc[j] = gelu_f(acc[j]);
@@ -502,9 +512,17 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             __syncwarp();  // every lane is done reading the input buffers: they may be overwritten
           }
           if (chunk_live) {
-            stage_row_bf16(acc, buf_a, lane);
+            // the staged 32 x 64 tile is exactly one SWIZZLE_128B TMA box: one elected lane stores it (rows / columns beyond
+            // the tensor are clipped by the tensor map), the warp moves on while the TMA engine drains the buffer
+            if (lane == 0) bulk_wait_read0();
             __syncwarp();
-            flush_bf16(p.out, et, cc, buf_a, lane);
+            stage_row_bf16(acc, buf_a, lane);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_4d(&tmO, buf_a, et.col0 + cc * 64, static_cast<int>(et.row0), et.mb, 0);
+              bulk_commit();
+            }
             if (p.flags & EPI_COLSUM) {
               // column sums of the stored (bf16-rounded) values from the staged tile: lane l owns columns 2l, 2l+1 of the chunk
               float s0 = 0.f, s1 = 0.f;
@@ -525,7 +543,9 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             }
             __syncwarp();
           }
-          if (n_in >= 1 && !early) {  // late mode: the buffers are free only now
+          if (n_in >= 1 && !early) {  // late mode: the buffers are free only once the output store has drained them
+            if (lane == 0) bulk_wait_read0();
+            __syncwarp();
             if (have_next) prefetch(et_pf, cc ^ 1, seq + 1);
             else cp_async_commit();
           }
@@ -536,6 +556,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
       ++local;
     }
     cp_async_wait<0>();
+    if (lane == 0) bulk_wait0();  // every output box has been written before the CTA (and its shared memory) goes away
   }
 
   tc_fence_before();

@@ -65,46 +65,72 @@ struct RowView {
 
 // ------------------------------------------------------------------------------------------------ LayerNorm forward
 // y = (x - mean) * rstd * gamma + beta  [then exact GELU if gelu != 0]; statistics in fp32 (F.layer_norm,
-// reference: WavLM/WavLM.py:342,559,666,675; Fp32LayerNorm WavLM/modules.py:30-42 for the conv stack)
-template <int VEC, int NCH>
-__global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv,
+// reference: WavLM/WavLM.py:342,559,666,675; Fp32LayerNorm WavLM/modules.py:30-42 for the conv stack).
+// One warp per row; gamma/beta live in shared memory, which keeps the register count at <= 64 and four blocks (32 warps)
+// resident per SM: the kernel is latency-, not bandwidth-bound (a row is a chain of loads and two shuffle reductions).
+// GATE: also emits the gru_rel_pos gate of the attention that consumes y (WavLM/modules.py:523-533): per head h,
+//   (ga, gb) = sigmoid(y_h . wa + ba, y_h . wb + bb),  gate[b,h,t] = ga * (gb * grep_a[h] - 1) + 2,
+// where wa / wb are the sums of the first / last four rows of grep_linear.weight and y_h is the STORED (bf16) head slice.
+// Needs VEC == 8 (a head's 64 columns = 8 consecutive lanes of one chunk).
+struct GateArgs {
+  const float* grep_w;  // [8, 64]
+  const float* grep_b;  // [8]
+  const float* grep_a;  // [H]
+  float* gate;          // [B, H, T]
+  int H, T;
+};
+
+template <int VEC, int NCH, bool GATE, bool GELU>
+__global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv,
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      __nv_bfloat16* __restrict__ y, RowView yv,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     long long rows, int gelu, float eps) {
+                                                     long long rows, float eps, GateArgs ga) {
   pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
+  constexpr int N = NCH * VEC;
+  __shared__ __align__(16) float gs[D], bs[D];
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    gs[c] = gamma[c];
+    bs[c] = beta[c];
+  }
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float g[NCH * VEC], b[NCH * VEC];
+  float wa[GATE ? 8 : 1], wb[GATE ? 8 : 1], gba = 0.f, gbb = 0.f;
+  if constexpr (GATE) {
+    static_assert(VEC == 8, "fused gate needs 8 columns per lane");
 #pragma unroll
-  for (int i = 0; i < NCH; ++i)
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      g[i * VEC + j] = gamma[(i * 32 + lane) * VEC + j];
-      b[i * VEC + j] = beta[(i * 32 + lane) * VEC + j];
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane & 7) * 8 + j;
+      wa[j] = ga.grep_w[c] + ga.grep_w[64 + c] + ga.grep_w[128 + c] + ga.grep_w[192 + c];
+      wb[j] = ga.grep_w[256 + c] + ga.grep_w[320 + c] + ga.grep_w[384 + c] + ga.grep_w[448 + c];
     }
+    gba = ga.grep_b[0] + ga.grep_b[1] + ga.grep_b[2] + ga.grep_b[3];
+    gbb = ga.grep_b[4] + ga.grep_b[5] + ga.grep_b[6] + ga.grep_b[7];
+  }
   for (long long r = warp_global; r < rows; r += nwarps) {
+    float v[N];
     const __nv_bfloat16* xr = x + xv.off(r);
-    float v[NCH * VEC];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) VecIO<VEC>::load(xr + (i * 32 + lane) * VEC, v + i * VEC);
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH * VEC; ++i) s += v[i];
+    for (int i = 0; i < N; ++i) s += v[i];
     const float mean = warp_sum(s) * (1.0f / D);
-    float q = 0.f;
+    float qv = 0.f;
 #pragma unroll
-    for (int i = 0; i < NCH * VEC; ++i) {
+    for (int i = 0; i < N; ++i) {
       const float d = v[i] - mean;
-      q += d * d;
+      qv += d * d;
     }
-    const float rstd = rsqrtf(warp_sum(q) * (1.0f / D) + eps);
+    const float rstd = rsqrtf(warp_sum(qv) * (1.0f / D) + eps);
 #pragma unroll
-    for (int i = 0; i < NCH * VEC; ++i) {
-      float o = (v[i] - mean) * rstd * g[i] + b[i];
-      if (gelu) o = gelu_f(o);
+    for (int i = 0; i < N; ++i) {
+      const int c = (i / VEC * 32 + lane) * VEC + i % VEC;
+      float o = (v[i] - mean) * rstd * gs[c] + bs[c];
+      if (GELU) o = gelu_f(o);
       v[i] = o;
     }
     __nv_bfloat16* yr = y + yv.off(r);
@@ -113,6 +139,30 @@ __global__ void __launch_bounds__(256) ln_fwd_kernel(const __nv_bfloat16* __rest
     if (lane == 0) {
       if (mean_out) mean_out[r] = mean;
       if (rstd_out) rstd_out[r] = rstd;
+    }
+    if constexpr (GATE) {
+      const long long bidx = r / ga.T, t = r % ga.T;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float yb = __bfloat162float(__float2bfloat16_rn(v[i * 8 + j]));  // what the attention kernel will read
+          sa = fmaf(yb, wa[j], sa);
+          sb = fmaf(yb, wb[j], sb);
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if ((lane & 7) == 0) {
+          const int h = i * 4 + (lane >> 3);
+          const float g1 = 1.0f / (1.0f + __expf(-(sa + gba)));
+          const float g2 = 1.0f / (1.0f + __expf(-(sb + gbb)));
+          ga.gate[(bidx * ga.H + h) * ga.T + t] = g1 * (g2 * ga.grep_a[h] - 1.0f) + 2.0f;
+        }
+      }
     }
   }
 }
@@ -226,6 +276,15 @@ static int dispatch_width(int D, F&& f) {
       set_last_error("row kernels support widths 64/128/256/512/768/1024, got %d", D);
       return -1;
   }
+}
+
+// one row per warp and iteration, 8 warps per block, four resident blocks per SM
+static int ln_fwd_grid(long long rows) {
+  long long blocks = ceil_div_ll(rows, 8);
+  const long long cap = static_cast<long long>(sm_count()) * 4;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return static_cast<int>(blocks);
 }
 
 static int row_grid(long long rows, int warps_per_block) {
@@ -528,10 +587,44 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
   if (rows == 0) return 0;
   RowView xv{x_bs, x_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GateArgs no_gate{nullptr, nullptr, nullptr, nullptr, 0, 1};
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
-    B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value>, dim3(row_grid(rows, 8)), dim3(256), 0, st, 
-        static_cast<const __nv_bfloat16*>(x), xv, gamma, beta, static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows,
-        gelu, 1e-5f));
+    if (gelu) {
+      B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value, false, true>, dim3(ln_fwd_grid(rows)),
+                                 dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
+                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate));
+    } else {
+      B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value, false, false>, dim3(ln_fwd_grid(rows)),
+                                 dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
+                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate));
+    }
+    return 0;
+  });
+  if (rc) return rc;
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+// LayerNorm forward that also writes the gru_rel_pos gate of the attention consuming y (replaces b200s_gate_fwd + one pass
+// over y).  D = H * 64 in {768, 1024}; x/y contiguous-row views as in b200s_layer_norm_fwd; gate: fp32 [B, H, T].
+int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                              long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                              const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                              b200s_stream stream) {
+  B200_CHECK_ARG(x && gamma && beta && y && grep_w && grep_b && grep_a && gate, "layer_norm_gate_fwd: null pointer");
+  B200_CHECK_ARG(D == H * 64 && (D == 256 || D == 512 || D == 768 || D == 1024),
+                 "layer_norm_gate_fwd: D=%d must be H*64 and one of 256/512/768/1024", D);
+  const long long rows = static_cast<long long>(T) * B;
+  if (rows == 0) return 0;
+  RowView xv{x_bs, x_rs, T}, yv{y_bs, y_rs, T};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const GateArgs ga{grep_w, grep_b, grep_a, gate, H, T};
+  int rc = dispatch_width(D, [&](auto vec, auto nch) {
+    if constexpr (decltype(vec)::value == 8) {
+      B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<8, decltype(nch)::value, true, false>, dim3(ln_fwd_grid(rows)), dim3(256), 0, st,
+                                 static_cast<const __nv_bfloat16*>(x), xv, gamma, beta, static_cast<__nv_bfloat16*>(y), yv, mean,
+                                 rstd, rows, 1e-5f, ga));
+    }
     return 0;
   });
   if (rc) return rc;

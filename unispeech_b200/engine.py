@@ -214,6 +214,31 @@ class Engine:
     def g(self, p):  # gradient view of a parameter
         return self.flat.view(p)
 
+    # ---- LayerNorm whose output feeds a gated attention: the gate (WavLM/modules.py:523-533) is computed in the same pass
+    def _uses_gate(self) -> bool:
+        return bool(getattr(self.cfg, "relative_position_embedding", False) and getattr(self.cfg, "gru_rel_pos", False))
+
+    def _ln_with_gate(self, x, ln, y, mean, rstd, T, B, D, consumer_idx):
+        """y = ln(x) and the gate of encoder.layers[consumer_idx].self_attn; remembered until that layer consumes y."""
+        a = self.m.encoder.layers[consumer_idx].self_attn
+        H = self.cfg.encoder_attention_heads
+        if D not in (256, 512, 768, 1024):  # the fused kernel needs 8 columns per lane; narrow models take two passes
+            ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, y, T * D, D, mean, rstd, T, B, D)
+            self._pending_gate = None
+            return None
+        gate = torch.empty(B, H, T, dtype=torch.float32, device=x.device)
+        ops.layer_norm_gate_fwd(x, T * D, D, ln.weight, ln.bias, y, T * D, D, mean, rstd, T, B, D, a.grep_linear.weight,
+                                a.grep_linear.bias, a.grep_a, H, gate)
+        self._pending_gate = (y.data_ptr(), consumer_idx, gate)
+        return gate
+
+    def _take_gate(self, x, idx):
+        pg = getattr(self, "_pending_gate", None)
+        self._pending_gate = None
+        if pg is not None and pg[0] == x.data_ptr() and pg[1] == idx:
+            return pg[2]
+        return None
+
     # ------------------------------------------------------------------------------------------------ conv stack
     def conv_forward(self, wav: torch.Tensor, save: bool):
         """ConvFeatureExtractionModel.forward (WavLM/WavLM.py:485-504) -> channels-last features [B, Tp, C] (valid rows T)."""
@@ -411,7 +436,10 @@ class Engine:
             mean = torch.empty(B * T, dtype=torch.float32, device=dev)
             rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
             ln = m.encoder.layer_norm
-            ops.layer_norm_fwd(xs, T * D, D, ln.weight, ln.bias, x0, T * D, D, mean, rstd, T, B, D)
+            if self._uses_gate() and len(m.encoder.layers) > 0:
+                self._ln_with_gate(xs, ln, x0, mean, rstd, T, B, D, 0)
+            else:
+                ops.layer_norm_fwd(xs, T * D, D, ln.weight, ln.bias, x0, T * D, D, mean, rstd, T, B, D)
             st.update(mean=mean, rstd=rstd)
             return x0, st
         return xs, st
@@ -459,17 +487,22 @@ class Engine:
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         pre_ln = cfg.layer_norm_first
         st = dict(x=x)
+        want_gate = tab is not None and cfg.gru_rel_pos
+        gate = self._take_gate(x, idx) if (want_gate and not pre_ln) else None
         if pre_ln:
             xn, st["mean1"], st["rstd1"] = e(B, T, D), f(M), f(M)
             ln = lyr.self_attn_layer_norm
-            ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, xn, T * D, D, st["mean1"], st["rstd1"], T, B, D)
+            if want_gate:
+                gate = self._ln_with_gate(x, ln, xn, st["mean1"], st["rstd1"], T, B, D, idx)
+                self._pending_gate = None
+            else:
+                ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, xn, T * D, D, st["mean1"], st["rstd1"], T, B, D)
             st["xn"] = xn
         else:
             xn = x
         qkv = e(B, T, 3 * D)
         ops.gemm_rows(xn, 0, D, M, 1, D, w["qkv"], 3 * D, qkv, 0, 3 * D, L.make_epilogue(bias=w["bqkv"]))
-        gate = None
-        if tab is not None and cfg.gru_rel_pos:
+        if want_gate and gate is None:  # the producer of x did not leave a gate behind (first use, layerdrop, foreign input)
             gate = f(B, H, T)
             ops.gate_fwd(xn, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, gate)
         ao, lse = e(B, T, D), f(B, H, T)
@@ -498,7 +531,10 @@ class Engine:
         else:
             out, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
             ln = lyr.final_layer_norm
-            ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
+            if want_gate and idx + 1 < len(m.encoder.layers):  # `out` is the next layer's input: leave its gate behind
+                self._ln_with_gate(y2, ln, out, st["mean2"], st["rstd2"], T, B, D, idx + 1)
+            else:
+                ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
         if save:
             st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8)
         return out, (st if save else None)

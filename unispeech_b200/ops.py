@@ -85,6 +85,12 @@ def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_p
            L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s())
 
 
+def layer_norm_gate_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate):
+    _call("b200s_layer_norm_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
+           L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(T), i32(B), i32(D), L.ptr(grep_w), L.ptr(grep_b), L.ptr(grep_a), i32(H),
+           L.ptr(gate), _s())
+
+
 def layer_norm_bwd(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
                    dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu=False):
     _call("b200s_layer_norm_bwd", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean),
