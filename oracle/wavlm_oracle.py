@@ -170,6 +170,9 @@ def parameter_shapes(cfg) -> Dict[str, Tuple[int, ...]]:
         sh[p + "final_layer_norm.bias"] = (D,)
     sh["encoder.layer_norm.weight"] = (D,)
     sh["encoder.layer_norm.bias"] = (D,)
+    if cfg.layer_norm_first and getattr(cfg, "layer_norm_for_extract", False):  # UniSpeech-SAT encoder, unispeech_sat.py:1196-1197
+        sh["encoder.layer_norm_for_extract.weight"] = (D,)
+        sh["encoder.layer_norm_for_extract.bias"] = (D,)
     return sh
 
 
@@ -346,8 +349,12 @@ def pos_conv_weight(sd) -> Tensor:
     return g * v / v.norm(2, dim=(0, 1), keepdim=True)
 
 
-def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer: Optional[int] = None):
-    """TransformerEncoder.forward + extract_features (out-of-place restatement of WavLM.py:564-612)."""
+def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, extract_layer: Optional[int] = None):
+    """TransformerEncoder.forward + extract_features (out-of-place restatement of WavLM.py:564-612).
+    Variants of the fairseq tree: `tgt_layer` may be a LIST of 1-based layer numbers (src/fairseq/models/wavlm/wavlm.py:
+    730-737: their outputs are collected, there is no pre-layer entry and no early exit); `extract_layer` (0-based) returns
+    that layer's output as a third value, passed through `encoder.layer_norm_for_extract` for pre-LN models when no target
+    layer is set (src/fairseq/models/unispeech_sat/unispeech_sat.py:1202-1255)."""
     if padding_mask is not None:
         x = x.masked_fill(padding_mask.unsqueeze(-1), 0.0)  # x[padding_mask] = 0, :574-575
     w = pos_conv_weight(sd)
@@ -360,7 +367,8 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer: Optio
         x = _ln(x, sd, "encoder.layer_norm")  # :581-582
     x = x.transpose(0, 1)  # B x T x C -> T x B x C
     layer_results = []
-    if tgt_layer is not None:
+    tgt_list = tgt_layer if isinstance(tgt_layer, (list, tuple)) else None
+    if tgt_layer is not None and tgt_list is None:
         layer_results.append(x)
     T, B, D = x.shape
     H = cfg.encoder_attention_heads
@@ -370,11 +378,17 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer: Optio
                           cfg.max_distance)
         position_bias = pb.unsqueeze(0).repeat(B, 1, 1, 1).view(B * H, T, T)  # modules.py:504-506
     r = None
+    er = None
     for i in range(cfg.encoder_layers):
         x = encoder_layer(sd, i, x, padding_mask, position_bias, cfg)
-        if tgt_layer is not None:
+        if tgt_list is not None:
+            if i + 1 in tgt_list:
+                layer_results.append(x)
+        elif tgt_layer is not None:
             layer_results.append(x)
-        if i == tgt_layer:
+        if extract_layer is not None and i == extract_layer:
+            er = x.transpose(0, 1)
+        if tgt_list is None and i == tgt_layer:
             r = x
             break
     if r is not None:
@@ -382,6 +396,10 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer: Optio
     x = x.transpose(0, 1)
     if cfg.layer_norm_first and tgt_layer is None:  # :567-568
         x = _ln(x, sd, "encoder.layer_norm")
+        if er is not None and "encoder.layer_norm_for_extract.weight" in sd:
+            er = _ln(er, sd, "encoder.layer_norm_for_extract")
+    if extract_layer is not None:
+        return x, layer_results, er
     return x, layer_results
 
 

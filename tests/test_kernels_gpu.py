@@ -309,6 +309,28 @@ def test_attn_fwd(cuda_device, B, T, H, bias, padded):
     assert err < 0.03, err
 
 
+def test_attn_fwd_rebase(cuda_device):
+    """Scores in later key tiles far above the first tile's maximum: the single-pass softmax must re-base (fast-path guard)."""
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(5)
+    B, T, H = 2, 520, 2
+    D = H * 64
+    qkv = torch.randn(B, T, 3 * D, device=dev)
+    qkv[:, 200:, D:2 * D] *= 30.0   # keys of the later tiles -> logits up to ~ +-100 nats
+    qkv[0, 300:330, D:2 * D] *= 4.0
+    qkv = bf(qkv)
+    gate = torch.rand(B, H, T, device=dev) * 2 + 0.2
+    tab = torch.randn(H, 2 * T - 1, device=dev)
+    out = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=dev)
+    ops.attn_fwd(qkv, gate, tab, None, out, lse, B, T, H, 0.125)
+    torch.cuda.synchronize()
+    ref = _attn_ref(qkv, gate, tab, None, B, T, H, 0.125)
+    assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+    assert (out.float() - ref).abs().max().item() < 0.05
+
+
 @pytest.mark.parametrize("fused", [True, False])
 @pytest.mark.parametrize("B,T,H,bias,padded", [(2, 100, 2, True, True), (1, 128, 2, True, False), (2, 333, 3, True, True),
                                                (1, 520, 4, True, False), (2, 257, 2, False, True), (1, 749, 3, True, False),

@@ -152,3 +152,31 @@ def test_state_dict_keys_match_reference_layout():
     for cfg in (O.tiny_config(pre_ln=False), O.tiny_config(pre_ln=True)):
         m = WavLM(WavLMConfig(vars(cfg)))
         assert {k: tuple(v.shape) for k, v in m.state_dict().items()} == O.parameter_shapes(cfg)
+
+
+def test_encoder_variants_fairseq_and_sat(cuda_device):
+    """Encoder-loop variants of the fairseq tree: `tgt_layer` as a list of 1-based layer numbers
+    (fairseq WavLM) and `extract_layer` + `layer_norm_for_extract` (UniSpeech-SAT encoder), against the oracle restatement."""
+    cfg = O.tiny_config(pre_ln=True, layer_norm_for_extract=True)
+    m = build(cfg, cuda_device)
+    sd = O.deterministic_state_dict(cfg)
+    assert "encoder.layer_norm_for_extract.weight" in m.state_dict()
+    wav, pmask = O.deterministic_waveform(2, 6400, seed=4, lengths=[6400, 5000])
+    ref = O.extract_features(sd, wav, cfg, padding_mask=pmask)
+    fpm = ref["padding_mask"]
+    # oracle encoder on the projected features (what encoder() receives inside extract_features)
+    xin = ref["features"]
+    n = cfg.encoder_layers
+    want_x, want_lr, want_er = O.encoder(sd, xin, fpm, cfg, tgt_layer=None, extract_layer=n - 2)
+    want_x2, want_lr2 = O.encoder(sd, xin, fpm, cfg, tgt_layer=[1, n])
+    with torch.no_grad():
+        xd = xin.to(cuda_device)
+        got_x, got_lr, got_er = m.encoder(xd, padding_mask=fpm.to(cuda_device), extract_layer=n - 2)
+        got_x2, got_lr2 = m.encoder.extract_features(xd, padding_mask=fpm.to(cuda_device), tgt_layer=[1, n])
+    cmp("x", got_x, want_x, mask=fpm)
+    cmp("extract_result", got_er, want_er, mask=fpm)
+    assert got_lr == [] and want_lr == []
+    assert len(got_lr2) == 2 == len(want_lr2)
+    for (g, _), w in zip(got_lr2, want_lr2):
+        cmp("layer_result", g.transpose(0, 1), w.transpose(0, 1), mask=fpm)
+    cmp("x2", got_x2, want_x2, mask=fpm)

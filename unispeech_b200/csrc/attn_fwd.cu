@@ -165,56 +165,81 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
       tc_fence_after();
       const bool msk = tile_flags[n] != 0;
       const uint32_t s_addr = tmem_s + lane_addr;
-      // ---- pass 1: row maximum of this tile
-      float mx = -INFINITY;
+      // The softmax is invariant to the reference value subtracted in the exponent, so after the first tile the running
+      // maximum does NOT have to be refreshed: probabilities are taken relative to the reference found so far (ONE pass over the
+      // scores instead of max-then-exp), fp32 row sums / accumulators absorb factors up to 2^64.  A warp falls back to the
+      // two-pass form while some row has no finite reference yet (first tile, or only masked keys so far) or if a score
+      // exceeds the reference by more than 64 (log2 units), which re-bases that tile.
+      bool fast = !__any_sync(0xffffffffu, m_run == -INFINITY);
+      bool folded = false;
+      float m_new, m_use, alpha_cur, lsum;
+      while (true) {
+        if (!fast) {
+          // ---- pass 1: row maximum of this tile
+          float mx = -INFINITY;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
-        uint32_t su[32];
-        tmem_ld_32x32b_x32(s_addr + c0, su);
-        tmem_ld_wait();
+          for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+            uint32_t su[32];
+            tmem_ld_32x32b_x32(s_addr + c0, su);
+            tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(su[j]) * sc;
-          if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-          if (msk) x += kbias[k0 + c0 + j];
-          mx = fmaxf(mx, x);
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(su[j]) * sc;
+              if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
+              if (msk) x += kbias[k0 + c0 + j];
+              mx = fmaxf(mx, x);
+            }
+          }
+          m_new = fmaxf(m_run, mx);
+          m_use = (m_new == -INFINITY) ? 0.f : m_new;
+          alpha_cur = fast_exp2(m_run - m_use);
+        } else {
+          m_new = m_run;
+          m_use = m_run;
+          alpha_cur = 1.0f;
         }
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float alpha_cur = fast_exp2(m_run - m_use);
-      // ---- the PV MMA of the previous tile has long finished: fold its result in (this also frees the P buffer and O tile)
-      if (n >= 1) {
-        mbar_wait(&o_full[wg], (n - 1) & 1);
-        tc_fence_after();
-        accumulate_o();
-      }
-      // ---- pass 2: probabilities, row sum, bf16 P tile into shared memory (operand layout)
-      float lsum = 0.f;
+        // ---- the PV MMA of the previous tile has long finished: fold its result in (this also frees the P buffer and O tile)
+        if (n >= 1 && !folded) {
+          mbar_wait(&o_full[wg], (n - 1) & 1);
+          tc_fence_after();
+          accumulate_o();
+          folded = true;
+        }
+        // ---- probabilities, row sum, bf16 P tile into shared memory (operand layout)
+        lsum = 0.f;
+        float over = -INFINITY;  // largest exponent argument seen (fast path guard)
+        const float neg_ref = -m_use;
 #pragma unroll 1
-      for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
-        uint32_t su[32];
-        tmem_ld_32x32b_x32(s_addr + c0, su);
-        tmem_ld_wait();
-        float pv[32];
+        for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
+          uint32_t su[32];
+          tmem_ld_32x32b_x32(s_addr + c0, su);
+          tmem_ld_wait();
+          float pv[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(su[j]) * sc;
-          if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-          if (msk) x += kbias[k0 + c0 + j];
-          const float e = fast_exp2(x - m_use);
-          pv[j] = e;
-          lsum += e;
-        }
+          for (int j = 0; j < 32; ++j) {
+            float x = fmaf(__uint_as_float(su[j]), sc, neg_ref);
+            if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
+            if (msk) x += kbias[k0 + c0 + j];
+            over = fmaxf(over, x);
+            const float e = fast_exp2(x);
+            pv[j] = e;
+            lsum += e;
+          }
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          uint4 w;
-          w.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
-          w.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
-          w.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
-          w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
-          store_sw128_chunk(sPw, r, (c0 >> 3) + g, w);
+          for (int g = 0; g < 4; ++g) {
+            uint4 w;
+            w.x = pack_bf16x2(pv[g * 8 + 0], pv[g * 8 + 1]);
+            w.y = pack_bf16x2(pv[g * 8 + 2], pv[g * 8 + 3]);
+            w.z = pack_bf16x2(pv[g * 8 + 4], pv[g * 8 + 5]);
+            w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
+            store_sw128_chunk(sPw, r, (c0 >> 3) + g, w);
+          }
         }
+        if (fast && __any_sync(0xffffffffu, over > 64.0f)) {
+          fast = false;  // re-base this tile on its own maximum (the P tile is simply rewritten)
+          continue;
+        }
+        break;
       }
       l_run = l_run * alpha_cur + lsum;
       m_run = m_new;

@@ -93,9 +93,15 @@ static int make_tmap(CUtensorMap* out, const ViewSpec& v) {
     set_last_error("tensor map base pointer %p is not 16-byte aligned", v.ptr);
     return -1;
   }
+  static int promo = -1;  // L2 promotion of the TMA loads: 256 B by default, B200S_TMAP_L2PROMO=0..3 (none/64/128/256) for A/B runs
+  if (promo < 0) {
+    const char* e = getenv("B200S_TMAP_L2PROMO");
+    promo = (e && e[0] >= '0' && e[0] <= '3') ? (e[0] - '0') : 3;
+  }
+  static const CUtensorMapL2promotion kPromo[4] = {CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                                                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(v.ptr), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, kPromo[promo], CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_last_error("cuTensorMapEncodeTiled failed (%d): dims {%lld,%lld,%lld,%lld} strides {%lld,%lld,%lld} box {%d,%d,%d,%d}",
                    static_cast<int>(r), v.dims[0], v.dims[1], v.dims[2], v.dims[3], v.strides[0], v.strides[1],

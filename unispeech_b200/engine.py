@@ -112,6 +112,7 @@ class Engine:
         self.prepared_version = None
         self.lut_cache: Dict[int, torch.Tensor] = {}
         self.flat: Optional[FlatGrads] = None
+        self._params = None
 
     # ------------------------------------------------------------------------------------------------ setup
     def _ensure_device(self, device):
@@ -179,7 +180,9 @@ class Engine:
         self.flat = FlatGrads(groups, device)
 
     def _param_version(self):
-        return tuple(p._version for p in self.m.parameters())
+        if self._params is None:  # Module.parameters() walks the whole module tree: cache the list (the set never changes)
+            self._params = list(self.m.parameters())
+        return tuple(p._version for p in self._params)
 
     def prepare(self, force=False):
         """fp32 masters -> bf16 GEMM operands (transposes, tap-major conv layouts, weight-normed pos_conv, fused qkv)."""

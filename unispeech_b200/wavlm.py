@@ -344,6 +344,9 @@ class TransformerEncoder(nn.Module):
         ])
         self.layer_norm_first = cfg.layer_norm_first
         self.layer_norm = nn.LayerNorm(D)
+        if self.layer_norm_first and getattr(cfg, "layer_norm_for_extract", False):
+            # UniSpeech-SAT encoder (src/fairseq/models/unispeech_sat/unispeech_sat.py:1196-1197): same state_dict key
+            self.layer_norm_for_extract = nn.LayerNorm(D)
         self.layerdrop = cfg.encoder_layerdrop
         self._owner = None
         for mod in self.modules():  # init_bert_params (WavLM/modules.py:168-200)
@@ -368,16 +371,28 @@ class TransformerEncoder(nn.Module):
         dtab = torch.zeros(H, 2 * T - 1, dtype=torch.float32, device=device) if torch.is_grad_enabled() else None
         return dict(tab=tab, dtab=dtab, lut=lut, has_first=False)
 
-    def forward(self, x, padding_mask=None, streaming_mask=None, layer=None):
-        x, layer_results = self.extract_features(x, padding_mask, streaming_mask, layer)
+    def forward(self, x, padding_mask=None, streaming_mask=None, layer=None, extract_layer=None):
+        """Returns (x, layer_results) like the reference WavLM encoder; with `extract_layer` (UniSpeech-SAT encoder,
+        unispeech_sat.py:1202-1210) a third value: that layer's output, normalised by `layer_norm_for_extract` for pre-LN models."""
+        res = self.extract_features(x, padding_mask, streaming_mask, layer, extract_layer=extract_layer)
+        x, layer_results = res[0], res[1]
+        er = res[2] if extract_layer is not None else None
         if self.layer_norm_first and layer is None:
             model = self._owner[0]
             xb = x if x.dtype == BF and x.is_contiguous() else x.to(BF).contiguous()
             x = _LNFn.apply(xb, model._engine_for(x.device), self.layer_norm)
+            if er is not None and hasattr(self, "layer_norm_for_extract"):
+                eb = er if er.dtype == BF and er.is_contiguous() else er.to(BF).contiguous()
+                er = _LNFn.apply(eb, model._engine_for(x.device), self.layer_norm_for_extract)
+        if extract_layer is not None:
+            return x, layer_results, er
         return x, layer_results
 
-    def extract_features(self, x, padding_mask=None, streaming_mask=None, tgt_layer=None):
-        """x: [B,T,D] (projected, masked features).  Out-of-place restatement of WavLM/WavLM.py:572-612."""
+    def extract_features(self, x, padding_mask=None, streaming_mask=None, tgt_layer=None, extract_layer=None):
+        """x: [B,T,D] (projected, masked features).  Out-of-place restatement of WavLM/WavLM.py:572-612.  `tgt_layer` may
+        also be a list of 1-based layer numbers (fairseq WavLM, src/fairseq/models/wavlm/wavlm.py:730-737: those layers' outputs
+        are collected without early exit); `extract_layer` (0-based) adds that layer's output as a third return value
+        (UniSpeech-SAT encoder, unispeech_sat.py:1236-1255)."""
         assert streaming_mask is None, "streaming masks are not supported"
         model = self._owner[0]
         eng = model._engine_for(x.device)
@@ -397,22 +412,31 @@ class TransformerEncoder(nn.Module):
         x0 = _StemFn.apply(x, self.pos_conv[0].bias, eng, xpad, T)
         x = x0.transpose(0, 1)  # B x T x C -> T x B x C (view)
         layer_results = []
-        if tgt_layer is not None:
+        tgt_list = tgt_layer if isinstance(tgt_layer, (list, tuple)) else None
+        if tgt_layer is not None and tgt_list is None:
             layer_results.append((x, None))
         r = None
+        er = None
         pos_bias = self._make_bias_state(T, x.device) if self.relative_position_embedding else None
         pad_u8 = padding_mask.to(torch.uint8).contiguous() if padding_mask is not None else None
         for i, layer in enumerate(self.layers):
             dropout_probability = np.random.random()
             if not self.training or (dropout_probability > self.layerdrop):
                 x, _z, pos_bias = layer(x, self_attn_padding_mask=pad_u8, need_weights=False, pos_bias=pos_bias)
-            if tgt_layer is not None:
+            if tgt_list is not None:
+                if i + 1 in tgt_list:
+                    layer_results.append((x, None))
+            elif tgt_layer is not None:
                 layer_results.append((x, None))
-            if i == tgt_layer:
+            if extract_layer is not None and i == extract_layer:
+                er = x.transpose(0, 1)
+            if tgt_list is None and i == tgt_layer:
                 r = x
                 break
         if r is not None:
             x = r
+        if extract_layer is not None:
+            return x.transpose(0, 1), layer_results, er
         return x.transpose(0, 1), layer_results
 
 
@@ -462,12 +486,14 @@ class WavLM(nn.Module):
                 raise NotImplementedError(
                     "training-mode dropout is not implemented in the fused kernels yet; set " + ", ".join(active) +
                     " to 0 (or call model.eval())")
-        for p in self.parameters():
+        eng = self._engine_for(device)
+        if eng._params is None:  # Module.parameters() walks the module tree (~2 ms for WavLM-Base): once per engine
+            eng._params = list(self.parameters())
+        for p in eng._params:
             if p.device != device or p.dtype != torch.float32:
                 raise RuntimeError("model parameters must be fp32 masters on the input's CUDA device (call model.float().cuda())")
-        eng = self._engine_for(device)
         eng.prepare()
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        if torch.is_grad_enabled() and any(p.requires_grad for p in eng._params):
             eng.flat.attach()
         return eng
 
