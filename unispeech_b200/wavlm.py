@@ -401,8 +401,10 @@ class TransformerEncoder(nn.Module):
         half = cfg.conv_pos // 2
         xpad = getattr(x, "_b200_xpad", None)
         if xpad is None:
-            # external caller (not extract_features): stage into the zero-padded pos_conv buffer and zero padded frames
+            # external caller (not extract_features): make sure the bf16 operands exist for the current parameters, then stage
+            # into the zero-padded pos_conv buffer and zero padded frames
             from . import ops
+            eng = model._begin(x.device)
             xpad = torch.zeros(B, T + cfg.conv_pos, D, dtype=BF, device=x.device)
             xpad[:, half:half + T] = x.to(BF)
             if padding_mask is not None:
