@@ -105,13 +105,13 @@ def cpu_step(cfg, B, secs, steps, threads):
 
 def best_cpu_threads(cfg):
     """The oracle's intra-op thread count that is fastest on this host (oversubscribing a 128-thread box is 80x slower than
-    16 threads): a 2 s utterance fwd+bwd is timed for a few candidates and the best one is used for the baseline."""
+    16 threads): two 5 s utterances fwd+bwd are timed for a few candidates and the best one is used for the baseline."""
     from oracle import wavlm_oracle as O
     ncpu = os.cpu_count() or 1
     cands = sorted({c for c in (8, 16, 32, 64) if c <= ncpu} | ({ncpu} if ncpu <= 64 else set()))
     sd = {k: v.clone().requires_grad_(True) for k, v in O.deterministic_state_dict(cfg).items()}
-    wav, _ = O.deterministic_waveform(1, 2 * SR, seed=5)
-    pm = torch.zeros(1, 2 * SR, dtype=torch.bool)
+    wav, _ = O.deterministic_waveform(2, 5 * SR, seed=5)
+    pm = torch.zeros(2, 5 * SR, dtype=torch.bool)
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)

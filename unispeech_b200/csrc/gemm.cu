@@ -467,8 +467,6 @@ int b200s_posconv_gemm(const void* xpad, long long xpad_bs, int T, int B, int D,
   if (check_epilogue(epi)) return -1;
 
   CUtensorMap ta, tb;
-  ViewSpec va{xpad, {D, taps, T, B}, {D, D, xpad_bs}, {64, 1, 128, 1}};
-  if (make_tmap(&ta, va)) return -3;
   ViewSpec vb{wp, {taps * 64LL, G * 64LL, 1, 1}, {taps * 64LL, 0, 0}, {64, 64, 1, 1}};
   if (make_tmap(&tb, vb)) return -3;
 
@@ -484,14 +482,36 @@ int b200s_posconv_gemm(const void* xpad, long long xpad_bs, int T, int B, int D,
   p.k_blocks = taps;
   p.k_blocks_per_batch = 0;
   p.k_blocks_per_split = taps;
-  // A coords: (g*Cg, kb, m0, mb)   B coords: (kb*64, g*64, 0, 0)
-  p.ca[0][3] = Cg; p.ca[1][6] = 1; p.ca[2][1] = 1; p.ca[3][2] = 1;
-  p.cb[0][4] = 1; p.cb[1][3] = 64;
   p.flags = 0;
   fill_epilogue(p, epi);
   p.out = {out, out_bs, out_ld};
   dim3 grid(G, p.m_tiles_per_batch * B, 1);
-  return launch_gemm<64, false, false>(ta, tb, p, grid, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+
+  if (taps <= 129 && !(p.debug & 16)) {
+    // windowed kernel: the A operand (256 input rows of this group's channels) is loaded once per tile, every tap reads it
+    // shifted by one row; rows past T + taps - 1 (end of this utterance's zero padding) are zero-filled by the tensor map
+    ViewSpec vw{xpad, {D, T + taps - 1, B, 1}, {D, B > 1 ? xpad_bs : 0, 0}, {64, 256, 1, 1}};
+    if (make_tmap(&ta, vw)) return -3;
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+      attr_err = cudaFuncSetAttribute(posconv_window_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      PosconvCfg::kSmemBytes);
+    });
+    B200_CHECK_CUDA(attr_err);
+    B200_CHECK_CUDA(launch_pdl(posconv_window_kernel, grid, dim3(PosconvCfg::kThreads), PosconvCfg::kSmemBytes, st, ta, tb, p,
+                               taps, Cg));
+    B200_CHECK_LAUNCH();
+    return 0;
+  }
+  // box-per-tap formulation (any tap count)
+  ViewSpec va{xpad, {D, taps, T, B}, {D, D, xpad_bs}, {64, 1, 128, 1}};
+  if (make_tmap(&ta, va)) return -3;
+  // A coords: (g*Cg, kb, m0, mb)   B coords: (kb*64, g*64, 0, 0)
+  p.ca[0][3] = Cg; p.ca[1][6] = 1; p.ca[2][1] = 1; p.ca[3][2] = 1;
+  p.cb[0][4] = 1; p.cb[1][3] = 64;
+  return launch_gemm<64, false, false>(ta, tb, p, grid, st);
 }
 
 int b200s_posconv_wgrad(const void* dy, long long dy_bs, long long dy_rs, const void* xpad, long long xpad_bs, int T,

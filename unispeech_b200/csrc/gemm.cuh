@@ -342,4 +342,111 @@ __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ 
   }
 }
 
+// ---------------------------------------------------------------------------------------------- pos_conv, windowed
+// Grouped Conv1d(k = taps, padding = taps/2) as an implicit GEMM whose A operand is loaded ONCE per tile: the 128 frames of a
+// tile need input rows m0 .. m0+127+taps-1 of the zero-padded activation, and tap j multiplies rows m0+j .. m0+j+127 -- the same
+// shared-memory tile, shifted by j rows.  One 256-row TMA box brings the window in; every tap is four tcgen05.mma whose A
+// descriptor starts j rows (j * 128 bytes) into the tile, with the descriptor's base offset telling the tensor core where in
+// the 8-row swizzle period that start lies.  Only the per-tap weight tile (8 KB) streams through the TMA ring, so the kernel
+// reads ~1/3 of the bytes of the box-per-tap formulation (which was bound by the L2 -> SM fabric).
+// grid (groups, m_tiles * batches); block 192 (TMA warp, MMA warp, 4 epilogue warps); fused tail = epilogue_chunk32.
+struct PosconvCfg {
+  static constexpr int kStages = 6;
+  static constexpr int kABytes = 256 * 128;  // 256 rows x 64 bf16
+  static constexpr int kBBytes = 64 * 128;   // 64 output channels x 64 input channels of one tap
+  static constexpr int kSmemBytes = kABytes + kStages * kBBytes + 1024;
+  static constexpr int kThreads = 192;
+};
+
+__global__ void __launch_bounds__(192) posconv_window_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                             const __grid_constant__ CUtensorMap tmB,
+                                                             const __grid_constant__ GemmParams p, int taps, int cg) {
+  pdl_launch_dependents();
+  using Cfg = PosconvCfg;
+  constexpr int kStages = Cfg::kStages;
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int g = blockIdx.x;
+  const int mb = blockIdx.y / p.m_tiles_per_batch;
+  const int m0 = (blockIdx.y % p.m_tiles_per_batch) * 128;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + Cfg::kABytes;
+  __shared__ uint64_t a_full, full_bar[kStages], empty_bar[kStages], tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    mbar_init(&a_full, 1);
+#pragma unroll
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(&tmem_full_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc(&tmem_base_smem, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&a_full, Cfg::kABytes);
+      tma_load_4d(sA, &tmA, &a_full, g * cg, m0, mb, 0);  // rows m0 .. m0+255 of this group's channels (zero-filled past the end)
+      for (int j = 0; j < taps; ++j) {
+        const int s = j % kStages;
+        mbar_wait(&empty_bar[s], ((j / kStages) & 1) ^ 1);
+        mbar_expect_tx(&full_bar[s], Cfg::kBBytes);
+        tma_load_4d(sB + s * Cfg::kBBytes, &tmB, &full_bar[s], j * 64, g * 64, 0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+      mbar_wait(&a_full, 0);
+      for (int j = 0; j < taps; ++j) {
+        const int s = j % kStages;
+        mbar_wait(&full_bar[s], (j / kStages) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(sA) + j * 128;  // the window shifted by j rows
+        const uint32_t sb = smem_u32(sB + s * Cfg::kBBytes);
+        const uint32_t bo = (p.debug & 8) ? 0u : static_cast<uint32_t>(j & 7);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem_base, make_smem_desc_sw128_bo(sa + k * 32, 16, 1024, bo), make_smem_desc_sw128(sb + k * 32, 16, 1024),
+                    idesc, (j > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int m_valid = min(128, p.m_rows - m0);
+    const bool row_ok = r < m_valid;
+    const int col_base = g * cg;
+    const EpiRow erow = make_epi_row(p, mb, static_cast<long long>(m0) + r);
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      if (c0 >= cg) break;
+      epilogue_chunk32(p, erow, tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c0, c0, cg, col_base, row_ok, lane);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    __syncwarp();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
 }  // namespace b200

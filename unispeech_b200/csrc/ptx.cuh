@@ -132,6 +132,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uin
   d |= static_cast<uint64_t>(2) << 61;
   return d;
 }
+// Same with the 3-bit base offset (bits [49,52)): needed when the matrix does not start on the 1024-byte repeat of the 128-byte
+// swizzle, e.g. a K-major tile read from row j of a larger TMA-written tile: base_offset = (start_address >> 7) & 7.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128_bo(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                            uint32_t base_offset) {
+  return make_smem_desc_sw128(smem_addr, lbo_bytes, sbo_bytes) | (static_cast<uint64_t>(base_offset & 7u) << 49);
+}
 // Instruction descriptor for kind::f16 with bf16 A/B, fp32 accumulate.
 //   c_format [4,6)=1 (F32); a_format [7,10)=1 (BF16); b_format [10,13)=1; a_major bit15; b_major bit16 (1 = MN-major);
 //   n_dim [17,23) = N>>3; m_dim [24,29) = M>>4.
