@@ -346,8 +346,7 @@ __global__ void __launch_bounds__(192) gemm_bf16_kernel(const __grid_constant__ 
 // Grouped Conv1d(k = taps, padding = taps/2) as an implicit GEMM whose A operand is loaded ONCE per tile: the 128 frames of a
 // tile need input rows m0 .. m0+127+taps-1 of the zero-padded activation, and tap j multiplies rows m0+j .. m0+j+127 -- the same
 // shared-memory tile, shifted by j rows.  One 256-row TMA box brings the window in; every tap is four tcgen05.mma whose A
-// descriptor starts j rows (j * 128 bytes) into the tile, with the descriptor's base offset telling the tensor core where in
-// the 8-row swizzle period that start lies.  Only the per-tap weight tile (8 KB) streams through the TMA ring, so the kernel
+// descriptor starts j rows (j * 128 bytes) into the tile (the swizzle follows the absolute address, see the MMA loop).  Only the per-tap weight tile (8 KB) streams through the TMA ring, so the kernel
 // reads ~1/3 of the bytes of the box-per-tap formulation (which was bound by the L2 -> SM fabric).
 // grid (groups, m_tiles * batches); block 192 (TMA warp, MMA warp, 4 epilogue warps); fused tail = epilogue_chunk32.
 struct PosconvCfg {
@@ -417,7 +416,10 @@ __global__ void __launch_bounds__(192) posconv_window_kernel(const __grid_consta
         tc_fence_after();
         const uint32_t sa = smem_u32(sA) + j * 128;  // the window shifted by j rows
         const uint32_t sb = smem_u32(sB + s * Cfg::kBBytes);
-        const uint32_t bo = (p.debug & 8) ? 0u : static_cast<uint32_t>(j & 7);
+        // base offset 0: measured on B200, the tensor core applies the 128-byte swizzle to the ABSOLUTE shared-memory address
+        // bits (as TMA does when it writes the tile), so a row-shifted start needs no correction (B200S_GEMM_DEBUG=8 sets the
+        // "(start >> 7) & 7" value the descriptor format documents for unaligned starts: it produces wrong results here)
+        const uint32_t bo = (p.debug & 8) ? static_cast<uint32_t>(j & 7) : 0u;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tmem_base, make_smem_desc_sw128_bo(sa + k * 32, 16, 1024, bo), make_smem_desc_sw128(sb + k * 32, 16, 1024),

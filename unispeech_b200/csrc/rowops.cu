@@ -171,33 +171,57 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __r
 // dz = dy * gelu'(gamma*xhat+beta) if gelu else dy;  dxhat = dz*gamma
 // dx = rstd * (dxhat - mean(dxhat) - xhat*mean(dxhat*xhat)) [+ dres];  dgamma += sum_rows dz*xhat; dbeta += sum_rows dz
 // optional colsum += sum_rows dx (as stored, bf16-rounded) -- the bias gradient of the producer of x.
+// dst[0..V) += v[0..V) on a lane-private shared-memory slice, with 16-byte accesses where possible (conflict-free: consecutive
+// lanes own consecutive V-float segments)
+template <int V>
+__device__ __forceinline__ void smem_add_vec(float* dst, const float* v) {
+  if constexpr (V % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+      float4 t = *reinterpret_cast<float4*>(dst + 4 * q);
+      t.x += v[4 * q]; t.y += v[4 * q + 1]; t.z += v[4 * q + 2]; t.w += v[4 * q + 3];
+      *reinterpret_cast<float4*>(dst + 4 * q) = t;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) dst[q] += v[q];
+  }
+}
+
 template <int VEC, int NCH>
-__global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
-                                                     const __nv_bfloat16* __restrict__ x, RowView xv,
-                                                     const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
-                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                     const __nv_bfloat16* __restrict__ dres, RowView dresv,
-                                                     __nv_bfloat16* __restrict__ dx, RowView dxv,
-                                                     float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                     float* __restrict__ colsum, long long rows, int gelu) {
+__global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
+                                                        const __nv_bfloat16* __restrict__ x, RowView xv,
+                                                        const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        const __nv_bfloat16* __restrict__ dres, RowView dresv,
+                                                        __nv_bfloat16* __restrict__ dx, RowView dxv,
+                                                        float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                        float* __restrict__ colsum, long long rows, int gelu) {
   pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
   constexpr int N = NCH * VEC;
-  __shared__ float red[8][D];
+  // The per-warp column partials (d gamma, d beta, column sums of dx) live in SHARED memory, not in 3*N registers per lane:
+  // the kernel is latency-bound (a row is loads -> two shuffle reductions -> store), and at 226 registers only one block
+  // (8 warps) fitted an SM.  Layout: acc[q][warp][D] fp32, then gamma[D], beta[D].
+  extern __shared__ __align__(16) float ln_smem[];
+  float* acc = ln_smem;
+  float* gs = ln_smem + 3 * 8 * D;
+  float* bs = gs + D;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  for (int c = threadIdx.x; c < 3 * 8 * D; c += blockDim.x) acc[c] = 0.f;
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    gs[c] = gamma[c];
+    bs[c] = gelu ? beta[c] : 0.f;
+  }
+  __syncthreads();
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float g[N], b[N], ag[N], ab[N], ac[N];
-#pragma unroll
-  for (int i = 0; i < NCH; ++i)
-#pragma unroll
-    for (int j = 0; j < VEC; ++j) {
-      g[i * VEC + j] = gamma[(i * 32 + lane) * VEC + j];
-      b[i * VEC + j] = gelu ? beta[(i * 32 + lane) * VEC + j] : 0.f;
-    }
-#pragma unroll
-  for (int i = 0; i < N; ++i) ag[i] = ab[i] = ac[i] = 0.f;
+  float* my_g = acc + (0 * 8 + warp) * D;
+  float* my_b = acc + (1 * 8 + warp) * D;
+  float* my_c = acc + (2 * 8 + warp) * D;
+  const bool want_gb = dgamma != nullptr || dbeta != nullptr;
+  const bool want_c = colsum != nullptr;
 
   for (long long r = warp_global; r < rows; r += nwarps) {
     float xh[N], dz[N];
@@ -211,56 +235,67 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(const __nv_bfloat16* __rest
     const float mean = mean_in[r], rstd = rstd_in[r];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      xh[i] = (xh[i] - mean) * rstd;
-      if (gelu) dz[i] *= gelu_grad_f(g[i] * xh[i] + b[i]);
-      ag[i] += dz[i] * xh[i];
-      ab[i] += dz[i];
-      const float dxh = dz[i] * g[i];
-      dz[i] = dxh;
-      s1 += dxh;
-      s2 += dxh * xh[i];
+    for (int ch = 0; ch < NCH; ++ch) {
+      const int c0 = (ch * 32 + lane) * VEC;
+      float pg[VEC], pb[VEC];
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        const int i = ch * VEC + j;
+        xh[i] = (xh[i] - mean) * rstd;
+        const float gi = gs[c0 + j];
+        if (gelu) dz[i] *= gelu_grad_f(gi * xh[i] + bs[c0 + j]);
+        pg[j] = dz[i] * xh[i];
+        pb[j] = dz[i];
+        const float dxh = dz[i] * gi;
+        dz[i] = dxh;
+        s1 += dxh;
+        s2 += dxh * xh[i];
+      }
+      if (want_gb) smem_add_vec<VEC>(my_g + c0, pg), smem_add_vec<VEC>(my_b + c0, pb);
     }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
-    float o[N];
     if (dres != nullptr) {
       const __nv_bfloat16* rr = dres + dresv.off(r);
+      float o[VEC];
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) VecIO<VEC>::load(rr + (i * 32 + lane) * VEC, o + i * VEC);
+      for (int i = 0; i < NCH; ++i) {
+        VecIO<VEC>::load(rr + (i * 32 + lane) * VEC, o);
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) dz[i * VEC + j] = o[j] + rstd * (dz[i * VEC + j] - s1 - xh[i * VEC + j] * s2);
+      }
     } else {
 #pragma unroll
-      for (int i = 0; i < N; ++i) o[i] = 0.f;
+      for (int i = 0; i < N; ++i) dz[i] = rstd * (dz[i] - s1 - xh[i] * s2);
     }
+    if (want_c) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      o[i] += rstd * (dz[i] - s1 - xh[i] * s2);
-      ac[i] += __bfloat162float(__float2bfloat16_rn(o[i]));
+      for (int ch = 0; ch < NCH; ++ch) {
+        float pc[VEC];
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) pc[j] = __bfloat162float(__float2bfloat16_rn(dz[ch * VEC + j]));
+        smem_add_vec<VEC>(my_c + (ch * 32 + lane) * VEC, pc);
+      }
     }
     __nv_bfloat16* outr = dx + dxv.off(r);
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(outr + (i * 32 + lane) * VEC, o + i * VEC);
+    for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(outr + (i * 32 + lane) * VEC, dz + i * VEC);
   }
 
-  // block reduction of the per-warp column partials, one quantity at a time through shared memory
+  // block reduction of the per-warp column partials
+  __syncthreads();
   const int nw = blockDim.x >> 5;
-  auto reduce_to = [&](const float* acc, float* dst) {
-    if (dst == nullptr) return;  // uniform across the block
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NCH; ++i)
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) red[warp][(i * 32 + lane) * VEC + j] = acc[i * VEC + j];
-    __syncthreads();
-    for (int c = threadIdx.x; c < D; c += blockDim.x) {
-      float s = 0.f;
-      for (int w = 0; w < nw; ++w) s += red[w][c];
-      atomicAdd(dst + c, s);
+  for (int c = threadIdx.x; c < D; c += blockDim.x) {
+    float sg = 0.f, sb = 0.f, sc = 0.f;
+    for (int w = 0; w < nw; ++w) {
+      sg += acc[(0 * 8 + w) * D + c];
+      sb += acc[(1 * 8 + w) * D + c];
+      sc += acc[(2 * 8 + w) * D + c];
     }
-  };
-  reduce_to(ag, dgamma);
-  reduce_to(ab, dbeta);
-  reduce_to(ac, colsum);
+    if (dgamma != nullptr) atomicAdd(dgamma + c, sg);
+    if (dbeta != nullptr) atomicAdd(dbeta + c, sb);
+    if (colsum != nullptr) atomicAdd(colsum + c, sc);
+  }
 }
 
 template <typename F>
@@ -648,11 +683,14 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   const long long cap = static_cast<long long>(sm_count()) * 2;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
+  const size_t smem = sizeof(float) * static_cast<size_t>(3 * 8 + 2) * D;  // column partials per warp + gamma + beta
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
-    B200_CHECK_CUDA(launch_pdl(ln_bwd_kernel<decltype(vec)::value, decltype(nch)::value>, dim3(static_cast<int>(blocks)), dim3(256), 0, st, 
-        static_cast<const __nv_bfloat16*>(dy), dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
-        static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv, dgamma, dbeta, colsum, rows,
-        gelu));
+    auto kern = ln_bwd_kernel<decltype(vec)::value, decltype(nch)::value>;
+    B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    B200_CHECK_CUDA(launch_pdl(kern, dim3(static_cast<int>(blocks)), dim3(256), smem, st,
+                               static_cast<const __nv_bfloat16*>(dy), dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd,
+                               gamma, beta, static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv,
+                               dgamma, dbeta, colsum, rows, gelu));
     return 0;
   });
   if (rc) return rc;
