@@ -34,8 +34,9 @@ int b200s_check_device(void);
 long long b200s_launch_count(void);
 
 /* ---- fused GEMM epilogue description (all tensors optional) ------------------------------------------------
- * value = acc (+ bias[col]);  if gelu: out_pre <- value (optional), value = gelu_erf(value)
- *         if dgelu: value *= gelu'(gelu_aux[row,col]);  value += res1 + res2;  out <- value
+ * value = acc (+ bias[col]);  if gelu: out_pre <- value (gelu = 1) or gelu'(value) (gelu = 2) (optional), value = gelu_erf(value)
+ *         if dgelu: value *= gelu'(gelu_aux[row,col]) (dgelu = 1) or gelu_aux[row,col] (dgelu = 2, aux written by a gelu = 2
+ *         forward: the backward epilogue is then a plain multiply);  value += res1 + res2;  out <- value
  * colsum (fp32[N], +=) accumulates column sums of the stored values (bias gradients). */
 typedef struct {
   const float* bias;
@@ -136,6 +137,10 @@ int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_bat
 int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs,
                     long long pre_rs, void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches,
                     int N, float* colsum, b200s_stream stream);
+/* Same; pre_is_grad != 0: `pre` already holds gelu'(pre-activation) (written by a gelu = 2 epilogue), out = dy * pre. */
+int b200s_dgelu_mul_ex(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs,
+                       long long pre_rs, void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches,
+                       int N, float* colsum, int pre_is_grad, b200s_stream stream);
 
 /* x[b,t,:] = mask_emb where mask[b,t]; = 0 where pad[b,t]   (apply_mask WavLM/WavLM.py:285-286; x[padding_mask]=0 :574-575) */
 int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,

@@ -125,3 +125,40 @@ def test_pair_gemm_cluster4_multicast(cuda_device, monkeypatch):
     assert (out2.float() - (a[:M2].float() @ w.float().t() + bias)).abs().max().item() < 0.06
     refw = y.float().t() @ x.float()
     assert (dw - refw).abs().max().item() < 1e-2 * max(1.0, refw.abs().max().item())
+
+
+@pytest.mark.parametrize("M,K,N", [(3000, 768, 768), (300, 256, 192)])  # pair kernel / single-CTA kernel
+def test_gelu_derivative_modes(cuda_device, M, K, N):
+    """gelu = 2: the forward epilogue stores gelu'(pre-activation); dgelu = 2: the backward epilogue multiplies by it."""
+    from unispeech_b200 import _lib as L
+    from unispeech_b200 import ops
+    torch.manual_seed(M + 1)
+    dev = cuda_device
+    a = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) / K ** 0.5)
+    bias = torch.randn(N, device=dev)
+    out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    grad = torch.empty_like(out)
+    ops.gemm_rows(a, 0, K, M, 1, K, w, N, out, 0, N, L.make_epilogue(bias=bias, gelu=2, out_pre=grad, pre_ld=N))
+    torch.cuda.synchronize()
+    acc = (a.float() @ w.float().t() + bias).requires_grad_(True)
+    y = F.gelu(acc)
+    g_ref = torch.autograd.grad(y.sum(), acc)[0]
+    assert (out.float() - y.detach()).abs().max().item() < 0.05
+    assert (grad.float() - g_ref).abs().max().item() < 0.02
+    # backward-style GEMM: acc2 * stored derivative + residual, column sums
+    r1 = bf(torch.randn(M, N, device=dev))
+    out2 = torch.empty_like(out)
+    colsum = torch.zeros(N, device=dev)
+    ops.gemm_rows(a, 0, K, M, 1, K, w, N, out2, 0, N,
+                  L.make_epilogue(dgelu=2, gelu_aux=grad, aux_ld=N, res1=r1, res1_ld=N, colsum=colsum))
+    torch.cuda.synchronize()
+    ref2 = (a.float() @ w.float().t()) * grad.float() + r1.float()
+    assert (out2.float() - ref2).abs().max().item() < 0.08
+    assert (colsum - out2.float().sum(0)).abs().max().item() < 0.02 * max(1.0, out2.float().sum(0).abs().max().item())
+    # elementwise kernel with a stored derivative
+    dy = bf(torch.randn(M, N, device=dev))
+    o3 = torch.empty_like(out)
+    ops.dgelu_mul(dy, 0, N, grad, 0, N, o3, 0, N, M, 1, N, None, pre_is_grad=True)
+    torch.cuda.synchronize()
+    assert (o3.float() - dy.float() * grad.float()).abs().max().item() < 0.02

@@ -98,6 +98,6 @@ def make_epilogue(bias=None, res1=None, res1_bs=0, res1_ld=0, res2=None, res2_bs
     e.out_pre = out_pre.data_ptr() if out_pre is not None else None
     e.pre_bs, e.pre_ld = int(pre_bs), int(pre_ld)
     e.colsum = colsum.data_ptr() if colsum is not None else None
-    e.gelu = 1 if gelu else 0
-    e.dgelu = 1 if dgelu else 0
+    e.gelu = int(gelu)    # 1: out_pre <- pre-activation, 2: out_pre <- gelu'(pre-activation)
+    e.dgelu = int(dgelu)  # 1: aux is the pre-activation, 2: aux already is gelu'(.)
     return e

@@ -260,10 +260,12 @@ static void fill_epilogue(GemmParams& p, const b200s_epilogue* e) {
   if (e->colsum) p.flags |= EPI_COLSUM;
   if (e->gelu) {
     p.flags |= EPI_GELU;
+    if (e->gelu == 2) p.flags |= EPI_GELU_STORE_GRAD;
     p.out2 = {e->out_pre, e->pre_bs, e->pre_ld};
   }
   if (e->dgelu) {
     p.flags |= EPI_DGELU;
+    if (e->dgelu == 2) p.flags |= EPI_AUX_IS_GRAD;
     p.aux = {const_cast<void*>(e->gelu_aux), e->aux_bs, e->aux_ld};
   }
   p.res1 = {const_cast<void*>(e->res1), e->res1_bs, e->res1_ld};

@@ -27,6 +27,8 @@ enum : int {
   EPI_ATOMIC = 8,    // fp32 atomicAdd into out (split-K / accumulation)
   EPI_COLSUM = 16,   // atomically accumulate column sums of the final value into colsum[col] (bias grads)
   EPI_ACCUM = 32,    // fp32 out += value, non-atomic (single writer per element: split-K disabled)
+  EPI_GELU_STORE_GRAD = 64,  // with EPI_GELU: out2 receives gelu'(acc + bias) instead of the pre-activation
+  EPI_AUX_IS_GRAD = 128,     // with EPI_DGELU: aux already holds gelu'(.) (written by an EPI_GELU_STORE_GRAD forward): acc *= aux
 };
 
 // variables the coordinate matrices multiply: {1, m0, mb, n_tile, k0, kbatch, kb, sub}
@@ -143,9 +145,16 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const EpiR
       const int col = col0 + g * 8;
       float* a8 = acc + g * 8;
       if (flags & EPI_GELU) {
-        if (e.out2 != nullptr) *reinterpret_cast<uint4*>(e.out2 + col) = pack_bf16x8(a8);
+        if (flags & EPI_GELU_STORE_GRAD) {
+          float g8[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a8[j] = gelu_f(a8[j]);
+          for (int j = 0; j < 8; ++j) a8[j] = gelu_with_grad_f(a8[j], g8[j]);
+          if (e.out2 != nullptr) *reinterpret_cast<uint4*>(e.out2 + col) = pack_bf16x8(g8);
+        } else {
+          if (e.out2 != nullptr) *reinterpret_cast<uint4*>(e.out2 + col) = pack_bf16x8(a8);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a8[j] = gelu_f(a8[j]);
+        }
       }
       if (flags & EPI_DGELU) {
         const uint4 w = *reinterpret_cast<const uint4*>(e.aux + col);
@@ -153,8 +162,8 @@ __device__ __forceinline__ void epilogue_chunk32(const GemmParams& p, const EpiR
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 f = unpack_bf16x2(wu[j]);
-          a8[2 * j] *= gelu_grad_f(f.x);
-          a8[2 * j + 1] *= gelu_grad_f(f.y);
+          a8[2 * j] *= (flags & EPI_AUX_IS_GRAD) ? f.x : gelu_grad_f(f.x);
+          a8[2 * j + 1] *= (flags & EPI_AUX_IS_GRAD) ? f.y : gelu_grad_f(f.y);
         }
       }
       if (e.res1 != nullptr) add_bf16x8(a8, e.res1 + col);

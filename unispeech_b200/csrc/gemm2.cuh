@@ -105,9 +105,10 @@ __device__ __noinline__ void flush_bf16(const EpiTensor t, const EpiTile et, int
   }
 }
 
-// This lane's row of a staged bf16 block: acc[j] (op)= staged[lane][j], j = 0..63
+// This lane's row of a staged bf16 block: acc[j] (op)= staged[lane][j], j = 0..63   (MUL_DGELU: multiply by gelu'(staged), or by
+// the staged value itself when it already is the derivative)
 template <bool MUL_DGELU>
-__device__ __forceinline__ void consume_row(float* acc, uint32_t buf, int lane) {
+__device__ __forceinline__ void consume_row(float* acc, uint32_t buf, int lane, bool aux_is_grad = false) {
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
     const uint4 w = lds128(buf + stg_off(lane, g));
@@ -116,8 +117,8 @@ __device__ __forceinline__ void consume_row(float* acc, uint32_t buf, int lane) 
     for (int j = 0; j < 4; ++j) {
       const float2 f = unpack_bf16x2(wu[j]);
       if (MUL_DGELU) {
-        acc[g * 8 + 2 * j] *= gelu_grad_f(f.x);
-        acc[g * 8 + 2 * j + 1] *= gelu_grad_f(f.y);
+        acc[g * 8 + 2 * j] *= aux_is_grad ? f.x : gelu_grad_f(f.x);
+        acc[g * 8 + 2 * j + 1] *= aux_is_grad ? f.y : gelu_grad_f(f.y);
       } else {
         acc[g * 8 + 2 * j] += f.x;
         acc[g * 8 + 2 * j + 1] += f.y;
@@ -476,10 +477,21 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
               }
             }
             if constexpr (KIND == EK_GELU) {
-              if (p.out2.p != nullptr) {  // pre-activation, saved for the backward pass (buffer 1 is free: n_in <= 1)
-                if (lane == 0) bulk_wait_read0();
+              const bool store_grad = (p.flags & EPI_GELU_STORE_GRAD) != 0;
+              if (p.out2.p != nullptr) {  // saved for the backward pass (buffer 1 is free: n_in <= 1): the pre-activation, or
+                if (lane == 0) bulk_wait_read0();  // directly gelu'(pre-activation) so that the backward epilogue is one multiply
                 __syncwarp();
-                stage_row_bf16(acc, buf_b, lane);
+                if (store_grad) {
+#pragma unroll
+                  for (int g = 0; g < 8; ++g) {
+                    float g8[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[g * 8 + j] = gelu_with_grad_f(acc[g * 8 + j], g8[j]);
+                    sts128(buf_b + stg_off(lane, g), pack_bf16x8(g8));
+                  }
+                } else {
+                  stage_row_bf16(acc, buf_b, lane);
+                }
                 fence_proxy_async_smem();  // generic-proxy writes -> visible to the TMA engine
                 __syncwarp();
                 if (lane == 0) {
@@ -487,8 +499,10 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
                   bulk_commit();
                 }
               }
+              if (!(store_grad && p.out2.p != nullptr)) {
 #pragma unroll
-              for (int j = 0; j < 64; ++j) acc[j] = gelu_f(acc[j]);
+                for (int j = 0; j < 64; ++j) acc[j] = gelu_f(acc[j]);
+              }
             }
           }
           // ---- inputs (prefetched with cp.async): wait, make them visible to the whole warp, consume row-wise
@@ -496,7 +510,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             if (early) cp_async_wait<1>(); else cp_async_wait<0>();
             __syncwarp();
             if constexpr (KIND == EK_DGELU) {
-              if (chunk_live) consume_row<true>(acc, buf_a, lane);
+              if (chunk_live) consume_row<true>(acc, buf_a, lane, (p.flags & EPI_AUX_IS_GRAD) != 0);
             }
 #pragma unroll 1
             for (int k = (KIND == EK_DGELU) ? 1 : 0; k < n_in; ++k) {

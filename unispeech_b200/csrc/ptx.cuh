@@ -312,6 +312,14 @@ __device__ __forceinline__ float gelu_f(float x) {
   const float h = gelu_half_erfc(x, e2);
   return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
 }
+// gelu(x) and gelu'(x) from ONE evaluation of h / e2 (the forward epilogues can store the derivative for the backward pass)
+__device__ __forceinline__ float gelu_with_grad_f(float x, float& grad) {
+  float e2;
+  const float h = gelu_half_erfc(x, e2);
+  const float cdf = x >= 0.f ? 1.0f - h : h;
+  grad = fmaf(x * 0.39894228040143268f, e2, cdf);
+  return fmaf(-fabsf(x), h, fmaxf(x, 0.f));
+}
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float e2;
   const float h = gelu_half_erfc(x, e2);

@@ -63,6 +63,21 @@ struct RowView {
   }
 };
 
+// V consecutive floats of a 16-byte aligned shared-memory array
+template <int V>
+__device__ __forceinline__ void smem_load_vec(const float* src, float* v) {
+  if constexpr (V % 4 == 0) {
+#pragma unroll
+    for (int q = 0; q < V / 4; ++q) {
+      const float4 t = *reinterpret_cast<const float4*>(src + 4 * q);
+      v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int q = 0; q < V; ++q) v[q] = src[q];
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ LayerNorm forward
 // y = (x - mean) * rstd * gamma + beta  [then exact GELU if gelu != 0]; statistics in fp32 (F.layer_norm,
 // reference: WavLM/WavLM.py:342,559,666,675; Fp32LayerNorm WavLM/modules.py:30-42 for the conv stack).
@@ -127,11 +142,16 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __r
     }
     const float rstd = rsqrtf(warp_sum(qv) * (1.0f / D) + eps);
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int c = (i / VEC * 32 + lane) * VEC + i % VEC;
-      float o = (v[i] - mean) * rstd * gs[c] + bs[c];
-      if (GELU) o = gelu_f(o);
-      v[i] = o;
+    for (int ch = 0; ch < NCH; ++ch) {
+      float gg[VEC], bb[VEC];
+      smem_load_vec<VEC>(gs + (ch * 32 + lane) * VEC, gg);  // 16-byte loads: scalar ones would be 8-way bank conflicts
+      smem_load_vec<VEC>(bs + (ch * 32 + lane) * VEC, bb);
+#pragma unroll
+      for (int j = 0; j < VEC; ++j) {
+        float o = (v[ch * VEC + j] - mean) * rstd * gg[j] + bb[j];
+        if (GELU) o = gelu_f(o);
+        v[ch * VEC + j] = o;
+      }
     }
     __nv_bfloat16* yr = y + yv.off(r);
 #pragma unroll
@@ -237,13 +257,15 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
       const int c0 = (ch * 32 + lane) * VEC;
-      float pg[VEC], pb[VEC];
+      float pg[VEC], pb[VEC], gg[VEC], bb[VEC];
+      smem_load_vec<VEC>(gs + c0, gg);
+      if (gelu) smem_load_vec<VEC>(bs + c0, bb);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const int i = ch * VEC + j;
         xh[i] = (xh[i] - mean) * rstd;
-        const float gi = gs[c0 + j];
-        if (gelu) dz[i] *= gelu_grad_f(gi * xh[i] + bs[c0 + j]);
+        const float gi = gg[j];
+        if (gelu) dz[i] *= gelu_grad_f(gi * xh[i] + bb[j]);
         pg[j] = dz[i] * xh[i];
         pb[j] = dz[i];
         const float dxh = dz[i] * gi;
@@ -369,7 +391,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
                                                         const __nv_bfloat16* __restrict__ pre, RowView prev,
                                                         __nv_bfloat16* __restrict__ out, RowView outv, int N,
-                                                        long long rows, float* __restrict__ colsum) {
+                                                        long long rows, float* __restrict__ colsum, int pre_is_grad) {
   pdl_grid_sync();
   const int c = blockIdx.x * 64 + (threadIdx.x & 31) * 2;
   const int rl = threadIdx.x >> 5;
@@ -378,7 +400,8 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __r
     for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += static_cast<long long>(gridDim.y) * 8) {
       const float2 d = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(dy + dyv.off(r) + c));
       const float2 p = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(pre + prev.off(r) + c));
-      const uint32_t w = pack_bf16x2(d.x * gelu_grad_f(p.x), d.y * gelu_grad_f(p.y));
+      const uint32_t w = pre_is_grad ? pack_bf16x2(d.x * p.x, d.y * p.y)
+                                     : pack_bf16x2(d.x * gelu_grad_f(p.x), d.y * gelu_grad_f(p.y));
       *reinterpret_cast<uint32_t*>(out + outv.off(r) + c) = w;
       const float2 f = unpack_bf16x2(w);
       a0 += f.x;
@@ -714,9 +737,9 @@ int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_bat
   return 0;
 }
 
-int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs, long long pre_rs,
-                    void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches, int N, float* colsum,
-                    b200s_stream stream) {
+int b200s_dgelu_mul_ex(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs, long long pre_rs,
+                       void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches, int N, float* colsum,
+                       int pre_is_grad, b200s_stream stream) {
   B200_CHECK_ARG(dy && pre && out, "dgelu_mul: null pointer");
   B200_CHECK_ARG(N % 2 == 0, "dgelu_mul: N must be even");
   const long long rows = static_cast<long long>(rows_per_batch) * batches;
@@ -726,9 +749,16 @@ int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void
   dim3 grid(ceil_div(N, 64), std::max(1, gy));
   B200_CHECK_CUDA(launch_pdl(dgelu_mul_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(dy), a, static_cast<const __nv_bfloat16*>(pre), b,
-      static_cast<__nv_bfloat16*>(out), c, N, rows, colsum));
+      static_cast<__nv_bfloat16*>(out), c, N, rows, colsum, pre_is_grad));
   B200_CHECK_LAUNCH();
   return 0;
+}
+
+int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs, long long pre_rs,
+                    void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches, int N, float* colsum,
+                    b200s_stream stream) {
+  return b200s_dgelu_mul_ex(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum, 0,
+                            stream);
 }
 
 int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
@@ -776,7 +806,7 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
                  "gate_bwd: null pointer");
   const long long rows = static_cast<long long>(T) * B;
   RowView xv{x_bs, x_rs, T}, dv{dx_bs, dx_rs, T};
-  long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 2), 2LL * sm_count());  // every block ends with ~530 global atomics on the same addresses
+  long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 2), 4LL * sm_count());  // (2 x SMs measured 60 % slower: the row loop is latency-bound)
   if (blocks < 1) blocks = 1;
   B200_CHECK_CUDA(launch_pdl(gate_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 8 * H * sizeof(float), static_cast<cudaStream_t>(stream), 
       static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, dgate,

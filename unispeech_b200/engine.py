@@ -287,7 +287,7 @@ class Engine:
                 st["y"].append(y); st["mean"].append(mean); st["rstd"].append(rstd)
             else:
                 y = torch.empty(B, Tpi, C, dtype=BF, device=dev) if save else None
-                epi = L.make_epilogue(gelu=True, out_pre=y, pre_bs=Tpi * C, pre_ld=C)
+                epi = L.make_epilogue(gelu=2, out_pre=y, pre_bs=Tpi * C, pre_ld=C)  # y = gelu'(conv output), used by backward
                 ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, out, Tpi * C, C, epi)
                 st["y"].append(y); st["mean"].append(None); st["rstd"].append(None)
             st["a"].append(out)
@@ -322,7 +322,7 @@ class Engine:
                                        ln.bias, None, 0, 0, gv, Tg * C, C, self.g(ln.weight), self.g(ln.bias), None, Ti, B, C,
                                        gelu=True)
                 else:
-                    ops.dgelu_mul(dA, Tpi * C, C, st["y"][i], Tpi * C, C, gv, Tg * C, C, Ti, B, C, None)
+                    ops.dgelu_mul(dA, Tpi * C, C, st["y"][i], Tpi * C, C, gv, Tg * C, C, Ti, B, C, None, pre_is_grad=True)
             gv = gpad[:, lead:]
             # ---- weight gradient: dW[co, (j,ci)] = sum dY[b,t,co] * a_{i-1}[b, s*t + j, ci]
             a_prev = st["a"][i - 1]
@@ -350,7 +350,7 @@ class Engine:
                 epi = None
                 if fuse_dgelu:
                     y_prev = st["y"][i - 1]
-                    epi = L.make_epilogue(dgelu=True, gelu_aux=y_prev.view(-1)[rho * C:], aux_bs=Tp_in * C, aux_ld=s * C)
+                    epi = L.make_epilogue(dgelu=2, gelu_aux=y_prev.view(-1)[rho * C:], aux_bs=Tp_in * C, aux_ld=s * C)
                 ops.gemm_rows(a_view, Tg * C, C, n_u, B, nm * C, self.wd[i][rho], C, dst.view(-1)[dst_off + rho * C:], dst_bs,
                               s * C, epi)
             if fuse_dgelu:
@@ -430,7 +430,7 @@ class Engine:
         xs = torch.empty(B, T, D, dtype=BF, device=dev)
         pre = torch.empty(B, T, D, dtype=BF, device=dev) if save else None
         pc = m.encoder.pos_conv[0]
-        epi = L.make_epilogue(bias=pc.bias, gelu=True, out_pre=pre, pre_bs=T * D, pre_ld=D, res1=xpad[:, half:],
+        epi = L.make_epilogue(bias=pc.bias, gelu=2, out_pre=pre, pre_bs=T * D, pre_ld=D, res1=xpad[:, half:],
                               res1_bs=Tpad * D, res1_ld=D)
         ops.posconv_gemm(xpad, Tpad * D, T, B, D, G, taps, self.pc_fwd, xs, T * D, D, epi)
         st = dict(xpad=xpad, pre=pre, xs=xs)
@@ -463,7 +463,8 @@ class Engine:
             dxs = dx0
         pc = m.encoder.pos_conv[0]
         dpre = torch.zeros(B, Tpad, D, dtype=BF, device=dev)
-        ops.dgelu_mul(dxs, T * D, D, st["pre"], T * D, D, dpre[:, half:], Tpad * D, D, T, B, D, self.g(pc.bias))
+        ops.dgelu_mul(dxs, T * D, D, st["pre"], T * D, D, dpre[:, half:], Tpad * D, D, T, B, D, self.g(pc.bias),
+                      pre_is_grad=True)
         dwp = torch.zeros(G, Cg, taps, 64, dtype=torch.float32, device=dev)
         ops.posconv_wgrad(dpre[:, half:], Tpad * D, D, xpad, Tpad * D, T, B, D, G, taps, dwp)
         work = torch.empty(2 * taps, dtype=torch.float32, device=dev)
@@ -526,7 +527,7 @@ class Engine:
         hg = e(B, T, Fd)
         hp = e(B, T, Fd) if save else None
         ops.gemm_rows(ffn_in, 0, D, M, 1, D, w["w1"], Fd, hg, 0, Fd,
-                      L.make_epilogue(bias=lyr.fc1.bias, gelu=True, out_pre=hp, pre_ld=Fd))
+                      L.make_epilogue(bias=lyr.fc1.bias, gelu=2, out_pre=hp, pre_ld=Fd))  # hp = gelu'(fc1 output)
         y2 = e(B, T, D)
         ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias, res1=x1, res1_ld=D))
         if pre_ln:
@@ -569,7 +570,7 @@ class Engine:
         ops.gemm_wgrad(dy2, 0, D, st["hg"], 0, Fd, M, 1, D, Fd, g(lyr.fc2.weight), Fd)
         dhp = e(B, T, Fd)
         ops.gemm_rows(dy2, 0, D, M, 1, D, w["w2T"], Fd, dhp, 0, Fd,
-                      L.make_epilogue(dgelu=True, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias)))
+                      L.make_epilogue(dgelu=2, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias)))
         ops.gemm_wgrad(dhp, 0, Fd, st["ffn_in"], 0, D, M, 1, Fd, D, g(lyr.fc1.weight), D)
         dx1 = e(B, T, D)
         if pre_ln:

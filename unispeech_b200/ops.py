@@ -103,9 +103,11 @@ def colsum(x, x_bs, x_rs, rows_per_batch, batches, N, out):
     _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())
 
 
-def dgelu_mul(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum_out=None):
-    _call("b200s_dgelu_mul", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(pre), L.ll(pre_bs), L.ll(pre_rs), L.ptr(out),
-           L.ll(out_bs), L.ll(out_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(colsum_out), _s())
+def dgelu_mul(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum_out=None,
+              pre_is_grad=False):
+    _call("b200s_dgelu_mul_ex", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(pre), L.ll(pre_bs), L.ll(pre_rs), L.ptr(out),
+           L.ll(out_bs), L.ll(out_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(colsum_out),
+           i32(1 if pre_is_grad else 0), _s())
 
 
 def frame_mask_fwd(x, x_bs, x_rs, T, B, D, mask, pad, mask_emb):
