@@ -105,6 +105,20 @@ int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, con
                          const uint8_t* key_pad, const float* lse, float* delta, float* dq_acc, void* dqkv,
                          float* dgate, float* dtab, int B, int T, int H, float scale, b200s_stream stream);
 
+/* Attention with dropout on the probabilities (attention_dropout; the dropout_p argument of
+ * F.multi_head_attention_forward, WavLM/modules.py:551): O = (softmax(..) o M) V / (1 - p).  M comes from the counter-based
+ * hash of csrc/dropout.cuh keyed by (key0, key1, (b*H+h)*T + i, j); the forward kernel also records it as a bit mask
+ * (drop_mask: b200s_attn_dropout_mask_words(B,T,H) uint32 words) which the fused backward re-reads, so the backward needs
+ * no key.  drop_p = 0 is exactly b200s_attn_fwd / b200s_attn_bwd_fused (drop_mask may be NULL). */
+int b200s_attn_fwd_dropout(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out,
+                           float* lse, int B, int T, int H, float scale, float drop_p, uint32_t key0, uint32_t key1,
+                           uint32_t* drop_mask, b200s_stream stream);
+int b200s_attn_bwd_fused_dropout(const void* qkv, const void* out, const void* dout, const float* gate,
+                                 const float* tab, const uint8_t* key_pad, const float* lse, float* delta,
+                                 float* dq_acc, void* dqkv, float* dgate, float* dtab, int B, int T, int H, float scale,
+                                 float drop_p, const uint32_t* drop_mask, b200s_stream stream);
+long long b200s_attn_dropout_mask_words(int B, int T, int H);
+
 /* ============================ row kernels (csrc/rowops.cu) ============================ */
 
 /* y = LayerNorm(x) * gamma + beta [then exact GELU]; saves mean / rstd (fp32 [rows]).  nn.LayerNorm / Fp32LayerNorm
@@ -141,6 +155,20 @@ int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void
 int b200s_dgelu_mul_ex(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs,
                        long long pre_rs, void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches,
                        int N, float* colsum, int pre_is_grad, b200s_stream stream);
+
+/* y = [res +] dropout(x), y may alias x.  nn.Dropout / F.dropout of the transformer stack (WavLM/WavLM.py:350,584,659-661,
+ * 702-738): keep(row, col) is a pure function of (key0, key1, logical row = b*rows_per_batch + r, col) (csrc/dropout.cuh),
+ * kept values are scaled by 1/(1-p).  The backward pass is the same call on the incoming gradient with the same key and
+ * res = NULL.  N % 8 == 0, 0 <= p < 1. */
+int b200s_dropout_rows(const void* x, long long x_bs, long long x_rs, const void* res, long long res_bs,
+                       long long res_rs, void* y, long long y_bs, long long y_rs, int rows_per_batch, int batches,
+                       int N, float p, uint32_t key0, uint32_t key1, b200s_stream stream);
+
+/* Host-side evaluation of the mask formulas (csrc/dropout.cuh), no device involved: bits word of counter `ctr`; per-row key
+ * of the attention mask (which = 0 / 1 for key0 / key1); 16-bit keep threshold of probability p. */
+uint32_t b200s_dropout_bits(uint32_t key0, uint32_t key1, uint32_t ctr);
+uint32_t b200s_dropout_row_key(uint32_t key, uint32_t row, int which);
+uint32_t b200s_dropout_threshold16(float p);
 
 /* x[b,t,:] = mask_emb where mask[b,t]; = 0 where pad[b,t]   (apply_mask WavLM/WavLM.py:285-286; x[padding_mask]=0 :574-575) */
 int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,
@@ -190,6 +218,24 @@ int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int 
                        void* wp_fwd, void* wp_dgrad, b200s_stream stream);
 int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const float* dwp, int D, int G, int taps,
                          float* work, float* dweight_v, float* dweight_g, b200s_stream stream);
+
+/* ============================ optimizer step on the flat gradient buffer (csrc/optim.cu) ============================ */
+
+/* *out += sum_i g[i]^2 (fp64 accumulator on the device; the caller zeroes it).  With the flat gradient buffer this is the global
+ * gradient norm of utils.clip_grad_norm_ (src/fairseq/utils.py:338-377) in one launch and without a host round trip. */
+int b200s_sumsq_f32(const float* g, long long n, double* out, b200s_stream stream);
+
+/* Fused fairseq Adam update (src/fairseq/optim/adam.py:150-228) of n_tensors fp32 master tensors whose gradients (g) and
+ * moments (m = exp_avg, v = exp_avg_sq) live in flat buffers:
+ *   g' = g * grad_scale * clip,   clip = max_norm > 0 ? min(1, max_norm / (|grad_scale| * sqrt(*sumsq) + 1e-6)) : 1
+ *        (multiply_grads + clip_grad_norm, src/fairseq/optim/fp16_optimizer.py:176-214, utils.py:378-381)
+ *   m = beta1 m + (1-beta1) g';  v = beta2 v + (1-beta2) g'^2;  p -= weight_decay*lr*p;
+ *   p -= lr*sqrt(1-beta2^step)/(1-beta1^step) * m / (sqrt(v) + eps);   g = 0 if zero_grad.
+ * table: DEVICE array of n_tensors records {float* param; int64 goff; int64 numel; int64 chunk0} (32 bytes; goff = element
+ * offset in g/m/v, multiple of 4; chunk0 = prefix sum of ceil(numel/2048)); total_chunks = sum of all chunks; step >= 1. */
+int b200s_adam_step(const void* table, int n_tensors, long long total_chunks, float* g, float* m, float* v,
+                    const double* sumsq, float grad_scale, float max_norm, float lr, float beta1, float beta2,
+                    float eps, float weight_decay, int step, int zero_grad, b200s_stream stream);
 
 #ifdef __cplusplus
 }

@@ -213,6 +213,103 @@ def deterministic_waveform(B: int, L: int, seed: int = 0, lengths: Optional[List
 
 
 # ----------------------------------------------------------------------------------------------------------------
+# training-mode dropout with the product's counter-based masks
+# ----------------------------------------------------------------------------------------------------------------
+_M32 = np.uint64(0xFFFFFFFF)
+_M64 = (1 << 64) - 1
+
+
+def _fmix32(h: np.ndarray) -> np.ndarray:
+    """MurmurHash3 finaliser on uint64 arrays holding 32-bit values (unispeech_b200/csrc/dropout.cuh: fmix32)."""
+    h = h ^ (h >> np.uint64(16))
+    h = (h * np.uint64(0x85EBCA6B)) & _M32
+    h = h ^ (h >> np.uint64(13))
+    h = (h * np.uint64(0xC2B2AE35)) & _M32
+    return h ^ (h >> np.uint64(16))
+
+
+def _drop_bits(k0, k1, ctr: np.ndarray) -> np.ndarray:
+    return _fmix32((((ctr ^ k1) * np.uint64(0x9E3779B1)) + k0) & _M32)
+
+
+def drop_threshold16(p: float) -> int:
+    return int(min(max(float(np.float32(p)) * 65536.0 + 0.5, 0.0), 65535.0))
+
+
+def _splitmix64(x: int) -> int:
+    x = (x + 0x9E3779B97F4A7C15) & _M64
+    z = ((x ^ (x >> 30)) * 0xBF58476D1CE4E5B9) & _M64
+    z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & _M64
+    return z ^ (z >> 31)
+
+
+class HashDropout:
+    """The reference draws its dropout masks from torch's Philox streams (nn.Dropout / F.dropout, WavLM/WavLM.py:350,584,
+    659-661,702-738; dropout_p of F.multi_head_attention_forward, WavLM/modules.py:551), which no other implementation can
+    reproduce bit for bit.  What CAN be held to the reference is the semantics y = x * keep / (1 - p) at every site: this class
+    restates (numpy, independent of the CUDA code) the product's counter-based keep/drop decisions so that the oracle applies
+    exactly the masks the kernels apply, and parity with dropout enabled is then a deterministic comparison.
+    Sites: 0 = dropout_input, 1 = encoder-level dropout, 4 + 4*layer + {0: dropout1, 1: activation dropout, 2: dropout3,
+    3: attention probabilities} (unispeech_b200/dropout.py)."""
+
+    SITE_INPUT, SITE_ENCODER = 0, 1
+
+    def __init__(self, seed: int):
+        self.seed = seed & _M64
+
+    @staticmethod
+    def layer_site(layer: int, which: int) -> int:
+        return 4 + 4 * layer + which
+
+    def key(self, site: int):
+        z = _splitmix64((self.seed ^ (site * 0xD1342543DE82EF95)) & _M64)
+        return np.uint64(z & 0xFFFFFFFF), np.uint64(z >> 32)
+
+    def keep_rows(self, site: int, rows: int, N: int, p: float) -> np.ndarray:
+        """bool [rows, N]: element (row, c) uses half (c & 1) of bits((row*N + c) >> 1)."""
+        assert N % 2 == 0
+        k0, k1 = self.key(site)
+        bits = _drop_bits(k0, k1, np.arange(rows * N // 2, dtype=np.uint64))
+        thr = np.uint64(drop_threshold16(p))
+        keep = np.stack([(bits & np.uint64(0xFFFF)) >= thr, (bits >> np.uint64(16)) >= thr], axis=1)
+        return keep.reshape(rows, N)
+
+    def keep_attn(self, site: int, B: int, H: int, T: int, p: float) -> np.ndarray:
+        """bool [B,H,T,T]: row id (b*H+h)*T+i gets its own key pair, key column j uses half (j & 1) of bits(j >> 1)."""
+        k0, k1 = self.key(site)
+        rowid = np.arange(B * H * T, dtype=np.uint64)
+        rk0 = _fmix32((k0 + rowid * np.uint64(0x9E3779B1)) & _M32)[:, None]
+        rk1 = _fmix32(k1 ^ ((rowid * np.uint64(0x85EBCA6B)) & _M32))[:, None]
+        j2 = np.arange((T + 1) // 2, dtype=np.uint64)[None, :]
+        bits = _fmix32((((j2 ^ rk1) * np.uint64(0x9E3779B1)) + rk0) & _M32)
+        thr = np.uint64(drop_threshold16(p))
+        keep = np.stack([(bits & np.uint64(0xFFFF)) >= thr, (bits >> np.uint64(16)) >= thr], axis=2)
+        return keep.reshape(B * H * T, -1)[:, :T].reshape(B, H, T, T)
+
+    def rows_btc(self, site: int, x: Tensor, p: float) -> Tensor:
+        """F.dropout on a [B,T,C] tensor (logical row b*T + t)."""
+        if p <= 0:
+            return x
+        B, T, C = x.shape
+        keep = torch.from_numpy(self.keep_rows(site, B * T, C, p)).view(B, T, C)
+        return x * keep.to(x.dtype) / (1.0 - p)
+
+    def rows_tbc(self, site: int, x: Tensor, p: float) -> Tensor:
+        """Same for the reference's T x B x C layout (the kernels index rows batch-major)."""
+        if p <= 0:
+            return x
+        return self.rows_btc(site, x.transpose(0, 1), p).transpose(0, 1)
+
+    def attn(self, site: int, probs: Tensor, B: int, H: int, p: float) -> Tensor:
+        """Dropout on the softmax probabilities [B*H,T,T]."""
+        if p <= 0:
+            return probs
+        T = probs.shape[-1]
+        keep = torch.from_numpy(self.keep_attn(site, B, H, T, p)).view(B * H, T, T)
+        return probs * keep.to(probs.dtype) / (1.0 - p)
+
+
+# ----------------------------------------------------------------------------------------------------------------
 # conv feature extractor  (ConvFeatureExtractionModel, WavLM/WavLM.py:378-449 ctor, 485-504 forward)
 # ----------------------------------------------------------------------------------------------------------------
 def conv_feature_extractor(sd: Dict[str, Tensor], source: Tensor, cfg, return_all: bool = False):
@@ -285,7 +382,7 @@ def gate_values(x_tbc: Tensor, grep_w: Tensor, grep_b: Tensor, grep_a: Tensor, H
 
 
 def self_attention(sd, prefix: str, x_tbc: Tensor, key_padding_mask: Optional[Tensor], position_bias: Optional[Tensor],
-                   cfg) -> Tensor:
+                   cfg, drop: Optional["HashDropout"] = None, drop_site: int = 0) -> Tensor:
     """softmax((xWq+bq)/sqrt(d) (xWk+bk)^T + gate*bias, -inf at padded keys) (xWv+bv), then out_proj."""
     T, B, D = x_tbc.shape
     H = cfg.encoder_attention_heads
@@ -307,6 +404,8 @@ def self_attention(sd, prefix: str, x_tbc: Tensor, key_padding_mask: Optional[Te
     if key_padding_mask is not None:
         scores = scores.view(B, H, T, T).masked_fill(key_padding_mask[:, None, None, :], float("-inf")).view(B * H, T, T)
     p = torch.softmax(scores, dim=-1)
+    if drop is not None:  # dropout_p of F.multi_head_attention_forward (modules.py:551): dropout on the probabilities
+        p = drop.attn(drop_site, p, B, H, cfg.attention_dropout)
     o = torch.bmm(p, v).transpose(0, 1).contiguous().view(T, B, D)
     return F.linear(o, sd[prefix + "out_proj.weight"], sd[prefix + "out_proj.bias"])
 
@@ -318,26 +417,30 @@ def _ln(x, sd, name):
     return F.layer_norm(x, (x.shape[-1],), sd[name + ".weight"], sd[name + ".bias"], 1e-5)
 
 
-def encoder_layer(sd, i: int, x: Tensor, padding_mask, position_bias, cfg) -> Tensor:
+def encoder_layer(sd, i: int, x: Tensor, padding_mask, position_bias, cfg, drop: Optional["HashDropout"] = None) -> Tensor:
     p = f"encoder.layers.{i}."
+    site = lambda which: HashDropout.layer_site(i, which)
+    d1 = (lambda t: drop.rows_tbc(site(0), t, cfg.dropout)) if drop is not None else (lambda t: t)  # self.dropout1, :659
+    d2 = (lambda t: drop.rows_tbc(site(1), t, cfg.activation_dropout)) if drop is not None else (lambda t: t)  # dropout2, :660
+    d3 = (lambda t: drop.rows_tbc(site(2), t, cfg.dropout)) if drop is not None else (lambda t: t)  # self.dropout3, :661
     residual = x
     if cfg.layer_norm_first:  # WavLM.py:691-714
         x = _ln(x, sd, p + "self_attn_layer_norm")
-        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg)
-        x = residual + x
+        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg, drop, site(3))
+        x = residual + d1(x)
         residual = x
         x = _ln(x, sd, p + "final_layer_norm")
-        x = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+        x = d2(F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"])))
         x = F.linear(x, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
-        x = residual + x
+        x = residual + d3(x)
     else:  # WavLM.py:715-740
-        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg)
-        x = residual + x
+        x = self_attention(sd, p + "self_attn.", x, padding_mask, position_bias, cfg, drop, site(3))
+        x = residual + d1(x)
         x = _ln(x, sd, p + "self_attn_layer_norm")
         residual = x
-        x = F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"]))
+        x = d2(F.gelu(F.linear(x, sd[p + "fc1.weight"], sd[p + "fc1.bias"])))
         x = F.linear(x, sd[p + "fc2.weight"], sd[p + "fc2.bias"])
-        x = residual + x
+        x = residual + d3(x)
         x = _ln(x, sd, p + "final_layer_norm")
     return x
 
@@ -349,7 +452,8 @@ def pos_conv_weight(sd) -> Tensor:
     return g * v / v.norm(2, dim=(0, 1), keepdim=True)
 
 
-def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, extract_layer: Optional[int] = None):
+def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, extract_layer: Optional[int] = None,
+            drop: Optional["HashDropout"] = None):
     """TransformerEncoder.forward + extract_features (out-of-place restatement of WavLM.py:564-612).
     Variants of the fairseq tree: `tgt_layer` may be a LIST of 1-based layer numbers (src/fairseq/models/wavlm/wavlm.py:
     730-737: their outputs are collected, there is no pre-layer entry and no early exit); `extract_layer` (0-based) returns
@@ -365,6 +469,8 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, 
     x = x + F.gelu(x_conv).transpose(1, 2)  # :577-579
     if not cfg.layer_norm_first:
         x = _ln(x, sd, "encoder.layer_norm")  # :581-582
+    if drop is not None:
+        x = drop.rows_btc(HashDropout.SITE_ENCODER, x, cfg.dropout)  # x = F.dropout(x, p=self.dropout, training), :584
     x = x.transpose(0, 1)  # B x T x C -> T x B x C
     layer_results = []
     tgt_list = tgt_layer if isinstance(tgt_layer, (list, tuple)) else None
@@ -380,7 +486,7 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, 
     r = None
     er = None
     for i in range(cfg.encoder_layers):
-        x = encoder_layer(sd, i, x, padding_mask, position_bias, cfg)
+        x = encoder_layer(sd, i, x, padding_mask, position_bias, cfg, drop)
         if tgt_list is not None:
             if i + 1 in tgt_list:
                 layer_results.append(x)
@@ -404,7 +510,8 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, 
 
 
 def extract_features(sd, source: Tensor, cfg, padding_mask: Optional[Tensor] = None,
-                     mask_indices: Optional[Tensor] = None, output_layer: Optional[int] = None):
+                     mask_indices: Optional[Tensor] = None, output_layer: Optional[int] = None,
+                     drop: Optional["HashDropout"] = None):
     """WavLM.extract_features, WavLM/WavLM.py:323-375.  `mask_indices` [B,T] bool replaces the host-RNG
     compute_mask_indices call of apply_mask (:271-309): masked frames are set to mask_emb."""
     feats = conv_feature_extractor(sd, source, cfg)  # :333-339 (feature_grad_mult handled by callers)
@@ -415,10 +522,12 @@ def extract_features(sd, source: Tensor, cfg, padding_mask: Optional[Tensor] = N
         padding_mask = frame_padding_mask(padding_mask, feats.size(1))
     if "post_extract_proj.weight" in sd:
         feats = F.linear(feats, sd["post_extract_proj.weight"], sd["post_extract_proj.bias"])
+    if drop is not None:
+        feats = drop.rows_btc(HashDropout.SITE_INPUT, feats, cfg.dropout_input)  # features = self.dropout_input(features), :350
     x = feats
     if mask_indices is not None:
         x = torch.where(mask_indices.unsqueeze(-1), sd["mask_emb"].to(x.dtype), x)  # x[mask_indices] = mask_emb
-    x, layer_results = encoder(sd, x, padding_mask, cfg, None if output_layer is None else output_layer - 1)
+    x, layer_results = encoder(sd, x, padding_mask, cfg, None if output_layer is None else output_layer - 1, drop=drop)
     return {"x": x, "padding_mask": padding_mask, "features": feats, "layer_results": layer_results}
 
 
@@ -443,3 +552,36 @@ def forward_flops(L: int, cfg) -> float:
     fl += 2.0 * T * D * (D // cfg.conv_pos_groups) * cfg.conv_pos
     fl += cfg.encoder_layers * (8.0 * T * D * D + 4.0 * T * T * D + 4.0 * T * D * Fd + 2.0 * T * H * 64 * 8)
     return fl
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# optimizer step  (utils.clip_grad_norm_ src/fairseq/utils.py:338-381; FP16Optimizer.multiply_grads / clip_grad_norm
+# src/fairseq/optim/fp16_optimizer.py:190-214; Adam.step src/fairseq/optim/adam.py:150-228)
+# ----------------------------------------------------------------------------------------------------------------
+def clip_coefficient(grads: List[Tensor], max_norm: float, multiply_factor: float = 1.0):
+    """Returns (grad_norm, factor to multiply every gradient with): norm of the per-tensor norms (utils.py:359-375) times the
+    pending multiply factor (fp16_optimizer.py:198-200), clip_coef = (max_norm / (norm + 1e-6)).clamp(max=1) (:207-209)."""
+    total = torch.norm(torch.stack([torch.norm(g.float(), p=2) for g in grads])) * abs(multiply_factor)
+    coef = multiply_factor
+    if max_norm > 0:
+        coef = coef * float((max_norm / (total + 1e-6)).clamp(max=1.0))
+    return total, coef
+
+
+def adam_step(params: List[Tensor], grads: List[Tensor], state: dict, lr: float, betas=(0.9, 0.999), eps: float = 1e-8,
+              weight_decay: float = 0.0):
+    """In-place fairseq Adam update of fp32 tensors (adam.py:176-222, amsgrad off); `state` holds step / exp_avg / exp_avg_sq."""
+    if not state:
+        state.update(step=0, exp_avg=[torch.zeros_like(p) for p in params], exp_avg_sq=[torch.zeros_like(p) for p in params])
+    state["step"] += 1
+    beta1, beta2 = betas
+    bias_correction1 = 1 - beta1 ** state["step"]
+    bias_correction2 = 1 - beta2 ** state["step"]
+    step_size = lr * math.sqrt(bias_correction2) / bias_correction1
+    for p, g, m, v in zip(params, grads, state["exp_avg"], state["exp_avg_sq"]):
+        m.mul_(beta1).add_(g, alpha=1 - beta1)
+        v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+        denom = v.sqrt().add_(eps)
+        if weight_decay != 0:
+            p.add_(p, alpha=-weight_decay * lr)
+        p.addcdiv_(m, denom, value=-step_size)

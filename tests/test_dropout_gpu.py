@@ -1,0 +1,242 @@
+"""Training-mode dropout on the GPU path.  The reference's Philox masks cannot be reproduced by any other implementation, so
+parity is held on the SEMANTICS (y = x * keep / (1-p) at every reference site) with the product's own counter-based masks:
+oracle.HashDropout restates the keep/drop decisions in numpy (checked against the compiled formulas in test_dropout_cpu.py),
+the kernels must reproduce those decisions bit for bit, and the whole model must then match the oracle run with the same masks
+to the usual bf16 tolerances, forward and backward."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import wavlm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def bf(t):
+    return t.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("B,T,N,p", [(2, 37, 128, 0.1), (3, 100, 768, 0.5), (1, 5, 3072, 0.05)])
+def test_dropout_rows_bit_exact(cuda_device, B, T, N, p):
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(N + T)
+    d = O.HashDropout(1234 + T)
+    site = 11
+    key = tuple(int(v) for v in d.key(site))
+    keep = torch.from_numpy(d.keep_rows(site, B * T, N, p)).view(B, T, N).to(dev)
+    # strided input view (rows of a padded buffer), contiguous output
+    buf = bf(torch.randn(B, T + 6, N, device=dev))
+    x = buf[:, 3:3 + T]
+    y = torch.full((B, T, N), 7.0, device=dev, dtype=torch.bfloat16)
+    ops.dropout_rows(x, (T + 6) * N, N, None, 0, 0, y, T * N, N, T, B, N, p, key)
+    torch.cuda.synchronize()
+    rp = torch.tensor(1.0, dtype=torch.float32) / (torch.tensor(1.0, dtype=torch.float32) - torch.tensor(p, dtype=torch.float32))
+    want = bf(torch.where(keep, x.float() * rp.item(), torch.zeros((), device=dev)))
+    assert torch.equal(y, want)
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.02
+    # with a residual (fp32 add before the single bf16 rounding; an FMA contraction may differ by one ulp of the sum)
+    res = bf(torch.randn(B, T, N, device=dev))
+    y2 = torch.empty_like(y)
+    ops.dropout_rows(x, (T + 6) * N, N, res, T * N, N, y2, T * N, N, T, B, N, p, key)
+    torch.cuda.synchronize()
+    want2 = torch.where(keep, x.float() * rp.item(), torch.zeros((), device=dev)) + res.float()
+    err = (y2.float() - want2).abs()
+    assert (err <= want2.abs() * 2 ** -7 + 1e-6).all()
+    # in place, and the "backward" use (same key on another tensor) applies the identical mask
+    xc = x.contiguous().clone()
+    ops.dropout_rows(xc, T * N, N, None, 0, 0, xc, T * N, N, T, B, N, p, key)
+    torch.cuda.synchronize()
+    assert torch.equal(xc, want)
+    # the rest of the padded buffer is untouched and a different key gives a different mask
+    y3 = torch.empty_like(y)
+    ops.dropout_rows(x, (T + 6) * N, N, None, 0, 0, y3, T * N, N, T, B, N, p, (key[0] ^ 1, key[1]))
+    torch.cuda.synchronize()
+    assert not torch.equal(y3, y)
+
+
+def _attn_ref_drop(qkv, gate, tab, pad, keep, p, B, T, H, scale):
+    D = H * 64
+    q, k, v = qkv.float().split(D, dim=-1)
+    q = q.view(B, T, H, 64).transpose(1, 2)
+    k = k.view(B, T, H, 64).transpose(1, 2)
+    v = v.view(B, T, H, 64).transpose(1, 2)
+    s = torch.matmul(q, k.transpose(-1, -2)) * scale
+    if tab is not None:
+        i = torch.arange(T, device=qkv.device)[:, None]
+        j = torch.arange(T, device=qkv.device)[None, :]
+        bias = tab[:, (j - i) + T - 1]
+        g = gate if gate is not None else torch.ones(B, H, T, device=qkv.device)
+        s = s + g.unsqueeze(-1) * bias.unsqueeze(0)
+    if pad is not None:
+        s = s.masked_fill(pad.bool()[:, None, None, :], float("-inf"))
+    pr = torch.softmax(s, dim=-1)
+    pr = pr * keep.to(pr.dtype) / (1.0 - p)
+    return torch.matmul(pr, v).transpose(1, 2).reshape(B, T, D)
+
+
+def _unpack_mask(words, B, T, H):
+    """uint32 words [B*H, 4n, 128n] (bit i&31 of word (i>>5, j)) -> bool [B,H,T,T]."""
+    n = (T + 127) // 128
+    w = words.view(B * H, 4 * n, 128 * n).cpu().numpy().astype(np.uint32)
+    bits = (w[:, :, None, :] >> np.arange(32, dtype=np.uint32)[None, None, :, None]) & 1   # [BH, 4n, 32, 128n]
+    full = bits.reshape(B * H, 128 * n, 128 * n)
+    return torch.from_numpy(full[:, :T, :T].astype(bool)).view(B, H, T, T)
+
+
+@pytest.mark.parametrize("B,T,H,bias,padded,p", [(2, 100, 2, True, True, 0.1), (1, 128, 2, True, False, 0.5),
+                                                 (2, 300, 3, True, True, 0.1), (2, 257, 2, False, True, 0.2),
+                                                 (1, 749, 3, True, False, 0.1), (1, 520, 1, True, False, 0.1)])
+def test_attn_dropout_fwd_bwd(cuda_device, B, T, H, bias, padded, p):
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(T + 3)
+    D = H * 64
+    qkv = bf(torch.randn(B, T, 3 * D, device=dev))
+    gate = (torch.rand(B, H, T, device=dev) * 2 + 0.2) if bias else None
+    tab = torch.randn(H, 2 * T - 1, device=dev) if bias else None
+    pad = None
+    if padded:
+        pad = torch.zeros(B, T, device=dev, dtype=torch.uint8)
+        pad[0, T - T // 3:] = 1
+    d = O.HashDropout(555 + T)
+    site = O.HashDropout.layer_site(2, 3)
+    key = tuple(int(v) for v in d.key(site))
+    out = torch.empty(B, T, D, device=dev, dtype=torch.bfloat16)
+    lse = torch.empty(B, H, T, device=dev)
+    words = torch.full((ops.attn_dropout_mask_words(B, T, H),), -1, dtype=torch.int32, device=dev)
+    ops.attn_fwd_dropout(qkv, gate, tab, pad, out, lse, B, T, H, 0.125, p, key, words)
+    torch.cuda.synchronize()
+    # 1. the recorded keep bits are exactly the hash decisions
+    got_keep = _unpack_mask(words, B, T, H)
+    want_keep = torch.from_numpy(d.keep_attn(site, B, H, T, p))
+    assert torch.equal(got_keep, want_keep), (got_keep != want_keep).float().mean().item()
+    keep = want_keep.to(dev)
+    # 2. forward (and the log-sum-exp is the one of the un-dropped softmax)
+    ref = _attn_ref_drop(qkv, gate, tab, pad, keep, p, B, T, H, 0.125)
+    assert torch.isfinite(out.float()).all()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 0.04, err
+    out0 = torch.empty_like(out)
+    lse0 = torch.empty_like(lse)
+    ops.attn_fwd(qkv, gate, tab, pad, out0, lse0, B, T, H, 0.125)
+    torch.cuda.synchronize()
+    assert torch.allclose(lse, lse0, atol=1e-4, rtol=1e-5)
+    # 3. backward
+    dout = bf(torch.randn(B, T, D, device=dev))
+    delta = torch.empty(B, H, T, device=dev)
+    dqkv = torch.zeros(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
+    dgate = torch.full((B, H, T), 7.0, device=dev) if bias else None
+    dtab = torch.zeros(H, 2 * T - 1, device=dev) if bias else None
+    dq_acc = torch.zeros(B, T, D, device=dev)
+    ops.attn_bwd_fused_dropout(qkv, out, dout, gate, tab, pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, 0.125, p, words)
+    torch.cuda.synchronize()
+    assert dq_acc.abs().max().item() == 0.0
+    qr = qkv.float().requires_grad_(True)
+    gr = gate.clone().requires_grad_(True) if bias else None
+    tr = tab.clone().requires_grad_(True) if bias else None
+    _attn_ref_drop(qr, gr, tr, pad, keep, p, B, T, H, 0.125).backward(dout.float())
+    assert torch.isfinite(dqkv.float()).all()
+    scale_ref = qr.grad.abs().max().item()
+    err = (dqkv.float() - qr.grad).abs().max().item()
+    assert err < 0.03 * max(1.0, scale_ref), (err, scale_ref)
+    for name, lo in (("dq", 0), ("dk", D), ("dv", 2 * D)):
+        g_, r_ = dqkv.float()[..., lo:lo + D], qr.grad[..., lo:lo + D]
+        cos = (g_ * r_).sum() / (g_.norm() * r_.norm() + 1e-30)
+        assert cos.item() > 0.999, (name, cos.item())
+    if bias:
+        e1 = (dgate - gr.grad).abs().max().item()
+        assert e1 < 0.03 * max(1.0, gr.grad.abs().max().item()), e1
+        e2 = (dtab - tr.grad).abs().max().item()
+        assert e2 < 0.03 * max(1.0, tr.grad.abs().max().item()), (e2, tr.grad.abs().max().item())
+
+
+def _build(cfg, device):
+    from unispeech_b200.wavlm import WavLM, WavLMConfig
+    m = WavLM(WavLMConfig(vars(cfg)))
+    m.load_state_dict(O.deterministic_state_dict(cfg), strict=True)
+    return m.to(device)
+
+
+MODEL_CASES = {
+    "tiny_postln_all": (lambda: O.tiny_config(pre_ln=False, dropout=0.1, attention_dropout=0.1, activation_dropout=0.1,
+                                              dropout_input=0.1), 2, 8000, [8000, 5000]),
+    "tiny_preln_all": (lambda: O.tiny_config(pre_ln=True, dropout=0.1, attention_dropout=0.1, activation_dropout=0.05,
+                                             dropout_input=0.2), 2, 6400, [6400, 4321]),
+    "tiny_postln_reference_defaults": (lambda: O.tiny_config(pre_ln=False, dropout=0.1, attention_dropout=0.1), 3, 48000,
+                                       [48000, 40000, 31111]),   # WavLMConfig defaults (WavLM/WavLM.py:180-185), T = 149
+    "tiny_preln_norelpos_attn_only": (lambda: O.tiny_config(pre_ln=True, relative_position_embedding=False, gru_rel_pos=False,
+                                                            attention_dropout=0.3), 2, 4000, [4000, 3000]),
+    "base2l_hidden_only": (lambda: O.base_config(encoder_layers=2, dropout=0.1), 1, 8000, None),
+}
+
+
+@pytest.mark.parametrize("name", sorted(MODEL_CASES))
+def test_model_with_dropout_vs_oracle_same_masks(cuda_device, name):
+    mk, B, L, lengths = MODEL_CASES[name]
+    cfg = mk()
+    dev = cuda_device
+    m = _build(cfg, dev).train()
+    seed = 20240 + len(name)
+    m.dropout_seed = seed
+    wav, pmask = O.deterministic_waveform(B, L, seed=1, lengths=lengths)
+    pm = pmask.to(dev) if lengths is not None else None
+    T = O.num_frames(L, cfg)
+    mi = O.hash_uniform("dropmask:" + name, (B, T)) > 0.4
+    x, fpm = m.extract_features(wav.to(dev), padding_mask=pm, mask=True, mask_indices=mi)
+    loss = O.probe_loss(x.float(), fpm, seed=2)
+    loss.backward()
+    torch.cuda.synchronize()
+    sdr = {k: v.clone().requires_grad_(True) for k, v in O.deterministic_state_dict(cfg).items()}
+    ref = O.extract_features(sdr, wav, cfg, padding_mask=pmask if lengths is not None else None, mask_indices=mi,
+                             drop=O.HashDropout(seed))
+    ref_loss = O.probe_loss(ref["x"], ref["padding_mask"], seed=2)
+    ref_loss.backward()
+    valid = ~ref["padding_mask"] if ref["padding_mask"] is not None else torch.ones(B, T, dtype=torch.bool)
+    dx = (x.detach().float().cpu() - ref["x"].detach())[valid].abs()
+    assert torch.isfinite(x.float()).all()
+    assert dx.max().item() < 0.15 and dx.mean().item() < 0.02, (dx.max().item(), dx.mean().item())
+    # the masks matter: the same model without dropout is far away from this output
+    ref0 = O.extract_features({k: v.detach() for k, v in sdr.items()}, wav, cfg,
+                              padding_mask=pmask if lengths is not None else None, mask_indices=mi)
+    assert (ref0["x"] - ref["x"].detach())[valid].abs().max().item() > 5 * dx.max().item()
+    params = dict(m.named_parameters())
+    bad = []
+    for k, v in sdr.items():
+        if v.grad is None:
+            continue
+        want, got = v.grad.double(), params[k].grad.detach().double().cpu()
+        if want.norm().item() < 1e-6 or k.endswith("k_proj.bias"):
+            continue
+        cos = ((got * want).sum() / (got.norm() * want.norm() + 1e-30)).item()
+        rel = abs(got.norm().item() - want.norm().item()) / want.norm().item()
+        if cos < 0.99 or rel > 0.08:
+            bad.append((k, round(cos, 4), round(rel, 4)))
+    assert not bad, bad
+
+
+def test_dropout_determinism_and_eval_mode(cuda_device):
+    cfg = O.tiny_config(pre_ln=False, dropout=0.1, attention_dropout=0.1)
+    dev = cuda_device
+    m = _build(cfg, dev).train()
+    wav, _ = O.deterministic_waveform(2, 8000, seed=1)
+    w = wav.to(dev)
+    with torch.no_grad():
+        m.dropout_seed = 1
+        a, _ = m.extract_features(w)
+        b, _ = m.extract_features(w)
+        m.dropout_seed = 2
+        c, _ = m.extract_features(w)
+        m.dropout_seed = None
+        torch.manual_seed(3)
+        d1, _ = m.extract_features(w)
+        d2, _ = m.extract_features(w)          # fresh seed per forward pass
+        torch.manual_seed(3)
+        d3, _ = m.extract_features(w)          # reproducible under torch.manual_seed
+        m.eval()
+        e, _ = m.extract_features(w)
+        want = O.extract_features(O.deterministic_state_dict(cfg), wav, cfg)["x"]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    assert not torch.equal(d1, d2) and torch.equal(d1, d3)
+    assert (e.float().cpu() - want).abs().max().item() < 0.12   # eval mode: no dropout at all

@@ -54,7 +54,7 @@ constexpr int kProdWarp = kCudaThreads / 32;
 
 }  // namespace
 
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __grid_constant__ CUtensorMap tm_qkv,
                                                                       const __grid_constant__ CUtensorMap tm_do,
                                                                       const __grid_constant__ AttnParams p,
@@ -231,6 +231,9 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     const float sc = p.scale * kLog2e;
     const float* tabrow = tab_s + r + N * kAttnTile - 1;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    // dropout keep bits written by the forward kernel: word (query block i >> 5, key) holds the bits of 32 consecutive queries
+    const uint32_t* mask_col =
+        DROP ? p.drop_mask + static_cast<long long>(b * p.H + h) * (4 * N) * (N * kAttnTile) + k0 + r : nullptr;
 
     // dQ tile of query tile qi: TMEM -> fp32 reductions into dq_acc[b, q, h*64 + ch*32 ..]
     auto flush_dq = [&](int qi) {
@@ -278,6 +281,8 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       const int i0 = qi * kAttnTile + hf * 64 + ch * kCW;  // first global query of this thread's columns
       mbar_wait(&st_full[hf], qi & 1);
       tc_fence_after();
+      uint32_t keep_bits = 0xffffffffu;
+      if (DROP) keep_bits = mask_col[static_cast<long long>(i0 >> 5) * (N * kAttnTile)] >> (i0 & 31);  // bit e = query i0 + e
       uint32_t su[kCW], du[kCW];
       tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + ch * kCW, su);
       tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + 64 + ch * kCW, du);
@@ -299,8 +304,14 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
             x = fmaf(c.z, tb, x);
           }
           const float pr = ex2f(x - c.x);
-          const float ds = pr * (__uint_as_float(du[j + e]) - c.y);
-          pr2[e] = pr;
+          float dpv = __uint_as_float(du[j + e]);
+          bool keep = true;
+          if (DROP) {  // O = (P o M) V / (1-p):  dP = M o (dO V^T) / (1-p);  dV takes the dropped probabilities (scaled at the end)
+            keep = ((keep_bits >> (j + e)) & 1u) != 0u;
+            dpv = keep ? dpv * p.drop_rp : 0.f;
+          }
+          const float ds = pr * (dpv - c.y);
+          pr2[e] = keep ? pr : 0.f;
           ds2[e] = ds * p.scale;
           w2[e] = c.w * ds;
           dgc[j + e] = ds * tb;
@@ -350,6 +361,10 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       const uint32_t col = ((ch < kNC / 2) ? kColDV : kColDK) + (ch & (kNC / 2 - 1)) * (128 / kNC);
       tmem_ld_32x32b_x32(tmem + lane_addr + col, t0);
       tmem_ld_wait();
+      if (DROP && ch < kNC / 2) {  // dV = (P o M)^T dO / (1-p)
+#pragma unroll
+        for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * p.drop_rp);
+      }
       if (key_valid) {
         __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + key) * (3 * D) + ((ch < kNC / 2) ? 2 * D : D) +
                              h * kHeadDim + (ch & (kNC / 2 - 1)) * (128 / kNC);
@@ -440,10 +455,13 @@ extern "C" {
 
 // Fused backward of b200s_attn_fwd.  Same contract as b200s_attn_bwd plus dq_acc: fp32 [B,T,D] workspace that must be ZERO
 // on entry and is zero again on return (the q gradient is reduced there across key tiles before it is rounded to bf16).
-int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, const float* gate, const float* tab,
-                         const uint8_t* key_pad, const float* lse, float* delta, float* dq_acc, void* dqkv, float* dgate,
-                         float* dtab, int B, int T, int H, float scale, b200s_stream stream) {
+int b200s_attn_bwd_fused_dropout(const void* qkv, const void* out, const void* dout, const float* gate, const float* tab,
+                                 const uint8_t* key_pad, const float* lse, float* delta, float* dq_acc, void* dqkv,
+                                 float* dgate, float* dtab, int B, int T, int H, float scale, float drop_p,
+                                 const uint32_t* drop_mask, b200s_stream stream) {
   B200_CHECK_ARG(qkv && out && dout && lse && delta && dqkv && dq_acc, "attn_bwd_fused: null pointer");
+  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_bwd_fused: dropout p=%f out of range [0,1)", static_cast<double>(drop_p));
+  B200_CHECK_ARG(drop_p == 0.f || drop_mask != nullptr, "attn_bwd_fused: dropout needs the mask written by b200s_attn_fwd_dropout");
   B200_CHECK_ARG(T >= 1 && T <= 2048, "attn_bwd_fused: T=%d out of range (1..2048)", T);
   B200_CHECK_ARG(!tab || (dgate && dtab), "attn_bwd_fused: bias given but dgate/dtab missing");
   const int D = H * kHeadDim;
@@ -469,23 +487,31 @@ int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, con
   p.dqkv = static_cast<__nv_bfloat16*>(dqkv);
   p.dgate = dgate;
   p.dtab = dtab;
+  const bool drop = drop_p > 0.f;
+  p.drop_mask = const_cast<uint32_t*>(drop_mask);
+  p.drop_rp = 1.0f / (1.0f - drop_p);
   const int N = p.n_tiles;
   const int smem = kFTab + sizeof(float) * ((N + 1) * kAttnTile * 2 + N * kAttnTile) + 1024;
   B200_CHECK_ARG(smem <= 232448 - 512, "attn_bwd_fused: T=%d needs %d bytes of shared memory", T, smem);
   dim3 grid(N, H, B);
-  if (tab != nullptr) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200_CHECK_CUDA(launch_pdl(attn_bwd_fused_kernel<true>, dim3(grid), dim3(kFThreads), smem, st, tm_qkv, tm_do, p, dq_acc));
-  } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_bwd_fused_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200_CHECK_CUDA(launch_pdl(attn_bwd_fused_kernel<false>, dim3(grid), dim3(kFThreads), smem, st, tm_qkv, tm_do, p, dq_acc));
-  }
+  void (*kern)(const CUtensorMap, const CUtensorMap, const AttnParams, float*) =
+      tab != nullptr ? (drop ? attn_bwd_fused_kernel<true, true> : attn_bwd_fused_kernel<true, false>)
+                     : (drop ? attn_bwd_fused_kernel<false, true> : attn_bwd_fused_kernel<false, false>);
+  B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kFThreads), smem, st, tm_qkv, tm_do, p, dq_acc));
   B200_CHECK_LAUNCH();
   const long long nvec = rows * (D / 8);
   const int blocks = static_cast<int>(std::min<long long>(ceil_div_ll(nvec, 256), 148 * 16));
   B200_CHECK_CUDA(launch_pdl(attn_dq_convert_kernel, dim3(blocks), dim3(256), 0, st, dq_acc, static_cast<__nv_bfloat16*>(dqkv), rows, D));
   B200_CHECK_LAUNCH();
   return 0;
+}
+
+int b200s_attn_bwd_fused(const void* qkv, const void* out, const void* dout, const float* gate, const float* tab,
+                         const uint8_t* key_pad, const float* lse, float* delta, float* dq_acc, void* dqkv, float* dgate,
+                         float* dtab, int B, int T, int H, float scale, b200s_stream stream) {
+  return b200s_attn_bwd_fused_dropout(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale,
+                                      0.f, nullptr, stream);
 }
 
 }  // extern "C"

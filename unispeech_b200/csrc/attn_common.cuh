@@ -8,6 +8,7 @@
 // Layout: q/k/v are column slices of the fused projection output qkv[B, T, 3D] (head h of q at columns h*64.., k at
 // D + h*64.., v at 2D + h*64..), read by TMA with a strided 3-D tensor map; no head-major reshuffle exists.
 #pragma once
+#include "dropout.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -31,7 +32,19 @@ struct AttnParams {
   __nv_bfloat16* dqkv;        // [B,T,3D]
   float* dgate;               // [B,H,T]
   float* dtab;                // [H, 2T-1] (atomic accumulation)
+  // dropout on the probabilities (attention_dropout, WavLM/modules.py:551): keep bits of query rows 32w..32w+31 against key
+  // j live in word drop_mask[((b*H + h) * 4*n_tiles + w) * 128*n_tiles + j] (bit i & 31 = query i), written by the forward
+  // kernel from the counter-based hash of dropout.cuh and re-read by the backward kernel; kept probabilities scale by drop_rp
+  uint32_t* drop_mask;
+  uint32_t drop_k0, drop_k1, drop_thr_hi;
+  float drop_rp;              // 1 / (1 - p)
 };
+
+// words of the attention dropout bit mask for a [B,H,T,T] probability tensor
+static inline long long attn_drop_mask_words(int B, int H, int T) {
+  const long long n = (T + kAttnTile - 1) / kAttnTile;
+  return static_cast<long long>(B) * H * (4 * n) * (kAttnTile * n);
+}
 
 // fill the shared-memory slice of the bias table used by query tile q0: tab_s[idx] = tab[h, idx + T-1-(q0+127)]
 __device__ __forceinline__ void load_tab_slice(float* tab_s, const float* tab, int h, int T, int q0, int n_tiles) {

@@ -34,7 +34,7 @@ constexpr int kFwdP = 98304;               // 2 x 32 KB (one P tile per warpgrou
 constexpr int kFwdTab = 163840;            // fp32 bias-table slice, key mask, tile flags
 constexpr int kFwdThreads = 288;           // 2 warpgroups + 1 producer warp
 
-template <bool HAS_BIAS>
+template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm,
                                                                  const __grid_constant__ AttnParams p) {
   pdl_grid_sync();
@@ -141,6 +141,16 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
     }
     const float sc = p.scale * kLog2e;
     const float* tabrow = tab_s + (2 * kAttnTile - 1 - r256);
+    // dropout on the probabilities: per-row hash keys, and where this warp's 32 rows keep their bits (one word per key column)
+    uint32_t rk0 = 0, rk1 = 0;
+    uint32_t* mask_row = nullptr;
+    if (DROP) {
+      const uint32_t rowid = static_cast<uint32_t>(b * p.H + h) * static_cast<uint32_t>(T) + static_cast<uint32_t>(q0 + r256);
+      rk0 = drop_row_k0(p.drop_k0, rowid);
+      rk1 = drop_row_k1(p.drop_k1, rowid);
+      if (q0 + wg * kAttnTile < N * kAttnTile)  // (a 256-row CTA may reach past the last 128-row tile: nothing to record there)
+        mask_row = p.drop_mask + (static_cast<long long>(b * p.H + h) * (4 * N) + ((q0 + r256) >> 5)) * (N * kAttnTile);
+    }
 
     float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
     float o[kHeadDim];
@@ -215,6 +225,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
           tmem_ld_32x32b_x32(s_addr + c0, su);
           tmem_ld_wait();
           float pv[32];
+          uint32_t mword = 0, hbits = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = fmaf(__uint_as_float(su[j]), sc, neg_ref);
@@ -222,9 +233,18 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
             if (msk) x += kbias[k0 + c0 + j];
             over = fmaxf(over, x);
             const float e = fast_exp2(x);
-            pv[j] = e;
-            lsum += e;
+            lsum += e;  // the softmax normaliser is taken before dropout
+            if (DROP) {
+              if ((j & 1) == 0) hbits = drop_bits(rk0, rk1, static_cast<uint32_t>(k0 + c0 + j) >> 1);
+              const bool keep = (j & 1) ? drop_keep_hi(hbits, p.drop_thr_hi) : drop_keep_lo(hbits, p.drop_thr_hi);
+              const uint32_t bal = __ballot_sync(0xffffffffu, keep);  // bit l = query row of lane l
+              if ((tid & 31) == j) mword = bal;
+              pv[j] = keep ? e : 0.f;
+            } else {
+              pv[j] = e;
+            }
           }
+          if (DROP && mask_row != nullptr) mask_row[k0 + c0 + (tid & 31)] = mword;
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 w;
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
     accumulate_o();
 
     if (row_valid) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      const float inv = l_run > 0.f ? (DROP ? p.drop_rp : 1.0f) / l_run : 0.f;
       __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * T + q0 + r256) * D + h * kHeadDim;
 #pragma unroll
       for (int g = 0; g < 8; ++g) {
@@ -307,9 +327,13 @@ extern "C" {
 // out[b,t,h*64+d] = softmax_j(scale q.k + gate*tab[j-i], key padding) v     (WavLM/modules.py:540-563 replaced)
 // qkv: bf16 [B,T,3D] fused projection output; gate: fp32 [B,H,T] or NULL; tab: fp32 [H,2T-1] or NULL (no bias);
 // key_pad: uint8 [B,T] or NULL; out: bf16 [B,T,D]; lse: fp32 [B,H,T] (log2-domain log-sum-exp, saved for backward).
-int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out, float* lse,
-                   int B, int T, int H, float scale, b200s_stream stream) {
+int b200s_attn_fwd_dropout(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out, float* lse,
+                           int B, int T, int H, float scale, float drop_p, uint32_t key0, uint32_t key1, uint32_t* drop_mask,
+                           b200s_stream stream) {
   B200_CHECK_ARG(qkv && out, "attn_fwd: null pointer");
+  B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_fwd: dropout p=%f out of range [0,1)", static_cast<double>(drop_p));
+  B200_CHECK_ARG(drop_p == 0.f || drop_mask != nullptr, "attn_fwd: dropout needs the mask buffer (b200s_attn_dropout_mask_words)");
+  B200_CHECK_ARG(static_cast<long long>(B) * H * T < (1LL << 32), "attn_fwd: B*H*T exceeds the 32-bit dropout row counter");
   B200_CHECK_ARG(T >= 1 && T <= 4096, "attn_fwd: T=%d out of range (1..4096)", T);
   const int D = H * kHeadDim;
   CUtensorMap tm;
@@ -322,19 +346,29 @@ int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const u
   p.gate = gate; p.tab = tab; p.key_pad = key_pad;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.lse = lse;
+  const bool drop = drop_p > 0.f;
+  p.drop_mask = drop_mask;
+  p.drop_k0 = key0; p.drop_k1 = key1;
+  p.drop_thr_hi = drop_threshold16(drop_p) << 16;
+  p.drop_rp = 1.0f / (1.0f - drop_p);
   const int smem = kFwdTab + sizeof(float) * ((p.n_tiles + 2) * kAttnTile + p.n_tiles * kAttnTile) +
                    sizeof(int) * p.n_tiles + 1024;
   dim3 grid(ceil_div(T, 2 * kAttnTile), H, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (tab != nullptr) {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<true>, dim3(grid), dim3(kFwdThreads), smem, st, tm, p));
-  } else {
-    B200_CHECK_CUDA(cudaFuncSetAttribute(attn_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    B200_CHECK_CUDA(launch_pdl(attn_fwd_kernel<false>, dim3(grid), dim3(kFwdThreads), smem, st, tm, p));
-  }
+  void (*kern)(const CUtensorMap, const AttnParams) =
+      tab != nullptr ? (drop ? attn_fwd_kernel<true, true> : attn_fwd_kernel<true, false>)
+                     : (drop ? attn_fwd_kernel<false, true> : attn_fwd_kernel<false, false>);
+  B200_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(kFwdThreads), smem, st, tm, p));
   B200_CHECK_LAUNCH();
   return 0;
 }
+
+int b200s_attn_fwd(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out, float* lse,
+                   int B, int T, int H, float scale, b200s_stream stream) {
+  return b200s_attn_fwd_dropout(qkv, gate, tab, key_pad, out, lse, B, T, H, scale, 0.f, 0u, 0u, nullptr, stream);
+}
+
+long long b200s_attn_dropout_mask_words(int B, int T, int H) { return attn_drop_mask_words(B, H, T); }
 
 }  // extern "C"

@@ -6,6 +6,7 @@
 
 #include "../../include/unispeech_b200.h"
 #include "common.h"
+#include "dropout.cuh"
 #include "ptx.cuh"
 
 namespace b200 {
@@ -422,6 +423,39 @@ __global__ void __launch_bounds__(256) dgelu_mul_kernel(const __nv_bfloat16* __r
   }
 }
 
+// ------------------------------------------------------------------------------------------------ dropout
+// y = [res +] dropout(x): nn.Dropout / F.dropout of the transformer stack (WavLM/WavLM.py:350,584,702,711,713,726,736,738).
+// The mask is a pure function of (key, logical row, column) (dropout.cuh), so the backward pass is the same kernel applied to
+// the incoming gradient with the same key (res = null).  8 bf16 per thread, grid-stride over 16-byte vectors; x == y is allowed.
+template <bool HAS_RES>
+__global__ void __launch_bounds__(256) dropout_rows_kernel(const __nv_bfloat16* x, RowView xv, const __nv_bfloat16* res,
+                                                           RowView rv, __nv_bfloat16* y, RowView yv, int N,
+                                                           unsigned total_vecs, uint32_t k0, uint32_t k1, uint32_t thr_hi,
+                                                           float rp) {
+  pdl_grid_sync();
+  const unsigned vec_per_row = static_cast<unsigned>(N) >> 3;
+  for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < total_vecs; v += gridDim.x * 256u) {
+    const unsigned row = v / vec_per_row;
+    const unsigned c = (v - row * vec_per_row) << 3;
+    float a[8];
+    VecIO<8>::load(x + xv.off(row) + c, a);
+    const uint32_t ctr0 = (row * static_cast<uint32_t>(N) + c) >> 1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t bits = drop_bits(k0, k1, ctr0 + q);
+      a[2 * q] = drop_keep_lo(bits, thr_hi) ? a[2 * q] * rp : 0.f;
+      a[2 * q + 1] = drop_keep_hi(bits, thr_hi) ? a[2 * q + 1] * rp : 0.f;
+    }
+    if (HAS_RES) {
+      float b[8];
+      VecIO<8>::load(res + rv.off(row) + c, b);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] += b[q];
+    }
+    VecIO<8>::store(y + yv.off(row) + c, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ frame masking
 // x[b,t,:] = 0 where pad[b,t];  = mask_emb where mask[b,t] and not pad   (apply_mask WavLM/WavLM.py:285-286, then
 // x[padding_mask] = 0 WavLM/WavLM.py:574-575).  In place on a [B,T,D] view.
@@ -759,6 +793,42 @@ int b200s_dgelu_mul(const void* dy, long long dy_bs, long long dy_rs, const void
                     b200s_stream stream) {
   return b200s_dgelu_mul_ex(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum, 0,
                             stream);
+}
+
+// host evaluation of the mask formulas of dropout.cuh (no device involved): lets CPU-only tests hold the numpy restatement used
+// by the parity tests to the code the kernels compile
+uint32_t b200s_dropout_bits(uint32_t key0, uint32_t key1, uint32_t ctr) { return drop_bits(key0, key1, ctr); }
+uint32_t b200s_dropout_row_key(uint32_t key, uint32_t row, int which) {
+  return which == 0 ? drop_row_k0(key, row) : drop_row_k1(key, row);
+}
+uint32_t b200s_dropout_threshold16(float p) { return drop_threshold16(p); }
+
+int b200s_dropout_rows(const void* x, long long x_bs, long long x_rs, const void* res, long long res_bs, long long res_rs,
+                       void* y, long long y_bs, long long y_rs, int rows_per_batch, int batches, int N, float p,
+                       uint32_t key0, uint32_t key1, b200s_stream stream) {
+  B200_CHECK_ARG(x && y, "dropout_rows: null pointer");
+  B200_CHECK_ARG(N > 0 && N % 8 == 0, "dropout_rows: N=%d must be a positive multiple of 8", N);
+  B200_CHECK_ARG(p >= 0.f && p < 1.f, "dropout_rows: p=%f out of range [0,1)", static_cast<double>(p));
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  B200_CHECK_ARG(rows * N < (1LL << 32), "dropout_rows: %lld x %d elements exceed the 32-bit mask counter", rows, N);
+  RowView xv{x_bs, x_rs, rows_per_batch}, rv{res_bs, res_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
+  const unsigned total = static_cast<unsigned>(rows * (N / 8));
+  const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(total, 256), 16LL * sm_count()));
+  const uint32_t thr_hi = drop_threshold16(p) << 16;
+  const float rp = 1.0f / (1.0f - p);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (res != nullptr) {
+    B200_CHECK_CUDA(launch_pdl(dropout_rows_kernel<true>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv,
+                               static_cast<const __nv_bfloat16*>(res), rv, static_cast<__nv_bfloat16*>(y), yv, N, total, key0,
+                               key1, thr_hi, rp));
+  } else {
+    B200_CHECK_CUDA(launch_pdl(dropout_rows_kernel<false>, dim3(grid), dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv,
+                               static_cast<const __nv_bfloat16*>(nullptr), rv, static_cast<__nv_bfloat16*>(y), yv, N, total,
+                               key0, key1, thr_hi, rp));
+  }
+  B200_CHECK_LAUNCH();
+  return 0;
 }
 
 int b200s_frame_mask_fwd(void* x, long long x_bs, long long x_rs, int T, int B, int D, const uint8_t* mask,

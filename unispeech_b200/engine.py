@@ -19,6 +19,7 @@ from typing import Dict, List, Optional
 import torch
 
 from . import _lib as L
+from . import dropout as DR
 from . import ops
 
 BF = torch.bfloat16
@@ -113,6 +114,7 @@ class Engine:
         self.lut_cache: Dict[int, torch.Tensor] = {}
         self.flat: Optional[FlatGrads] = None
         self._params = None
+        self.drop: Optional[DR.DropState] = None  # set per forward pass by WavLM._begin (training-mode dropout)
 
     # ------------------------------------------------------------------------------------------------ setup
     def _ensure_device(self, device):
@@ -213,6 +215,10 @@ class Engine:
         if T not in self.lut_cache:
             self.lut_cache[T] = relative_positions_bucket_lut(T, self.cfg.num_buckets, self.cfg.max_distance).to(self.dev)
         return self.lut_cache[T]
+
+    def active_drop(self) -> Optional[DR.DropState]:
+        """Dropout state of the current forward pass (None in eval mode or when every probability is 0)."""
+        return self.drop if self.m.training else None
 
     def g(self, p):  # gradient view of a parameter
         return self.flat.view(p)
@@ -398,9 +404,12 @@ class Engine:
         xv = xpad[:, half:]
         epi = L.make_epilogue(bias=m.post_extract_proj.bias)
         ops.gemm_rows(fn, T * C, C, T, B, C, self.wp, D, xv, Tpad * D, D, epi)
+        d = self.active_drop()
+        if d is not None and d.p_input > 0:  # features = dropout_input(features), WavLM/WavLM.py:350
+            ops.dropout_rows(xv, Tpad * D, D, None, 0, 0, xv, Tpad * D, D, T, B, D, d.p_input, d.key(DR.SITE_INPUT))
         features = xv[:, :T].clone() if want_features else None
         ops.frame_mask_fwd(xv, Tpad * D, D, T, B, D, mask_u8, pad_u8, m.mask_emb)
-        return dict(fn=fn, mean=mean, rstd=rstd, xpad=xpad, feats=feats if save else None, features=features)
+        return dict(fn=fn, mean=mean, rstd=rstd, xpad=xpad, feats=feats if save else None, features=features, drop=d)
 
     def project_backward(self, st, dxm, T, mask_u8, pad_u8):
         """dxm: gradient w.r.t. the masked projection output, bf16 [B,T,D] (modified in place). Returns d(features) [B,Tp,C]."""
@@ -411,6 +420,9 @@ class Engine:
         Tp, C = feats.shape[1], feats.shape[2]
         dev = dxm.device
         ops.frame_mask_bwd(dxm, T * D, D, T, B, D, mask_u8, pad_u8, self.g(m.mask_emb))
+        d = st["drop"]
+        if d is not None and d.p_input > 0:
+            ops.dropout_rows(dxm, T * D, D, None, 0, 0, dxm, T * D, D, T, B, D, d.p_input, d.key(DR.SITE_INPUT))
         ops.colsum(dxm, T * D, D, T, B, D, self.g(m.post_extract_proj.bias))
         ops.gemm_wgrad(dxm, T * D, D, st["fn"], T * C, C, T, B, D, C, self.g(m.post_extract_proj.weight), C)
         dfn = torch.empty(B, T, C, dtype=BF, device=dev)
@@ -433,19 +445,26 @@ class Engine:
         epi = L.make_epilogue(bias=pc.bias, gelu=2, out_pre=pre, pre_bs=T * D, pre_ld=D, res1=xpad[:, half:],
                               res1_bs=Tpad * D, res1_ld=D)
         ops.posconv_gemm(xpad, Tpad * D, T, B, D, G, taps, self.pc_fwd, xs, T * D, D, epi)
-        st = dict(xpad=xpad, pre=pre, xs=xs)
+        d = self.active_drop()
+        d = d if (d is not None and d.p > 0) else None
+        st = dict(xpad=xpad, pre=pre, xs=xs, drop=d)
         if not cfg.layer_norm_first:
             x0 = torch.empty(B, T, D, dtype=BF, device=dev)
             mean = torch.empty(B * T, dtype=torch.float32, device=dev)
             rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
             ln = m.encoder.layer_norm
-            if self._uses_gate() and len(m.encoder.layers) > 0:
+            if d is None and self._uses_gate() and len(m.encoder.layers) > 0:
                 self._ln_with_gate(xs, ln, x0, mean, rstd, T, B, D, 0)
-            else:
+            else:  # (with dropout the first layer's gate must see the DROPPED x: it is computed by that layer instead)
                 ops.layer_norm_fwd(xs, T * D, D, ln.weight, ln.bias, x0, T * D, D, mean, rstd, T, B, D)
+                self._pending_gate = None
             st.update(mean=mean, rstd=rstd)
-            return x0, st
-        return xs, st
+            out = x0
+        else:
+            out = xs
+        if d is not None:  # x = F.dropout(x, p=self.dropout), WavLM/WavLM.py:584 (in place: nothing below needs the undropped value)
+            ops.dropout_rows(out, T * D, D, None, 0, 0, out, T * D, D, T, B, D, d.p, d.key(DR.SITE_ENCODER))
+        return out, st
 
     def posconv_backward(self, st, dx0, T):
         m, cfg = self.m, self.cfg
@@ -454,6 +473,11 @@ class Engine:
         dev = xpad.device
         G, taps, half = cfg.conv_pos_groups, cfg.conv_pos, cfg.conv_pos // 2
         Cg = D // G
+        d = st["drop"]
+        if d is not None:
+            dx0d = torch.empty(B, T, D, dtype=BF, device=dev)
+            ops.dropout_rows(dx0, T * D, D, None, 0, 0, dx0d, T * D, D, T, B, D, d.p, d.key(DR.SITE_ENCODER))
+            dx0 = dx0d
         if not cfg.layer_norm_first:
             ln = m.encoder.layer_norm
             dxs = torch.empty(B, T, D, dtype=BF, device=dev)
@@ -490,7 +514,14 @@ class Engine:
         e = lambda *s: torch.empty(*s, dtype=BF, device=dev)
         f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
         pre_ln = cfg.layer_norm_first
-        st = dict(x=x)
+        d = self.active_drop()
+        p_h = d.p if d is not None else 0.0
+        p_a = d.p_attn if d is not None else 0.0
+        p_act = d.p_act if d is not None else 0.0
+        if p_a > 0 and T > 2048:
+            raise NotImplementedError("attention_dropout > 0 is implemented in the fused attention kernels for T <= 2048 frames "
+                                      f"(got T={T}); set attention_dropout=0 for longer inputs")
+        st = dict(x=x, drop=d)
         want_gate = tab is not None and cfg.gru_rel_pos
         gate = self._take_gate(x, idx) if (want_gate and not pre_ln) else None
         if pre_ln:
@@ -510,9 +541,19 @@ class Engine:
             gate = f(B, H, T)
             ops.gate_fwd(xn, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, gate)
         ao, lse = e(B, T, D), f(B, H, T)
-        ops.attn_fwd(qkv, gate, tab, pad_u8, ao, lse, B, T, H, 64 ** -0.5)
+        dmask = None
+        if p_a > 0:  # dropout on the probabilities (WavLM/modules.py:551); the kernel leaves the keep bits for the backward
+            dmask = torch.empty(ops.attn_dropout_mask_words(B, T, H), dtype=torch.int32, device=dev)
+            ops.attn_fwd_dropout(qkv, gate, tab, pad_u8, ao, lse, B, T, H, 64 ** -0.5, p_a,
+                                 d.key(DR.layer_site(idx, DR.L_ATTENTION)), dmask)
+        else:
+            ops.attn_fwd(qkv, gate, tab, pad_u8, ao, lse, B, T, H, 64 ** -0.5)
         y1 = e(B, T, D)
-        ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias, res1=x, res1_ld=D))
+        if p_h > 0:  # x + dropout1(out_proj(attn)), WavLM/WavLM.py:702-703,726-727
+            ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias))
+            ops.dropout_rows(y1, T * D, D, x, T * D, D, y1, T * D, D, T, B, D, p_h, d.key(DR.layer_site(idx, DR.L_DROPOUT1)))
+        else:
+            ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias, res1=x, res1_ld=D))
         if pre_ln:
             x1 = y1
             x1n, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
@@ -528,8 +569,18 @@ class Engine:
         hp = e(B, T, Fd) if save else None
         ops.gemm_rows(ffn_in, 0, D, M, 1, D, w["w1"], Fd, hg, 0, Fd,
                       L.make_epilogue(bias=lyr.fc1.bias, gelu=2, out_pre=hp, pre_ld=Fd))  # hp = gelu'(fc1 output)
+        if p_act > 0:  # dropout2 after the activation (WavLM/WavLM.py:711,736); the same mask folded into the stored
+            # derivative makes the backward epilogue (dy * hp) the gradient through activation AND dropout
+            k_act = d.key(DR.layer_site(idx, DR.L_ACTIVATION))
+            ops.dropout_rows(hg, T * Fd, Fd, None, 0, 0, hg, T * Fd, Fd, T, B, Fd, p_act, k_act)
+            if hp is not None:
+                ops.dropout_rows(hp, T * Fd, Fd, None, 0, 0, hp, T * Fd, Fd, T, B, Fd, p_act, k_act)
         y2 = e(B, T, D)
-        ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias, res1=x1, res1_ld=D))
+        if p_h > 0:  # residual + dropout3(fc2(.)), WavLM/WavLM.py:713-714,738-739
+            ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias))
+            ops.dropout_rows(y2, T * D, D, x1, T * D, D, y2, T * D, D, T, B, D, p_h, d.key(DR.layer_site(idx, DR.L_DROPOUT3)))
+        else:
+            ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias, res1=x1, res1_ld=D))
         if pre_ln:
             out = y2
         else:
@@ -540,7 +591,8 @@ class Engine:
             else:
                 ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
         if save:
-            st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8)
+            st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8,
+                      dmask=dmask)
         return out, (st if save else None)
 
     def layer_backward(self, idx: int, st, dout: torch.Tensor, dtab):
@@ -558,18 +610,32 @@ class Engine:
         g = self.g
         pre_ln = cfg.layer_norm_first
         tab, pad = st["tab"], st["pad"]
+        d = st["drop"]
+        p_h = d.p if d is not None else 0.0
+        p_a = d.p_attn if d is not None else 0.0
+
+        def through_dropout(dy, which):  # gradient entering a dropped branch: same mask, same scale (dy itself feeds the residual)
+            dz = e(B, T, D)
+            ops.dropout_rows(dy, T * D, D, None, 0, 0, dz, T * D, D, T, B, D, p_h, d.key(DR.layer_site(idx, which)))
+            return dz
+
         # ---------------- FFN block
         if pre_ln:
             dy2 = dout                                           # x2 = x1 + fc2(...)
-            ops.colsum(dy2, T * D, D, T, B, D, g(lyr.fc2.bias))
+            dz2 = through_dropout(dy2, DR.L_DROPOUT3) if p_h > 0 else dy2
+            ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias))
         else:
             dy2 = e(B, T, D)
             ln = lyr.final_layer_norm
             ops.layer_norm_bwd(dout, T * D, D, st["y2"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, None, 0, 0,
-                               dy2, T * D, D, g(ln.weight), g(ln.bias), g(lyr.fc2.bias), T, B, D)
-        ops.gemm_wgrad(dy2, 0, D, st["hg"], 0, Fd, M, 1, D, Fd, g(lyr.fc2.weight), Fd)
+                               dy2, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(lyr.fc2.bias), T, B, D)
+            dz2 = dy2
+            if p_h > 0:
+                dz2 = through_dropout(dy2, DR.L_DROPOUT3)
+                ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias))
+        ops.gemm_wgrad(dz2, 0, D, st["hg"], 0, Fd, M, 1, D, Fd, g(lyr.fc2.weight), Fd)
         dhp = e(B, T, Fd)
-        ops.gemm_rows(dy2, 0, D, M, 1, D, w["w2T"], Fd, dhp, 0, Fd,
+        ops.gemm_rows(dz2, 0, D, M, 1, D, w["w2T"], Fd, dhp, 0, Fd,
                       L.make_epilogue(dgelu=2, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias)))
         ops.gemm_wgrad(dhp, 0, Fd, st["ffn_in"], 0, D, M, 1, Fd, D, g(lyr.fc1.weight), D)
         dx1 = e(B, T, D)
@@ -580,17 +646,22 @@ class Engine:
             ops.layer_norm_bwd(dffn_in, T * D, D, st["x1"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, dy2, T * D, D,
                                dx1, T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
             dy1 = dx1                                            # x1 = x + out_proj(attn)
-            ops.colsum(dy1, T * D, D, T, B, D, g(a.out_proj.bias))
+            dz1 = through_dropout(dy1, DR.L_DROPOUT1) if p_h > 0 else dy1
+            ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
         else:
             ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dx1, 0, D, L.make_epilogue(res1=dy2, res1_ld=D))
             dy1 = e(B, T, D)
             ln = lyr.self_attn_layer_norm
             ops.layer_norm_bwd(dx1, T * D, D, st["y1"], T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, None, 0, 0,
-                               dy1, T * D, D, g(ln.weight), g(ln.bias), g(a.out_proj.bias), T, B, D)
+                               dy1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D)
+            dz1 = dy1
+            if p_h > 0:
+                dz1 = through_dropout(dy1, DR.L_DROPOUT1)
+                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
         # ---------------- attention block
-        ops.gemm_wgrad(dy1, 0, D, st["ao"], 0, D, M, 1, D, D, g(a.out_proj.weight), D)
+        ops.gemm_wgrad(dz1, 0, D, st["ao"], 0, D, M, 1, D, D, g(a.out_proj.weight), D)
         dao = e(B, T, D)
-        ops.gemm_rows(dy1, 0, D, M, 1, D, w["oT"], D, dao, 0, D, None)
+        ops.gemm_rows(dz1, 0, D, M, 1, D, w["oT"], D, dao, 0, D, None)
         dqkv = e(B, T, 3 * D)
         delta = f(B, H, T)
         gate = st["gate"]
@@ -600,8 +671,12 @@ class Engine:
             if getattr(self, "_dq_acc_key", None) != key:  # fp32 dQ accumulator: zero on entry, re-zeroed by the kernel
                 self._dq_acc = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
                 self._dq_acc_key = key
-            ops.attn_bwd_fused(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, self._dq_acc, dqkv, dgate,
-                               dtab if tab is not None else None, B, T, H, 64 ** -0.5)
+            if p_a > 0:
+                ops.attn_bwd_fused_dropout(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, self._dq_acc, dqkv, dgate,
+                                           dtab if tab is not None else None, B, T, H, 64 ** -0.5, p_a, st["dmask"])
+            else:
+                ops.attn_bwd_fused(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, self._dq_acc, dqkv, dgate,
+                                   dtab if tab is not None else None, B, T, H, 64 ** -0.5)
         else:
             ops.attn_bwd(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, dqkv, dgate,
                          dtab if tab is not None else None, B, T, H, 64 ** -0.5)

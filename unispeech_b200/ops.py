@@ -200,3 +200,42 @@ def attn_bwd(qkv, out, dout, gate, tab, key_pad, lse, delta, dqkv, dgate, dtab, 
 def attn_bwd_fused(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale):
     _call("b200s_attn_bwd_fused", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
            L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
+
+
+# ------------------------------------------------------------------------------------------------- dropout
+u32 = C.c_uint32
+
+
+def dropout_rows(x, x_bs, x_rs, res, res_bs, res_rs, y, y_bs, y_rs, rows_per_batch, batches, N, p, key):
+    """y = [res +] dropout(x) with the counter-based mask of csrc/dropout.cuh; `key` = (key0, key1).  y may alias x."""
+    _call("b200s_dropout_rows", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(res), L.ll(res_bs), L.ll(res_rs), L.ptr(y), L.ll(y_bs),
+           L.ll(y_rs), i32(rows_per_batch), i32(batches), i32(N), f32(p), u32(key[0]), u32(key[1]), _s())
+
+
+def attn_dropout_mask_words(B, T, H) -> int:
+    n = (T + 127) // 128
+    return B * H * (4 * n) * (128 * n)
+
+
+def attn_fwd_dropout(qkv, gate, tab, key_pad, out, lse, B, T, H, scale, p, key, drop_mask):
+    _call("b200s_attn_fwd_dropout", L.ptr(qkv), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(out), L.ptr(lse), i32(B), i32(T),
+           i32(H), f32(scale), f32(p), u32(key[0]), u32(key[1]), L.ptr(drop_mask), _s())
+
+
+def attn_bwd_fused_dropout(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale, p,
+                           drop_mask):
+    _call("b200s_attn_bwd_fused_dropout", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad),
+           L.ptr(lse), L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale),
+           f32(p), L.ptr(drop_mask), _s())
+
+
+# ------------------------------------------------------------------------------------------------- optimizer
+def sumsq_f32(g, n, out):
+    _call("b200s_sumsq_f32", L.ptr(g), L.ll(n), L.ptr(out), _s())
+
+
+def adam_step(table, n_tensors, total_chunks, g, m, v, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step,
+              zero_grad):
+    _call("b200s_adam_step", L.ptr(table), i32(n_tensors), L.ll(total_chunks), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(sumsq),
+           f32(grad_scale), f32(max_norm), f32(lr), f32(beta1), f32(beta2), f32(eps), f32(weight_decay), i32(step),
+           i32(1 if zero_grad else 0), _s())

@@ -20,6 +20,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .dropout import DropState
 from .engine import BF, Engine
 from .masking import compute_mask_indices
 
@@ -469,6 +470,7 @@ class WavLM(nn.Module):
         for lyr in self.encoder.layers:
             lyr._owner = owner
         self._engine: Optional[Engine] = None
+        self.dropout_seed: Optional[int] = None  # None: draw a fresh seed per forward; an int pins the dropout masks (tests)
 
     # ---- engine plumbing
     def _engine_for(self, device) -> Engine:
@@ -480,15 +482,9 @@ class WavLM(nn.Module):
         return self._engine
 
     def _begin(self, device) -> Engine:
-        if self.training:
-            c = self.cfg
-            active = [n for n in ("dropout", "attention_dropout", "activation_dropout", "dropout_input", "dropout_features")
-                      if getattr(c, n) > 0]
-            if active:
-                raise NotImplementedError(
-                    "training-mode dropout is not implemented in the fused kernels yet; set " + ", ".join(active) +
-                    " to 0 (or call model.eval())")
         eng = self._engine_for(device)
+        # training-mode dropout: one seed per forward pass (torch CPU generator, or `self.dropout_seed` when a caller pins it)
+        eng.drop = DropState.for_model(self.cfg, self.training, self.dropout_seed)
         if eng._params is None:  # Module.parameters() walks the module tree (~2 ms for WavLM-Base): once per engine
             eng._params = list(self.parameters())
         for p in eng._params:
