@@ -2,8 +2,10 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--model base|large] [--impl ours|reference]
 
-N=1 workload = BASELINE.json configs[1]: WavLM-Base, batch 16 x 15 s synthetic 16 kHz waveform per GPU, masking on, fwd + bwd of the
-whole encoder through the public API (`WavLM.extract_features` + probe loss + `backward()`), bf16 kernels, dropout 0.
+Workload = the model BASELINE.json's metric names: WavLM-Large, batch 8 x 20 s synthetic 16 kHz waveform per GPU (configs[2]'s
+per-GPU batch; it fits one B200), masking on, fwd + bwd of the whole encoder through the public API (`WavLM.extract_features` +
+probe loss + `backward()`), bf16 kernels, dropout 0 as in BASELINE.md section 3.  At N=1 the line also carries, under `also`,
+WavLM-Base 16 x 15 s (configs[1]) and the same Large workload with the reference's default dropouts (0.1 / 0.1).
 N>1 (launched with torch.distributed.run): same per-GPU batch (weak scaling), plus ONE NCCL allreduce of the flat fp32
 gradient buffer per step.  Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks.
 Inputs are far larger than L2 (the first conv activation alone is 786 MB), so no explicit L2 flush is needed.
@@ -134,7 +136,7 @@ def run_reference(args):
     if rank != 0:
         return
     threads = best_cpu_threads(cfg)
-    cb, csecs = (4, secs) if args.model != "tiny" else (B, secs)
+    cb, csecs = {"tiny": B, "base": 4, "large": 2}[args.model], secs
     steps = max(1, min(args.steps, 3))
     for _ in range(min(args.warmup, 1)):
         cpu_step(cfg, cb, csecs, 1, threads)
@@ -153,15 +155,111 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+class Workload:
+    """One model + one synthetic batch per rank, stepped through the public API (extract_features + probe loss + backward
+    [+ the gradient allreduce for N > 1])."""
+
+    def __init__(self, model_name, dev, rank, world, dropout=0.0):
+        from oracle import wavlm_oracle as O  # parameter / input generators only
+        from unispeech_b200.wavlm import WavLM, WavLMConfig
+        self.name, self.dev, self.world, self.dropout = model_name, dev, world, dropout
+        cfg, B, secs = model_config(model_name)
+        if dropout > 0:  # the reference's WavLMConfig defaults: dropout = attention_dropout = 0.1 (WavLM/WavLM.py:180-181)
+            cfg.dropout, cfg.attention_dropout = dropout, dropout
+        self.cfg, self.B, self.secs = cfg, B, secs
+        self.L = secs * SR
+        self.T = O.num_frames(self.L, cfg)
+        model = WavLM(WavLMConfig(vars(cfg)))
+        model.load_state_dict(O.deterministic_state_dict(cfg))
+        self.model = model.to(dev).train()
+        gen = torch.Generator().manual_seed(1337 + rank)
+        wav = torch.randn(B, self.L, generator=gen)
+        wav = torch.nn.functional.layer_norm(wav, (self.L,)) if cfg.normalize else wav
+        self.wav_host = wav.pin_memory()
+        self.pad_host = torch.zeros(B, self.L, dtype=torch.bool)  # the reference always passes an (all-False) mask in training (S14)
+        self.wav_dev = self.wav_host.to(dev)
+        self.R = torch.randn(B, self.T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        self.loss_host = torch.zeros(1).pin_memory()
+        self.fwd_flops = O.forward_flops(self.L, cfg)
+
+    def step(self, e2e: bool, collective: bool = True):
+        from unispeech_b200.parallel import all_reduce_grads
+        model = self.model
+        if model._engine is not None and model._engine.flat is not None:
+            model.grad_buffer().zero_()
+            model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
+        wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
+        x, _ = model.extract_features(wav, padding_mask=self.pad_host, mask=True)
+        loss = (x.float() * self.R).sum()
+        loss.backward()
+        if self.world > 1 and collective:
+            all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
+        if e2e:
+            self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def timed(self, n_steps: int, e2e: bool) -> float:
+        """Milliseconds for exactly n_steps: barrier + synchronize on both sides, CUDA events, max over ranks."""
+        import torch.distributed as dist
+        if self.world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(n_steps):
+            self.step(e2e)
+        ev1.record()
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier()
+        ms = ev0.elapsed_time(ev1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=self.dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = t.item()
+        return ms
+
+    def audio_seconds(self, n_steps: int) -> float:
+        return self.world * self.B * self.secs * n_steps
+
+    def describe(self) -> str:
+        drop = f"dropout {self.dropout} / attention_dropout {self.dropout}" if self.dropout > 0 else "dropout 0"
+        return (f"WavLM-{self.name} fwd+bwd, batch {self.B} x {self.secs} s per GPU, 16 kHz synthetic, mask_prob "
+                f"{self.cfg.mask_prob}, {drop}, all-False padding mask")
+
+    def free(self):
+        self.model = self.R = self.wav_dev = None
+        torch.cuda.empty_cache()
+
+
+def quick_line(w: Workload, steps: int, warmup: int, e2e: bool = True):
+    """Secondary measurement (reported under `also`): same timing rules, fewer outputs."""
+    for _ in range(warmup):
+        w.step(False)
+    ms = w.timed(steps, False)
+    out = {"workload": w.describe(), "value": w.audio_seconds(steps) / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms / steps,
+           "model_tflops": 3 * w.fwd_flops * w.world * w.B * steps / (ms * 1e-3) / 1e12}
+    if e2e:
+        for _ in range(2):
+            w.step(True)
+        ms_e = w.timed(steps, True)
+        out["e2e"] = {"value": w.audio_seconds(steps) / (ms_e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e / steps}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--model", default="base", choices=["base", "large", "tiny"])
+    ap.add_argument("--model", default="large", choices=["base", "large", "tiny"],
+                    help="large = the model BASELINE.json's metric names (configs[2] per-GPU batch 8 x 20 s); base = configs[1]")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout = attention_dropout of the headline run (BASELINE.md "
+                    "section 3 times both arms with dropout 0; the reference's config default 0.1 is reported under `also`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (WavLM-Base, reference dropouts)")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -169,10 +267,7 @@ def main():
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
-    from oracle import wavlm_oracle as O  # parameter / input generators and the CPU baseline only
     from unispeech_b200 import _lib, ops
-    from unispeech_b200.parallel import all_reduce_grads
-    from unispeech_b200.wavlm import WavLM, WavLMConfig
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -183,65 +278,16 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    cfg, B, secs = model_config(args.model)
-    L_ = secs * SR
-    T = O.num_frames(L_, cfg)
-    model = WavLM(WavLMConfig(vars(cfg)))
-    model.load_state_dict(O.deterministic_state_dict(cfg))
-    model = model.to(dev).train()
-
-    gen = torch.Generator().manual_seed(1337 + rank)
-    wav_host = torch.randn(B, L_, generator=gen).pin_memory()
-    wav_host = torch.nn.functional.layer_norm(wav_host, (L_,)) if cfg.normalize else wav_host
-    wav_host = wav_host.pin_memory()
-    pad_host = torch.zeros(B, L_, dtype=torch.bool)  # the reference always passes an (all-False) mask in training (S14)
-    wav_dev = wav_host.to(dev)
-    R = torch.randn(B, T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
-    loss_host = torch.zeros(1).pin_memory()
-
-    def eager_step(e2e: bool, collective: bool = True):
-        if model._engine is not None and model._engine.flat is not None:
-            model.grad_buffer().zero_()
-            model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
-        wav = wav_host.to(dev, non_blocking=True) if e2e else wav_dev
-        x, _ = model.extract_features(wav, padding_mask=pad_host, mask=True)
-        loss = (x.float() * R).sum()
-        loss.backward()
-        if world > 1 and collective:
-            all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
-        if e2e:
-            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
-        return loss
-
-    def step(e2e: bool):
-        return eager_step(e2e)
-
-    def timed(n_steps: int, e2e: bool):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(n_steps):
-            step(e2e)
-        ev1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = ev0.elapsed_time(ev1)
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = t.item()
-        return ms
+    w = Workload(args.model, dev, rank, world, dropout=args.dropout)
+    cfg, B, secs, T = w.cfg, w.B, w.secs, w.T
 
     for _ in range(args.warmup):
-        step(False)
+        w.step(False)
     torch.cuda.synchronize()
     if args.ncu_step:
         # exactly one warmed-up step between cudaProfilerStart/Stop: run under `ncu --profile-from-start off ...`
         torch.cuda.profiler.start()
-        step(False)
+        w.step(False)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -251,23 +297,23 @@ def main():
     lc0 = _lib.load().b200s_launch_count
     lc0.restype = __import__("ctypes").c_longlong
     n0 = lc0()
-    ms = timed(args.steps, False)
+    ms = w.timed(args.steps, False)
     launches = lc0() - n0
     clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
-        step(True)
-    ms_e2e = timed(args.steps, True)
+        w.step(True)
+    ms_e2e = w.timed(args.steps, True)
 
     # host cost of enqueueing one step (launch queue empty at the start, two steps timed without synchronising): if this
     # approaches ms_per_step the run is launch-bound, not GPU-bound
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(2):
-        step(False)
+        w.step(False)
     host_ms = (time.perf_counter() - t0) * 1e3 / 2
     torch.cuda.synchronize()
 
-    audio_s = world * B * secs * args.steps
+    audio_s = w.audio_seconds(args.steps)
     value = audio_s / (ms * 1e-3)
     e2e_value = audio_s / (ms_e2e * 1e-3)
 
@@ -276,7 +322,7 @@ def main():
     if rank == 0 and not args.no_profile:
         prof = ops.Profiler()
         ops.set_profiler(prof)
-        eager_step(False, collective=False)  # rank 0 only: no collective in this extra, per-op-timed step
+        w.step(False, collective=False)  # rank 0 only: no collective in this extra, per-op-timed step
         torch.cuda.synchronize()
         ops.set_profiler(None)
         breakdown = prof.summary()
@@ -286,10 +332,11 @@ def main():
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        gemm_ms = sum(v["ms"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
-        gemm_flops = sum(v["flops"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
+        is_gemm = lambda k: k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad")
+        gemm_ms = sum(v["ms"] for k, v in breakdown.items() if is_gemm(k))
+        gemm_flops = sum(v["flops"] for k, v in breakdown.items() if is_gemm(k))
         achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
-        n_gemm = sum(v["calls"] for k, v in breakdown.items() if k.startswith("gemm") or k.startswith("posconv_gemm") or k.startswith("posconv_wgrad"))
+        n_gemm = sum(v["calls"] for k, v in breakdown.items() if is_gemm(k))
         traffic, traffic_src = None, None
         try:  # DRAM bytes of the same launches from the committed ncu capture of one step (profiles/, same workload)
             tj = json.load(open(os.path.join(ROOT, "profiles", f"gemm_traffic_{args.model}.json")))
@@ -304,31 +351,49 @@ def main():
                     "us_per_launch": gemm_ms * 1e3 / max(n_gemm, 1), "traffic": traffic, "traffic_source": traffic_src,
                     "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
 
+    # ---- secondary measurements (N = 1 only): the reference's default dropouts on the same workload, and WavLM-Base (configs[1])
+    also = None
+    if world == 1 and not args.no_also and args.model != "tiny":
+        also = {}
+        w.free()
+        try:
+            if args.dropout == 0.0:
+                wd = Workload(args.model, dev, rank, world, dropout=0.1)
+                also["reference_default_dropouts"] = quick_line(wd, args.steps, 3, e2e=False)
+                wd.free()
+            other = "base" if args.model == "large" else "large"
+            wo = Workload(other, dev, rank, world, dropout=0.0)
+            also[f"wavlm_{other}"] = quick_line(wo, args.steps, 3, e2e=True)
+            wo.free()
+        except Exception as exc:  # a secondary line must never cost the headline
+            also["error"] = f"{type(exc).__name__}: {exc}"
+
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
         threads = best_cpu_threads(cfg)
-        cb = 4 if args.model != "tiny" else B
+        cb = {"tiny": B, "base": 4, "large": 2}[args.model]
         v, s = cpu_step(cfg, cb, secs, 1, threads)
         cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
                         "sample": f"oracle fwd+bwd fp32, {cb} x {secs} s, 1 step ({s:.1f} s); thread count auto-tuned "
                                   f"(host has {os.cpu_count()} logical CPUs)"}
 
     if rank == 0:
-        fwd_flops = O.forward_flops(L_, cfg)
+        fwd_flops = w.fwd_flops
         line = {
             "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": f"WavLM-{args.model} fwd+bwd, batch {B} x {secs} s per GPU, 16 kHz synthetic, mask_prob "
-                                   f"{cfg.mask_prob}, dropout 0, all-False padding mask", "global_batch": world * B,
+            "config": {"workload": w.describe(), "global_batch": world * B,
                        "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", 
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
-            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": wav_host.numel() * 4,
+            "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": w.wav_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "model_tflops": 3 * fwd_flops * world * B * args.steps / (ms * 1e-3) / 1e12,
         }
+        if also is not None:
+            line["also"] = also
         if breakdown is not None:
             line["breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
         print(json.dumps(line))

@@ -1,5 +1,5 @@
 """Micro-benchmark of the attention kernels at the WavLM-Base (16 x 749, 12 heads) and -Large (8 x 999, 16 heads) shapes.
-    python tools/bench_attn.py [--reps 10] [--only base|large]"""
+    python tools/bench_attn.py [--reps 10] [--only base|large] [--dropout 0.1]"""
 import argparse, os, sys
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -9,6 +9,7 @@ from unispeech_b200 import ops
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--only", default=None)
+ap.add_argument("--dropout", type=float, default=0.0, help="also time the kernels with dropout on the probabilities")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 for name, B, T, H in (("base", 16, 749, 12), ("large", 8, 999, 16)):
@@ -33,6 +34,11 @@ for name, B, T, H in (("base", 16, 749, 12), ("large", 8, 999, 16)):
         "bwd_fused": lambda: ops.attn_bwd_fused(qkv, out, dout, gate, tab, pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, 0.125),
         "bwd_2kernel": lambda: ops.attn_bwd(qkv, out, dout, gate, tab, pad, lse, delta, dqkv, dgate, dtab, B, T, H, 0.125),
     }
+    if args.dropout > 0:
+        words = torch.empty(ops.attn_dropout_mask_words(B, T, H), dtype=torch.int32, device=dev)
+        fns["fwd_dropout"] = lambda: ops.attn_fwd_dropout(qkv, gate, tab, pad, out, lse, B, T, H, 0.125, args.dropout, (123, 456), words)
+        fns["bwd_fused_dropout"] = lambda: ops.attn_bwd_fused_dropout(qkv, out, dout, gate, tab, pad, lse, delta, dq_acc, dqkv, dgate,
+                                                                      dtab, B, T, H, 0.125, args.dropout, words)
     fl = 4.0 * B * H * T * T * 64
     for k, fn in fns.items():
         for _ in range(2):
@@ -45,5 +51,5 @@ for name, B, T, H in (("base", 16, 749, 12), ("large", 8, 999, 16)):
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / args.reps
-        mult = 1.0 if k == "fwd" else 2.5
-        print(f"{name:6s} {k:12s} {ms*1e3:9.1f} us   {fl*mult/ms/1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+        mult = 1.0 if k.startswith("fwd") else 2.5
+        print(f"{name:6s} {k:18s} {ms*1e3:9.1f} us   {fl*mult/ms/1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
