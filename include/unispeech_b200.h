@@ -237,6 +237,34 @@ int b200s_adam_step(const void* table, int n_tensors, long long total_chunks, fl
                     const double* sumsq, float grad_scale, float max_norm, float lr, float beta1, float beta2,
                     float eps, float weight_decay, int step, int zero_grad, b200s_stream stream);
 
+/* ============================ masked-prediction loss head (csrc/nce.cu) ============================ */
+/* final_proj + cosine-similarity NCE logits + sum-reduced cross entropy of the pre-training models
+ * (src/fairseq/models/wavlm/wavlm.py:426-438,525-576; src/fairseq/criterions/wavlm_criterion.py:63-87), built around the
+ * tcgen05 GEMMs above: z[s,c] = cos(proj_s, E_c)/temp = (proj En^T)[s,c] / (|proj_s| temp), loss = w * sum_s CE(z[s,:], target_s)
+ * (the reference's {positive} U {negatives != positive} softmax IS the softmax over the C classes). */
+
+/* out[s,:] = x[idx[s],:]  (x[masked_indices], wavlm.py:541,558) and its autograd dx[idx[s],:] += src[s,:] (distinct rows) */
+int b200s_gather_rows(const void* x, long long x_rs, const int* idx, int S, int D, void* out, long long out_rs,
+                      b200s_stream stream);
+int b200s_scatter_add_rows(const void* src, long long src_rs, const int* idx, int S, int D, void* dx, long long dx_rs,
+                           b200s_stream stream);
+/* en[c,:] = bf16(E_c / max(|E_c|,1e-8)) for c < C, zero rows up to Cpad; en_t = its transpose [Dp, Cpad]; invn[c] = 1/max(|E_c|,1e-8) */
+int b200s_nce_prep(const float* label_embs, int C, int Cpad, int Dp, void* en, void* en_t, float* invn,
+                   b200s_stream stream);
+/* zraw = proj En^T (bf16 [S,Cpad], from b200s_gemm_rows).  Writes g[s,c] = weight (softmax(z)_c - [c==target_s]) / (|proj_s| temp)
+ * (bf16 [S,Cpad], zero in the padded columns), pn[s] = 1/|proj_s|, rvec[s] = sum_c g[s,c] cos[s,c]; adds weight * sum_s CE to
+ * *loss_sum (fp64) and the number of frames whose target has the largest logit to *correct (compute_correct,
+ * wavlm_criterion.py:116-126; may be NULL). */
+int b200s_nce_ce(const void* proj, long long proj_rs, int Dp, const void* zraw, long long z_rs, const int* target, int S,
+                 int C, int Cpad, float logit_temp, float weight, void* g, long long g_rs, float* pn, float* rvec,
+                 double* loss_sum, int* correct, b200s_stream stream);
+/* dproj[s,:] -= rvec[s] * pn[s] * proj[s,:]   (dproj holds g En on entry: the gradient through 1/|proj_s|) */
+int b200s_nce_dproj(void* dproj, long long d_rs, const void* proj, long long p_rs, int S, int Dp, const float* pn,
+                    const float* rvec, b200s_stream stream);
+/* d_label_embs[c,:] += (d_en_c - (d_en_c . En_c) En_c) / |E_c|,  d_en = g^T proj (fp32 [>=C, Dp], from b200s_gemm_wgrad) */
+int b200s_nce_dlabel(const float* d_en, const float* label_embs, const float* invn, int C, int Dp, float* d_label_embs,
+                     b200s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -585,3 +585,55 @@ def adam_step(params: List[Tensor], grads: List[Tensor], state: dict, lr: float,
         if weight_decay != 0:
             p.add_(p, alpha=-weight_decay * lr)
         p.addcdiv_(m, denom, value=-step_size)
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# masked-prediction head + criterion  (src/fairseq/models/wavlm/wavlm.py:426-438 compute_nce, :525-576 forward tail;
+# src/fairseq/criterions/wavlm_criterion.py:52-138 get_loss)
+# ----------------------------------------------------------------------------------------------------------------
+def compute_nce(x: Tensor, pos: Tensor, negs: Tensor, logit_temp: float) -> Tensor:
+    """wavlm.py:426-438 verbatim in structure: [S, C+1] logits, column 0 = positive, -inf where a negative equals the positive."""
+    neg_is_pos = (pos == negs).all(-1)
+    pos = pos.unsqueeze(0)
+    targets = torch.cat([pos, negs], dim=0)
+    logits = torch.cosine_similarity(x.float(), targets.float(), dim=-1).type_as(x)
+    logits = logits / logit_temp
+    if neg_is_pos.any():
+        logits[1:][neg_is_pos] = float("-inf")
+    return logits.transpose(0, 1)
+
+
+def masked_prediction_logits(x: Tensor, sel: Tensor, target_list: List[Tensor], final_proj_w: Tensor, final_proj_b: Tensor,
+                             label_embs_concat: Tensor, num_classes: List[int], untie_final_proj: bool, logit_temp: float):
+    """Logit lists of wavlm.py:525-553 for the frames selected by the bool [B,T] mask `sel` (masked or unmasked set)."""
+    proj = F.linear(x[sel], final_proj_w, final_proj_b)
+    projs = proj.chunk(len(target_list), dim=-1) if untie_final_proj else [proj for _ in target_list]
+    label_embs_list = label_embs_concat.split(num_classes, 0)
+    out = []
+    for i, (p, t) in enumerate(zip(projs, target_list)):
+        y = torch.index_select(label_embs_list[i], 0, t[sel].long())
+        negs = label_embs_list[i].unsqueeze(1).expand(-1, p.size(0), -1)
+        out.append(compute_nce(p, y, negs, logit_temp))
+    return out
+
+
+def wavlm_criterion(logit_m_list: List[Tensor], logit_u_list: List[Tensor], pred_masked_weight: float, pred_nomask_weight: float,
+                    features_pen: Optional[Tensor] = None, loss_weights: Optional[List[float]] = None):
+    """WavLMCriterion.get_loss (wavlm_criterion.py:52-103, :116-138 for the accuracy counts): positives sit at index 0."""
+    loss, sample_size, log = 0.0, 0, {}
+    for tag, lst, w in (("m", logit_m_list, pred_masked_weight), ("u", logit_u_list, pred_nomask_weight)):
+        parts = []
+        for i, lg in enumerate(lst):
+            tgt = lg.new_zeros(lg.size(0), dtype=torch.long)
+            l_ = F.cross_entropy(lg.float(), tgt, reduction="sum")
+            parts.append(l_)
+            log[f"loss_{tag}_{i}"] = l_.detach()
+            mx, mn = lg.argmax(-1) == 0, lg.argmin(-1) == 0
+            log[f"correct_{tag}_{i}"] = int(mx.long().sum() - (mx & mn).long().sum())
+            log[f"count_{tag}_{i}"] = mx.numel()
+        if w > 0 and parts:
+            loss = loss + w * sum(parts)
+            sample_size += lst[0].size(0)
+    if loss_weights is not None and features_pen is not None and loss_weights[0] != 0:
+        loss = loss + loss_weights[0] * features_pen.float() * sample_size
+    return loss, sample_size, log

@@ -1,0 +1,115 @@
+"""Masked-prediction head + criterion against the oracle's restatement of the fairseq code
+(compute_nce / forward tail / WavLMCriterion.get_loss).  The bf16 path keeps the logits in bf16 like the reference does in
+mixed precision (`.type_as(x)`, wavlm.py:433), so the loss is held to 2 % and gradients to cosine > 0.98 of the fp32 oracle."""
+import pytest
+import torch
+
+from oracle import wavlm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _head_state(cfg, D, Dt, Ctot, Dp):
+    return {"final_proj.weight": O.hash_uniform("fp.w", (Dt, D), -0.08, 0.08), "final_proj.bias": O.hash_uniform("fp.b", (Dt,), -0.1, 0.1),
+            "label_embs_concat": O.hash_uniform("lab", (Ctot, Dp), 0.0, 1.0)}
+
+
+def _run_case(dev, cfg, num_classes, untie, final_dim, B, L, lengths, pm_w, pu_w, loss_weights):
+    from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+    D = cfg.encoder_embed_dim
+    n = len(num_classes)
+    Dt = final_dim * (n if untie else 1)
+    pcfg = WavLMPretrainConfig(dict(vars(cfg), final_dim=final_dim, untie_final_proj=untie, logit_temp=0.1))
+    m = WavLMForPretraining(pcfg, num_classes)
+    sd = O.deterministic_state_dict(cfg)
+    head = _head_state(cfg, D, Dt, sum(num_classes), final_dim)
+    m.load_state_dict({**sd, **head}, strict=True)
+    m = m.to(dev).train()
+    wav, pmask = O.deterministic_waveform(B, L, seed=1, lengths=lengths)
+    T = O.num_frames(L, cfg)
+    mi = O.hash_uniform("premask", (B, T)) > 0.35
+    target_list = [(O.hash_uniform(f"tgt{i}", (B, T + 3), 0.0, 1.0) * C).long().clamp(max=C - 1) for i, C in enumerate(num_classes)]
+    out = m(wav.to(dev), target_list=target_list, padding_mask=pmask if lengths is not None else None, mask=True, mask_indices=mi)
+    loss, sample_size, log = m.criterion(out, pred_masked_weight=pm_w, pred_nomask_weight=pu_w, loss_weights=loss_weights)
+    loss.backward()
+    torch.cuda.synchronize()
+
+    # ---- oracle: same weights, fp32, reference-format logits
+    sdr = {k: v.clone().requires_grad_(True) for k, v in {**sd, **head}.items()}
+    conv = O.conv_feature_extractor(sdr, wav, cfg)
+    ref = O.extract_features(sdr, wav, cfg, padding_mask=pmask if lengths is not None else None, mask_indices=mi)
+    fpm = ref["padding_mask"] if ref["padding_mask"] is not None else torch.zeros(B, T, dtype=torch.bool)
+    tl = [t[:, :T] for t in target_list]   # label_rate 50 Hz == frame rate: forward_targets keeps the first T labels
+    args = (sdr["final_proj.weight"], sdr["final_proj.bias"], sdr["label_embs_concat"], num_classes, untie, 0.1)
+    lm = O.masked_prediction_logits(ref["x"], torch.logical_and(~fpm, mi), tl, *args)
+    lu = O.masked_prediction_logits(ref["x"], torch.logical_and(~fpm, ~mi), tl, *args) if pu_w > 0 else []
+    pen = conv.float().pow(2).mean()
+    want, want_ss, want_log = O.wavlm_criterion(lm, lu, pm_w, pu_w, pen, loss_weights)
+    want.backward()
+
+    assert sample_size == want_ss
+    assert abs(loss.item() - want.item()) < 0.02 * abs(want.item()) + 0.5, (loss.item(), want.item())
+    for i in range(n):
+        got_l = log[f"loss_m_{i}"].item()
+        assert abs(got_l - want_log[f"loss_m_{i}"].item()) < 0.02 * want_log[f"loss_m_{i}"].item() + 0.5
+        assert log[f"count_m_{i}"] == want_log[f"count_m_{i}"]
+        assert abs(int(log[f"correct_m_{i}"].item()) - want_log[f"correct_m_{i}"]) <= max(2, want_log[f"count_m_{i}"] // 20)
+    params = dict(m.named_parameters())
+    bad = []
+    for k, v in sdr.items():
+        if v.grad is None or k.endswith("k_proj.bias"):
+            continue
+        w_, g_ = v.grad.double(), params[k].grad.detach().double().cpu()
+        if w_.norm().item() < 1e-7:
+            continue
+        cos = ((g_ * w_).sum() / (g_.norm() * w_.norm() + 1e-30)).item()
+        rel = abs(g_.norm().item() - w_.norm().item()) / w_.norm().item()
+        if cos < 0.98 or rel > (0.1 if w_.numel() > 16 else 0.25):
+            bad.append((k, round(cos, 4), round(rel, 4)))
+    assert not bad, bad
+    return loss.item(), want.item()
+
+
+def test_head_tiny_single_label_set(cuda_device):
+    _run_case(cuda_device, O.tiny_config(pre_ln=False), [37], False, 64, 2, 8000, [8000, 5000], 1.0, 0.0, None)
+
+
+def test_head_tiny_two_untied_label_sets_with_unmasked_and_features_pen(cuda_device):
+    _run_case(cuda_device, O.tiny_config(pre_ln=True), [20, 100], True, 64, 2, 6400, [6400, 4321], 1.0, 0.5, [10.0])
+
+
+def test_head_tiny_two_tied_label_sets(cuda_device):
+    _run_case(cuda_device, O.tiny_config(pre_ln=False), [64, 130], False, 128, 2, 8000, None, 1.0, 0.0, None)
+
+
+def test_head_base_dims_504_classes(cuda_device):
+    """WavLM-Base widths (D = 768, final_dim = 256, 504 classes = the k-means dictionary of the released recipes), 2 layers."""
+    _run_case(cuda_device, O.base_config(encoder_layers=2), [504], False, 256, 2, 16000, [16000, 12000], 1.0, 0.0, [10.0])
+
+
+def test_optimisation_steps_reduce_the_loss(cuda_device):
+    """End to end: forward -> criterion -> backward -> FusedAdam, repeated: the masked-prediction loss goes down."""
+    from unispeech_b200.optim import FusedAdam
+    from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+    dev = cuda_device
+    cfg = O.tiny_config(pre_ln=True)
+    m = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=64)), [30])
+    sd = O.deterministic_state_dict(cfg)
+    m.load_state_dict({**sd, **_head_state(cfg, cfg.encoder_embed_dim, 64, 30, 64)}, strict=True)
+    m = m.to(dev).train()
+    wav, _ = O.deterministic_waveform(2, 8000, seed=1)
+    T = O.num_frames(8000, cfg)
+    mi = O.hash_uniform("premask", (2, T)) > 0.35
+    tl = [(O.hash_uniform("tgt", (2, T), 0.0, 1.0) * 30).long().clamp(max=29)]
+    opt, losses = None, []
+    for it in range(6):
+        out = m(wav.to(dev), target_list=tl, mask=True, mask_indices=mi)
+        loss, ss, _ = m.criterion(out)
+        loss.backward()
+        if opt is None:
+            opt = FusedAdam(m, lr=2e-3, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+        opt.multiply_grads(1.0 / ss)
+        opt.clip_grad_norm(10.0)
+        opt.step(zero_grad=True)
+        losses.append(loss.item() / ss)
+    assert losses[-1] < losses[0] - 0.05, losses

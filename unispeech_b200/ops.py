@@ -239,3 +239,29 @@ def adam_step(table, n_tensors, total_chunks, g, m, v, sumsq, grad_scale, max_no
     _call("b200s_adam_step", L.ptr(table), i32(n_tensors), L.ll(total_chunks), L.ptr(g), L.ptr(m), L.ptr(v), L.ptr(sumsq),
            f32(grad_scale), f32(max_norm), f32(lr), f32(beta1), f32(beta2), f32(eps), f32(weight_decay), i32(step),
            i32(1 if zero_grad else 0), _s())
+
+
+# ------------------------------------------------------------------------------------------------- masked-prediction head
+def gather_rows(x, x_rs, idx, S, D, out, out_rs):
+    _call("b200s_gather_rows", L.ptr(x), L.ll(x_rs), L.ptr(idx), i32(S), i32(D), L.ptr(out), L.ll(out_rs), _s())
+
+
+def scatter_add_rows(src, src_rs, idx, S, D, dx, dx_rs):
+    _call("b200s_scatter_add_rows", L.ptr(src), L.ll(src_rs), L.ptr(idx), i32(S), i32(D), L.ptr(dx), L.ll(dx_rs), _s())
+
+
+def nce_prep(label_embs, C, Cpad, Dp, en, en_t, invn):
+    _call("b200s_nce_prep", L.ptr(label_embs), i32(C), i32(Cpad), i32(Dp), L.ptr(en), L.ptr(en_t), L.ptr(invn), _s())
+
+
+def nce_ce(proj, proj_rs, Dp, zraw, z_rs, target, S, C, Cpad, logit_temp, weight, g, g_rs, pn, rvec, loss_sum, correct):
+    _call("b200s_nce_ce", L.ptr(proj), L.ll(proj_rs), i32(Dp), L.ptr(zraw), L.ll(z_rs), L.ptr(target), i32(S), i32(C), i32(Cpad),
+           f32(logit_temp), f32(weight), L.ptr(g), L.ll(g_rs), L.ptr(pn), L.ptr(rvec), L.ptr(loss_sum), L.ptr(correct), _s())
+
+
+def nce_dproj(dproj, d_rs, proj, p_rs, S, Dp, pn, rvec):
+    _call("b200s_nce_dproj", L.ptr(dproj), L.ll(d_rs), L.ptr(proj), L.ll(p_rs), i32(S), i32(Dp), L.ptr(pn), L.ptr(rvec), _s())
+
+
+def nce_dlabel(d_en, label_embs, invn, C, Dp, d_label_embs):
+    _call("b200s_nce_dlabel", L.ptr(d_en), L.ptr(label_embs), L.ptr(invn), i32(C), i32(Dp), L.ptr(d_label_embs), _s())

@@ -535,6 +535,7 @@ class WavLM(nn.Module):
         """Same contract as the reference.  `mask_indices` (bool [B,T], optional) lets a caller inject the masked frames instead
         of sampling them (used by the parity tests; the reference's sampler is host numpy RNG)."""
         feats, T = self._extractor(source)
+        self._last_conv = feats  # conv features [B, Tp, C] (valid rows T): `features_pen` of the pre-training criterion reads them
         eng = self._engine
         B = source.shape[0]
         # `padding_mask` may live on the host (as it does in the reference's collater): the frame mask and the span sampler
