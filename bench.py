@@ -159,28 +159,42 @@ class Workload:
     """One model + one synthetic batch per rank, stepped through the public API (extract_features + probe loss + backward
     [+ the gradient allreduce for N > 1])."""
 
-    def __init__(self, model_name, dev, rank, world, dropout=0.0):
+    def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False):
         from oracle import wavlm_oracle as O  # parameter / input generators only
         from unispeech_b200.wavlm import WavLM, WavLMConfig
         self.name, self.dev, self.world, self.dropout = model_name, dev, world, dropout
         cfg, B, secs = model_config(model_name)
         if dropout > 0:  # the reference's WavLMConfig defaults: dropout = attention_dropout = 0.1 (WavLM/WavLM.py:180-181)
             cfg.dropout, cfg.attention_dropout = dropout, dropout
-        self.cfg, self.B, self.secs = cfg, B, secs
-        self.L = secs * SR
+        self.cfg, self.B, self.secs, self.ragged = cfg, B, secs, ragged
+        # BASELINE.json configs[4]: utterances of 4 .. 30 s (seeded per rank), zero-padded to the longest of the batch, with the
+        # sample-level padding mask the reference collater builds; the fixed-length workloads use `secs` for every utterance
+        def lengths_of(r):
+            if not ragged:
+                return [secs * SR] * B
+            g = torch.Generator().manual_seed(4242 + r)
+            return [int(v) for v in torch.randint(4 * SR, 30 * SR + 1, (B,), generator=g)]
+        self.lengths = lengths_of(rank)
+        self.all_lengths = [lengths_of(r) for r in range(world)]
+        self.L = max(self.lengths)
         self.T = O.num_frames(self.L, cfg)
         model = WavLM(WavLMConfig(vars(cfg)))
         model.load_state_dict(O.deterministic_state_dict(cfg))
         self.model = model.to(dev).train()
         gen = torch.Generator().manual_seed(1337 + rank)
         wav = torch.randn(B, self.L, generator=gen)
-        wav = torch.nn.functional.layer_norm(wav, (self.L,)) if cfg.normalize else wav
+        self.pad_host = torch.zeros(B, self.L, dtype=torch.bool)  # the reference always passes a mask in training (all-False when nothing is padded, S14)
+        for b, n in enumerate(self.lengths):
+            if cfg.normalize:  # per-utterance normalisation of the data path (utterance_mixing_dataset.py:571-573), before padding
+                wav[b, :n] = torch.nn.functional.layer_norm(wav[b, :n], (n,))
+            wav[b, n:] = 0.0
+            self.pad_host[b, n:] = True
         self.wav_host = wav.pin_memory()
-        self.pad_host = torch.zeros(B, self.L, dtype=torch.bool)  # the reference always passes an (all-False) mask in training (S14)
         self.wav_dev = self.wav_host.to(dev)
         self.R = torch.randn(B, self.T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
         self.loss_host = torch.zeros(1).pin_memory()
-        self.fwd_flops = O.forward_flops(self.L, cfg)
+        self.fwd_flops = O.forward_flops(self.L, cfg)          # padded shape (what the kernels execute)
+        self.valid_fwd_flops = sum(O.forward_flops(n, cfg) for n in self.lengths) / B   # per utterance at its own length
 
     def step(self, e2e: bool, collective: bool = True):
         from unispeech_b200.parallel import all_reduce_grads
@@ -220,10 +234,19 @@ class Workload:
         return ms
 
     def audio_seconds(self, n_steps: int) -> float:
-        return self.world * self.B * self.secs * n_steps
+        """VALID (unpadded) audio seconds over all ranks: padding is overhead, not credit."""
+        return sum(sum(l) for l in self.all_lengths) / SR * n_steps
+
+    def padded_audio_seconds(self, n_steps: int) -> float:
+        return sum(len(l) * max(l) for l in self.all_lengths) / SR * n_steps
 
     def describe(self) -> str:
         drop = f"dropout {self.dropout} / attention_dropout {self.dropout}" if self.dropout > 0 else "dropout 0"
+        if self.ragged:
+            secs = ", ".join(f"{n / SR:.1f}" for n in self.lengths)
+            return (f"WavLM-{self.name} fwd+bwd, ragged batch of {self.B} utterances per GPU drawn from 4..30 s (rank 0: {secs} s), "
+                    f"zero-padded to {self.L / SR:.1f} s with a sample-level padding mask, 16 kHz synthetic, mask_prob "
+                    f"{self.cfg.mask_prob}, {drop}; value counts VALID audio only")
         return (f"WavLM-{self.name} fwd+bwd, batch {self.B} x {self.secs} s per GPU, 16 kHz synthetic, mask_prob "
                 f"{self.cfg.mask_prob}, {drop}, all-False padding mask")
 
@@ -238,7 +261,10 @@ def quick_line(w: Workload, steps: int, warmup: int, e2e: bool = True):
         w.step(False)
     ms = w.timed(steps, False)
     out = {"workload": w.describe(), "value": w.audio_seconds(steps) / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms / steps,
-           "model_tflops": 3 * w.fwd_flops * w.world * w.B * steps / (ms * 1e-3) / 1e12}
+           "model_tflops": 3 * w.valid_fwd_flops * w.world * w.B * steps / (ms * 1e-3) / 1e12}
+    if w.ragged:
+        out["padded_equivalent_value"] = w.padded_audio_seconds(steps) / (ms * 1e-3)
+        out["padded_model_tflops"] = 3 * w.fwd_flops * w.world * w.B * steps / (ms * 1e-3) / 1e12
     if e2e:
         for _ in range(2):
             w.step(True)
@@ -257,6 +283,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dropout", type=float, default=0.0, help="dropout = attention_dropout of the headline run (BASELINE.md "
                     "section 3 times both arms with dropout 0; the reference's config default 0.1 is reported under `also`)")
+    ap.add_argument("--ragged", action="store_true", help="BASELINE.json configs[4]: variable-length batch 4..30 s with padding mask")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (WavLM-Base, reference dropouts)")
@@ -278,7 +305,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    w = Workload(args.model, dev, rank, world, dropout=args.dropout)
+    w = Workload(args.model, dev, rank, world, dropout=args.dropout, ragged=args.ragged)
     cfg, B, secs, T = w.cfg, w.B, w.secs, w.T
 
     for _ in range(args.warmup):
@@ -361,6 +388,10 @@ def main():
                 wd = Workload(args.model, dev, rank, world, dropout=0.1)
                 also["reference_default_dropouts"] = quick_line(wd, args.steps, 3, e2e=False)
                 wd.free()
+            if not args.ragged and args.model == "large":
+                wr = Workload("large", dev, rank, world, dropout=0.0, ragged=True)
+                also["wavlm_large_ragged_4_30s"] = quick_line(wr, args.steps, 3, e2e=False)
+                wr.free()
             other = "base" if args.model == "large" else "large"
             wo = Workload(other, dev, rank, world, dropout=0.0)
             also[f"wavlm_{other}"] = quick_line(wo, args.steps, 3, e2e=True)
@@ -378,20 +409,22 @@ def main():
                                   f"(host has {os.cpu_count()} logical CPUs)"}
 
     if rank == 0:
-        fwd_flops = w.fwd_flops
+        fwd_flops = w.valid_fwd_flops
         line = {
             "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w.describe(), "global_batch": world * B,
                        "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", 
-                       "algorithmic_gflop_per_audio_s": 3 * fwd_flops / secs / 1e9},
+                       "algorithmic_gflop_per_audio_s": 3 * fwd_flops * B / (sum(w.lengths) / SR) / 1e9},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": w.wav_host.numel() * 4,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms,
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "model_tflops": 3 * fwd_flops * world * B * args.steps / (ms * 1e-3) / 1e12,
         }
+        if args.ragged:
+            line["padded_equivalent_value"] = w.padded_audio_seconds(args.steps) / (ms * 1e-3)
         if also is not None:
             line["also"] = also
         if breakdown is not None:

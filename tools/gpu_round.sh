@@ -4,10 +4,10 @@
 TAG=${1:-x}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,temperature.gpu --format=csv > gpurun_out/smi_$TAG.txt 2>&1
-timeout 300 python -m pytest tests/test_dropout_gpu.py tests/test_optim_gpu.py tests/test_pretrain_gpu.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_new_$TAG.log 2>&1
+timeout 300 python -m pytest tests/test_dropout_gpu.py tests/test_optim_gpu.py tests/test_pretrain_gpu.py tests/test_ragged_gpu.py -m gpu -q --tb=short -p no:cacheprovider > gpurun_out/pytest_new_$TAG.log 2>&1
 NEW=$?
 echo "new tests exit $NEW"; tail -5 gpurun_out/pytest_new_$TAG.log
-timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --deselect tests/test_dropout_gpu.py --deselect tests/test_optim_gpu.py --deselect tests/test_pretrain_gpu.py > gpurun_out/pytest_all_$TAG.log 2>&1
+timeout 600 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider --deselect tests/test_dropout_gpu.py --deselect tests/test_optim_gpu.py --deselect tests/test_pretrain_gpu.py --deselect tests/test_ragged_gpu.py > gpurun_out/pytest_all_$TAG.log 2>&1
 echo "suite exit $?"; tail -3 gpurun_out/pytest_all_$TAG.log
 timeout 200 python __graft_entry__.py smoke > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke exit $?"; tail -2 gpurun_out/smoke_$TAG.log
 if [ $NEW -eq 0 ]; then
