@@ -199,6 +199,13 @@ int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, i
                     const float* gamma, const float* beta, int mode, const double* stats, float* bstats,
                     const float* fmean, const float* frstd, const void* da, long long da_bs, float* dw,
                     float* dgamma, float* dbeta, b200s_stream stream);
+/* Same, with a bf16 workspace [B, ws_bs/C rows >= T, C] for the gradient w.r.t. the raw convolution output (mode 1 only; may
+ * alias `da`, which is then consumed): the LayerNorm-mode backward becomes one pass over the frames plus one streaming
+ * weight-gradient reduction instead of two full recomputing passes. */
+int b200s_conv0_bwd_ws(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w,
+                       const float* gamma, const float* beta, int mode, const double* stats, float* bstats,
+                       const float* fmean, const float* frstd, const void* da, long long da_bs, void* dconv_ws,
+                       long long ws_bs, float* dw, float* dgamma, float* dbeta, b200s_stream stream);
 
 /* ============================ parameter preparation (csrc/prep.cu) ============================ */
 
@@ -207,7 +214,8 @@ int b200s_scale_copy_f32(const float* src, float* dst, long long n, float scale,
 int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, long long ld, void* dstT,
                       long long ldT, b200s_stream stream);
 /* all nn.Linear operands of the model in ONE launch: descs = device array of n_descs 56-byte records
- * {const float* src; bf16* dst; bf16* dstT; int64 ld, ldT; int32 N, K, tile_begin, tiles_k} (32x32 tiles, prefix-summed) */
+ * {const float* src; bf16* dst; bf16* dstT; int64 ld, ldT; int32 N, K, tile_begin, tiles_k} (64x64 tiles: tiles_k = ceil(K/64),
+ * tile_begin = prefix sum of ceil(N/64)*ceil(K/64)) */
 int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b200s_stream stream);
 /* nn.Conv1d weight [Co,Ci,k] -> forward operand [Co, k*Ci] / per-phase input-gradient operand / gradient un-layout */
 int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream);

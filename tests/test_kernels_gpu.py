@@ -191,6 +191,16 @@ def test_conv0_fwd_bwd(cuda_device, Cc, mode):
     for got, want, name in ((dw, wr.grad, "dw"), (dg, gr.grad, "dgamma"), (db, br.grad, "dbeta")):
         err = (got - want).abs().max().item()
         assert err < 5e-3 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
+    if mode == 1:
+        # two-pass variant with a dconv workspace: separate buffer, then aliasing the incoming gradient (as the engine does)
+        for ws in (torch.zeros_like(dap), dap):
+            dw2, dg2, db2 = torch.zeros_like(w), torch.zeros_like(gamma), torch.zeros_like(beta)
+            ops.conv0_bwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, dap, Tp * Cc, dw2, dg2, db2,
+                          dconv_ws=ws, ws_bs=Tp * Cc)
+            torch.cuda.synchronize()
+            for got, want, name in ((dw2, wr.grad, "dw"), (dg2, gr.grad, "dgamma"), (db2, br.grad, "dbeta")):
+                err = (got - want).abs().max().item()
+                assert err < 8e-3 * max(1.0, want.abs().max().item()), (name, err, want.abs().max().item())
 
 
 def test_prep_kernels(cuda_device):
@@ -381,3 +391,28 @@ def test_attn_bwd(cuda_device, B, T, H, bias, padded, fused):
         assert e1 < 0.03 * max(1.0, gr.grad.abs().max().item()), e1
         e2 = (dtab - tr.grad).abs().max().item()
         assert e2 < 0.03 * max(1.0, tr.grad.abs().max().item()), (e2, tr.grad.abs().max().item())
+
+
+def test_prep_linear_batched_shapes(cuda_device):
+    """One launch, several nn.Linear masters (aligned and ragged shapes): bf16 copy and bf16 transpose, bit exact."""
+    import struct
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(3)
+    shapes = [(70, 100), (64, 64), (130, 36), (1, 5), (256, 768), (192, 64), (66, 130)]
+    recs, tiles, keep = [], 0, []
+    for N, K in shapes:
+        src = torch.randn(N, K, device=dev)
+        dst = torch.full((N, K), 9.0, device=dev, dtype=torch.bfloat16)
+        dstT = torch.full((K, N), 9.0, device=dev, dtype=torch.bfloat16)
+        tk = (K + 63) // 64
+        recs.append(struct.pack("<QQQqqiiii", src.data_ptr(), dst.data_ptr(), dstT.data_ptr(), K, N, N, K, tiles, tk))
+        tiles += ((N + 63) // 64) * tk
+        keep.append((src, dst, dstT))
+    descs = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(dev)
+    ops.prep_linear_batched(descs, len(recs), tiles)
+    torch.cuda.synchronize()
+    for (N, K), (src, dst, dstT) in zip(shapes, keep):
+        want = src.to(torch.bfloat16)
+        assert torch.equal(dst, want), (N, K)
+        assert torch.equal(dstT, want.t().contiguous()), (N, K)

@@ -352,6 +352,101 @@ __global__ void __launch_bounds__(256) conv0_bwd_dw_kernel(const float* __restri
   }
 }
 
+// LayerNorm-mode backward in two light passes instead of two heavy ones.  The single-kernel form above needs 16 x 10 weight
+// gradient accumulators per lane on top of the LayerNorm state, which does not fit the register file, so it ran TWICE (taps 0-4,
+// taps 5-9), each time recomputing the convolution, gelu' and the LayerNorm backward of every frame (2.8 ms of a 41 ms
+// WavLM-Large step).  Pass A does that work once, with few registers (two blocks per SM), leaves dconv (the gradient w.r.t. the
+// raw convolution output, bf16) in a workspace -- which may be the incoming gradient buffer itself -- and reduces dgamma / dbeta.
+// Pass B is a pure streaming reduction dW[c, j] += sum_t dconv[t, c] * wav[s t + j] over all taps at once.
+template <int C>
+__global__ void __launch_bounds__(256, 2) conv0_ln_bwd_dconv_kernel(const float* __restrict__ wav, long long L, int T, int k, int s,
+                                                                    const float* __restrict__ w, const float* __restrict__ gamma,
+                                                                    const float* __restrict__ beta,
+                                                                    const float* __restrict__ fmean, const float* __restrict__ frstd,
+                                                                    const __nv_bfloat16* da, long long da_bs, __nv_bfloat16* dconv,
+                                                                    long long dc_bs, float* __restrict__ dgamma,
+                                                                    float* __restrict__ dbeta) {
+  pdl_grid_sync();
+  using M = LaneMap<C>;
+  extern __shared__ float smem[];
+  float* w_s = smem;
+  float* red = smem + kMaxTaps * C;
+  load_weights<C>(w, k, w_s);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* wav_b = wav + static_cast<long long>(b) * L;
+  float g[M::CPL], be[M::CPL], ag[M::CPL], ab[M::CPL];
+#pragma unroll
+  for (int gi = 0; gi < M::NG; ++gi)
+#pragma unroll
+    for (int v = 0; v < M::V; ++v) {
+      const int c = M::chan(lane, gi, v);
+      g[gi * M::V + v] = gamma[c];
+      be[gi * M::V + v] = beta[c];
+    }
+#pragma unroll
+  for (int i = 0; i < M::CPL; ++i) ag[i] = ab[i] = 0.f;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
+    float acc[M::CPL], d[M::CPL];
+    conv_frame<C>(wav_b, L, t, k, s, w_s, lane, acc, nullptr);
+    load_frame<C>(da + b * da_bs + static_cast<long long>(t) * C, d, lane);
+    const float m = fmean[static_cast<long long>(b) * T + t], r = frstd[static_cast<long long>(b) * T + t];
+    float q1 = 0.f, q2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < M::CPL; ++i) {
+      const float xh = (acc[i] - m) * r;
+      const float dz = d[i] * gelu_grad_f(g[i] * xh + be[i]);
+      ag[i] += dz * xh;
+      ab[i] += dz;
+      const float dxh = dz * g[i];
+      acc[i] = xh;
+      d[i] = dxh;
+      q1 += dxh;
+      q2 += dxh * xh;
+    }
+    q1 = warp_sum(q1) * (1.0f / C);
+    q2 = warp_sum(q2) * (1.0f / C);
+#pragma unroll
+    for (int i = 0; i < M::CPL; ++i) d[i] = r * (d[i] - q1 - acc[i] * q2);
+    store_frame<C>(dconv + b * dc_bs + static_cast<long long>(t) * C, d, lane);
+  }
+  block_channel_atomic<C, float>(ag, dgamma, 1, red);
+  block_channel_atomic<C, float>(ab, dbeta, 1, red);
+}
+
+template <int C, int K>
+__global__ void __launch_bounds__(256) conv0_dw_from_dconv_kernel(const float* __restrict__ wav, long long L, int T, int k, int s,
+                                                                  const __nv_bfloat16* __restrict__ dconv, long long dc_bs,
+                                                                  float* __restrict__ dw) {
+  pdl_grid_sync();
+  using M = LaneMap<C>;
+  extern __shared__ float smem[];
+  float* red = smem;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.y;
+  const float* wav_b = wav + static_cast<long long>(b) * L;
+  float acc_dw[K][M::CPL];
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+#pragma unroll
+    for (int i = 0; i < M::CPL; ++i) acc_dw[j][i] = 0.f;
+  for (int t = blockIdx.x * 8 + warp; t < T; t += gridDim.x * 8) {
+    float d[M::CPL];
+    load_frame<C>(dconv + b * dc_bs + static_cast<long long>(t) * C, d, lane);
+    const long long p = static_cast<long long>(t) * s + lane;
+    const float xv = (lane < k && p < L) ? wav_b[p] : 0.f;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float xj = __shfl_sync(0xffffffffu, xv, j);  // 0 for j >= k
+#pragma unroll
+      for (int i = 0; i < M::CPL; ++i) acc_dw[j][i] = fmaf(d[i], xj, acc_dw[j][i]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j)
+    if (j < k) block_channel_atomic<C, float>(acc_dw[j], dw + j, k, red);  // dw layout [C, 1, k]
+}
+
 int conv0_gn_stats_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, double* stats,
                           cudaStream_t st);
 int conv0_gn_bwd_launch(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
@@ -411,10 +506,12 @@ int b200s_conv0_fwd(const float* wav, long long L, int B, int T, int C, int k, i
 
 // Backward: da = gradient w.r.t. the layer output (after norm + GELU), bf16 [B, rows, C].  Accumulates dw [C,1,k], dgamma,
 // dbeta (fp32 atomics).  bstats: fp32 [B,C,12] workspace (mode 0, zeroed here).  The waveform receives no gradient.
-int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
-                    const float* beta, int mode, const double* stats, float* bstats, const float* fmean,
-                    const float* frstd, const void* da, long long da_bs, float* dw, float* dgamma, float* dbeta,
-                    b200s_stream stream) {
+// dconv_ws (mode 1, optional): bf16 workspace [B, ws_bs/C rows >= T, C] for the gradient w.r.t. the raw convolution output; it
+// may alias `da` (the incoming gradient is then consumed).  With it the LayerNorm-mode backward is two light passes (see above).
+int b200s_conv0_bwd_ws(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
+                       const float* beta, int mode, const double* stats, float* bstats, const float* fmean,
+                       const float* frstd, const void* da, long long da_bs, void* dconv_ws, long long ws_bs, float* dw,
+                       float* dgamma, float* dbeta, b200s_stream stream) {
   B200_CHECK_ARG(wav && w && gamma && beta && da && dw && dgamma && dbeta, "conv0_bwd: null pointer");
   B200_CHECK_ARG(k <= kMaxTaps && k >= 1, "conv0_bwd: kernel size %d > %d", k, kMaxTaps);
   B200_CHECK_ARG((mode == 0 && stats && bstats) || (mode == 1 && fmean && frstd), "conv0_bwd: missing statistics");
@@ -428,6 +525,16 @@ int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, i
       (void)grid;
       if (int rc = conv0_gn_bwd_launch(wav, L, B, T, kC, k, s, w, gamma, beta, stats, bstats, da, da_bs, dw, dgamma, dbeta, st))
         return rc;
+    } else if (dconv_ws != nullptr && k <= 10) {
+      B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_ln_bwd_dconv_kernel<kC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(sm)));
+      B200_CHECK_CUDA(launch_pdl(conv0_ln_bwd_dconv_kernel<kC>, dim3(grid), dim3(256), sm, st, wav, L, T, k, s, w, gamma, beta, fmean,
+                                 frstd, dap, da_bs, static_cast<__nv_bfloat16*>(dconv_ws), ws_bs, dgamma, dbeta));
+      B200_CHECK_LAUNCH();
+      const size_t sm_red = sizeof(float) * 8 * kC;
+      B200_CHECK_CUDA(launch_pdl(conv0_dw_from_dconv_kernel<kC, 10>, dim3(grid), dim3(256), sm_red, st, wav, L, T, k, s,
+                                 static_cast<const __nv_bfloat16*>(dconv_ws), ws_bs, dw));
+      B200_CHECK_LAUNCH();
     } else {
       B200_CHECK_CUDA(cudaFuncSetAttribute(conv0_bwd_dw_kernel<kC, 1, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            static_cast<int>(sm)));
@@ -439,6 +546,14 @@ int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, i
     }
   })
   return 0;
+}
+
+int b200s_conv0_bwd(const float* wav, long long L, int B, int T, int C, int k, int s, const float* w, const float* gamma,
+                    const float* beta, int mode, const double* stats, float* bstats, const float* fmean,
+                    const float* frstd, const void* da, long long da_bs, float* dw, float* dgamma, float* dbeta,
+                    b200s_stream stream) {
+  return b200s_conv0_bwd_ws(wav, L, B, T, C, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, da, da_bs, nullptr, 0, dw,
+                            dgamma, dbeta, stream);
 }
 
 }  // extern "C"

@@ -42,7 +42,9 @@ __global__ void prep_linear_kernel(const float* __restrict__ src, int N, int K, 
 }
 
 // Batched variant: ONE launch prepares every nn.Linear operand of the model (descriptor table in device memory, built once;
-// the master parameters never move).  Block -> (descriptor, 32x32 tile) by binary search over the tile prefix sums.
+// the master parameters never move).  Block -> (descriptor, 64x64 tile) by binary search over the tile prefix sums.
+// The kernel is pure HBM traffic (4 B read + 2 x 2 B written per weight, 1.26 GB + 1.26 GB per WavLM-Large step): 16-byte
+// loads of the fp32 rows, 8-byte stores of the bf16 rows, 128-byte rows of the transposed copy through a padded smem tile.
 struct PrepLinearDesc {
   const float* src;
   __nv_bfloat16* dst;
@@ -50,11 +52,12 @@ struct PrepLinearDesc {
   long long ld, ldT;
   int N, K;
   int tile_begin;  // first global tile index of this descriptor
-  int tiles_k;     // ceil(K / 32)
+  int tiles_k;     // ceil(K / 64)
 };
-__global__ void prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ descs, int n_descs) {
+constexpr int kPrepTile = 64;
+__global__ void __launch_bounds__(256) prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ descs, int n_descs) {
   pdl_grid_sync();
-  __shared__ float tile[32][33];
+  __shared__ float tile[kPrepTile][kPrepTile + 1];
   int lo = 0, hi = n_descs - 1;
   const int t = blockIdx.x;
   while (lo < hi) {
@@ -63,21 +66,57 @@ __global__ void prep_linear_batched_kernel(const PrepLinearDesc* __restrict__ de
   }
   const PrepLinearDesc d = descs[lo];
   const int lt = t - d.tile_begin;
-  const int n0 = (lt / d.tiles_k) * 32, k0 = (lt % d.tiles_k) * 32;
-  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-    const int n = n0 + i, k = k0 + threadIdx.x;
-    float v = 0.f;
-    if (n < d.N && k < d.K) {
-      v = d.src[static_cast<long long>(n) * d.K + k];
-      if (d.dst) d.dst[static_cast<long long>(n) * d.ld + k] = __float2bfloat16_rn(v);
+  const int n0 = (lt / d.tiles_k) * kPrepTile, k0 = (lt % d.tiles_k) * kPrepTile;
+  const int tid = threadIdx.x;
+  {
+    const int tx = tid & 15, ty = tid >> 4;  // 16 threads x 4 floats per row, 16 rows per step
+    const int k = k0 + tx * 4;
+    const bool vec_ok = (k + 3 < d.K) && ((d.K & 3) == 0) && ((d.ld & 3) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(d.src) & 15) == 0) && (d.dst == nullptr || (reinterpret_cast<uintptr_t>(d.dst) & 7) == 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int r = ty + 16 * i, n = n0 + r;
+      float v[4] = {0.f, 0.f, 0.f, 0.f};
+      if (n < d.N) {
+        if (vec_ok) {
+          const float4 f = *reinterpret_cast<const float4*>(d.src + static_cast<long long>(n) * d.K + k);
+          v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+          if (d.dst) {
+            uint2 w;
+            w.x = pack_bf16x2(v[0], v[1]);
+            w.y = pack_bf16x2(v[2], v[3]);
+            *reinterpret_cast<uint2*>(d.dst + static_cast<long long>(n) * d.ld + k) = w;
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (k + e < d.K) {
+              v[e] = d.src[static_cast<long long>(n) * d.K + k + e];
+              if (d.dst) d.dst[static_cast<long long>(n) * d.ld + k + e] = __float2bfloat16_rn(v[e]);
+            }
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) tile[r][tx * 4 + e] = v[e];
     }
-    tile[i][threadIdx.x] = v;
   }
   __syncthreads();
   if (d.dstT) {
-    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
-      const int k = k0 + i, n = n0 + threadIdx.x;
-      if (n < d.N && k < d.K) d.dstT[static_cast<long long>(k) * d.ldT + n] = __float2bfloat16_rn(tile[threadIdx.x][i]);
+    const int tx = tid & 31, ty = tid >> 5;  // 32 threads x 2 columns (n) per transposed row, 8 rows (k) per step
+    const int n = n0 + tx * 2;
+    const bool pair_ok = (n + 1 < d.N) && ((d.ldT & 1) == 0) && ((reinterpret_cast<uintptr_t>(d.dstT) & 3) == 0);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int kk = ty + 8 * i, k = k0 + kk;
+      if (k >= d.K) continue;
+      const float a = tile[tx * 2][kk], b2 = tile[tx * 2 + 1][kk];
+      __nv_bfloat16* o = d.dstT + static_cast<long long>(k) * d.ldT + n;
+      if (pair_ok) {
+        *reinterpret_cast<uint32_t*>(o) = pack_bf16x2(a, b2);
+      } else {
+        if (n < d.N) o[0] = __float2bfloat16_rn(a);
+        if (n + 1 < d.N) o[1] = __float2bfloat16_rn(b2);
+      }
     }
   }
 }
@@ -210,11 +249,11 @@ int b200s_prep_linear(const float* src, int N, int K, float scale, void* dst, lo
 }
 
 // descs: DEVICE array of n_descs records {const float* src; bf16* dst; bf16* dstT; int64 ld, ldT; int32 N, K, tile_begin,
-// tiles_k} (48 bytes each, tile_begin = prefix sum of ceil(N/32)*ceil(K/32)); total_tiles = sum of all tiles.
+// tiles_k} (56 bytes each, tiles_k = ceil(K/64), tile_begin = prefix sum of ceil(N/64)*ceil(K/64)); total_tiles = sum of all tiles.
 int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b200s_stream stream) {
   B200_CHECK_ARG(descs && n_descs > 0 && total_tiles > 0, "prep_linear_batched: bad arguments");
   static_assert(sizeof(PrepLinearDesc) == 56, "descriptor layout is part of the ABI");
-  B200_CHECK_CUDA(launch_pdl(prep_linear_batched_kernel, dim3(total_tiles), dim3(dim3(32, 8)), 0, static_cast<cudaStream_t>(stream), 
+  B200_CHECK_CUDA(launch_pdl(prep_linear_batched_kernel, dim3(total_tiles), dim3(256), 0, static_cast<cudaStream_t>(stream), 
       static_cast<const PrepLinearDesc*>(descs), n_descs));
   B200_CHECK_LAUNCH();
   return 0;

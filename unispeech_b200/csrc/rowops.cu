@@ -209,6 +209,46 @@ __device__ __forceinline__ void smem_add_vec(float* dst, const float* v) {
   }
 }
 
+// Bank-conflict-free placement of a [D] fp32 row whose lanes own VEC consecutive columns: with VEC = 8 the natural layout puts
+// the lanes 32 bytes apart, so a 128-bit access by a warp touches every other 16-byte slot and runs at half rate (ncu: 2.6 bank
+// conflicts per shared request in the LayerNorm backward, which made it MIO-bound at 20 % of the HBM peak).  Here the two
+// float4 halves of a lane's 8 columns go to two separate 512-byte planes, lanes 16 bytes apart.
+template <int VEC>
+__device__ __forceinline__ int perm_col(int c) {
+  if constexpr (VEC == 8) {
+    const int ch = c >> 8, rem = c & 255, lane = rem >> 3, j = rem & 7;
+    return ((ch * 2 + (j >> 2)) * 32 + lane) * 4 + (j & 3);
+  } else {
+    return c;
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void smem_load_perm(const float* base, int ch, int lane, float* v) {
+  if constexpr (VEC == 8) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const float4 t = *reinterpret_cast<const float4*>(base + ((ch * 2 + k) * 32 + lane) * 4);
+      v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+    }
+  } else {
+    smem_load_vec<VEC>(base + (ch * 32 + lane) * VEC, v);
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void smem_add_perm(float* base, int ch, int lane, const float* v) {
+  if constexpr (VEC == 8) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      float4* p = reinterpret_cast<float4*>(base + ((ch * 2 + k) * 32 + lane) * 4);
+      float4 t = *p;
+      t.x += v[4 * k]; t.y += v[4 * k + 1]; t.z += v[4 * k + 2]; t.w += v[4 * k + 3];
+      *p = t;
+    }
+  } else {
+    smem_add_vec<VEC>(base + (ch * 32 + lane) * VEC, v);
+  }
+}
+
 template <int VEC, int NCH>
 __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
                                                         const __nv_bfloat16* __restrict__ x, RowView xv,
@@ -232,8 +272,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
   const int warp = threadIdx.x >> 5;
   for (int c = threadIdx.x; c < 3 * 8 * D; c += blockDim.x) acc[c] = 0.f;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
-    gs[c] = gamma[c];
-    bs[c] = gelu ? beta[c] : 0.f;
+    gs[perm_col<VEC>(c)] = gamma[c];
+    bs[perm_col<VEC>(c)] = gelu ? beta[c] : 0.f;
   }
   __syncthreads();
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -257,10 +297,9 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
-      const int c0 = (ch * 32 + lane) * VEC;
       float pg[VEC], pb[VEC], gg[VEC], bb[VEC];
-      smem_load_vec<VEC>(gs + c0, gg);
-      if (gelu) smem_load_vec<VEC>(bs + c0, bb);
+      smem_load_perm<VEC>(gs, ch, lane, gg);
+      if (gelu) smem_load_perm<VEC>(bs, ch, lane, bb);
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
         const int i = ch * VEC + j;
@@ -274,7 +313,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
         s1 += dxh;
         s2 += dxh * xh[i];
       }
-      if (want_gb) smem_add_vec<VEC>(my_g + c0, pg), smem_add_vec<VEC>(my_b + c0, pb);
+      if (want_gb) smem_add_perm<VEC>(my_g, ch, lane, pg), smem_add_perm<VEC>(my_b, ch, lane, pb);
     }
     s1 = warp_sum(s1) * (1.0f / D);
     s2 = warp_sum(s2) * (1.0f / D);
@@ -297,7 +336,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
         float pc[VEC];
 #pragma unroll
         for (int j = 0; j < VEC; ++j) pc[j] = __bfloat162float(__float2bfloat16_rn(dz[ch * VEC + j]));
-        smem_add_vec<VEC>(my_c + (ch * 32 + lane) * VEC, pc);
+        smem_add_perm<VEC>(my_c, ch, lane, pc);
       }
     }
     __nv_bfloat16* outr = dx + dxv.off(r);
@@ -310,10 +349,11 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
   const int nw = blockDim.x >> 5;
   for (int c = threadIdx.x; c < D; c += blockDim.x) {
     float sg = 0.f, sb = 0.f, sc = 0.f;
+    const int pc = perm_col<VEC>(c);
     for (int w = 0; w < nw; ++w) {
-      sg += acc[(0 * 8 + w) * D + c];
-      sb += acc[(1 * 8 + w) * D + c];
-      sc += acc[(2 * 8 + w) * D + c];
+      sg += acc[(0 * 8 + w) * D + pc];
+      sb += acc[(1 * 8 + w) * D + pc];
+      sc += acc[(2 * 8 + w) * D + pc];
     }
     if (dgamma != nullptr) atomicAdd(dgamma + c, sg);
     if (dbeta != nullptr) atomicAdd(dbeta + c, sb);
@@ -563,6 +603,9 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __re
 
 // backward of the gate: dgate[b,h,t] -> dx_gate[b,t,h*64+c] (bf16, written densely: every head slice of every row),
 // dW[o,c], db[o], d grep_a[h].   dW rows 0-3 are identical (= d wa) and rows 4-7 identical (= d wb).
+// One warp per row; EIGHT lanes per head (8 columns = one 16-byte vector each), so a warp covers four heads per iteration and
+// the two dot products of a head are 3-step shuffle reductions over 8 lanes (the earlier one-head-per-warp mapping spent its
+// time in 5-step, 32-lane reductions: 62 us per WavLM-Large layer for 32 MB of traffic).
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int H, int T,
                                                        long long rows, const float* __restrict__ grep_w,
                                                        const float* __restrict__ grep_b, const float* __restrict__ grep_a,
@@ -572,19 +615,26 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
+  const int hs = lane >> 3;   // head slot inside the group of four heads
+  const int q = lane & 7;     // which 8 of the head's 64 columns
   const long long warp_global = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const long long nwarps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
-  float wa0 = 0.f, wa1 = 0.f, wb0 = 0.f, wb1 = 0.f, ba = 0.f, bb = 0.f;
+  float wa[8], wb[8], ba = 0.f, bb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) wa[i] = wb[i] = 0.f;
 #pragma unroll
   for (int o = 0; o < 4; ++o) {
-    wa0 += grep_w[o * 64 + lane * 2];
-    wa1 += grep_w[o * 64 + lane * 2 + 1];
-    wb0 += grep_w[(o + 4) * 64 + lane * 2];
-    wb1 += grep_w[(o + 4) * 64 + lane * 2 + 1];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      wa[i] += grep_w[o * 64 + q * 8 + i];
+      wb[i] += grep_w[(o + 4) * 64 + q * 8 + i];
+    }
     ba += grep_b[o];
     bb += grep_b[o + 4];
   }
-  float dwa0 = 0.f, dwa1 = 0.f, dwb0 = 0.f, dwb1 = 0.f, dba = 0.f, dbb = 0.f;
+  float dwa[8], dwb[8], dba = 0.f, dbb = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) dwa[i] = dwb[i] = 0.f;
   extern __shared__ float dga_smem[];  // [warps][H] partial d grep_a
   for (int h = lane; h < H; h += 32) dga_smem[warp * H + h] = 0.f;
   __syncwarp();
@@ -592,42 +642,69 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     const __nv_bfloat16* xr = x + xv.off(r);
     __nv_bfloat16* dr = dxg + dxv.off(r);
     const long long b = r / T, t = r % T;
-#pragma unroll 4
-    for (int h = 0; h < H; ++h) {
-      const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
-      const float sa = warp_sum(f.x * wa0 + f.y * wa1) + ba;
-      const float sb = warp_sum(f.x * wb0 + f.y * wb1) + bb;
-      const float ga = 1.0f / (1.0f + __expf(-sa));
-      const float gb = 1.0f / (1.0f + __expf(-sb));
-      const float a = grep_a[h];
-      const float dg = dgate[(b * H + h) * T + t];
+    for (int h0 = 0; h0 < H; h0 += 4) {
+      const int h = h0 + hs;
+      const bool live = h < H;
+      float f[8];
+      if (live) {
+        VecIO<8>::load(xr + h * 64 + q * 8, f);
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+      }
+      const float dg = live ? dgate[(b * H + h) * T + t] : 0.f;
+      const float a = live ? grep_a[h] : 0.f;
+      float pa = 0.f, pb = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        pa = fmaf(f[i], wa[i], pa);
+        pb = fmaf(f[i], wb[i], pb);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {  // the 8 lanes of a head are contiguous: xor 1, 2, 4 stays inside the group
+        pa += __shfl_xor_sync(0xffffffffu, pa, o);
+        pb += __shfl_xor_sync(0xffffffffu, pb, o);
+      }
+      const float ga = 1.0f / (1.0f + __expf(-(pa + ba)));
+      const float gb = 1.0f / (1.0f + __expf(-(pb + bb)));
       const float dsa = dg * (gb * a - 1.0f) * ga * (1.0f - ga);
       const float dsb = dg * ga * a * gb * (1.0f - gb);
-      dwa0 += dsa * f.x; dwa1 += dsa * f.y;
-      dwb0 += dsb * f.x; dwb1 += dsb * f.y;
-      if (lane == 0) {
-        dba += dsa;
-        dbb += dsb;
-        dga_smem[warp * H + h] += dg * ga * gb;
+      float o8[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        dwa[i] = fmaf(dsa, f[i], dwa[i]);
+        dwb[i] = fmaf(dsb, f[i], dwb[i]);
+        o8[i] = dsa * wa[i] + dsb * wb[i];
       }
-      *reinterpret_cast<uint32_t*>(dr + h * 64 + lane * 2) = pack_bf16x2(dsa * wa0 + dsb * wb0, dsa * wa1 + dsb * wb1);
+      if (live) {
+        if (q == 0) {
+          dba += dsa;
+          dbb += dsb;
+          dga_smem[warp * H + h] += dg * ga * gb;
+        }
+        VecIO<8>::store(dr + h * 64 + q * 8, o8);
+      }
     }
   }
-  // block-level reduction first (one set of global atomics per block, not per warp: all blocks hit the same 1 KB)
-  __shared__ float red_w[8][130];
-  red_w[warp][lane * 2] = dwa0;
-  red_w[warp][lane * 2 + 1] = dwa1;
-  red_w[warp][64 + lane * 2] = dwb0;
-  red_w[warp][64 + lane * 2 + 1] = dwb1;
-  if (lane == 0) {
-    red_w[warp][128] = dba;
-    red_w[warp][129] = dbb;
+  // block-level reduction first (one set of global atomics per block, not per warp: all blocks hit the same 1 KB):
+  // column c of d wa / d wb is spread over the 4 head slots of every warp
+  __shared__ float red_w[8][4][130];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    red_w[warp][hs][q * 8 + i] = dwa[i];
+    red_w[warp][hs][64 + q * 8 + i] = dwb[i];
+  }
+  if (q == 0) {
+    red_w[warp][hs][128] = dba;
+    red_w[warp][hs][129] = dbb;
   }
   __syncthreads();
   const int nw = blockDim.x >> 5;
   if (threadIdx.x < 130) {
     float s = 0.f;
-    for (int w8 = 0; w8 < nw; ++w8) s += red_w[w8][threadIdx.x];
+    for (int w8 = 0; w8 < nw; ++w8)
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s += red_w[w8][k][threadIdx.x];
     // every one of the 4 rows that were summed receives the same gradient
     if (threadIdx.x < 128) {
       const int half = threadIdx.x >> 6, c = threadIdx.x & 63;

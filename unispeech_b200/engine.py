@@ -158,9 +158,9 @@ class Engine:
 
         def add(src, N, K, dst, ld, dstT, ldT):
             nonlocal tiles
-            tk = (K + 31) // 32
+            tk = (K + 63) // 64  # 64 x 64 tiles (b200s_prep_linear_batched)
             recs.append(struct.pack("<QQQqqiiii", src.data_ptr(), dst.data_ptr(), dstT.data_ptr(), ld, ldT, N, K, tiles, tk))
-            tiles += ((N + 31) // 32) * tk
+            tiles += ((N + 63) // 64) * tk
 
         add(m.post_extract_proj.weight.data, D, C, self.wp, C, self.wpT, D)
         for lyr, w in zip(m.encoder.layers, self.lw):
@@ -379,8 +379,11 @@ class Engine:
             dA = dfeat
         if ln_mode:
             fmean, frstd = st["stats0"]
+            # (the incoming gradient buffer doubles as the dconv workspace: it is engine-owned scratch, consumed here)
+            ws = dA if (n > 1 and dA.dtype == BF and dA.is_contiguous() and k0 <= 10) else None
             ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 1, None, None, fmean,
-                          frstd, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias))
+                          frstd, dA, geo.Tp[0] * C, self.g(blk0[0].weight), self.g(norm0.weight), self.g(norm0.bias),
+                          dconv_ws=ws, ws_bs=geo.Tp[0] * C)
         else:
             bstats = torch.empty(B, C, 12, dtype=torch.float32, device=dev)
             ops.conv0_bwd(wav, L_, B, geo.T[0], C, k0, s0, blk0[0].weight, norm0.weight, norm0.bias, 0, st["stats0"], bstats,

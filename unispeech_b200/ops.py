@@ -145,10 +145,17 @@ def conv0_fwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, fmean, frstd
            L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(fmean), L.ptr(frstd), L.ptr(out), L.ll(out_bs), _s())
 
 
-def conv0_bwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, da, da_bs, dw, dgamma, dbeta):
-    _call("b200s_conv0_bwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
-           L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(bstats), L.ptr(fmean), L.ptr(frstd), L.ptr(da), L.ll(da_bs),
-           L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), _s())
+def conv0_bwd(wav, L_, B, T, Cc, k, s, w, gamma, beta, mode, stats, bstats, fmean, frstd, da, da_bs, dw, dgamma, dbeta,
+              dconv_ws=None, ws_bs=0):
+    """`dconv_ws` (LayerNorm mode): bf16 workspace for the gradient w.r.t. the raw convolution output; may be `da` itself."""
+    if dconv_ws is None:
+        _call("b200s_conv0_bwd", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
+               L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(bstats), L.ptr(fmean), L.ptr(frstd), L.ptr(da), L.ll(da_bs),
+               L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), _s())
+    else:
+        _call("b200s_conv0_bwd_ws", L.ptr(wav), L.ll(L_), i32(B), i32(T), i32(Cc), i32(k), i32(s), L.ptr(w), L.ptr(gamma),
+               L.ptr(beta), i32(mode), L.ptr(stats), L.ptr(bstats), L.ptr(fmean), L.ptr(frstd), L.ptr(da), L.ll(da_bs),
+               L.ptr(dconv_ws), L.ll(ws_bs), L.ptr(dw), L.ptr(dgamma), L.ptr(dbeta), _s())
 
 
 # ------------------------------------------------------------------------------------------------- parameter prep
