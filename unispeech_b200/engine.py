@@ -646,11 +646,14 @@ class Engine:
             dffn_in = e(B, T, D)
             ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dffn_in, 0, D, None)
             ln = lyr.final_layer_norm
+            # (without dropout1 the out_proj bias gradient is the column sum of dx1: taken inside the LayerNorm backward)
             ops.layer_norm_bwd(dffn_in, T * D, D, st["x1"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, dy2, T * D, D,
-                               dx1, T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
+                               dx1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D)
             dy1 = dx1                                            # x1 = x + out_proj(attn)
-            dz1 = through_dropout(dy1, DR.L_DROPOUT1) if p_h > 0 else dy1
-            ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
+            dz1 = dy1
+            if p_h > 0:
+                dz1 = through_dropout(dy1, DR.L_DROPOUT1)
+                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
         else:
             ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dx1, 0, D, L.make_epilogue(res1=dy2, res1_ld=D))
             dy1 = e(B, T, D)
