@@ -159,10 +159,11 @@ class Workload:
     """One model + one synthetic batch per rank, stepped through the public API (extract_features + probe loss + backward
     [+ the gradient allreduce for N > 1])."""
 
-    def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False):
+    def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False, pretrain=False):
         from oracle import wavlm_oracle as O  # parameter / input generators only
         from unispeech_b200.wavlm import WavLM, WavLMConfig
-        self.name, self.dev, self.world, self.dropout = model_name, dev, world, dropout
+        self.name, self.dev, self.world, self.dropout, self.pretrain = model_name, dev, world, dropout, pretrain
+        self.opt = None
         cfg, B, secs = model_config(model_name)
         if dropout > 0:  # the reference's WavLMConfig defaults: dropout = attention_dropout = 0.1 (WavLM/WavLM.py:180-181)
             cfg.dropout, cfg.attention_dropout = dropout, dropout
@@ -178,8 +179,20 @@ class Workload:
         self.all_lengths = [lengths_of(r) for r in range(world)]
         self.L = max(self.lengths)
         self.T = O.num_frames(self.L, cfg)
-        model = WavLM(WavLMConfig(vars(cfg)))
-        model.load_state_dict(O.deterministic_state_dict(cfg))
+        if pretrain:
+            # full optimisation step of the masked-prediction pre-training: 504-class k-means labels
+            # at 50 Hz, final_dim 768 (the released Large recipe), WavLMCriterion with features_pen x 10, Adam(0.9, 0.98), clip 1.0
+            from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+            model = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=768 if model_name == "large" else 256)), [504])
+            sd = O.deterministic_state_dict(cfg)
+            sd["final_proj.weight"] = O.hash_uniform("fp.w", tuple(model.final_proj.weight.shape), -0.03, 0.03)
+            sd["final_proj.bias"] = torch.zeros_like(model.final_proj.bias)
+            sd["label_embs_concat"] = O.hash_uniform("lab", tuple(model.label_embs_concat.shape), 0.0, 1.0)
+            model.load_state_dict(sd)
+            self.labels = [torch.randint(0, 504, (B, self.T), generator=torch.Generator().manual_seed(99 + rank))]
+        else:
+            model = WavLM(WavLMConfig(vars(cfg)))
+            model.load_state_dict(O.deterministic_state_dict(cfg))
         self.model = model.to(dev).train()
         gen = torch.Generator().manual_seed(1337 + rank)
         wav = torch.randn(B, self.L, generator=gen)
@@ -200,14 +213,36 @@ class Workload:
         from unispeech_b200.parallel import all_reduce_grads
         model = self.model
         if model._engine is not None and model._engine.flat is not None:
-            model.grad_buffer().zero_()
+            if not self.pretrain:  # (the optimizer step of the pre-training workload zeroes the gradients itself)
+                model.grad_buffer().zero_()
             model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
         wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
+        if self.pretrain:
+            return self.pretrain_step(wav, e2e, collective)
         x, _ = model.extract_features(wav, padding_mask=self.pad_host, mask=True)
         loss = (x.float() * self.R).sum()
         loss.backward()
         if self.world > 1 and collective:
             all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
+        if e2e:
+            self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        return loss
+
+    def pretrain_step(self, wav, e2e: bool, collective: bool):
+        """forward -> masked-prediction criterion -> backward -> [allreduce] -> scale / clip / Adam (gradients zeroed by the update)."""
+        from unispeech_b200.optim import FusedAdam
+        from unispeech_b200.parallel import all_reduce_grads
+        model = self.model
+        out = model(wav, target_list=self.labels, padding_mask=self.pad_host, mask=True)
+        loss, sample_size, _ = model.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.0, loss_weights=[10.0])
+        loss.backward()
+        if self.world > 1 and collective:
+            all_reduce_grads(model.grad_buffer())
+        if self.opt is None:
+            self.opt = FusedAdam(model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
+        self.opt.multiply_grads(self.world / max(sample_size, 1))   # trainer.py:796-801 (sample_size is per rank here: equal shards)
+        self.opt.clip_grad_norm(1.0)
+        self.opt.step(zero_grad=True)
         if e2e:
             self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
@@ -242,6 +277,10 @@ class Workload:
 
     def describe(self) -> str:
         drop = f"dropout {self.dropout} / attention_dropout {self.dropout}" if self.dropout > 0 else "dropout 0"
+        if self.pretrain:
+            return (f"WavLM-{self.name} full optimisation step: fwd + masked-prediction head (504 classes, final_dim "
+                    f"{self.model.final_dim}) + WavLMCriterion (features_pen x 10) + bwd + gradient scale / clip 1.0 / Adam, batch "
+                    f"{self.B} x {self.secs} s per GPU, mask_prob {self.cfg.mask_prob}, {drop}")
         if self.ragged:
             secs = ", ".join(f"{n / SR:.1f}" for n in self.lengths)
             return (f"WavLM-{self.name} fwd+bwd, ragged batch of {self.B} utterances per GPU drawn from 4..30 s (rank 0: {secs} s), "
@@ -251,7 +290,7 @@ class Workload:
                 f"{self.cfg.mask_prob}, {drop}, all-False padding mask")
 
     def free(self):
-        self.model = self.R = self.wav_dev = None
+        self.model = self.R = self.wav_dev = self.opt = None
         torch.cuda.empty_cache()
 
 
@@ -284,6 +323,7 @@ def main():
     ap.add_argument("--dropout", type=float, default=0.0, help="dropout = attention_dropout of the headline run (BASELINE.md "
                     "section 3 times both arms with dropout 0; the reference's config default 0.1 is reported under `also`)")
     ap.add_argument("--ragged", action="store_true", help="BASELINE.json configs[4]: variable-length batch 4..30 s with padding mask")
+    ap.add_argument("--pretrain", action="store_true", help="time the full optimisation step (loss head + criterion + optimizer)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (WavLM-Base, reference dropouts)")
@@ -305,7 +345,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    w = Workload(args.model, dev, rank, world, dropout=args.dropout, ragged=args.ragged)
+    w = Workload(args.model, dev, rank, world, dropout=args.dropout, ragged=args.ragged, pretrain=args.pretrain)
     cfg, B, secs, T = w.cfg, w.B, w.secs, w.T
 
     for _ in range(args.warmup):
@@ -392,6 +432,10 @@ def main():
                 wr = Workload("large", dev, rank, world, dropout=0.0, ragged=True)
                 also["wavlm_large_ragged_4_30s"] = quick_line(wr, args.steps, 3, e2e=False)
                 wr.free()
+            if not args.ragged:
+                wp = Workload(args.model, dev, rank, world, dropout=0.0, pretrain=True)
+                also[f"wavlm_{args.model}_pretrain_step"] = quick_line(wp, args.steps, 3, e2e=True)
+                wp.free()
             other = "base" if args.model == "large" else "large"
             wo = Workload(other, dev, rank, world, dropout=0.0)
             also[f"wavlm_{other}"] = quick_line(wo, args.steps, 3, e2e=True)
