@@ -23,6 +23,17 @@ __device__ __forceinline__ float fast_exp2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 32 x 32 bit-matrix transpose across a warp: on entry bit j of lane l's word is element (l, j); on return bit l of lane j's
+// word is that element.  Five butterfly stages (one shuffle + three logic ops each) replace 32 ballots.
+__device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = (s == 16) ? 0x0000FFFFu : (s == 8) ? 0x00FF00FFu : (s == 4) ? 0x0F0F0F0Fu : (s == 2) ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+  }
+  return x;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -225,7 +236,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
           tmem_ld_32x32b_x32(s_addr + c0, su);
           tmem_ld_wait();
           float pv[32];
-          uint32_t mword = 0, hbits = 0;
+          uint32_t rowbits = 0, hbits = 0;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float x = fmaf(__uint_as_float(su[j]), sc, neg_ref);
@@ -237,14 +248,17 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
             if (DROP) {
               if ((j & 1) == 0) hbits = drop_bits(rk0, rk1, static_cast<uint32_t>(k0 + c0 + j) >> 1);
               const bool keep = (j & 1) ? drop_keep_hi(hbits, p.drop_thr_hi) : drop_keep_lo(hbits, p.drop_thr_hi);
-              const uint32_t bal = __ballot_sync(0xffffffffu, keep);  // bit l = query row of lane l
-              if ((tid & 31) == j) mword = bal;
+              if (keep) rowbits |= (1u << j);  // this row's decisions for the 32 key columns
               pv[j] = keep ? e : 0.f;
             } else {
               pv[j] = e;
             }
           }
-          if (DROP && mask_row != nullptr) mask_row[k0 + c0 + (tid & 31)] = mword;
+          if (DROP) {
+            // the backward walks key-major: store, per key column, one word whose bit l is the decision of query row l of this warp
+            const uint32_t mword = warp_bit_transpose(rowbits, tid & 31);
+            if (mask_row != nullptr) mask_row[k0 + c0 + (tid & 31)] = mword;
+          }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
             uint4 w;
