@@ -25,6 +25,7 @@ CASES = {
 def test_all_fixtures_are_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
     names.remove("mask_indices")  # span-sampler fixture, covered by tests/test_api_cpu.py
+    names.remove("train_heads")   # compute_nce / clip_grad_norm_ / Adam fixture, covered by test_training_heads_match_reference_code
     assert names == sorted(CASES)
 
 
@@ -100,3 +101,36 @@ def test_bucket_values_known_answers():
 def test_frame_counts():
     cfg = O.base_config()
     assert [O.num_frames(16000 * s, cfg) for s in (4, 10, 15, 20, 30)] == [199, 499, 749, 999, 1499]
+
+
+def test_training_heads_match_reference_code():
+    """compute_nce / clip_grad_norm_ / Adam restatements against outputs of the reference's own source text
+    (tools/make_head_golden.py executes src/fairseq/models/wavlm/wavlm.py:426-438, utils.py:338-381 and optim/adam.py:100-228)."""
+    import torch.nn.functional as F
+    g = np.load(os.path.join(GOLD, "train_heads.npz"))
+    S, C, Dp = (int(v) for v in g["nce_shape"])
+    temp = float(g["nce_temp"])
+    proj = O.hash_uniform("g.proj", (S, Dp), -1.0, 1.0)
+    E = O.hash_uniform("g.emb", (C, Dp), 0.0, 1.0)
+    tgt = (O.hash_uniform("g.tgt", (S,), 0.0, 1.0) * C).long().clamp(max=C - 1)
+    logits = O.compute_nce(proj, torch.index_select(E, 0, tgt), E.unsqueeze(1).expand(-1, S, -1), temp)
+    want = torch.from_numpy(g["nce_logits"])
+    assert torch.equal(torch.isinf(logits), torch.isinf(want))
+    fin = ~torch.isinf(want)
+    assert (logits[fin] - want[fin]).abs().max().item() < 1e-5
+    loss, ss, _ = O.wavlm_criterion([logits], [], 1.0, 0.0)
+    assert abs(loss.item() - float(g["nce_loss"])) < 1e-3 and ss == S
+    # the fused formulation used by the kernels (plain CE over the C classes) gives the same number
+    z = F.normalize(proj, dim=-1) @ F.normalize(E, dim=-1).t() / temp
+    assert abs(F.cross_entropy(z, tgt, reduction="sum").item() - float(g["nce_loss"])) < 1e-3
+    # optimizer: three steps of clip (max_norm 1.5) + Adam(lr 3e-3, betas (0.9, 0.98), eps 1e-6, weight_decay 0.01)
+    shapes = [(5, 7), (3,), (2, 3, 4)]
+    params = [O.hash_uniform(f"g.p{i}", s, -1.0, 1.0) for i, s in enumerate(shapes)]
+    state = {}
+    for step in range(3):
+        grads = [O.hash_uniform(f"g.g{step}.{i}", s, -1.0, 1.0) * (0.5 + step) for i, s in enumerate(shapes)]
+        norm, coef = O.clip_coefficient(grads, 1.5)
+        assert abs(norm.item() - float(g["adam_norms"][step])) < 1e-4
+        O.adam_step(params, [x * coef for x in grads], state, 3e-3, (0.9, 0.98), 1e-6, 0.01)
+    for i, p in enumerate(params):
+        assert torch.allclose(p, torch.from_numpy(g[f"adam_p{i}"]), rtol=1e-5, atol=1e-6), i

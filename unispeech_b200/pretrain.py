@@ -164,6 +164,7 @@ class WavLMForPretraining(WavLM):
             return out
         T = res["x"].shape[1]
         out["mask_indices"] = res["mask_indices"]
+        out["padding_mask_host"] = res.get("padding_mask_host")  # host copy of the frame mask when the caller's mask was on the host
         out["target_list"] = self.forward_targets(T, target_list) if target_list is not None else None
         feats = self._last_conv
         out["features_pen"] = feats[:, :T].float().pow(2).mean() if feats is not None else None  # wavlm.py:484
@@ -179,7 +180,11 @@ class WavLMForPretraining(WavLM):
         mi, pm, targets = net_output["mask_indices"], net_output["padding_mask"], net_output["target_list"]
         assert mi is not None and targets is not None, "forward(..., target_list=..., mask=True) must run first"
         mi_h = mi.cpu() if mi.device.type != "cpu" else mi
-        pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
+        # frame selection happens on the host, like the reference's collater-side masks: with a host padding mask there is no
+        # device round trip at all (a device-only mask costs one synchronising copy here)
+        pm_h = net_output.get("padding_mask_host")
+        if pm_h is None:
+            pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
         x2d = x.reshape(B * T, D)
         if x2d.dtype != BF or not x2d.is_contiguous():
             x2d = x2d.to(BF).contiguous()

@@ -555,7 +555,7 @@ class WavLM(nn.Module):
         xv._b200_xpad = eng._last_xpad
         x, layer_results = self.encoder(xv, padding_mask=fpm, layer=None if output_layer is None else output_layer - 1)
         res = {"x": x, "padding_mask": fpm, "features": features, "layer_results": layer_results,
-               "mask_indices": mask_indices}
+               "mask_indices": mask_indices, "padding_mask_host": fpm_host}
         self._last = res
         feature = res["features"] if ret_conv else res["x"]
         if ret_layer_results:
