@@ -190,6 +190,7 @@ class Workload:
             sd["label_embs_concat"] = O.hash_uniform("lab", tuple(model.label_embs_concat.shape), 0.0, 1.0)
             model.load_state_dict(sd)
             self.labels = [torch.randint(0, 504, (B, self.T), generator=torch.Generator().manual_seed(99 + rank))]
+            self.final_dim = model.final_dim
         else:
             model = WavLM(WavLMConfig(vars(cfg)))
             model.load_state_dict(O.deterministic_state_dict(cfg))
@@ -279,7 +280,7 @@ class Workload:
         drop = f"dropout {self.dropout} / attention_dropout {self.dropout}" if self.dropout > 0 else "dropout 0"
         if self.pretrain:
             return (f"WavLM-{self.name} full optimisation step: fwd + masked-prediction head (504 classes, final_dim "
-                    f"{self.model.final_dim}) + WavLMCriterion (features_pen x 10) + bwd + gradient scale / clip 1.0 / Adam, batch "
+                    f"{self.final_dim}) + WavLMCriterion (features_pen x 10) + bwd + gradient scale / clip 1.0 / Adam, batch "
                     f"{self.B} x {self.secs} s per GPU, mask_prob {self.cfg.mask_prob}, {drop}")
         if self.ragged:
             secs = ", ".join(f"{n / SR:.1f}" for n in self.lengths)

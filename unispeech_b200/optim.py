@@ -20,7 +20,11 @@ _CHUNK = 2048
 
 class FusedAdam:
     def __init__(self, model, lr: float = 1e-3, betas: Tuple[float, float] = (0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0):
+                 weight_decay: float = 0.0, exclude=()):
+        """`exclude`: parameters to leave alone.  fairseq's Adam skips a parameter whose `.grad` is None (adam.py:160-161); here
+        every parameter has a view of the flat gradient buffer, so one the backward pass never reaches would see a ZERO gradient
+        and still be weight-decayed.  The frozen feature extractor (`feature_grad_mult <= 0`: the conv stack runs under no_grad,
+        WavLM/WavLM.py:333-339) is excluded automatically; name anything else that is frozen."""
         eng = model._engine
         if eng is None or eng.flat is None:
             raise RuntimeError("run one forward pass on the GPU (or call model._engine_for(device)) before building the optimizer: "
@@ -37,9 +41,12 @@ class FusedAdam:
         self._multiply_factor = 1.0
         self._max_norm = 0.0
         self._have_norm = False
+        skip = {id(p) for p in exclude}
+        if getattr(model, "feature_grad_mult", 1.0) <= 0:
+            skip |= {id(p) for p in model.feature_extractor.parameters()}
         recs, chunks, self._ptrs = [], 0, []
         for p in flat.params:
-            if not p.requires_grad:
+            if not p.requires_grad or id(p) in skip:
                 continue
             if p.dtype != torch.float32 or not p.is_contiguous():
                 raise RuntimeError("FusedAdam needs contiguous fp32 master parameters")
