@@ -295,6 +295,31 @@ class Workload:
         torch.cuda.empty_cache()
 
 
+def parity_line(dev, model_name: str):
+    """The other half of BASELINE.json's metric ("...; max-abs hidden diff"): final hidden states of this GPU path against the
+    committed fixture generated from the UNMODIFIED reference (tools/make_golden.py: fp32 CPU, the model's real widths, 2 layers,
+    1 x 0.5 s), same weights and waveform.  The full-depth parity evidence is the GPU test suite; this is the number in the run."""
+    import numpy as np
+    from oracle import wavlm_oracle as O
+    from unispeech_b200.wavlm import WavLM, WavLMConfig
+    name = {"large": "large2l_halfsec", "base": "base2l_halfsec"}.get(model_name)
+    if name is None:
+        return None
+    g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    cfg = (O.large_config if model_name == "large" else O.base_config)(encoder_layers=2)
+    m = WavLM(WavLMConfig(vars(cfg)))
+    m.load_state_dict(O.deterministic_state_dict(cfg))
+    m = m.to(dev).eval()
+    wav, _ = O.deterministic_waveform(1, 8000, seed=1)
+    with torch.no_grad():
+        x, _ = m.extract_features(wav.to(dev))
+    want = torch.from_numpy(g["x_final"]).float()
+    d = (x.float().cpu() - want).abs()
+    return {"max_abs_hidden_diff": d.max().item(), "mean_abs_hidden_diff": d.mean().item(), "hidden_abs_max": want.abs().max().item(),
+            "tolerance_max_abs": 0.12, "against": f"tests/golden/{name}.npz (unmodified reference WavLM forward, fp32 CPU; WavLM-{model_name} "
+                                                  "widths, 2 layers, 1 x 0.5 s, same weights and waveform)"}
+
+
 def quick_line(w: Workload, steps: int, warmup: int, e2e: bool = True):
     """Secondary measurement (reported under `also`): same timing rules, fewer outputs."""
     for _ in range(warmup):
@@ -419,6 +444,13 @@ def main():
                     "us_per_launch": gemm_ms * 1e3 / max(n_gemm, 1), "traffic": traffic, "traffic_source": traffic_src,
                     "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
 
+    parity = None
+    if rank == 0 and not args.no_profile:
+        try:
+            parity = parity_line(dev, args.model)
+        except Exception as exc:  # never at the expense of the measured line
+            parity = {"error": f"{type(exc).__name__}: {exc}"}
+
     # ---- secondary measurements (N = 1 only): the reference's default dropouts on the same workload, and WavLM-Base (configs[1])
     also = None
     if world == 1 and not args.no_also and args.model != "tiny":
@@ -468,6 +500,8 @@ def main():
             "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
             "model_tflops": 3 * fwd_flops * world * B * args.steps / (ms * 1e-3) / 1e12,
         }
+        if parity is not None:
+            line["parity"] = parity
         if args.ragged:
             line["padded_equivalent_value"] = w.padded_audio_seconds(args.steps) / (ms * 1e-3)
         if also is not None:
