@@ -637,3 +637,95 @@ def wavlm_criterion(logit_m_list: List[Tensor], logit_u_list: List[Tensor], pred
     if loss_weights is not None and features_pen is not None and loss_weights[0] != 0:
         loss = loss + loss_weights[0] * features_pen.float() * sample_size
     return loss, sample_size, log
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# UniSpeech-SAT utterance-contrastive branch (BASELINE config #4; no CUDA path yet: oracle groundwork)
+#   sample_instances   src/fairseq/models/unispeech_sat/unispeech_sat.py:487-543
+#   compute_nce        :545-557          compute_pred_spk / forward tail   :699-745
+#   GumbelVectorQuantizer.forward (eval mode: hard arg-max codes)   src/fairseq/modules/gumbel_vector_quantizer.py:141-201
+# ----------------------------------------------------------------------------------------------------------------
+def sat_sample_instances(y: Tensor, num: int, n_instances: int, cross_sample_instances: int):
+    """Negative 'instances' for every position: `n_instances` drawn inside the utterance and `cross_sample_instances` drawn over
+    the whole batch, never the position itself.  Same torch.randint call order as the reference, so it is reproducible under
+    torch.manual_seed.  Returns (instances [N, B, T, C], flat indices [B, N*T])."""
+    bsz, tsz, fsz = y.shape
+    y = y.reshape(-1, fsz)
+    cross_high, high = tsz * bsz, tsz
+    with torch.no_grad():
+        if n_instances > 0:
+            tszs = torch.arange(num).unsqueeze(-1).expand(-1, n_instances).flatten()
+            instance_idxs = torch.randint(low=0, high=high - 1, size=(bsz, n_instances * num))
+            instance_idxs[instance_idxs >= tszs] += 1
+        if cross_sample_instances > 0:
+            tszs = torch.arange(num).unsqueeze(-1).expand(-1, cross_sample_instances).flatten()
+            cross_instance_idxs = torch.randint(low=0, high=cross_high - 1, size=(bsz, cross_sample_instances * num))
+            cross_instance_idxs[cross_instance_idxs >= tszs] += 1
+    if n_instances > 0:
+        for i in range(1, bsz):
+            instance_idxs[i] += i * high
+    else:
+        instance_idxs = cross_instance_idxs
+    if cross_sample_instances > 0 and n_instances > 0:
+        instance_idxs = torch.cat([instance_idxs, cross_instance_idxs], dim=1)
+    instances = y[instance_idxs.view(-1)]
+    instances = instances.view(bsz, n_instances + cross_sample_instances, num, fsz).permute(1, 0, 2, 3)
+    return instances, instance_idxs
+
+
+def sat_compute_nce(x: Tensor, pos: Tensor, instances: Tensor, logit_temp: float, replace_inf: bool = True) -> Tensor:
+    instance_is_pos = (pos == instances).all(-1)
+    targets = torch.cat([pos.unsqueeze(0), instances], dim=0)
+    logits = torch.cosine_similarity(x.float(), targets.float(), dim=-1).type_as(x) / logit_temp
+    if instance_is_pos.any() and replace_inf:
+        logits[1:][instance_is_pos] = float("-inf")
+    return logits.transpose(0, 1)
+
+
+def gumbel_vq_eval(x: Tensor, weight_proj_w: Tensor, weight_proj_b: Tensor, vars_: Tensor, groups: int, num_vars: int):
+    """Eval-mode GumbelVectorQuantizer.forward (time_first, combine_groups=False, weight_proj_depth=1): hard arg-max code per
+    group, concatenated codebook vectors, plus the two perplexities the criterion logs."""
+    bsz, tsz, fsz = x.shape
+    lg = F.linear(x.reshape(-1, fsz), weight_proj_w, weight_proj_b).view(bsz * tsz * groups, -1)
+    k = lg.argmax(-1)
+    hard = lg.new_zeros(*lg.shape).scatter_(-1, k.view(-1, 1), 1.0).view(bsz * tsz, groups, -1)
+    hard_probs = hard.float().mean(0)
+    code_ppl = torch.exp(-torch.sum(hard_probs * torch.log(hard_probs + 1e-7), dim=-1)).sum()
+    avg_probs = torch.softmax(lg.view(bsz * tsz, groups, -1).float(), dim=-1).mean(0)
+    prob_ppl = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-7), dim=-1)).sum()
+    q = (hard.view(bsz * tsz, -1).unsqueeze(-1) * vars_).view(bsz * tsz, groups, num_vars, -1).sum(-2).view(bsz, tsz, -1)
+    return {"x": q, "code_perplexity": code_ppl, "prob_perplexity": prob_ppl, "num_vars": num_vars * groups}
+
+
+def sat_utterance_contrastive_loss(spk_x: Tensor, padding_mask: Tensor, mask_indices: Tensor, spk_proj_w: Tensor, spk_proj_b: Tensor,
+                                   n_instances: int, cross_sample_instances: int, logit_temp: float, quantizer=None,
+                                   project_q=None):
+    """Masked branch of unispeech_sat.py:699-758.  `spk_x` [B,T,C] is the `utterance_contrastive_layer` output (the encoder's
+    `extract_layer` result); every utterance must have the same number of masked, unpadded frames (`.view(B, -1, C)`, :742).
+    `quantizer` = dict(weight_proj_w, weight_proj_b, vars, groups, num_vars) in eval mode or None; `project_q` = (w, b) or None.
+    Returns (loss_spk, mean_targets, contrastive_acc, quantizer outputs or None)."""
+    B = spk_x.size(0)
+    b_pos = torch.arange(B).unsqueeze(1).expand(B, spk_x.size(1))
+    masked = ~padding_mask & mask_indices
+    x = spk_x[masked].view(B, -1, spk_x.size(-1))
+    proj_x = F.linear(x, spk_proj_w, spk_proj_b)
+    x_b_pos = b_pos[masked].view(B, -1)
+    q = None
+    if quantizer is not None:
+        q = gumbel_vq_eval(x, **quantizer)
+        y = F.linear(q["x"], project_q[0], project_q[1])
+    else:
+        y = proj_x
+    N = n_instances + cross_sample_instances
+    samples, samples_idx = sat_sample_instances(y, y.size(1), n_instances, cross_sample_instances)
+    samples_b_pos = x_b_pos.reshape(-1)[samples_idx.view(-1)].view(B, N, x.size(1)).permute(1, 0, 2)
+    x_pos_batch = x_b_pos[..., 0].unsqueeze(1).unsqueeze(0).expand_as(samples_b_pos)
+    samples_targets = (samples_b_pos == x_pos_batch).long()
+    targets = torch.cat((x.new_ones(1, B, x.size(1), dtype=torch.long), samples_targets), dim=0)
+    proj_flat = proj_x.reshape(-1, proj_x.size(-1))
+    y_flat = y.reshape(-1, y.size(-1))
+    samples = samples.reshape(samples.size(0), -1, y_flat.size(-1))
+    targets = targets.reshape(targets.size(0), -1).transpose(0, 1)
+    logits = sat_compute_nce(proj_flat, y_flat, samples, logit_temp, replace_inf=False)
+    loss = F.binary_cross_entropy_with_logits(logits, targets.type_as(logits), reduction="none").mean()
+    return loss, targets.float().mean(), ((logits >= 0.0) == targets).float().mean(), q

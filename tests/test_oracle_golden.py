@@ -26,6 +26,7 @@ def test_all_fixtures_are_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
     names.remove("mask_indices")  # span-sampler fixture, covered by tests/test_api_cpu.py
     names.remove("train_heads")   # compute_nce / clip_grad_norm_ / Adam fixture, covered by test_training_heads_match_reference_code
+    names.remove("sat_heads")     # UniSpeech-SAT utterance-contrastive fixture, covered by test_sat_utterance_contrastive_branch_...
     assert names == sorted(CASES)
 
 
@@ -134,3 +135,32 @@ def test_training_heads_match_reference_code():
         O.adam_step(params, [x * coef for x in grads], state, 3e-3, (0.9, 0.98), 1e-6, 0.01)
     for i, p in enumerate(params):
         assert torch.allclose(p, torch.from_numpy(g[f"adam_p{i}"]), rtol=1e-5, atol=1e-6), i
+
+
+def test_sat_utterance_contrastive_branch_matches_reference_code():
+    """Oracle groundwork for BASELINE config #4: sample_instances / compute_nce / compute_pred_spk / eval-mode Gumbel quantizer
+    restatements against outputs of the reference's own source text (tools/make_sat_golden.py)."""
+    g = np.load(os.path.join(GOLD, "sat_heads.npz"))
+    B, T, C, Dp, temp = 3, 14, 16, 8, 0.1
+    for i, (use_q, n_inst, cross, seed) in enumerate(g["cases"].tolist()):
+        tag = f"sat{int(use_q)}{n_inst}{cross}"
+        spk_x = O.hash_uniform(tag + ".x", (B, T, C), -1.0, 1.0)
+        mask = torch.from_numpy(g[f"mask_{i}"])
+        pad = torch.zeros(B, T, dtype=torch.bool)
+        sw, sb = O.hash_uniform(tag + ".sw", (Dp, C), -0.5, 0.5), O.hash_uniform(tag + ".sb", (Dp,), -0.1, 0.1)
+        quant, pq = None, None
+        if use_q:
+            groups, num_vars, vq_dim = 2, 5, 12
+            quant = dict(weight_proj_w=O.hash_uniform(tag + ".qw", (groups * num_vars, C), -1.0, 1.0),
+                         weight_proj_b=O.hash_uniform(tag + ".qb", (groups * num_vars,), -0.1, 0.1),
+                         vars_=O.hash_uniform(tag + ".qv", (1, groups * num_vars, vq_dim // groups), 0.0, 1.0), groups=groups,
+                         num_vars=num_vars)
+            pq = (O.hash_uniform(tag + ".pw", (Dp, vq_dim), -0.5, 0.5), O.hash_uniform(tag + ".pb", (Dp,), -0.1, 0.1))
+        torch.manual_seed(int(seed))
+        loss, mean_t, acc, q = O.sat_utterance_contrastive_loss(spk_x, pad, mask, sw, sb, int(n_inst), int(cross), temp, quant, pq)
+        want = g[f"out_{i}"]
+        assert abs(loss.item() - want[0]) < 1e-5, (i, loss.item(), want[0])
+        assert abs(mean_t.item() - want[1]) < 1e-6 and abs(acc.item() - want[2]) < 1e-6
+        if use_q:
+            assert abs(q["code_perplexity"].item() - want[3]) < 1e-4 and abs(q["prob_perplexity"].item() - want[4]) < 1e-4
+            assert q["num_vars"] == int(want[5])
