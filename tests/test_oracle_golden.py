@@ -26,6 +26,7 @@ def test_all_fixtures_are_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
     names.remove("mask_indices")  # span-sampler fixture, covered by tests/test_api_cpu.py
     names.remove("train_heads")   # compute_nce / clip_grad_norm_ / Adam fixture, covered by test_training_heads_match_reference_code
+    names.remove("utterance_mixing")  # host data-path fixture, covered by tests/test_api_cpu.py
     names.remove("sat_heads")     # UniSpeech-SAT utterance-contrastive fixture, covered by test_sat_utterance_contrastive_branch_...
     assert names == sorted(CASES)
 
