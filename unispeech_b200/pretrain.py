@@ -152,6 +152,28 @@ class WavLMForPretraining(WavLM):
         self.final_proj = None
         self.label_embs_concat = None
 
+    # ---- BaseFairseqModel surface the trainer / criterion touch (src/fairseq/models/fairseq_model.py:102-158, wavlm.py:599-627)
+    def set_num_updates(self, num_updates: int):
+        self.num_updates = num_updates
+
+    def upgrade_state_dict_named(self, state_dict, name):
+        return state_dict
+
+    def get_extra_losses(self, net_output):
+        """(losses, names) exactly as wavlm.py:611-620: the feature penalty when the forward pass produced it."""
+        extra_losses, names = [], []
+        if net_output.get("features_pen") is not None:
+            extra_losses.append(net_output["features_pen"])
+            names.append("features_pen")
+        return extra_losses, names
+
+    def get_logits(self, net_output, is_masked=True):
+        raise NotImplementedError("the [S, C+1] logit lists of the reference are never materialised on this path: use "
+                                  "`model.criterion(net_output, ...)`, which returns the same loss / sample_size / accuracy counts as "
+                                  "WavLMCriterion.get_loss")
+
+    get_targets = get_logits
+
     def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
                 mask_indices=None):
         """fairseq WavLMModel.forward.  With `features_only=False` the result carries everything the criterion needs
