@@ -155,6 +155,17 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+_SD_CACHE = {}
+
+
+def cached_state_dict(name: str, cfg):
+    """Hash-generated parameters are deterministic per architecture: generate them once per process (20 s of CPU for WavLM-Large)."""
+    from oracle import wavlm_oracle as O
+    if name not in _SD_CACHE:
+        _SD_CACHE[name] = O.deterministic_state_dict(cfg)
+    return _SD_CACHE[name]
+
+
 class Workload:
     """One model + one synthetic batch per rank, stepped through the public API (extract_features + probe loss + backward
     [+ the gradient allreduce for N > 1])."""
@@ -184,7 +195,7 @@ class Workload:
             # at 50 Hz, final_dim 768 (the released Large recipe), WavLMCriterion with features_pen x 10, Adam(0.9, 0.98), clip 1.0
             from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
             model = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=768 if model_name == "large" else 256)), [504])
-            sd = O.deterministic_state_dict(cfg)
+            sd = dict(cached_state_dict(model_name, cfg))
             sd["final_proj.weight"] = O.hash_uniform("fp.w", tuple(model.final_proj.weight.shape), -0.03, 0.03)
             sd["final_proj.bias"] = torch.zeros_like(model.final_proj.bias)
             sd["label_embs_concat"] = O.hash_uniform("lab", tuple(model.label_embs_concat.shape), 0.0, 1.0)
@@ -193,7 +204,7 @@ class Workload:
             self.final_dim = model.final_dim
         else:
             model = WavLM(WavLMConfig(vars(cfg)))
-            model.load_state_dict(O.deterministic_state_dict(cfg))
+            model.load_state_dict(cached_state_dict(model_name, cfg))
         self.model = model.to(dev).train()
         gen = torch.Generator().manual_seed(1337 + rank)
         wav = torch.randn(B, self.L, generator=gen)
