@@ -156,6 +156,16 @@ int b200s_dgelu_mul_ex(const void* dy, long long dy_bs, long long dy_rs, const v
                        long long pre_rs, void* out, long long out_bs, long long out_rs, int rows_per_batch, int batches,
                        int N, float* colsum, int pre_is_grad, b200s_stream stream);
 
+/* *out += sum of x^2 over a bf16 rows view (fp64 accumulator, caller zeroes it): numerator of the feature penalty
+ * `features.float().pow(2).mean()` (src/fairseq/models/wavlm/wavlm.py:484).  N % 8 == 0. */
+int b200s_sumsq_rows(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, double* out,
+                     b200s_stream stream);
+/* Backward of GradMultiply.apply(features, scale) (WavLM/modules.py:60-69, WavLM/WavLM.py:333-336) fused with the gradient of
+ * the feature penalty taken on its output (fairseq wavlm.py:477-484), in place on the bf16 gradient rows g:
+ *   g <- scale * (g + (*pen_grad * pen_mul) * x);   pen_grad = DEVICE float (upstream gradient of the penalty scalar) or NULL. */
+int b200s_grad_multiply(void* g, long long g_bs, long long g_rs, const void* x, long long x_bs, long long x_rs,
+                        int rows_per_batch, int batches, int N, float scale, const float* pen_grad, float pen_mul,
+                        b200s_stream stream);
 /* y = [res +] dropout(x), y may alias x.  nn.Dropout / F.dropout of the transformer stack (WavLM/WavLM.py:350,584,659-661,
  * 702-738): keep(row, col) is a pure function of (key0, key1, logical row = b*rows_per_batch + r, col) (csrc/dropout.cuh),
  * kept values are scaled by 1/(1-p).  The backward pass is the same call on the incoming gradient with the same key and
@@ -232,6 +242,12 @@ int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const flo
 /* *out += sum_i g[i]^2 (fp64 accumulator on the device; the caller zeroes it).  With the flat gradient buffer this is the global
  * gradient norm of utils.clip_grad_norm_ (src/fairseq/utils.py:338-377) in one launch and without a host round trip. */
 int b200s_sumsq_f32(const float* g, long long n, double* out, b200s_stream stream);
+
+/* Same sum restricted to the tensors of an optimizer descriptor table (the layout b200s_adam_step takes): gradients of
+ * parameters the optimizer does not own (excluded / frozen) are not counted -- fairseq's clip_grad_norm_ only sees
+ * parameters whose .grad exists (src/fairseq/utils.py:338-345). */
+int b200s_sumsq_table(const void* table, int n_tensors, long long total_chunks, const float* g, double* out,
+                      b200s_stream stream);
 
 /* Fused fairseq Adam update (src/fairseq/optim/adam.py:150-228) of n_tensors fp32 master tensors whose gradients (g) and
  * moments (m = exp_avg, v = exp_avg_sq) live in flat buffers:

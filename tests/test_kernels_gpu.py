@@ -315,7 +315,10 @@ def test_attn_fwd(cuda_device, B, T, H, bias, padded):
     torch.cuda.synchronize()
     ref = _attn_ref(qkv, gate, tab, pad, B, T, H, 0.125)
     assert torch.isfinite(out.float()).all()
-    err = (out.float() - ref).abs().max().item()
+    d = (out.float() - ref).abs()
+    if padded:  # rows of padded QUERY frames are unspecified-but-finite (zeros where a whole 256-row block is padded): the
+        d = d[pad == 0]  # reference's values there never reach a valid frame (padded keys are masked)
+    err = d.max().item()
     assert err < 0.03, err
 
 
@@ -361,8 +364,8 @@ def test_attn_bwd(cuda_device, B, T, H, bias, padded, fused):
     lse = torch.empty(B, H, T, device=dev)
     ops.attn_fwd(qkv, gate, tab, pad, out, lse, B, T, H, 0.125)
     dout = bf(torch.randn(B, T, D, device=dev))
-    if padded:  # the model never feeds gradient from padded query rows' outputs differently; keep them generic here
-        pass
+    if padded:  # padded query frames carry no gradient in the model (the loss never reads them); their forward values are unspecified
+        dout[pad.bool()] = 0
     delta = torch.empty(B, H, T, device=dev)
     dqkv = torch.zeros(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
     dgate = torch.zeros(B, H, T, device=dev) if bias else None

@@ -14,8 +14,9 @@ def _head_state(cfg, D, Dt, Ctot, Dp):
             "label_embs_concat": O.hash_uniform("lab", (Ctot, Dp), 0.0, 1.0)}
 
 
-def _run_case(dev, cfg, num_classes, untie, final_dim, B, L, lengths, pm_w, pu_w, loss_weights):
+def _run_case(dev, cfg, num_classes, untie, final_dim, B, L, lengths, pm_w, pu_w, loss_weights, feature_grad_mult=1.0):
     from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+    cfg.feature_grad_mult = feature_grad_mult
     D = cfg.encoder_embed_dim
     n = len(num_classes)
     Dt = final_dim * (n if untie else 1)
@@ -46,6 +47,12 @@ def _run_case(dev, cfg, num_classes, untie, final_dim, B, L, lengths, pm_w, pu_w
     pen = conv.float().pow(2).mean()
     want, want_ss, want_log = O.wavlm_criterion(lm, lu, pm_w, pu_w, pen, loss_weights)
     want.backward()
+    if feature_grad_mult != 1.0:
+        # GradMultiply sits on the extractor output BEFORE both consumers (the projection and the feature penalty, fairseq
+        # wavlm.py:477-484): every gradient entering the conv stack -- the penalty's too -- is scaled, nothing else is
+        for k, v in sdr.items():
+            if k.startswith("feature_extractor.") and v.grad is not None:
+                v.grad.mul_(feature_grad_mult)
 
     assert sample_size == want_ss
     assert abs(loss.item() - want.item()) < 0.02 * abs(want.item()) + 0.5, (loss.item(), want.item())
@@ -85,6 +92,47 @@ def test_head_tiny_two_tied_label_sets(cuda_device):
 def test_head_base_dims_504_classes(cuda_device):
     """WavLM-Base widths (D = 768, final_dim = 256, 504 classes = the k-means dictionary of the released recipes), 2 layers."""
     _run_case(cuda_device, O.base_config(encoder_layers=2), [504], False, 256, 2, 16000, [16000, 12000], 1.0, 0.0, [10.0])
+
+
+def test_feature_grad_mult_scales_the_penalty_gradient_too(cuda_device):
+    """The released recipes: feature_grad_mult = 0.1 with loss_weights = [10] (features_pen).  The extractor's gradients must be
+    0.1 x (main-loss gradient + penalty gradient); an implementation that scales only the projection branch is 10x off on the
+    penalty part and fails the norm check of the conv weights."""
+    _run_case(cuda_device, O.tiny_config(pre_ln=True), [40], False, 64, 2, 6400, [6400, 4321], 1.0, 0.0, [10.0],
+              feature_grad_mult=0.1)
+
+
+def test_clip_norm_ignores_parameters_the_optimizer_does_not_own(cuda_device):
+    """A frozen / excluded parameter keeps receiving gradients from the backward kernels (they write the flat buffer for every
+    parameter they reach) but must not count in the clip norm, and repeated `step(zero_grad=True)` must not let it grow
+    (fairseq clips over the optimizer's parameters only, src/fairseq/utils.py:338-345)."""
+    from unispeech_b200.optim import FusedAdam
+    from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+    dev = cuda_device
+    cfg = O.tiny_config(pre_ln=True)
+    m = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=64)), [30])
+    sd = O.deterministic_state_dict(cfg)
+    m.load_state_dict({**sd, **_head_state(cfg, cfg.encoder_embed_dim, 64, 30, 64)}, strict=True)
+    m = m.to(dev).train()
+    wav, _ = O.deterministic_waveform(2, 8000, seed=1)
+    T = O.num_frames(8000, cfg)
+    mi = O.hash_uniform("premask", (2, T)) > 0.35
+    tl = [(O.hash_uniform("tgt", (2, T), 0.0, 1.0) * 30).long().clamp(max=29)]
+    frozen = [m.encoder.layers[0].fc1.weight, m.encoder.layers[0].fc1.bias]
+    opt, norms = None, []
+    for it in range(3):
+        out = m(wav.to(dev), target_list=tl, mask=True, mask_indices=mi)
+        loss, ss, _ = m.criterion(out)
+        loss.backward()
+        if opt is None:
+            opt = FusedAdam(m, lr=0.0, exclude=frozen)  # lr 0: the same gradients every step
+        own = [p for p in m.parameters() if all(p is not f for f in frozen)]
+        want = torch.sqrt(sum((p.grad.double() ** 2).sum() for p in own)).item()
+        got = opt.clip_grad_norm(1.0).item()
+        assert abs(got - want) < 1e-4 * want, (it, got, want)
+        norms.append(got)
+        opt.step(zero_grad=True)
+    assert abs(norms[2] - norms[0]) < 1e-3 * norms[0], norms
 
 
 def test_optimisation_steps_reduce_the_loss(cuda_device):

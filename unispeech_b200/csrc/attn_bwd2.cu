@@ -1,25 +1,29 @@
 // Fused attention backward with the gated relative-position bias (autograd of WavLM/modules.py:521-563): ONE tensor-core
-// kernel produces dQ, dK, dV, d gate and d tab, so the probabilities are recomputed once (the two-kernel version in
-// attn_bwd.cu recomputes S, dP and the exponentials twice, and its tensor-core and CUDA-core phases never overlap).
+// kernel produces dQ, dK, dV, d gate and d tab, so the probabilities are recomputed once.
 //
-// CTA = 128 keys of one (batch, head); it walks over the queries in HALF tiles of 64 (transposed orientation: thread = key
-// row, so dK / dV accumulate in TMEM over the whole loop and need no cross-thread reduction):
-//   S^T  = K Q_h^T          128x64x64   -> TMEM stage h&1, columns [0,64)
-//   dP^T = V dO_h^T         128x64x64   -> TMEM stage h&1, columns [64,128)
-//   P^T  = exp2(S^T*scale*log2e + gate_i*log2e*tab[j-i] + keymask_j - lse_i);   dS^T = P^T o (dP^T - Delta_i)
-//   dV  += P^T  dO_h        (P^T, dS^T written once to shared memory as bf16 K-major operand tiles)
-//   dK  += dS^T Q_h * scale
-//   dQ_i = dS K * scale     once per full 128-query tile (dS^T read as an MN-major A operand), accumulator read back from
-//                           TMEM and added to an fp32 [B,T,D] buffer with vector reductions (one writer CTA per key tile)
-//   d gate_i = sum_j dS_ij tab[j-i]        column sums over the key rows: warp butterfly + shared-memory accumulators
-//   d tab[d] = sum_i gate_i dS_{i,i+d}     diagonal sums of a staged bf16 tile (double buffered), per-CTA accumulators
-// Warp roles: warps 0-7 = CUDA-core warps (thread t: key row t & 127, query columns 32*(t>>7).. of the half tile);
-// warps 8-11 = producer warpgroup (lane 0 of warp 8 issues every TMA load and MMA; the group only exists so that
-// setmaxnreg can hand its registers to the CUDA-core warpgroups).  All hand-offs are mbarriers, there is no __syncthreads in the loop; the
-// S^T/dP^T accumulators are double buffered in TMEM so the MMAs of half tile n+1 run under the exponentials of n.
+// CTA = 128 keys of one (batch, head); it walks over the 128-row query tiles.  Orientation: THREAD = QUERY ROW (TMEM lane),
+// as in the forward kernel, so everything that is per query -- lse, Delta, the gate -- is a register, d gate is a thread-local
+// sum, and the Toeplitz bias entries a thread needs are consecutive table words (64-bit loads from two shifted copies).
+// Per query tile i (two 64-key halves so that S / dP of the next tile are produced under the exponentials of this one):
+//   S_hf  = Q_i K_hf^T        128x64x64   -> TMEM stage hf, columns [0,64)
+//   dP_hf = dO_i V_hf^T       128x64x64   -> TMEM stage hf, columns [64,128)
+//   P  = exp2(S*scale*log2e + gate_i*log2e*tab[j-i] + keymask_j - lse_i);   dS = P o (dP - Delta_i) * scale
+//   P, dS -> shared memory once, bf16 [128 queries][128 keys] operand tiles (two 64-key blocks)
+//   dV += P^T dO_i           A = P tile read MN-major (M = keys), accumulates in TMEM over the whole loop
+//   dK += dS^T Q_i           same with the dS tile
+//   dQ_i = dS K              A = dS tile read K-major; read back from TMEM and added to an fp32 [B,T,D] buffer with vector
+//                            reductions (one writer CTA per key tile)
+//   d gate_i += sum_j dS_ij tab[j-i]        thread-local FMA, one global atomic per thread and tile
+//   d tab[d]  = sum_i gate_i dS_{i,i+d}     diagonal sums of a staged bf16 tile gate*dS (one per half), per-CTA accumulators
+// Warp roles: warps 0-15 = CUDA-core warps: warpgroup g = (key half g>>1, 32-column group g&1), thread = query row;
+// warp 16 = producer (its lane 0 issues every TMA load and MMA).  All hand-offs are mbarriers (+ one 256-thread named barrier per half that
+// recycles the diagonal staging tile).
+// Padding: a CTA whose 128 keys are all padded writes zero dK / dV rows and exits; query tiles that are fully padded at the end
+// of the utterance are not visited (their probabilities are zero: the forward leaves lse = +inf there).
 #include "../../include/unispeech_b200.h"
 #include "attn_common.cuh"
 #include "common.h"
+#include <type_traits>
 
 namespace b200 {
 
@@ -33,24 +37,37 @@ __device__ __forceinline__ float ex2f(float x) {
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ uint32_t bit_transpose32(uint32_t x, int lane) {  // see warp_bit_transpose in attn_fwd.cu
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const uint32_t m = (s == 16) ? 0x0000FFFFu : (s == 8) ? 0x00FF00FFu : (s == 4) ? 0x0F0F0F0Fu : (s == 2) ? 0x33333333u : 0x55555555u;
+    const uint32_t y = __shfl_xor_sync(0xffffffffu, x, s);
+    x = (lane & s) ? ((x & ~m) | ((y >> s) & m)) : ((x & m) | ((y << s) & ~m));
+  }
+  return x;
+}
 
 // shared-memory map (bytes from the 1024-aligned base)
 constexpr int kFK = 0;             // K tile          16 KB
 constexpr int kFV = 16384;         // V tile          16 KB
 constexpr int kFQ = 32768;         // Q tiles, 2 stages x 16 KB
 constexpr int kFDO = 65536;        // dO tiles, 2 stages x 16 KB
-constexpr int kFPT = 98304;        // P^T  : two [128 keys][64 queries] blocks (one per half tile), 32 KB
-constexpr int kFDST = 131072;      // dS^T : same layout, 32 KB
-constexpr int kFW = 163840;        // gate*dS^T staging for the diagonal sums: 2 x [128][66] bf16
+constexpr int kFP = 98304;         // P  : [128 queries][128 keys] as two 64-key blocks, 32 KB
+constexpr int kFDS = 131072;       // dS : same layout, 32 KB
+constexpr int kFW = 163840;        // gate*dS staging for the diagonal sums: one [128 queries][66] bf16 tile per key half
 constexpr int kWStride2 = 66;      // bf16 per staged row (33 words: conflict-free row writes and diagonal reads)
 constexpr int kFWBytes = 128 * kWStride2 * 2;   // 16896
-constexpr int kFVec = kFW + 2 * kFWBytes;        // 197632: colvec [2][128] float4
-constexpr int kFTab = kFVec + 2 * 128 * 16;      // 201728: tab_s[(N+1)*128], dtab_acc[(N+1)*128], dgate_s[N*128]
-constexpr int kNC = 4;                        // threads per key row: each handles kCW query columns of a 64-wide half tile
-constexpr int kCW = 64 / kNC;                 // 16
-constexpr int kCudaThreads = 128 * kNC;       // 16 CUDA-core warps: four per scheduler hide the TMEM / SFU / LDS latencies
-constexpr int kFThreads = kCudaThreads + 128; // + 1 producer warpgroup (only its first lane works)
+constexpr int kFTab = kFW + 2 * kFWBytes;        // 197632: tab copies [2][tab_stride], dtab_acc[(N+1)*128]
+constexpr int kCudaThreads = 512;             // 16 CUDA-core warps: four per scheduler hide the TMEM / SFU / LDS latencies
+constexpr int kFThreads = kCudaThreads + 32;  // + 1 producer warp (only its first lane works): 17 warps x 120 registers
 constexpr int kProdWarp = kCudaThreads / 32;
+
+// floats of ONE copy of the bias-table slice: (N + 1) * 128 entries + 18, so that the second copy (shifted by one element)
+// starts 18 banks further: the 64-bit loads of a half warp, whose lanes alternate between the copies, touch 32 distinct banks
+__host__ __device__ constexpr int bwd_tab_stride(int N) { return (N + 1) * kAttnTile + 18; }
 
 }  // namespace
 
@@ -63,7 +80,6 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int k0 = blockIdx.x * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
-  const int NH = 2 * N;  // half tiles
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // 1024-aligned, still a __shared__ pointer (LDS/STS, not generic)
@@ -71,15 +87,51 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   uint8_t* sV = smem + kFV;
   uint8_t* sQ = smem + kFQ;
   uint8_t* sDO = smem + kFDO;
-  uint8_t* sPT = smem + kFPT;
-  uint8_t* sDST = smem + kFDST;
-  float4* colvec = reinterpret_cast<float4*>(smem + kFVec);  // [2][128] {lse2, delta, gate*log2e, gate}
-  float* tab_s = reinterpret_cast<float*>(smem + kFTab);     // [(N+1)*128]
-  float* dtab_acc = tab_s + (N + 1) * kAttnTile;             // [(N+1)*128]
-  float* dgate_s = dtab_acc + (N + 1) * kAttnTile;           // [N*128]
+  uint8_t* sP = smem + kFP;
+  uint8_t* sDS = smem + kFDS;
+  float* tab_s = reinterpret_cast<float*>(smem + kFTab);  // [2][tab_stride]: copy c holds slice[l + c]
+  const int tab_stride = bwd_tab_stride(N);
+  float* dtab_acc = tab_s + (HAS_BIAS ? 2 * tab_stride : 0);  // [(N+1)*128]
 
-  __shared__ uint64_t kv_full, qdo_full[2], qdo_free[2], st_full[2], ready[2], mma_done[2], dq_full, acc_done;
+  __shared__ uint64_t kv_full, qdo_full[2], qdo_free[2], st_full[2], ready[2], mma_done, dq_full, acc_done;
   __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t key_mask_s[4];  // bit j of word j>>5: key k0 + j is padded / beyond T
+
+  // ---- padding: which of this CTA's keys are masked, and how many query tiles hold a valid query
+  {
+    bool masked = false;
+    if (tid < kAttnTile) {
+      const int j = k0 + tid;
+      masked = (j >= T) || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + j] != 0);
+      const uint32_t bal = __ballot_sync(0xffffffffu, masked);
+      if (lane == 0) key_mask_s[warp] = bal;
+    }
+    const int n_masked = __syncthreads_count(masked);
+    if (n_masked == kAttnTile) {
+      // nothing attends to these keys: dK = dV = 0
+      if (tid < kAttnTile && k0 + tid < T) {
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + k0 + tid) * (3 * D) + D + h * kHeadDim;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          *reinterpret_cast<uint4*>(dst + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+          *reinterpret_cast<uint4*>(dst + D + g * 8) = make_uint4(0u, 0u, 0u, 0u);
+        }
+      }
+      return;
+    }
+  }
+  int NQ = N;  // query tiles to visit
+  if (p.key_pad != nullptr) {
+    NQ = 1;
+    for (int t = 0; t < N; ++t) {
+      bool live = false;
+      if (tid < kAttnTile) {
+        const int i = t * kAttnTile + tid;
+        live = (i < T) && (p.key_pad[static_cast<long long>(b) * T + i] == 0);
+      }
+      if (__syncthreads_count(live) != 0) NQ = t + 1;
+    }
+  }
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -89,9 +141,9 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       mbar_init(&qdo_full[i], 1);
       mbar_init(&qdo_free[i], 1);
       mbar_init(&st_full[i], 1);
-      mbar_init(&ready[i], kCudaThreads);
-      mbar_init(&mma_done[i], 1);
+      mbar_init(&ready[i], kCudaThreads / 2);
     }
+    mbar_init(&mma_done, 1);
     mbar_init(&dq_full, 1);
     mbar_init(&acc_done, 1);
     fence_mbar_init();
@@ -99,69 +151,48 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
 
-  // per-CTA tables: tab_s[l] = tab[h, l + base], base = k0 - (N*128-1) + (T-1); element (key row r, query i) -> l = r + N*128-1 - i
+  // per-CTA tables: slice[l] = tab[h, l + base], base = k0 - (N*128-1) + (T-1); element (query i, key k0 + j) -> l = j - i + N*128-1
   const int tab_base = k0 - (N * kAttnTile - 1) + (T - 1);
   if (HAS_BIAS) {
     const int len = (N + 1) * kAttnTile;
-    for (int l = tid; l < len; l += kFThreads) {
-      const int gi = l + tab_base;
-      tab_s[l] = (gi >= 0 && gi < 2 * T - 1) ? p.tab[static_cast<long long>(h) * (2 * T - 1) + gi] : 0.f;
-      dtab_acc[l] = 0.f;
+    const float* tab_h = p.tab + static_cast<long long>(h) * (2 * T - 1);
+    for (int l = tid; l < 2 * len; l += kFThreads) {
+      const int c = l / len, k = l - c * len;
+      const int gi = k + c + tab_base;
+      tab_s[c * tab_stride + k] = (gi >= 0 && gi < 2 * T - 1) ? tab_h[gi] : 0.f;
     }
-    for (int l = tid; l < N * kAttnTile; l += kFThreads) dgate_s[l] = 0.f;
+    for (int l = tid; l < len; l += kFThreads) dtab_acc[l] = 0.f;
   }
-  auto load_colvec = [&](int qi) {  // executed by threads 0..127: one query column each
-    const int i = qi * kAttnTile + tid;
-    float4 v;
-    if (i < T) {
-      const long long idx = (static_cast<long long>(b) * p.H + h) * T + i;
-      const float g = HAS_BIAS ? ((p.gate != nullptr) ? p.gate[idx] : 1.0f) : 0.f;
-      v.x = p.lse[idx];
-      v.y = p.delta[idx];
-      v.z = g * kLog2e;
-      v.w = g;
-    } else {
-      v.x = INFINITY;  // p = exp2(-inf) = 0 for out-of-range queries
-      v.y = 0.f;
-      v.z = 0.f;
-      v.w = 0.f;
-    }
-    colvec[(qi & 1) * kAttnTile + tid] = v;
-  };
-  if (tid < kAttnTile) load_colvec(0);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
-  // TMEM columns: S^T/dP^T stage s at s*128 (S^T) and s*128+64 (dP^T); dV 256; dK 320; dQ 384
+  // TMEM columns: stage hf at hf*128: S [0,64), dP [64,128); dV 256; dK 320; dQ 384
   constexpr uint32_t kColDV = 256, kColDK = 320, kColDQ = 384;
 
   if (warp >= kProdWarp) {
-    // registers are granted per warpgroup (96 per thread at launch): the producer group keeps 40, the CUDA-core groups get 104
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     if (warp == kProdWarp && lane == 0) {
       // ================================================================== TMA producer + MMA issuer
-      constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);   // K-major A (K/V), K-major B (Q/dO half tile)
-      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);  // K-major A (P^T/dS^T), MN-major B (dO/Q)
-      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);   // MN-major A (dS^T read as dS), MN-major B (K)
+      constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);   // K-major A (Q / dO), K-major B (K / V half)
+      constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);  // MN-major A (P / dS read transposed), MN-major B (dO / Q)
+      constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);   // K-major A (dS), MN-major B (K)
       auto load_qdo = [&](int qi) {
         const int s = qi & 1;
         mbar_expect_tx(&qdo_full[s], 32768);
         tma_load_4d(sQ + s * 16384, &tm_qkv, &qdo_full[s], h * kHeadDim, qi * kAttnTile, b, 0);
         tma_load_4d(sDO + s * 16384, &tm_do, &qdo_full[s], h * kHeadDim, qi * kAttnTile, b, 0);
       };
-      auto issue_st = [&](int hh) {  // S^T and dP^T of half tile hh into TMEM stage hh & 1
-        const int qi = hh >> 1, hf = hh & 1;
-        const uint32_t ak = smem_u32(sK), av = smem_u32(sV);
-        const uint32_t bq = smem_u32(sQ + (qi & 1) * 16384 + hf * 8192), bd = smem_u32(sDO + (qi & 1) * 16384 + hf * 8192);
+      auto issue_st = [&](int qi, int hf) {  // S and dP of (query tile qi, key half hf) into TMEM stage hf
+        const uint32_t aq = smem_u32(sQ + (qi & 1) * 16384), ad = smem_u32(sDO + (qi & 1) * 16384);
+        const uint32_t bk = smem_u32(sK + hf * 8192), bv = smem_u32(sV + hf * 8192);
         const uint32_t d0 = tmem + hf * 128;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(d0, make_smem_desc_sw128(ak + k * 32, 16, 1024), make_smem_desc_sw128(bq + k * 32, 16, 1024), idesc_st,
+          umma_bf16(d0, make_smem_desc_sw128(aq + k * 32, 16, 1024), make_smem_desc_sw128(bk + k * 32, 16, 1024), idesc_st,
                     k > 0 ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          umma_bf16(d0 + 64, make_smem_desc_sw128(av + k * 32, 16, 1024), make_smem_desc_sw128(bd + k * 32, 16, 1024),
+          umma_bf16(d0 + 64, make_smem_desc_sw128(ad + k * 32, 16, 1024), make_smem_desc_sw128(bv + k * 32, 16, 1024),
                     idesc_st, k > 0 ? 1u : 0u);
         umma_commit(&st_full[hf]);
       };
@@ -170,50 +201,46 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       tma_load_4d(sK, &tm_qkv, &kv_full, D + h * kHeadDim, k0, b, 0);
       tma_load_4d(sV, &tm_qkv, &kv_full, 2 * D + h * kHeadDim, k0, b, 0);
       load_qdo(0);
-      if (N > 1) load_qdo(1);
+      if (NQ > 1) load_qdo(1);
       mbar_wait(&kv_full, 0);
       mbar_wait(&qdo_full[0], 0);
       tc_fence_after();
-      issue_st(0);
-      issue_st(1);
+      issue_st(0, 0);
+      issue_st(0, 1);
 
-      for (int hh = 0; hh < NH; ++hh) {
-        const int qi = hh >> 1, hf = hh & 1, st = qi & 1;
-        mbar_wait(&ready[hf], qi & 1);  // P^T / dS^T of this half tile are in shared memory; TMEM stage hf has been read
-        tc_fence_after();
-        const uint32_t apt = smem_u32(sPT + hf * 16384), ads = smem_u32(sDST + hf * 16384);
-        const uint32_t bdo = smem_u32(sDO + st * 16384 + hf * 8192), bq = smem_u32(sQ + st * 16384 + hf * 8192);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // dV += P^T dO   (K = 64 queries)
-          umma_bf16(tmem + kColDV, make_smem_desc_sw128(apt + k * 32, 16, 1024),
-                    make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc_acc, (hh > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // dK += dS^T Q
-          umma_bf16(tmem + kColDK, make_smem_desc_sw128(ads + k * 32, 16, 1024),
-                    make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc_acc, (hh > 0 || k > 0) ? 1u : 0u);
-        if (hf == 1) {
-          // dQ_i = dS K over the full 128-query tile: A = dS^T tile read MN-major (M = queries: two 64-wide atoms 16 KB
-          // apart, K = key rows: 16 rows = 2048 B per step), B = K tile MN-major
-          const uint32_t adq = smem_u32(sDST), bk = smem_u32(sK);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)
-            umma_bf16(tmem + kColDQ, make_smem_desc_sw128(adq + k * 2048, 16384, 1024),
-                      make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
-          umma_commit(&dq_full);
-          umma_commit(&qdo_free[st]);  // every MMA reading Q_i / dO_i has been issued before this commit
-        }
-        umma_commit(&mma_done[hf]);
-        if (hh + 2 < NH) {
-          const int q2 = (hh + 2) >> 1;
-          if (hf == 0) {  // first half of a new query tile: its TMA load must have landed
-            mbar_wait(&qdo_full[q2 & 1], (q2 >> 1) & 1);
-            tc_fence_after();
+      for (int qi = 0; qi < NQ; ++qi) {
+        const int st = qi & 1;
+#pragma unroll 1
+        for (int hf = 0; hf < 2; ++hf) {
+          mbar_wait(&ready[hf], qi & 1);  // P / dS / W of this half are staged; TMEM stage hf has been read
+          tc_fence_after();
+          if (qi + 1 < NQ) {
+            if (hf == 0) {
+              mbar_wait(&qdo_full[(qi + 1) & 1], ((qi + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_st(qi + 1, hf);  // next tile's scores first: the CUDA-core warps never wait for the accumulation MMAs
           }
-          issue_st(hh + 2);
-        } else if (hh + 1 == NH) {
-          umma_commit(&acc_done);
         }
-        if (hf == 1 && qi + 2 < N) {  // refill this Q/dO stage once its readers have retired
+        const uint32_t ap = smem_u32(sP), ads = smem_u32(sDS);
+        const uint32_t bdo = smem_u32(sDO + st * 16384), bq = smem_u32(sQ + st * 16384), bk = smem_u32(sK);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dV += P^T dO   (K = 128 queries, 16 per step)
+          umma_bf16(tmem + kColDV, make_smem_desc_sw128(ap + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(bdo + k * 2048, 8192, 1024), idesc_acc, (qi > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dK += dS^T Q
+          umma_bf16(tmem + kColDK, make_smem_desc_sw128(ads + k * 2048, 16384, 1024),
+                    make_smem_desc_sw128(bq + k * 2048, 8192, 1024), idesc_acc, (qi > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)  // dQ_i = dS K    (K = 128 keys: two 64-key blocks, 16 per step)
+          umma_bf16(tmem + kColDQ, make_smem_desc_sw128(ads + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                    make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
+        umma_commit(&dq_full);
+        umma_commit(&mma_done);
+        umma_commit(&qdo_free[st]);
+        if (qi + 1 == NQ) umma_commit(&acc_done);
+        if (qi + 2 < NQ) {  // refill this Q/dO stage once its readers have retired
           mbar_wait(&qdo_free[st], (qi >> 1) & 1);
           load_qdo(qi + 2);
         }
@@ -221,161 +248,196 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     }
   } else {
     // ==================================================================== CUDA-core warps
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
-    const int r = tid & (kAttnTile - 1);  // key row inside the tile == TMEM lane
-    const int ch = tid >> 7;              // which kCW query columns of the 64-wide half tile
-    const int key = k0 + r;
-    const bool key_valid = key < T;
-    const bool key_masked = !key_valid || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + key] != 0);
-    const float kb = key_masked ? -INFINITY : 0.f;
+    const int g = warp >> 2;              // warpgroup 0..3
+    const int hf = g >> 1;                // key half of this warpgroup
+    const int j0 = hf * 64 + (g & 1) * 32;  // first of this thread's 32 key columns (inside the 128-key tile)
+    const int r = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
+    const int ht = tid & 255;             // thread index inside the half (diagonal-sum tasks)
     const float sc = p.scale * kLog2e;
-    const float* tabrow = tab_s + r + N * kAttnTile - 1;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    // dropout keep bits written by the forward kernel: word (query block i >> 5, key) holds the bits of 32 consecutive queries
-    const uint32_t* mask_col =
-        DROP ? p.drop_mask + static_cast<long long>(b * p.H + h) * (4 * N) * (N * kAttnTile) + k0 + r : nullptr;
+    const uint32_t kmask = key_mask_s[j0 >> 5];  // bit jj: key column j0 + jj is masked
+    const bool any_masked = (key_mask_s[0] | key_mask_s[1] | key_mask_s[2] | key_mask_s[3]) != 0u;  // uniform over the CTA
+    // bias entries of (row r, keys j0 + jj) in query tile qi: slice[tstart - qi*128 + jj]
+    const int tstart = j0 - r + N * kAttnTile - 1;
+    const float* tab_row = tab_s + (tstart & 1) * tab_stride + (tstart & ~1);  // 8-byte aligned in the copy of matching parity
+    uint32_t* wtile = reinterpret_cast<uint32_t*>(smem + kFW + hf * kFWBytes);
+    const long long bh = static_cast<long long>(b) * p.H + h;
 
-    // dQ tile of query tile qi: TMEM -> fp32 reductions into dq_acc[b, q, h*64 + ch*32 ..]
+    // per-row scalars of query tile qi (prefetched one tile ahead)
+    float lse2 = INFINITY, dsc = 0.f, gl = 0.f, gos = 0.f;
+    auto load_row = [&](int qi, float& a_lse, float& a_dsc, float& a_gl, float& a_gos) {
+      const int i = qi * kAttnTile + r;
+      if (i < T) {
+        const float gt = HAS_BIAS ? ((p.gate != nullptr) ? p.gate[bh * T + i] : 1.0f) : 0.f;
+        a_lse = p.lse[bh * T + i];
+        a_dsc = p.delta[bh * T + i] * p.scale;
+        a_gl = gt * kLog2e;
+        a_gos = gt / p.scale;
+      } else {
+        a_lse = INFINITY;  // p = exp2(-inf) = 0 for out-of-range queries
+        a_dsc = 0.f; a_gl = 0.f; a_gos = 0.f;
+      }
+    };
+    load_row(0, lse2, dsc, gl, gos);
+
+    // dQ tile of query tile qi: TMEM -> fp32 reductions into dq_acc[b, q, h*64 + g*16 ..]  (thread = query row, 16 columns)
     auto flush_dq = [&](int qi) {
       mbar_wait(&dq_full, qi & 1);
       tc_fence_after();
-      uint32_t t0[kCW];
-      tmem_ld_32x32b_x16(tmem + lane_addr + kColDQ + ch * kCW, t0);
+      uint32_t t0[16];
+      tmem_ld_32x32b_x16(tmem + lane_addr + kColDQ + g * 16, t0);
       tmem_ld_wait();
-      const int q = qi * kAttnTile + r;  // TMEM lane = query row of the dQ accumulator
+      const int q = qi * kAttnTile + r;
       if (q < T) {
-        float* dst = dq_acc + (static_cast<long long>(b) * T + q) * D + h * kHeadDim + ch * kCW;
+        float* dst = dq_acc + (static_cast<long long>(b) * T + q) * D + h * kHeadDim + g * 16;
 #pragma unroll
-        for (int g = 0; g < kCW / 4; ++g)
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + g * 4), "f"(__uint_as_float(t0[g * 4 + 0])),
-                       "f"(__uint_as_float(t0[g * 4 + 1])), "f"(__uint_as_float(t0[g * 4 + 2])),
-                       "f"(__uint_as_float(t0[g * 4 + 3]))
-                       : "memory");  // the staged dS^T already carries the softmax scale
+        for (int v = 0; v < 4; ++v)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + v * 4), "f"(__uint_as_float(t0[v * 4 + 0])),
+                       "f"(__uint_as_float(t0[v * 4 + 1])), "f"(__uint_as_float(t0[v * 4 + 2])),
+                       "f"(__uint_as_float(t0[v * 4 + 3]))
+                       : "memory");  // the staged dS already carries the softmax scale
       }
     };
-    // diagonal sums of the staged gate*dS^T tile of half tile hh (thread: diagonal d = r, query columns 32*ch..)
-    // Element (key row rr, local query c) of the staged tile belongs to diagonal rr - c; thread (d = r, ch) walks
-    // rr = (d + c) & 127 over its kCW columns: the wrap point is a per-thread constant, so every load is base + immediate.
-    const int diag_w0 = kAttnTile - r - ch * kCW;  // columns e >= diag_w0 (e = c - ch*kCW) are on the wrapped diagonal
-    const uint32_t diag_base = static_cast<uint32_t>(r * kWStride2 + ch * kCW * (kWStride2 + 1)) * 2u;
-    auto diag_sums = [&](int hh) {
-      const uint32_t w_nowrap = smem_u32(smem + kFW + (hh & 1) * kFWBytes) + diag_base;
-      const uint32_t w_wrap = w_nowrap - static_cast<uint32_t>(kAttnTile * kWStride2 * 2);
-      float acc_all = 0.f, acc_pos = 0.f;
+    // diagonal sums of the staged gate*dS tile of (query tile qi, this half).  Task (e, s): elements (i = (jj - e) & 127, jj)
+    // for jj = 16 s .. 16 s + 15: diagonal jj - i = e (not wrapped, jj >= e) or e - 128 (wrapped).  The wrap point is a per-task
+    // constant, so every load is base + immediate.
+    auto diag_task = [&](int qi, int e, int s) {
+      const int w0 = e - 16 * s;  // columns jj = 16 s + c with c < w0 are on the wrapped diagonal
+      const uint32_t base_nw = smem_u32(wtile) + static_cast<uint32_t>((16 * s - e) * kWStride2 + 16 * s) * 2u;
+      const uint32_t base_w = base_nw + static_cast<uint32_t>(kAttnTile * kWStride2 * 2);
+      float acc_all = 0.f, acc_nw = 0.f;
 #pragma unroll
-      for (int e = 0; e < kCW; ++e) {
-        const bool wrapped = e >= diag_w0;
+      for (int c = 0; c < 16; ++c) {
+        const bool wrapped = c < w0;
         uint32_t v16;
-        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v16) : "r"((wrapped ? w_wrap : w_nowrap) + e * (kWStride2 + 1) * 2));
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v16) : "r"((wrapped ? base_w : base_nw) + c * (kWStride2 + 1) * 2));
         const float v = __uint_as_float(v16 << 16);
         acc_all += v;
-        if (!wrapped) acc_pos += v;
+        if (!wrapped) acc_nw += v;
       }
-      const int l_pos = r + N * kAttnTile - 1 - (hh >> 1) * kAttnTile - (hh & 1) * 64;
-      atomicAdd(&dtab_acc[l_pos], acc_pos);
-      if (diag_w0 < kCW) atomicAdd(&dtab_acc[l_pos - kAttnTile], acc_all - acc_pos);
+      const int l_nw = hf * 64 - qi * kAttnTile + e + N * kAttnTile - 1;
+      if (w0 < 16) atomicAdd(&dtab_acc[l_nw], acc_nw);
+      if (w0 > 0) atomicAdd(&dtab_acc[l_nw - kAttnTile], acc_all - acc_nw);
     };
 
-    for (int hh = 0; hh < NH; ++hh) {
-      const int qi = hh >> 1, hf = hh & 1;
-      const int i0 = qi * kAttnTile + hf * 64 + ch * kCW;  // first global query of this thread's columns
+    for (int qi = 0; qi < NQ; ++qi) {
       mbar_wait(&st_full[hf], qi & 1);
       tc_fence_after();
+      // next tile's row scalars: in flight under this tile's arithmetic
+      float n_lse = INFINITY, n_dsc = 0.f, n_gl = 0.f, n_gos = 0.f;
+      if (qi + 1 < NQ) load_row(qi + 1, n_lse, n_dsc, n_gl, n_gos);
       uint32_t keep_bits = 0xffffffffu;
-      if (DROP) keep_bits = mask_col[static_cast<long long>(i0 >> 5) * (N * kAttnTile)] >> (i0 & 31);  // bit e = query i0 + e
-      uint32_t su[kCW], du[kCW];
-      tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + ch * kCW, su);
-      tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + 64 + ch * kCW, du);
-      if (hf == 1 && qi >= 1) flush_dq(qi - 1);  // dQ of the previous query tile finished a whole phase ago
-      tmem_ld_wait();
-      const float4* cv = colvec + (qi & 1) * kAttnTile + hf * 64 + ch * kCW;
-      uint32_t pw[kCW / 2], dw[kCW / 2], ww[kCW / 2];
-      float dgc[kCW];
+      if (DROP) {  // word (32-query block, key column) holds the bits of this warp's 32 rows: transpose to one word per row
+        const long long blk = bh * (4 * N) + ((qi * kAttnTile + r) >> 5);
+        const uint32_t wcol = p.drop_mask[blk * (N * kAttnTile) + k0 + j0 + lane];
+        keep_bits = bit_transpose32(wcol, lane);
+      }
+      float dg = 0.f;
+      const float* trow = tab_row - qi * kAttnTile;
+      uint32_t* wrow = wtile + r * (kWStride2 / 2) + (g & 1) * 16;
+
+      // 16 key columns at a time: probabilities / dS / gate*dS packed to bf16 in registers, then staged.  The first stores of a
+      // tile wait for the accumulation MMAs of the previous tile (which read the P / dS tiles); by then half of this tile's
+      // arithmetic is done.
+      auto body = [&](auto MSK) {
+        constexpr bool kMsk = decltype(MSK)::value;
 #pragma unroll
-      for (int j = 0; j < kCW; j += 2) {
-        float pr2[2], ds2[2], w2[2];
+        for (int sub = 0; sub < 2; ++sub) {
+          uint32_t su[16], du[16];
+          tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + (g & 1) * 32 + sub * 16, su);
+          tmem_ld_32x32b_x16(tmem + lane_addr + hf * 128 + 64 + (g & 1) * 32 + sub * 16, du);
+          tmem_ld_wait();
+          uint32_t pw[8], dw[8], ww[8];
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const float4 c = cv[j + e];
-          float x = fmaf(__uint_as_float(su[j + e]), sc, kb);
-          float tb = 0.f;
+          for (int q = 0; q < 8; ++q) {
+            float2 tb = make_float2(0.f, 0.f);
+            if (HAS_BIAS) tb = *reinterpret_cast<const float2*>(trow + sub * 16 + 2 * q);
+            const float tbv[2] = {tb.x, tb.y};
+            float pr2[2], ds2[2], w2[2] = {0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int jj = sub * 16 + 2 * q + e;
+              float x = fmaf(__uint_as_float(su[2 * q + e]), sc, -lse2);
+              if (HAS_BIAS) x = fmaf(gl, tbv[e], x);
+              float pr = ex2f(x);
+              if (kMsk) pr = ((kmask >> jj) & 1u) ? 0.f : pr;
+              float dpv = __uint_as_float(du[2 * q + e]);
+              bool keep = true;
+              if (DROP) {  // O = (P o M) V / (1-p):  dP = M o (dO V^T) / (1-p);  dV takes the dropped probabilities (scaled at the end)
+                keep = ((keep_bits >> jj) & 1u) != 0u;
+                dpv = keep ? dpv * p.drop_rp : 0.f;
+              }
+              const float ds = pr * fmaf(dpv, p.scale, -dsc);  // dS * scale
+              pr2[e] = keep ? pr : 0.f;
+              ds2[e] = ds;
+              if (HAS_BIAS) {
+                dg = fmaf(ds, tbv[e], dg);
+                w2[e] = gos * ds;
+              }
+            }
+            pw[q] = pack_bf16x2(pr2[0], pr2[1]);
+            dw[q] = pack_bf16x2(ds2[0], ds2[1]);
+            if (HAS_BIAS) ww[q] = pack_bf16x2(w2[0], w2[1]);
+          }
+          if (sub == 0 && qi >= 1) {
+            // the accumulation MMAs of the previous tile have retired: the P / dS tiles may be overwritten, and its dQ is complete
+            mbar_wait(&mma_done, (qi - 1) & 1);
+            flush_dq(qi - 1);
+          }
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            store_sw128_chunk(sP, r, (j0 >> 3) + sub * 2 + c, make_uint4(pw[c * 4], pw[c * 4 + 1], pw[c * 4 + 2], pw[c * 4 + 3]));
+            store_sw128_chunk(sDS, r, (j0 >> 3) + sub * 2 + c, make_uint4(dw[c * 4], dw[c * 4 + 1], dw[c * 4 + 2], dw[c * 4 + 3]));
+          }
           if (HAS_BIAS) {
-            tb = tabrow[-(i0 + j + e)];
-            x = fmaf(c.z, tb, x);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) wrow[sub * 8 + j] = ww[j];
           }
-          const float pr = ex2f(x - c.x);
-          float dpv = __uint_as_float(du[j + e]);
-          bool keep = true;
-          if (DROP) {  // O = (P o M) V / (1-p):  dP = M o (dO V^T) / (1-p);  dV takes the dropped probabilities (scaled at the end)
-            keep = ((keep_bits >> (j + e)) & 1u) != 0u;
-            dpv = keep ? dpv * p.drop_rp : 0.f;
-          }
-          const float ds = pr * (dpv - c.y);
-          pr2[e] = keep ? pr : 0.f;
-          ds2[e] = ds * p.scale;
-          w2[e] = c.w * ds;
-          dgc[j + e] = ds * tb;
         }
-        pw[j >> 1] = pack_bf16x2(pr2[0], pr2[1]);
-        dw[j >> 1] = pack_bf16x2(ds2[0], ds2[1]);
-        ww[j >> 1] = pack_bf16x2(w2[0], w2[1]);
+      };
+      if (any_masked) body(std::true_type{}); else body(std::false_type{});
+
+      if (HAS_BIAS && p.dgate != nullptr) {
+        const int i = qi * kAttnTile + r;
+        if (i < T) atomicAdd(p.dgate + bh * T + i, dg * (1.0f / p.scale));
       }
-      if (HAS_BIAS) {
-        // d gate: sum over the 32 key rows of this warp for each of its query columns, then one shared atomic per column
-        const float csum = warp_colsum16(dgc, lane);
-        if ((lane & 1) == 0) atomicAdd(&dgate_s[i0 + (lane >> 1)], csum);
-      }
-      if (hh >= 1) {
-        // Every thread has staged half tile hh-1 (needed by its diagonal sums; the same wait orders the reuse of the double-
-        // buffered staging tile and of the colvec buffers).  Waiting HERE, a whole phase after the arrivals, means the warps
-        // never run in lock step: a warp may be up to one phase ahead of the slowest one.
-        mbar_wait(&ready[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
-        if (HAS_BIAS) diag_sums(hh - 1);
-        // MMAs that read the P^T / dS^T blocks (and, in order, everything issued before them) have retired
-        mbar_wait(&mma_done[(hh - 1) & 1], ((hh - 1) >> 1) & 1);
-      }
-#pragma unroll
-      for (int g = 0; g < kCW / 8; ++g) {
-        store_sw128_chunk(sPT, r, hf * 8 + ch * (kCW / 8) + g, make_uint4(pw[g * 4], pw[g * 4 + 1], pw[g * 4 + 2], pw[g * 4 + 3]));
-        store_sw128_chunk(sDST, r, hf * 8 + ch * (kCW / 8) + g, make_uint4(dw[g * 4], dw[g * 4 + 1], dw[g * 4 + 2], dw[g * 4 + 3]));
-      }
-      if (HAS_BIAS) {
-        uint32_t* wrow = reinterpret_cast<uint32_t*>(smem + kFW + (hh & 1) * kFWBytes) + r * (kWStride2 / 2) + ch * (kCW / 2);
-#pragma unroll
-        for (int j = 0; j < kCW / 2; ++j) wrow[j] = ww[j];
-      }
-      if (hf == 0 && qi + 1 < N && tid < kAttnTile) load_colvec(qi + 1);  // other buffer: last read in query tile qi-1
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive_cta(&ready[hf]);
+      lse2 = n_lse; dsc = n_dsc; gl = n_gl; gos = n_gos;
+      if (HAS_BIAS) {
+        mbar_wait(&ready[hf], qi & 1);  // all 256 threads of this half have staged their rows
+        diag_task(qi, ht & 127, ht >> 7);
+        diag_task(qi, ht & 127, (ht >> 7) + 2);
+        named_bar_sync(1 + hf, kCudaThreads / 2);  // the staging tile of this half may be overwritten
+      }
     }
-    // ---- tail: last staged tile's diagonals, last dQ tile, then the dK / dV accumulators
-    mbar_wait(&ready[(NH - 1) & 1], ((NH - 1) >> 1) & 1);
-    if (HAS_BIAS) diag_sums(NH - 1);
-    flush_dq(N - 1);
+    // ---- tail: last dQ tile, then the dK / dV accumulators
+    flush_dq(NQ - 1);
     mbar_wait(&acc_done, 0);
     tc_fence_after();
     {
-      // 128 key rows x (64 dV + 64 dK) columns over 512 threads: ch 0,1 -> dV columns 32*(ch&1).., ch 2,3 -> dK
+      // 128 key rows x (64 dV + 64 dK) columns over 512 threads: g 0,1 -> dV columns 32*(g&1).., g 2,3 -> dK
       uint32_t t0[32];
-      const uint32_t col = ((ch < kNC / 2) ? kColDV : kColDK) + (ch & (kNC / 2 - 1)) * (128 / kNC);
+      const uint32_t col = ((g < 2) ? kColDV : kColDK) + (g & 1) * 32;
       tmem_ld_32x32b_x32(tmem + lane_addr + col, t0);
       tmem_ld_wait();
-      if (DROP && ch < kNC / 2) {  // dV = (P o M)^T dO / (1-p)
+      if (DROP && g < 2) {  // dV = (P o M)^T dO / (1-p)
 #pragma unroll
         for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * p.drop_rp);
       }
-      if (key_valid) {
-        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + key) * (3 * D) + ((ch < kNC / 2) ? 2 * D : D) +
-                             h * kHeadDim + (ch & (kNC / 2 - 1)) * (128 / kNC);
+      const int key = k0 + r;
+      if (key < T) {
+        __nv_bfloat16* dst = p.dqkv + (static_cast<long long>(b) * T + key) * (3 * D) + ((g < 2) ? 2 * D : D) + h * kHeadDim +
+                             (g & 1) * 32;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int v = 0; v < 4; ++v) {
           uint4 w;
-          w.x = pack_bf16x2(__uint_as_float(t0[g * 8 + 0]), __uint_as_float(t0[g * 8 + 1]));
-          w.y = pack_bf16x2(__uint_as_float(t0[g * 8 + 2]), __uint_as_float(t0[g * 8 + 3]));
-          w.z = pack_bf16x2(__uint_as_float(t0[g * 8 + 4]), __uint_as_float(t0[g * 8 + 5]));
-          w.w = pack_bf16x2(__uint_as_float(t0[g * 8 + 6]), __uint_as_float(t0[g * 8 + 7]));
-          *reinterpret_cast<uint4*>(dst + g * 8) = w;
+          w.x = pack_bf16x2(__uint_as_float(t0[v * 8 + 0]), __uint_as_float(t0[v * 8 + 1]));
+          w.y = pack_bf16x2(__uint_as_float(t0[v * 8 + 2]), __uint_as_float(t0[v * 8 + 3]));
+          w.z = pack_bf16x2(__uint_as_float(t0[v * 8 + 4]), __uint_as_float(t0[v * 8 + 5]));
+          w.w = pack_bf16x2(__uint_as_float(t0[v * 8 + 6]), __uint_as_float(t0[v * 8 + 7]));
+          *reinterpret_cast<uint4*>(dst + v * 8) = w;
         }
       }
     }
@@ -384,17 +446,13 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   tc_fence_before();
   __syncthreads();
   if (HAS_BIAS) {
-    // per-CTA accumulators -> global (the relative-position table is shared by all layers: atomics; d gate: one CTA per key tile)
+    // per-CTA accumulators -> global (the relative-position table is shared by all layers: atomics)
     if (p.dtab != nullptr) {
       for (int l = tid; l < (N + 1) * kAttnTile; l += kFThreads) {
         const int gi = l + tab_base;
         const float v = dtab_acc[l];
         if (gi >= 0 && gi < 2 * T - 1 && v != 0.f) atomicAdd(p.dtab + static_cast<long long>(h) * (2 * T - 1) + gi, v);
       }
-    }
-    if (p.dgate != nullptr) {
-      for (int i = tid; i < N * kAttnTile; i += kFThreads)
-        if (i < T) atomicAdd(p.dgate + (static_cast<long long>(b) * p.H + h) * T + i, dgate_s[i]);
     }
   }
   if (warp == 0) {
@@ -491,7 +549,7 @@ int b200s_attn_bwd_fused_dropout(const void* qkv, const void* out, const void* d
   p.drop_mask = const_cast<uint32_t*>(drop_mask);
   p.drop_rp = 1.0f / (1.0f - drop_p);
   const int N = p.n_tiles;
-  const int smem = kFTab + sizeof(float) * ((N + 1) * kAttnTile * 2 + N * kAttnTile) + 1024;
+  const int smem = kFTab + sizeof(float) * ((tab != nullptr ? 2 * bwd_tab_stride(N) : 0) + (N + 1) * kAttnTile) + 1024;
   B200_CHECK_ARG(smem <= 232448 - 512, "attn_bwd_fused: T=%d needs %d bytes of shared memory", T, smem);
   dim3 grid(N, H, B);
   void (*kern)(const CUtensorMap, const CUtensorMap, const AttnParams, float*) =

@@ -1,20 +1,29 @@
 // Flash-style attention forward with the WavLM gated relative-position bias, tcgen05 + TMEM + TMA (sm_100a).
 //
-// One CTA = 256 query rows of one (batch, head): two warpgroups (WG) of 128 threads, each owning one 128-row query tile,
-// plus one TMA producer warp.  Thread r of a WG owns query row r (TMEM lane r): the row maximum / sum of the online softmax
-// are thread-local, no shuffles.  The two WGs share every K/V tile (one TMA load feeds both) and ping-pong on the tensor
-// core: while one WG runs its softmax on the CUDA cores, the other WG's S = Q K^T and O = P V MMAs run.
+// One CTA = 256 query rows of one (batch, head): two softmax warpgroups (WG) of 128 threads, each owning one 128-row query
+// tile, one TMA producer warp and one MMA-issuing warp.  Thread r of a WG owns query row r (TMEM lane r): the row reference /
+// sum of the softmax are thread-local, no shuffles.  Both WGs share every K/V tile (one TMA load feeds both).
 // Per WG and key tile n (128 keys):
-//   S_n  = Q K_n^T           tcgen05.mma 128x128x64  -> TMEM
-//   p    = exp2(S*scale*log2e + gate_i*log2e*tab[j-i] + keymask - m)   (two passes over TMEM: max, then exp)
+//   S_n  = Q K_n^T           tcgen05.mma 128x128x64  -> TMEM (128 columns)
+//   p    = exp2(S*scale*log2e + gate_i*log2e*tab[j-i] + keymask - m_i)      ONE pass over the scores
 //   P_n -> shared memory in the K-major SWIZZLE_128B operand layout (bf16)
-//   O_n  = P_n V_n           tcgen05.mma 128x64x128, V_n read as an MN-major operand straight from the TMA tile
-//   O_reg = O_reg*alpha + O_{n-1}   (registers; the rescale never touches TMEM and is deferred by one tile, so the PV MMA
-//                                    of tile n overlaps the softmax of tile n+1)
-// K/V stages are released by tcgen05.commit arrivals of BOTH WGs' issuing threads (mbarrier count 2).
+//   O   += P_n V_n           tcgen05.mma 128x64x128 ACCUMULATING IN TMEM over the whole key loop (V_n read MN-major from the TMA tile)
+// The softmax is invariant to the reference m_i subtracted in the exponent, so m_i is fixed by the first tile that has a finite
+// score for the row and never refreshed: the accumulator needs no per-tile rescale and never leaves TMEM until the epilogue
+// (fp32 sums / accumulators absorb factors up to 2^80).  If a later score outgrows the reference by more than that, the warp
+// re-bases: it rescales its 32 accumulator rows in TMEM (tcgen05.ld / st) and recomputes the tile -- a correctness path that
+// real inputs do not take.
+// The MMA warp issues, per (tile, WG) in a fixed alternating order, S(n+1) and then PV(n) as soon as that WG's P_n is staged:
+// the next scores are ready ~one MMA later, and the tensor core runs under the other WG's exponentials.
+// Padding: key tiles that are fully padded at the END of the utterance are skipped (the loop runs over n_eff tiles), and a CTA
+// whose 256 query rows are all padded only writes zeros -- padded frames never influence valid ones (keys are masked) and the
+// reference's values there are unspecified garbage, so the ragged batch does not pay for its padding.
+// The per-head Toeplitz bias table is kept in shared memory as FOUR copies shifted by 0..3 elements, so the 32 consecutive
+// entries a thread needs per 32-column chunk are 8 aligned 128-bit loads instead of 32 scalar ones.
 #include "../../include/unispeech_b200.h"
 #include "attn_common.cuh"
 #include "common.h"
+#include <type_traits>
 
 namespace b200 {
 
@@ -34,23 +43,42 @@ __device__ __forceinline__ uint32_t warp_bit_transpose(uint32_t x, int lane) {
   }
   return x;
 }
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+__device__ __forceinline__ void mbar_arrive_rel(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// registers -> 32 lanes x 32 consecutive fp32 TMEM columns (inverse of tmem_ld_32x32b_x32)
+__device__ __forceinline__ void tmem_st_32x32b_x32(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]),
+      "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]),
+      "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 constexpr int kFwdQ = 0;                   // 2 x 16 KB (one Q tile per warpgroup)
 constexpr int kFwdK = 32768;               // 2 stages x 16 KB
 constexpr int kFwdV = 65536;               // 2 stages x 16 KB
 constexpr int kFwdP = 98304;               // 2 x 32 KB (one P tile per warpgroup)
-constexpr int kFwdTab = 163840;            // fp32 bias-table slice, key mask, tile flags
-constexpr int kFwdThreads = 288;           // 2 warpgroups + 1 producer warp
+constexpr int kFwdTab = 163840;            // fp32 bias-table copies, key mask, tile flags
+constexpr int kFwdThreads = 320;           // 2 softmax warpgroups + TMA warp + MMA warp
+constexpr int kTabCopies = 4;
+constexpr float kRebase = 1.2089258e24f;   // 2^80: a tile whose row sum reaches this is re-based on its own maximum
+
+// floats of ONE bias-table copy: (N + 2) * 128 entries + 8 so that consecutive copies start 8 banks apart (conflict-free
+// 128-bit loads across the quarter warp, whose lanes alternate between the four copies)
+__host__ __device__ constexpr int fwd_tab_stride(int N) { return (N + 2) * kAttnTile + 8; }
 
 template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_constant__ CUtensorMap tm,
                                                                  const __grid_constant__ AttnParams p) {
   pdl_grid_sync();
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int wg = warp >> 2;  // 0, 1 = softmax warpgroups; 2 = producer warp
+  const int wg = warp >> 2;  // 0, 1 = softmax warpgroups; 2 = TMA warp (8) and MMA warp (9)
   const int q0 = blockIdx.x * 2 * kAttnTile, h = blockIdx.y, b = blockIdx.z;
   const int T = p.T, D = p.D, N = p.n_tiles;
 
@@ -60,12 +88,44 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
   uint8_t* sK = smem + kFwdK;
   uint8_t* sV = smem + kFwdV;
   uint8_t* sP = smem + kFwdP;
-  float* tab_s = reinterpret_cast<float*>(smem + kFwdTab);  // [(N+2)*128]: index j - r + 255, r = row inside the 256-row block
-  float* kbias = tab_s + (N + 2) * kAttnTile;                // [N*128]
-  int* tile_flags = reinterpret_cast<int*>(kbias + N * kAttnTile);
+  float* tab_s = reinterpret_cast<float*>(smem + kFwdTab);           // [4][fwd_tab_stride(N)]: copy c holds slice[i + c]
+  const int tab_stride = fwd_tab_stride(N);
+  float* kbias = tab_s + (HAS_BIAS ? kTabCopies * tab_stride : 0);  // [N*128]
+  int* tile_flags = reinterpret_cast<int*>(kbias + N * kAttnTile);  // [N]: 0 no masked key, 1 some, 2 all
 
-  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], o_full[2];
+  __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_ready[2], pv_done[2];
   __shared__ uint32_t tmem_base_s;
+
+  // ---- key padding: additive mask, per-tile flags, number of key tiles that hold any valid key (uniform over the CTA)
+  int n_eff = 1;
+  for (int t = 0; t < N; ++t) {
+    bool masked = false;
+    if (tid < kAttnTile) {
+      const int j = t * kAttnTile + tid;
+      masked = (j >= T) || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + j] != 0);
+      kbias[j] = masked ? -INFINITY : 0.f;
+    }
+    const int cnt = __syncthreads_count(masked);
+    if (tid == 0) tile_flags[t] = (cnt == 0) ? 0 : (cnt == kAttnTile ? 2 : 1);
+    if (cnt != kAttnTile) n_eff = t + 1;
+  }
+  // ---- a CTA whose query rows are all padded (or beyond T) has nothing to compute
+  if (p.key_pad != nullptr) {
+    bool live = false;
+    if (tid < 2 * kAttnTile) {
+      const int i = q0 + tid;
+      live = (i < T) && (p.key_pad[static_cast<long long>(b) * T + i] == 0);
+    }
+    if (__syncthreads_count(live) == 0) {
+      if (tid < 2 * kAttnTile && q0 + tid < T) {
+        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + q0 + tid) * D + h * kHeadDim);
+#pragma unroll
+        for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.lse != nullptr) p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + tid] = INFINITY;
+      }
+      return;
+    }
+  }
 
   if (tid == 0) {
     tma_prefetch_desc(&tm);
@@ -73,10 +133,11 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
     for (int i = 0; i < 2; ++i) {
       mbar_init(&k_full[i], 1);
       mbar_init(&v_full[i], 1);
-      mbar_init(&k_empty[i], 2);  // one tcgen05.commit arrival per warpgroup
-      mbar_init(&v_empty[i], 2);
-      mbar_init(&s_full[i], 1);   // index = warpgroup
-      mbar_init(&o_full[i], 1);
+      mbar_init(&k_empty[i], 1);   // tcgen05.commit after the second warpgroup's S MMA
+      mbar_init(&v_empty[i], 1);   // ... after the second warpgroup's PV MMA
+      mbar_init(&s_full[i], 1);    // index = warpgroup
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&p_ready[i], kAttnTile);
     }
     fence_mbar_init();
   }
@@ -85,24 +146,25 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
   if (HAS_BIAS) {
     const int len = (N + 2) * kAttnTile;
     const int base = (T - 1) - (q0 + 2 * kAttnTile - 1);
-    for (int i = tid; i < len; i += blockDim.x) {
-      const int gi = i + base;
-      tab_s[i] = (gi >= 0 && gi < 2 * T - 1) ? p.tab[static_cast<long long>(h) * (2 * T - 1) + gi] : 0.f;
+    const float* tab_h = p.tab + static_cast<long long>(h) * (2 * T - 1);
+    for (int i = tid; i < kTabCopies * len; i += kFwdThreads) {
+      const int c = i / len, k = i - c * len;
+      const int gi = k + c + base;
+      tab_s[c * tab_stride + k] = (gi >= 0 && gi < 2 * T - 1) ? tab_h[gi] : 0.f;
     }
   }
-  load_key_mask(kbias, tile_flags, p.key_pad, b, T, N);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
 
-  if (wg == 2) {
+  if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer warp
     if ((tid & 31) == 0) {
       mbar_expect_tx(&q_full, 32768);
       tma_load_4d(sQ, &tm, &q_full, h * kHeadDim, q0, b, 0);
       tma_load_4d(sQ + 16384, &tm, &q_full, h * kHeadDim, q0 + kAttnTile, b, 0);
-      for (int n = 0; n < N; ++n) {
+      for (int n = 0; n < n_eff; ++n) {
         const int s = n & 1;
         const uint32_t ph = (n >> 1) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);
@@ -113,37 +175,62 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
         tma_load_4d(sV + s * 16384, &tm, &v_full[s], 2 * D + h * kHeadDim, n * kAttnTile, b, 0);
       }
     }
-  } else {
-    // ------------------------------------------------------------------ softmax / MMA-issuing warpgroups
-    constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
-    const int r = tid & 127;                 // row inside this warpgroup's tile == TMEM lane
-    const int r256 = wg * kAttnTile + r;     // row inside the CTA's 256-row block
-    const bool issuer = (r == 0);
-    const bool row_valid = (q0 + r256) < T;
-    const uint32_t tmem_s = tmem + wg * 256;        // S: 128 columns
-    const uint32_t tmem_o = tmem + wg * 256 + 128;  // O tile: 64 columns
-    uint8_t* sQw = sQ + wg * 16384;
-    uint8_t* sPw = sP + wg * 32768;
-    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
-
-    auto issue_s = [&](int n) {  // S_n = Q K_n^T, then release the K stage once the MMAs retire
-      const uint32_t a = smem_u32(sQw), bb = smem_u32(sK + (n & 1) * 16384);
+  } else if (warp == 9) {
+    // ------------------------------------------------------------------ MMA-issuing warp (one thread)
+    if ((tid & 31) == 0) {
+      constexpr uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+      auto issue_s = [&](int w, int n) {  // S_n of warpgroup w
+        const uint32_t a = smem_u32(sQ + w * 16384), bb = smem_u32(sK + (n & 1) * 16384);
 #pragma unroll
-      for (int k = 0; k < 4; ++k)
-        umma_bf16(tmem_s, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw128(bb + k * 32, 16, 1024), idesc_s,
-                  k > 0 ? 1u : 0u);
-      umma_commit(&s_full[wg]);
-      umma_commit(&k_empty[n & 1]);
-    };
-
-    if (issuer) {
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tmem + w * 256, make_smem_desc_sw128(a + k * 32, 16, 1024), make_smem_desc_sw128(bb + k * 32, 16, 1024),
+                    idesc_s, k > 0 ? 1u : 0u);
+        umma_commit(&s_full[w]);
+      };
       mbar_wait(&q_full, 0);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      issue_s(0);
+      issue_s(0, 0);
+      issue_s(1, 0);
+      umma_commit(&k_empty[0]);
+      for (int n = 0; n < n_eff; ++n) {
+#pragma unroll 1
+        for (int w = 0; w < 2; ++w) {
+          mbar_wait(&p_ready[w], n & 1);  // P_n of this warpgroup is staged and its S_n has been read
+          tc_fence_after();
+          if (n + 1 < n_eff) {
+            if (w == 0) {
+              mbar_wait(&k_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
+              tc_fence_after();
+            }
+            issue_s(w, n + 1);
+            if (w == 1) umma_commit(&k_empty[(n + 1) & 1]);
+          }
+          if (w == 0) {
+            mbar_wait(&v_full[n & 1], (n >> 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t a = smem_u32(sP + w * 32768), bb = smem_u32(sV + (n & 1) * 16384);
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            umma_bf16(tmem + w * 256 + 128, make_smem_desc_sw128(a + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
+                      make_smem_desc_sw128(bb + k * 2048, 8192, 1024), idesc_pv, (n > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&pv_done[w]);
+          if (w == 1) umma_commit(&v_empty[n & 1]);
+        }
+      }
     }
-    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ softmax warpgroups
+    const int r = tid & 127;                 // row inside this warpgroup's tile == TMEM lane
+    const int r256 = wg * kAttnTile + r;     // row inside the CTA's 256-row block
+    const int lane = tid & 31;
+    const bool row_valid = (q0 + r256) < T;
+    const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const uint32_t s_addr = tmem + wg * 256 + lane_addr;        // S: 128 columns
+    const uint32_t o_addr = tmem + wg * 256 + 128 + lane_addr;  // O: 64 columns
+    uint8_t* sPw = sP + wg * 32768;
 
     float gl = 0.f;
     if (HAS_BIAS) {
@@ -151,7 +238,10 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
       gl = g * kLog2e;
     }
     const float sc = p.scale * kLog2e;
-    const float* tabrow = tab_s + (2 * kAttnTile - 1 - r256);
+    // this row's window of the bias table: entry (key j) = slice[j + 255 - r256]; copy a = (255 - r256) & 3 is the one in which
+    // that window starts on a 16-byte boundary
+    const int toff = 2 * kAttnTile - 1 - r256;
+    const float4* tab4 = reinterpret_cast<const float4*>(tab_s + (toff & 3) * tab_stride + (toff & ~3));
     // dropout on the probabilities: per-row hash keys, and where this warp's 32 rows keep their bits (one word per key column)
     uint32_t rk0 = 0, rk1 = 0;
     uint32_t* mask_row = nullptr;
@@ -163,101 +253,97 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
         mask_row = p.drop_mask + (static_cast<long long>(b * p.H + h) * (4 * N) + ((q0 + r256) >> 5)) * (N * kAttnTile);
     }
 
-    float m_run = -INFINITY, l_run = 0.f, alpha_prev = 0.f;
-    float o[kHeadDim];
-#pragma unroll
-    for (int i = 0; i < kHeadDim; ++i) o[i] = 0.f;
+    float m_ref = -INFINITY, l_run = 0.f;
 
-    auto accumulate_o = [&]() {
-      uint32_t t0[32], t1[32];
-      tmem_ld_32x32b_x32(tmem_o + lane_addr, t0);
-      tmem_ld_32x32b_x32(tmem_o + lane_addr + 32, t1);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        o[i] = o[i] * alpha_prev + __uint_as_float(t0[i]);
-        o[32 + i] = o[32 + i] * alpha_prev + __uint_as_float(t1[i]);
-      }
-    };
-
-    for (int n = 0; n < N; ++n) {
+    for (int n = 0; n < n_eff; ++n) {
       const int k0 = n * kAttnTile;
       mbar_wait(&s_full[wg], n & 1);
       tc_fence_after();
       const bool msk = tile_flags[n] != 0;
-      const uint32_t s_addr = tmem_s + lane_addr;
-      // The softmax is invariant to the reference value subtracted in the exponent, so after the first tile the running
-      // maximum does NOT have to be refreshed: probabilities are taken relative to the reference found so far (ONE pass over the
-      // scores instead of max-then-exp), fp32 row sums / accumulators absorb factors up to 2^64.  A warp falls back to the
-      // two-pass form while some row has no finite reference yet (first tile, or only masked keys so far) or if a score
-      // exceeds the reference by more than 64 (log2 units), which re-bases that tile.
-      bool fast = !__any_sync(0xffffffffu, m_run == -INFINITY);
-      bool folded = false;
-      float m_new, m_use, alpha_cur, lsum;
-      while (true) {
-        if (!fast) {
-          // ---- pass 1: row maximum of this tile
-          float mx = -INFINITY;
-#pragma unroll 1
-          for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
-            uint32_t su[32];
-            tmem_ld_32x32b_x32(s_addr + c0, su);
-            tmem_ld_wait();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float x = __uint_as_float(su[j]) * sc;
-              if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-              if (msk) x += kbias[k0 + c0 + j];
-              mx = fmaxf(mx, x);
-            }
-          }
-          m_new = fmaxf(m_run, mx);
-          m_use = (m_new == -INFINITY) ? 0.f : m_new;
-          alpha_cur = fast_exp2(m_run - m_use);
-        } else {
-          m_new = m_run;
-          m_use = m_run;
-          alpha_cur = 1.0f;
-        }
-        // ---- the PV MMA of the previous tile has long finished: fold its result in (this also frees the P buffer and O tile)
-        if (n >= 1 && !folded) {
-          mbar_wait(&o_full[wg], (n - 1) & 1);
-          tc_fence_after();
-          accumulate_o();
-          folded = true;
-        }
-        // ---- probabilities, row sum, bf16 P tile into shared memory (operand layout)
-        lsum = 0.f;
-        float over = -INFINITY;  // largest exponent argument seen (fast path guard)
-        const float neg_ref = -m_use;
+
+      auto tile_max = [&]() {  // row maximum of the exponent argument over this tile (bias and key mask included)
+        float mx = -INFINITY;
 #pragma unroll 1
         for (int c0 = 0; c0 < kAttnTile; c0 += 32) {
           uint32_t su[32];
           tmem_ld_32x32b_x32(s_addr + c0, su);
           tmem_ld_wait();
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            float4 tb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_BIAS) tb = tab4[(k0 + c0) / 4 + q];
+            float x0 = __uint_as_float(su[4 * q]) * sc, x1 = __uint_as_float(su[4 * q + 1]) * sc;
+            float x2 = __uint_as_float(su[4 * q + 2]) * sc, x3 = __uint_as_float(su[4 * q + 3]) * sc;
+            if (HAS_BIAS) {
+              x0 = fmaf(gl, tb.x, x0); x1 = fmaf(gl, tb.y, x1); x2 = fmaf(gl, tb.z, x2); x3 = fmaf(gl, tb.w, x3);
+            }
+            if (msk) {
+              const float4 kb = *reinterpret_cast<const float4*>(kbias + k0 + c0 + 4 * q);
+              x0 += kb.x; x1 += kb.y; x2 += kb.z; x3 += kb.w;
+            }
+            mx = fmaxf(fmaxf(mx, fmaxf(x0, x1)), fmaxf(x2, x3));
+          }
+        }
+        return mx;
+      };
+
+      // rows that have not seen a finite score yet take this tile's maximum as their reference (first tile, or only masked
+      // keys so far); they hold l = 0 and an all-zero accumulator, so nothing has to be rescaled
+      if (__any_sync(0xffffffffu, m_ref == -INFINITY)) {
+        const float mx = tile_max();
+        if (m_ref == -INFINITY) m_ref = mx;
+      }
+      bool p_free = (n == 0);  // PV(n-1) must have consumed the P buffer before it is overwritten
+      // one pass over the tile: probabilities (relative to m_ref) -> bf16 P tile in shared memory; returns the row sum.
+      // MSK is a compile-time flag so that the common tiles (no padded key) carry no mask arithmetic at all.
+      auto softmax_tile = [&](auto MSK) -> float {
+        constexpr bool kMsk = decltype(MSK)::value;
+        const float neg_ref = (m_ref == -INFINITY) ? 0.f : -m_ref;
+        float part0 = 0.f, part1 = 0.f, part2 = 0.f, part3 = 0.f;
+        uint32_t sa[32], sb[32];
+        tmem_ld_32x32b_x32(s_addr, sa);
+        tmem_ld_wait();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = cc * 32;
+          uint32_t* su = (cc & 1) ? sb : sa;
+          if (cc + 1 < 4) tmem_ld_32x32b_x32(s_addr + c0 + 32, (cc & 1) ? sa : sb);  // next chunk in flight under this one
           float pv[32];
           uint32_t rowbits = 0, hbits = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = fmaf(__uint_as_float(su[j]), sc, neg_ref);
-            if (HAS_BIAS) x = fmaf(gl, tabrow[k0 + c0 + j], x);
-            if (msk) x += kbias[k0 + c0 + j];
-            over = fmaxf(over, x);
-            const float e = fast_exp2(x);
-            lsum += e;  // the softmax normaliser is taken before dropout
-            if (DROP) {
-              if ((j & 1) == 0) hbits = drop_bits(rk0, rk1, static_cast<uint32_t>(k0 + c0 + j) >> 1);
-              const bool keep = (j & 1) ? drop_keep_hi(hbits, p.drop_thr_hi) : drop_keep_lo(hbits, p.drop_thr_hi);
-              if (keep) rowbits |= (1u << j);  // this row's decisions for the 32 key columns
-              pv[j] = keep ? e : 0.f;
-            } else {
-              pv[j] = e;
+          for (int q = 0; q < 8; ++q) {
+            float4 tb = make_float4(0.f, 0.f, 0.f, 0.f), kb = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (HAS_BIAS) tb = tab4[(k0 + c0) / 4 + q];
+            if (kMsk) kb = *reinterpret_cast<const float4*>(kbias + k0 + c0 + 4 * q);
+            const float tbv[4] = {tb.x, tb.y, tb.z, tb.w};
+            const float kbv[4] = {kb.x, kb.y, kb.z, kb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * q + e;
+              float x = fmaf(__uint_as_float(su[j]), sc, neg_ref);
+              if (HAS_BIAS) x = fmaf(gl, tbv[e], x);
+              if (kMsk) x += kbv[e];
+              const float ex = fast_exp2(x);
+              // four independent partial sums: the normaliser (taken before dropout) is not one 128-long dependent chain
+              if (e == 0) part0 += ex; else if (e == 1) part1 += ex; else if (e == 2) part2 += ex; else part3 += ex;
+              if (DROP) {
+                if ((j & 1) == 0) hbits = drop_bits(rk0, rk1, static_cast<uint32_t>(k0 + c0 + j) >> 1);
+                const bool keep = (j & 1) ? drop_keep_hi(hbits, p.drop_thr_hi) : drop_keep_lo(hbits, p.drop_thr_hi);
+                if (keep) rowbits |= (1u << j);  // this row's decisions for the 32 key columns
+                pv[j] = keep ? ex : 0.f;
+              } else {
+                pv[j] = ex;
+              }
             }
           }
           if (DROP) {
             // the backward walks key-major: store, per key column, one word whose bit l is the decision of query row l of this warp
-            const uint32_t mword = warp_bit_transpose(rowbits, tid & 31);
-            if (mask_row != nullptr) mask_row[k0 + c0 + (tid & 31)] = mword;
+            const uint32_t mword = warp_bit_transpose(rowbits, lane);
+            if (mask_row != nullptr) mask_row[k0 + c0 + lane] = mword;
+          }
+          if (!p_free) {
+            mbar_wait(&pv_done[wg], (n - 1) & 1);
+            p_free = true;
           }
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -268,57 +354,74 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
             w.w = pack_bf16x2(pv[g * 8 + 6], pv[g * 8 + 7]);
             store_sw128_chunk(sPw, r, (c0 >> 3) + g, w);
           }
+          if (cc + 1 < 4) tmem_ld_wait();
         }
-        if (fast && __any_sync(0xffffffffu, over > 64.0f)) {
-          fast = false;  // re-base this tile on its own maximum (the P tile is simply rewritten)
-          continue;
+        return (part0 + part1) + (part2 + part3);
+      };
+      float lsum;
+#pragma unroll 1
+      while (true) {
+        lsum = msk ? softmax_tile(std::true_type{}) : softmax_tile(std::false_type{});
+        if (!__any_sync(0xffffffffu, !(lsum < kRebase))) break;
+        // ---- re-base (rare): a score outgrew the reference by 2^80.  Move this warp's rows to the tile maximum: rescale the row
+        // sums and the accumulator rows in TMEM (all PV MMAs issued so far have retired once pv_done(n-1) fired; PV(n) cannot
+        // be issued before this warpgroup arrives on p_ready), then recompute the tile.
+        const float m_new = fmaxf(m_ref, tile_max());
+        const float factor = (m_ref == -INFINITY) ? 0.f : fast_exp2(m_ref - m_new);
+        if (n >= 1) {
+          mbar_wait(&pv_done[wg], (n - 1) & 1);
+          p_free = true;
+          tc_fence_after();
+          uint32_t t0[32];
+#pragma unroll 1
+          for (int hlf = 0; hlf < 2; ++hlf) {
+            tmem_ld_32x32b_x32(o_addr + hlf * 32, t0);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) t0[i] = __float_as_uint(__uint_as_float(t0[i]) * factor);
+            tmem_st_32x32b_x32(o_addr + hlf * 32, t0);
+          }
+          tmem_st_wait();
         }
-        break;
+        l_run *= factor;
+        m_ref = m_new;
       }
-      l_run = l_run * alpha_cur + lsum;
-      m_run = m_new;
-      alpha_prev = alpha_cur;
+      l_run += lsum;
 
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
-      named_bar_sync(1 + wg, kAttnTile);  // this warpgroup only: P complete, S and O tile fully read
-      if (issuer) {
-        tc_fence_after();
-        mbar_wait(&v_full[n & 1], (n >> 1) & 1);
-        tc_fence_after();
-        const uint32_t a = smem_u32(sPw), bb = smem_u32(sV + (n & 1) * 16384);
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          umma_bf16(tmem_o, make_smem_desc_sw128(a + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                    make_smem_desc_sw128(bb + k * 2048, 8192, 1024), idesc_pv, k > 0 ? 1u : 0u);
-        umma_commit(&o_full[wg]);
-        umma_commit(&v_empty[n & 1]);
-        if (n + 1 < N) {
-          mbar_wait(&k_full[(n + 1) & 1], ((n + 1) >> 1) & 1);
-          tc_fence_after();
-          issue_s(n + 1);
-        }
-      }
-      __syncwarp();
+      mbar_arrive_rel(&p_ready[wg]);
     }
-    mbar_wait(&o_full[wg], (N - 1) & 1);
+    mbar_wait(&pv_done[wg], (n_eff - 1) & 1);
     tc_fence_after();
-    accumulate_o();
 
+    uint32_t t0[32], t1[32];
+    tmem_ld_32x32b_x32(o_addr, t0);
+    tmem_ld_32x32b_x32(o_addr + 32, t1);
+    tmem_ld_wait();
     if (row_valid) {
       const float inv = l_run > 0.f ? (DROP ? p.drop_rp : 1.0f) / l_run : 0.f;
       __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * T + q0 + r256) * D + h * kHeadDim;
 #pragma unroll
-      for (int g = 0; g < 8; ++g) {
+      for (int g = 0; g < 4; ++g) {
         uint4 w;
-        w.x = pack_bf16x2(o[g * 8 + 0] * inv, o[g * 8 + 1] * inv);
-        w.y = pack_bf16x2(o[g * 8 + 2] * inv, o[g * 8 + 3] * inv);
-        w.z = pack_bf16x2(o[g * 8 + 4] * inv, o[g * 8 + 5] * inv);
-        w.w = pack_bf16x2(o[g * 8 + 6] * inv, o[g * 8 + 7] * inv);
+        w.x = pack_bf16x2(__uint_as_float(t0[g * 8 + 0]) * inv, __uint_as_float(t0[g * 8 + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(t0[g * 8 + 2]) * inv, __uint_as_float(t0[g * 8 + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(t0[g * 8 + 4]) * inv, __uint_as_float(t0[g * 8 + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(t0[g * 8 + 6]) * inv, __uint_as_float(t0[g * 8 + 7]) * inv);
         *reinterpret_cast<uint4*>(dst + g * 8) = w;
       }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        uint4 w;
+        w.x = pack_bf16x2(__uint_as_float(t1[g * 8 + 0]) * inv, __uint_as_float(t1[g * 8 + 1]) * inv);
+        w.y = pack_bf16x2(__uint_as_float(t1[g * 8 + 2]) * inv, __uint_as_float(t1[g * 8 + 3]) * inv);
+        w.z = pack_bf16x2(__uint_as_float(t1[g * 8 + 4]) * inv, __uint_as_float(t1[g * 8 + 5]) * inv);
+        w.w = pack_bf16x2(__uint_as_float(t1[g * 8 + 6]) * inv, __uint_as_float(t1[g * 8 + 7]) * inv);
+        *reinterpret_cast<uint4*>(dst + 32 + g * 8) = w;
+      }
       if (p.lse != nullptr)
-        p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + r256] = (l_run > 0.f) ? (m_run + log2f(l_run)) : INFINITY;
+        p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + r256] = (l_run > 0.f) ? (m_ref + log2f(l_run)) : INFINITY;
     }
   }
 
@@ -341,6 +444,7 @@ extern "C" {
 // out[b,t,h*64+d] = softmax_j(scale q.k + gate*tab[j-i], key padding) v     (WavLM/modules.py:540-563 replaced)
 // qkv: bf16 [B,T,3D] fused projection output; gate: fp32 [B,H,T] or NULL; tab: fp32 [H,2T-1] or NULL (no bias);
 // key_pad: uint8 [B,T] or NULL; out: bf16 [B,T,D]; lse: fp32 [B,H,T] (log2-domain log-sum-exp, saved for backward).
+// Rows of `out` at padded query frames are unspecified-but-finite (zeros where a whole 256-row block is padded).
 int b200s_attn_fwd_dropout(const void* qkv, const float* gate, const float* tab, const uint8_t* key_pad, void* out, float* lse,
                            int B, int T, int H, float scale, float drop_p, uint32_t key0, uint32_t key1, uint32_t* drop_mask,
                            b200s_stream stream) {
@@ -348,14 +452,16 @@ int b200s_attn_fwd_dropout(const void* qkv, const float* gate, const float* tab,
   B200_CHECK_ARG(drop_p >= 0.f && drop_p < 1.f, "attn_fwd: dropout p=%f out of range [0,1)", static_cast<double>(drop_p));
   B200_CHECK_ARG(drop_p == 0.f || drop_mask != nullptr, "attn_fwd: dropout needs the mask buffer (b200s_attn_dropout_mask_words)");
   B200_CHECK_ARG(static_cast<long long>(B) * H * T < (1LL << 32), "attn_fwd: B*H*T exceeds the 32-bit dropout row counter");
-  B200_CHECK_ARG(T >= 1 && T <= 4096, "attn_fwd: T=%d out of range (1..4096)", T);
   const int D = H * kHeadDim;
   CUtensorMap tm;
-  if (make_qkv_tmap(&tm, qkv, T, B, 3 * D, kAttnTile)) return -3;
   AttnParams p;
   memset(&p, 0, sizeof(p));
   p.T = T; p.H = H; p.B = B; p.D = D;
   p.n_tiles = ceil_div(T, kAttnTile);
+  const int smem = kFwdTab + sizeof(float) * ((tab != nullptr ? kTabCopies * fwd_tab_stride(p.n_tiles) : 0) + p.n_tiles * kAttnTile) +
+                   sizeof(int) * p.n_tiles + 1024;
+  B200_CHECK_ARG(T >= 1 && smem <= 232448 - 1024, "attn_fwd: T=%d out of range (needs %d bytes of shared memory)", T, smem);
+  if (make_qkv_tmap(&tm, qkv, T, B, 3 * D, kAttnTile)) return -3;
   p.scale = scale;
   p.gate = gate; p.tab = tab; p.key_pad = key_pad;
   p.out = static_cast<__nv_bfloat16*>(out);
@@ -365,8 +471,6 @@ int b200s_attn_fwd_dropout(const void* qkv, const float* gate, const float* tab,
   p.drop_k0 = key0; p.drop_k1 = key1;
   p.drop_thr_hi = drop_threshold16(drop_p) << 16;
   p.drop_rp = 1.0f / (1.0f - drop_p);
-  const int smem = kFwdTab + sizeof(float) * ((p.n_tiles + 2) * kAttnTile + p.n_tiles * kAttnTile) +
-                   sizeof(int) * p.n_tiles + 1024;
   dim3 grid(ceil_div(T, 2 * kAttnTile), H, B);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   void (*kern)(const CUtensorMap, const AttnParams) =

@@ -68,6 +68,44 @@ __device__ __forceinline__ void adam_one(float& p, float& g, float& m, float& v,
   if (h.zero_grad) g = 0.f;
 }
 
+// Squared norm of the gradients of the tensors in the descriptor table ONLY (fairseq's clip_grad_norm_ sees the parameters the
+// optimizer owns whose .grad exists, src/fairseq/utils.py:338-345): regions of the flat buffer that belong to excluded / frozen
+// parameters are not counted.  Same block -> tensor mapping as the update kernel.
+__global__ void __launch_bounds__(kAdamThreads) sumsq_table_kernel(const AdamTensor* __restrict__ table, int n_tensors,
+                                                                   const float* __restrict__ g, double* __restrict__ out) {
+  pdl_grid_sync();
+  int lo = 0, hi = n_tensors - 1;
+  const long long c = blockIdx.x;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (table[mid].chunk0 <= c) lo = mid; else hi = mid - 1;
+  }
+  const AdamTensor t = table[lo];
+  const long long base = (c - t.chunk0) * kAdamChunk;
+  float acc = 0.f;
+#pragma unroll
+  for (int part = 0; part < kAdamChunk / (kAdamThreads * 4); ++part) {
+    const long long i = base + (part * kAdamThreads + threadIdx.x) * 4;
+    if (i >= t.numel) break;
+    const float* gp = g + t.goff + i;
+    if (i + 4 <= t.numel) {
+      const float4 G = *reinterpret_cast<const float4*>(gp);   // every view of the flat buffer starts 16-byte aligned
+      acc += G.x * G.x + G.y * G.y + G.z * G.z + G.w * G.w;
+    } else {
+      for (int e = 0; e < 4 && i + e < t.numel; ++e) acc = fmaf(gp[e], gp[e], acc);
+    }
+  }
+  double d = static_cast<double>(warp_sum(acc));
+  __shared__ double red[kAdamThreads / 32];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kAdamThreads / 32; ++w) s += red[w];
+    atomicAdd(out, s);
+  }
+}
+
 __global__ void __launch_bounds__(kAdamThreads) adam_step_kernel(const AdamTensor* __restrict__ table, int n_tensors,
                                                                  float* __restrict__ g, float* __restrict__ m,
                                                                  float* __restrict__ v, const double* __restrict__ sumsq,
@@ -134,6 +172,16 @@ int b200s_sumsq_f32(const float* g, long long n, double* out, b200s_stream strea
   if (n == 0) return 0;
   const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(n / 4 + 1, 256), 8LL * sm_count()));
   B200_CHECK_CUDA(launch_pdl(sumsq_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), g, n, out));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_sumsq_table(const void* table, int n_tensors, long long total_chunks, const float* g, double* out,
+                      b200s_stream stream) {
+  B200_CHECK_ARG(table && g && out && n_tensors > 0 && total_chunks > 0, "sumsq_table: bad arguments");
+  B200_CHECK_ARG(total_chunks < (1LL << 31), "sumsq_table: too many chunks");
+  B200_CHECK_CUDA(launch_pdl(sumsq_table_kernel, dim3(static_cast<unsigned>(total_chunks)), dim3(kAdamThreads), 0,
+                             static_cast<cudaStream_t>(stream), static_cast<const AdamTensor*>(table), n_tensors, g, out));
   B200_CHECK_LAUNCH();
   return 0;
 }

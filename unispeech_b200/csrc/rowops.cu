@@ -496,6 +496,60 @@ __global__ void __launch_bounds__(256) dropout_rows_kernel(const __nv_bfloat16* 
   }
 }
 
+// ------------------------------------------------------------------------------------------------ GradMultiply / features_pen
+// features_pen = mean(features^2) over the valid rows (src/fairseq/models/wavlm/wavlm.py:484; WavLM/WavLM.py has no penalty):
+// one pass, fp64 accumulator on the device (no host synchronisation).
+__global__ void __launch_bounds__(256) sumsq_rows_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int N,
+                                                         unsigned total_vecs, double* __restrict__ out) {
+  pdl_grid_sync();
+  const unsigned vec_per_row = static_cast<unsigned>(N) >> 3;
+  float acc = 0.f;
+  for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < total_vecs; v += gridDim.x * 256u) {
+    const unsigned row = v / vec_per_row;
+    const unsigned c = (v - row * vec_per_row) << 3;
+    float a[8];
+    VecIO<8>::load(x + xv.off(row) + c, a);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc = fmaf(a[q], a[q], acc);
+  }
+  double d = static_cast<double>(warp_sum(acc));
+  __shared__ double red[8];
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < 8; ++w) t += red[w];
+    atomicAdd(out, t);
+  }
+}
+
+// Backward of GradMultiply.apply(features, scale) (WavLM/modules.py:60-69; WavLM/WavLM.py:333-336) fused with the gradient of the
+// feature penalty taken on its output (fairseq wavlm.py:477-484):   g <- scale * (g + coef * x),   coef = *pen_grad * pen_mul
+// (pen_grad: the upstream gradient of the penalty scalar, a DEVICE float, or NULL for none).  In place on g.
+__global__ void __launch_bounds__(256) grad_multiply_kernel(__nv_bfloat16* __restrict__ g, RowView gv,
+                                                            const __nv_bfloat16* __restrict__ x, RowView xv, int N,
+                                                            unsigned total_vecs, float scale, const float* __restrict__ pen_grad,
+                                                            float pen_mul) {
+  pdl_grid_sync();
+  const unsigned vec_per_row = static_cast<unsigned>(N) >> 3;
+  const float coef = (pen_grad != nullptr) ? (*pen_grad) * pen_mul : 0.f;
+  for (unsigned v = blockIdx.x * 256u + threadIdx.x; v < total_vecs; v += gridDim.x * 256u) {
+    const unsigned row = v / vec_per_row;
+    const unsigned c = (v - row * vec_per_row) << 3;
+    float a[8];
+    VecIO<8>::load(g + gv.off(row) + c, a);
+    if (pen_grad != nullptr) {
+      float b[8];
+      VecIO<8>::load(x + xv.off(row) + c, b);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] = fmaf(coef, b[q], a[q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] *= scale;
+    VecIO<8>::store(g + gv.off(row) + c, a);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ frame masking
 // x[b,t,:] = 0 where pad[b,t];  = mask_emb where mask[b,t] and not pad   (apply_mask WavLM/WavLM.py:285-286, then
 // x[padding_mask] = 0 WavLM/WavLM.py:574-575).  In place on a [B,T,D] view.
@@ -904,6 +958,41 @@ int b200s_dropout_rows(const void* x, long long x_bs, long long x_rs, const void
                                static_cast<const __nv_bfloat16*>(nullptr), rv, static_cast<__nv_bfloat16*>(y), yv, N, total,
                                key0, key1, thr_hi, rp));
   }
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_sumsq_rows(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, double* out,
+                     b200s_stream stream) {
+  B200_CHECK_ARG(x && out, "sumsq_rows: null pointer");
+  B200_CHECK_ARG(N > 0 && N % 8 == 0, "sumsq_rows: N=%d must be a positive multiple of 8", N);
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  B200_CHECK_ARG(rows * (N / 8) < (1LL << 32), "sumsq_rows: too many elements");
+  RowView xv{x_bs, x_rs, rows_per_batch};
+  const unsigned total = static_cast<unsigned>(rows * (N / 8));
+  const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(total, 256), 8LL * sm_count()));
+  B200_CHECK_CUDA(launch_pdl(sumsq_rows_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const __nv_bfloat16*>(x), xv, N, total, out));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_grad_multiply(void* g, long long g_bs, long long g_rs, const void* x, long long x_bs, long long x_rs,
+                        int rows_per_batch, int batches, int N, float scale, const float* pen_grad, float pen_mul,
+                        b200s_stream stream) {
+  B200_CHECK_ARG(g, "grad_multiply: null pointer");
+  B200_CHECK_ARG(pen_grad == nullptr || x != nullptr, "grad_multiply: the penalty gradient needs the features");
+  B200_CHECK_ARG(N > 0 && N % 8 == 0, "grad_multiply: N=%d must be a positive multiple of 8", N);
+  const long long rows = static_cast<long long>(rows_per_batch) * batches;
+  if (rows == 0) return 0;
+  B200_CHECK_ARG(rows * (N / 8) < (1LL << 32), "grad_multiply: too many elements");
+  RowView gv{g_bs, g_rs, rows_per_batch}, xv{x_bs, x_rs, rows_per_batch};
+  const unsigned total = static_cast<unsigned>(rows * (N / 8));
+  const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(total, 256), 16LL * sm_count()));
+  B200_CHECK_CUDA(launch_pdl(grad_multiply_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<__nv_bfloat16*>(g), gv, static_cast<const __nv_bfloat16*>(x), xv, N, total, scale,
+                             pen_grad, pen_mul));
   B200_CHECK_LAUNCH();
   return 0;
 }

@@ -85,6 +85,55 @@ class FlatGrads:
                 p.grad = v
 
 
+def grad_layout(m):
+    """[(stage, [groups of parameters])] in the order the backward pass COMPLETES the gradients: loss heads and the final
+    encoder LayerNorm first, then the layers from the last to the first (q/k/v adjacent so the fused [3D, D] weight gradient is
+    one GEMM), then the stem (pos_conv, projection, mask embedding), then the conv stack from its last layer to its first.
+    The flat buffer is laid out in this order, so a contiguous slice is final as soon as its last stage has run backward and
+    can be all-reduced while the rest of the backward pass is still running (parallel.OverlappedGradSync)."""
+    layers = list(m.encoder.layers)
+    taken = set()
+
+    def take(ps):
+        out = [p for p in ps if id(p) not in taken]
+        taken.update(id(p) for p in out)
+        return out
+
+    per_layer = []
+    for lyr in layers:
+        a = lyr.self_attn
+        w = take([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
+        b = take([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias])
+        rest = take(list(lyr.parameters()))
+        per_layer.append([w, b, rest])
+    conv = []
+    for blk in reversed(list(m.feature_extractor.conv_layers)):
+        conv += take(list(blk.parameters()))
+    stem = take(list(m.encoder.pos_conv.parameters()))
+    if m.post_extract_proj is not None:
+        stem += take(list(m.post_extract_proj.parameters()))
+    stem += take(list(m.layer_norm.parameters())) + take([m.mask_emb])
+    head = take(list(m.parameters()))  # everything else: encoder.layer_norm[_for_extract], final_proj, label embeddings, ...
+    stages = [("head", [head])]
+    for i in reversed(range(len(layers))):
+        stages.append((("layer", i), per_layer[i]))
+    stages.append(("stem", [stem]))
+    stages.append(("conv", [conv]))
+    return stages
+
+
+def build_flat_grads(m, device):
+    """(FlatGrads, {stage: [first, last) element}, [stages in backward order]) for a model (host logic, any device)."""
+    stages = grad_layout(m)
+    flat = FlatGrads([g for _, groups in stages for g in groups], device)
+    ranges = {}
+    for stage, groups in stages:
+        ps = [p for g in groups for p in g]
+        if ps:
+            ranges[stage] = (flat.offsets[id(ps[0])], flat.offsets[id(ps[-1])] + (ps[-1].numel() + 3) // 4 * 4)
+    return flat, ranges, [st for st, _ in stages if st in ranges]
+
+
 class ConvGeom:
     """Frame counts and buffer geometry of the strided conv stack (WavLM/WavLM.py:378-449)."""
 
@@ -115,6 +164,11 @@ class Engine:
         self.flat: Optional[FlatGrads] = None
         self._params = None
         self.drop: Optional[DR.DropState] = None  # set per forward pass by WavLM._begin (training-mode dropout)
+        self.grad_sync = None  # parallel.OverlappedGradSync: told when a stage of the backward pass has produced its gradients
+
+    def backward_stage_done(self, stage):
+        if self.grad_sync is not None:
+            self.grad_sync.stage_done(stage)
 
     # ------------------------------------------------------------------------------------------------ setup
     def _ensure_device(self, device):
@@ -171,15 +225,8 @@ class Engine:
         self.prep_descs = torch.frombuffer(bytearray(b"".join(recs)), dtype=torch.uint8).to(device)
         self.prep_n, self.prep_tiles = len(recs), tiles
         self.prep_ptrs = [(lyr.self_attn.k_proj.weight, w["wqkv_master"]) for lyr, w in zip(m.encoder.layers, self.lw)]
-        # flat gradient buffer, q/k/v adjacent per layer
-        groups = []
-        for lyr in m.encoder.layers:
-            a = lyr.self_attn
-            groups.append([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight])
-            groups.append([a.q_proj.bias, a.k_proj.bias, a.v_proj.bias])
-        seen = {id(p) for g in groups for p in g}
-        groups.append([p for p in m.parameters() if id(p) not in seen])
-        self.flat = FlatGrads(groups, device)
+        # flat gradient buffer in backward-completion order, q/k/v adjacent per layer
+        self.flat, self.stage_ranges, self.stage_order = build_flat_grads(m, device)
 
     def _param_version(self):
         if self._params is None:  # Module.parameters() walks the whole module tree: cache the list (the set never changes)

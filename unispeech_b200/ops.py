@@ -219,6 +219,17 @@ def dropout_rows(x, x_bs, x_rs, res, res_bs, res_rs, y, y_bs, y_rs, rows_per_bat
            L.ll(y_rs), i32(rows_per_batch), i32(batches), i32(N), f32(p), u32(key[0]), u32(key[1]), _s())
 
 
+def sumsq_rows(x, x_bs, x_rs, rows_per_batch, batches, N, out):
+    """*out (fp64, device) += sum x^2 over the bf16 rows view."""
+    _call("b200s_sumsq_rows", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())
+
+
+def grad_multiply(g, g_bs, g_rs, x, x_bs, x_rs, rows_per_batch, batches, N, scale, pen_grad=None, pen_mul=0.0):
+    """g <- scale * (g + (*pen_grad * pen_mul) * x) in place (GradMultiply backward fused with the feature-penalty gradient)."""
+    _call("b200s_grad_multiply", L.ptr(g), L.ll(g_bs), L.ll(g_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch),
+          i32(batches), i32(N), f32(scale), L.ptr(pen_grad), f32(pen_mul), _s())
+
+
 def attn_dropout_mask_words(B, T, H) -> int:
     n = (T + 127) // 128
     return B * H * (4 * n) * (128 * n)
@@ -239,6 +250,10 @@ def attn_bwd_fused_dropout(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_ac
 # ------------------------------------------------------------------------------------------------- optimizer
 def sumsq_f32(g, n, out):
     _call("b200s_sumsq_f32", L.ptr(g), L.ll(n), L.ptr(out), _s())
+
+
+def sumsq_table(table, n_tensors, total_chunks, g, out):
+    _call("b200s_sumsq_table", L.ptr(table), i32(n_tensors), L.ll(total_chunks), L.ptr(g), L.ptr(out), _s())
 
 
 def adam_step(table, n_tensors, total_chunks, g, m, v, sumsq, grad_scale, max_norm, lr, beta1, beta2, eps, weight_decay, step,

@@ -70,7 +70,9 @@ class FusedAdam:
     def clip_grad_norm(self, max_norm: float) -> torch.Tensor:
         """Global gradient norm (device tensor, no sync); gradients are clipped inside `step()` (fp16_optimizer.py:194-214)."""
         self._sumsq.zero_()
-        ops.sumsq_f32(self.g, self.g.numel(), self._sumsq)
+        # only the tensors this optimizer owns: gradients the backward kernels leave in the flat buffer for excluded / frozen
+        # parameters do not count (fairseq's clip_grad_norm_ sees the optimizer's parameters, src/fairseq/utils.py:338-345)
+        ops.sumsq_table(self._table, self._n, self._chunks, self.g, self._sumsq)
         self._max_norm = float(max_norm)
         self._have_norm = True
         return self._sumsq.sqrt().float() * abs(self._multiply_factor)

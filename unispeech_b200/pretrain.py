@@ -123,6 +123,7 @@ class WavLMForPretraining(WavLM):
 
     def __init__(self, cfg: WavLMPretrainConfig, num_classes: List[int]):
         super().__init__(cfg)
+        self._want_features_pen = True
         if cfg.target_glu:
             raise NotImplementedError("target_glu is not implemented in the fused masked-prediction head")
         D = cfg.encoder_embed_dim
@@ -188,8 +189,7 @@ class WavLMForPretraining(WavLM):
         out["mask_indices"] = res["mask_indices"]
         out["padding_mask_host"] = res.get("padding_mask_host")  # host copy of the frame mask when the caller's mask was on the host
         out["target_list"] = self.forward_targets(T, target_list) if target_list is not None else None
-        feats = self._last_conv
-        out["features_pen"] = feats[:, :T].float().pow(2).mean() if feats is not None else None  # wavlm.py:484
+        out["features_pen"] = self._last_pen  # mean(features^2) after GradMultiply, wavlm.py:477-484 (kernel, inside _ConvFn)
         return out
 
     def criterion(self, net_output: Dict, pred_masked_weight: float = 1.0, pred_nomask_weight: float = 0.0,

@@ -96,20 +96,46 @@ def _on_forward_stream(bwd):
 
 
 class _ConvFn(torch.autograd.Function):
+    """Conv stack + GradMultiply (WavLM/WavLM.py:333-336, WavLM/modules.py:60-69) + the feature penalty of the pre-training
+    models (`features.float().pow(2).mean()` taken AFTER GradMultiply, src/fairseq/models/wavlm/wavlm.py:477-484): the penalty is
+    an output of this Function, so its gradient and the gradient arriving from the projection reach the extractor together and
+    BOTH are scaled by `feature_grad_mult` in one pass (`b200s_grad_multiply`)."""
+
     @staticmethod
-    def forward(ctx, anchor, eng: Engine, wav):
+    def forward(ctx, anchor, eng: Engine, wav, want_pen):
+        from . import ops
         ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0])
         st = eng.conv_forward(wav, save)
-        ctx.eng, ctx.st = eng, (st if save else None)
-        return st["a"][-1], st
+        feats = st["a"][-1]
+        B, Tp, C = feats.shape
+        T = st["geo"].T[-1]
+        pen = None
+        if want_pen:
+            acc = torch.zeros(1, dtype=torch.float64, device=feats.device)
+            ops.sumsq_rows(feats, Tp * C, C, T, B, C, acc)
+            pen = (acc / float(B * T * C)).float().reshape(())
+        ctx.eng, ctx.st, ctx.feats, ctx.T = eng, (st if save else None), (feats if save else None), T
+        return feats, st, pen
 
     @staticmethod
     @_on_forward_stream
-    def backward(ctx, dfeat, _unused=None):
-        ctx.eng.conv_backward(ctx.st, dfeat.contiguous())
-        ctx.st = None
-        return None, None, None
+    def backward(ctx, dfeat, _unused=None, dpen=None):
+        from . import ops
+        feats = ctx.feats
+        B, Tp, C = feats.shape
+        T = ctx.T
+        if dfeat is None:  # only the penalty was used
+            dfeat = torch.zeros_like(feats)
+        g = dfeat if (dfeat.dtype == BF and dfeat.is_contiguous()) else dfeat.to(BF).contiguous()
+        mult = float(ctx.eng.cfg.feature_grad_mult)
+        if mult != 1.0 or dpen is not None:
+            pg = dpen.float().contiguous() if dpen is not None else None
+            ops.grad_multiply(g, Tp * C, C, feats, Tp * C, C, T, B, C, mult, pg, 2.0 / float(B * T * C))
+        ctx.eng.conv_backward(ctx.st, g)
+        ctx.st = ctx.feats = None
+        ctx.eng.backward_stage_done("conv")
+        return None, None, None, None
 
 
 class _ProjFn(torch.autograd.Function):
@@ -127,11 +153,9 @@ class _ProjFn(torch.autograd.Function):
     @staticmethod
     @_on_forward_stream
     def backward(ctx, dxv, _dfeatures):
-        mult = ctx.eng.cfg.feature_grad_mult
         dfeat = ctx.eng.project_backward(ctx.st, dxv.contiguous(), ctx.T, ctx.mask, ctx.pad)
-        if mult != 1.0:
-            dfeat.mul_(mult)  # GradMultiply (WavLM/modules.py:60-69): scale of the gradient entering the extractor
-        ctx.st = None
+        ctx.st = None  # (GradMultiply is applied where the gradient enters the extractor: _ConvFn.backward)
+        ctx.eng.backward_stage_done("stem")
         return dfeat, None, None, None, None, None, None
 
 
@@ -180,6 +204,7 @@ class _LayerFn(torch.autograd.Function):
             H = eng.cfg.encoder_attention_heads
             ops.relpos_table_bwd(dtab, bs["lut"], dtab.shape[1], H, eng.g(emb))
         ctx.st = None
+        eng.backward_stage_done(("layer", ctx.idx))
         return dx, None, None, None, None, None
 
 
@@ -505,11 +530,13 @@ class WavLM(nn.Module):
         eng = self._begin(source.device)
         wav = source.float().contiguous()
         w0 = self.feature_extractor.conv_layers[0][0].weight
+        want_pen = bool(getattr(self, "_want_features_pen", False))
         if self.feature_grad_mult > 0:
-            feats, st = _ConvFn.apply(w0, eng, wav)
+            feats, st, pen = _ConvFn.apply(w0, eng, wav, want_pen)
         else:
             with torch.no_grad():
-                feats, st = _ConvFn.apply(w0, eng, wav)
+                feats, st, pen = _ConvFn.apply(w0, eng, wav, want_pen)
+        self._last_pen = pen
         return feats, st["geo"].T[-1]
 
     # ---- reference API
