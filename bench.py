@@ -6,12 +6,14 @@ Workload = the model BASELINE.json's metric names: WavLM-Large, batch 8 x 20 s s
 per-GPU batch; it fits one B200), masking on, fwd + bwd of the whole encoder through the public API (`WavLM.extract_features` +
 probe loss + `backward()`), bf16 kernels, dropout 0 as in BASELINE.md section 3.  At N=1 the line also carries, under `also`,
 WavLM-Base 16 x 15 s (configs[1]) and the same Large workload with the reference's default dropouts (0.1 / 0.1).
-N>1 (launched with torch.distributed.run): same per-GPU batch (weak scaling), plus ONE NCCL allreduce of the flat fp32
-gradient buffer per step.  Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks.
+N>1 (launched with torch.distributed.run): same per-GPU batch (weak scaling), plus the gradient average of the flat fp32
+gradient buffer: NCCL all-reduce (AVG) in a few contiguous buckets issued WHILE the backward pass runs (parallel.OverlappedGradSync).
+Timing: CUDA events around exactly K steps, barrier + synchronize on both sides, max over ranks.
 Inputs are far larger than L2 (the first conv activation alone is 786 MB), so no explicit L2 flush is needed.
 
-`--impl reference` times the CPU oracle (the restatement of the reference's PyTorch path, pinned to the reference by golden
-fixtures) on the host cores with all threads, on a bounded sample of the same workload.
+`--impl reference` times the reference's own CPU implementation: the UNMODIFIED `WavLM/{WavLM,modules}.py` vendored into
+`oracle/_ref` by `oracle/build_ref.py` (kind "reference"; the oracle port only if that copy is absent), fwd+bwd on a bounded
+sample of the same workload, on the host cores.
 """
 from __future__ import annotations
 
@@ -33,14 +35,10 @@ SR = 16000
 
 
 def model_config(name: str):
-    from oracle import wavlm_oracle as O
-    if name == "base":
-        return O.base_config(), 16, 15
-    if name == "large":
-        return O.large_config(), 8, 20
-    if name == "tiny":
-        return O.tiny_config(), 4, 2
-    raise ValueError(name)
+    from types import SimpleNamespace
+    from unispeech_b200 import workloads
+    cfg, B, secs = workloads.model_config(name)
+    return SimpleNamespace(**cfg), B, secs
 
 
 class ClockSampler:
@@ -83,51 +81,70 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_step(cfg, B, secs, steps, threads):
-    """One bounded CPU sample: oracle fwd+bwd on B x secs of audio, all host threads.  Returns audio-s/s and seconds."""
+def _cpu_arm(cfg):
+    """(kind, make_step): the reference's own CPU path when oracle/_ref holds the unmodified reference modules, else the oracle
+    port.  make_step(B, secs) -> callable running one fwd+bwd (probe loss) and returning nothing."""
+    from oracle import build_ref
     from oracle import wavlm_oracle as O
-    torch.set_num_threads(threads)
-    sd = {k: v.clone().requires_grad_(True) for k, v in O.deterministic_state_dict(cfg).items()}
-    wav, _ = O.deterministic_waveform(B, secs * SR, seed=3)
-    pm = torch.zeros(B, secs * SR, dtype=torch.bool)
-    T = O.num_frames(secs * SR, cfg)
-    mi = O.hash_uniform("benchmask", (B, T)) > 0.3
-    times = []
-    for _ in range(steps):
-        t0 = time.perf_counter()
-        res = O.extract_features(sd, wav, cfg, padding_mask=pm, mask_indices=mi)
-        loss = O.probe_loss(res["x"], res["padding_mask"], seed=2)
-        loss.backward()
-        for v in sd.values():
-            v.grad = None
-        times.append(time.perf_counter() - t0)
-    best = sorted(times)[len(times) // 2]
-    return B * secs / best, best
+    sd = O.deterministic_state_dict(cfg)
+    if build_ref.available():
+        m = build_ref.build_model(cfg, sd, train=True)
+
+        def make_step(B, secs):
+            wav, _ = O.deterministic_waveform(B, secs * SR, seed=3)
+            pm = torch.zeros(B, secs * SR, dtype=torch.bool)
+
+            def step():
+                m.zero_grad(set_to_none=True)
+                x, fpm = m.extract_features(wav, padding_mask=pm, mask=True)  # the reference's own host-RNG span sampler
+                O.probe_loss(x, fpm, seed=2).backward()
+            return step
+        return "reference", make_step
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+
+    def make_step(B, secs):
+        wav, _ = O.deterministic_waveform(B, secs * SR, seed=3)
+        pm = torch.zeros(B, secs * SR, dtype=torch.bool)
+        mi = O.hash_uniform("benchmask", (B, O.num_frames(secs * SR, cfg))) > 0.3
+
+        def step():
+            res = O.extract_features(sdr, wav, cfg, padding_mask=pm, mask_indices=mi)
+            O.probe_loss(res["x"], res["padding_mask"], seed=2).backward()
+            for v in sdr.values():
+                v.grad = None
+        return step
+    return "port", make_step
 
 
-def best_cpu_threads(cfg):
-    """The oracle's intra-op thread count that is fastest on this host (oversubscribing a 128-thread box is 80x slower than
-    16 threads): two 5 s utterances fwd+bwd are timed for a few candidates and the best one is used for the baseline."""
-    from oracle import wavlm_oracle as O
+def cpu_measure(cfg, B, secs, steps, warmup=1):
+    """Bounded CPU sample: fwd+bwd on B x secs of audio.  Thread policy (fixed): the fastest of {16, 32, all} intra-op threads on a
+    2 x 5 s probe (a 128-thread host oversubscribed with 128 threads is ~80x slower than with 16), then `warmup` untimed and
+    `steps` timed steps; the MEDIAN step is reported.  Returns dict(value, seconds, threads, kind)."""
+    kind, make_step = _cpu_arm(cfg)
     ncpu = os.cpu_count() or 1
-    cands = sorted({c for c in (8, 16, 32, 64) if c <= ncpu} | ({ncpu} if ncpu <= 64 else set()))
-    sd = {k: v.clone().requires_grad_(True) for k, v in O.deterministic_state_dict(cfg).items()}
-    wav, _ = O.deterministic_waveform(2, 5 * SR, seed=5)
-    pm = torch.zeros(2, 5 * SR, dtype=torch.bool)
+    cands = sorted({c for c in (16, 32) if c <= ncpu} | ({ncpu} if ncpu <= 64 else set())) or [ncpu]
+    probe = make_step(2, 5)
     best, best_t = cands[0], float("inf")
     for c in cands:
         torch.set_num_threads(c)
         ts = []
         for _ in range(2):
             t0 = time.perf_counter()
-            res = O.extract_features(sd, wav, cfg, padding_mask=pm)
-            O.probe_loss(res["x"], res["padding_mask"], seed=2).backward()
-            for v in sd.values():
-                v.grad = None
+            probe()
             ts.append(time.perf_counter() - t0)
         if min(ts) < best_t:
             best, best_t = c, min(ts)
-    return best
+    torch.set_num_threads(best)
+    step = make_step(B, secs)
+    for _ in range(warmup):
+        step()
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    med = sorted(times)[len(times) // 2]
+    return {"value": B * secs / med, "seconds": med, "threads": best, "kind": kind, "steps": steps}
 
 
 def run_reference(args):
@@ -135,35 +152,22 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = best_cpu_threads(cfg)
     cb, csecs = {"tiny": B, "base": 4, "large": 2}[args.model], secs
-    steps = max(1, min(args.steps, 3))
-    for _ in range(min(args.warmup, 1)):
-        cpu_step(cfg, cb, csecs, 1, threads)
-    value, step_s = cpu_step(cfg, cb, csecs, steps, threads)
+    steps = max(3, min(args.steps, 5))
+    r = cpu_measure(cfg, cb, csecs, steps, warmup=1)
+    what = ("the UNMODIFIED reference modules WavLM/{WavLM,modules}.py (oracle/_ref; out-of-place encoder patch for autograd)"
+            if r["kind"] == "reference" else "oracle port (CPU restatement of the reference PyTorch path)")
     line = {
-        "impl": "reference", "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": step_s * 1e3, "higher_is_better": True,
+        "impl": "reference", "metric": "audio-sec/sec fwd+bwd", "value": r["value"], "unit": "audio-s/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": 1, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"WavLM-{args.model} fwd+bwd, oracle (CPU restatement of the reference PyTorch path), "
-                               f"bounded sample {cb} x {csecs} s per step"},
-        "cpu_baseline": {"value": value, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                         "sample": f"{cb} x {csecs} s, {steps} step(s), median; thread count auto-tuned (host has "
-                                   f"{os.cpu_count()} logical CPUs)"},
-        "e2e": {"value": value, "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": f"WavLM-{args.model} fwd+bwd on the host CPU, {what}, bounded sample {cb} x {csecs} s per step"},
+        "cpu_baseline": {"value": r["value"], "unit": "audio-s/s", "cores": r["threads"], "kind": r["kind"],
+                         "sample": f"{cb} x {csecs} s per step, 1 warm-up + {steps} timed steps, median; fastest of 16 / 32 / all "
+                                   f"intra-op threads on a 2 x 5 s probe (host has {os.cpu_count()} logical CPUs)"},
+        "e2e": {"value": r["value"], "unit": "audio-s/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
-
-
-_SD_CACHE = {}
-
-
-def cached_state_dict(name: str, cfg):
-    """Hash-generated parameters are deterministic per architecture: generate them once per process (20 s of CPU for WavLM-Large)."""
-    from oracle import wavlm_oracle as O
-    if name not in _SD_CACHE:
-        _SD_CACHE[name] = O.deterministic_state_dict(cfg)
-    return _SD_CACHE[name]
 
 
 class Workload:
@@ -171,10 +175,10 @@ class Workload:
     [+ the gradient allreduce for N > 1])."""
 
     def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False, pretrain=False):
-        from oracle import wavlm_oracle as O  # parameter / input generators only
+        from unispeech_b200 import workloads
         from unispeech_b200.wavlm import WavLM, WavLMConfig
         self.name, self.dev, self.world, self.dropout, self.pretrain = model_name, dev, world, dropout, pretrain
-        self.opt = None
+        self.opt, self.sync = None, None
         cfg, B, secs = model_config(model_name)
         if dropout > 0:  # the reference's WavLMConfig defaults: dropout = attention_dropout = 0.1 (WavLM/WavLM.py:180-181)
             cfg.dropout, cfg.attention_dropout = dropout, dropout
@@ -189,22 +193,18 @@ class Workload:
         self.lengths = lengths_of(rank)
         self.all_lengths = [lengths_of(r) for r in range(world)]
         self.L = max(self.lengths)
-        self.T = O.num_frames(self.L, cfg)
+        self.T = workloads.num_frames(self.L, vars(cfg))
         if pretrain:
             # full optimisation step of the masked-prediction pre-training: 504-class k-means labels
             # at 50 Hz, final_dim 768 (the released Large recipe), WavLMCriterion with features_pen x 10, Adam(0.9, 0.98), clip 1.0
             from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+            torch.manual_seed(20 + 0)  # random init of the architecture (the reference's initialisers), same on every rank
             model = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=768 if model_name == "large" else 256)), [504])
-            sd = dict(cached_state_dict(model_name, cfg))
-            sd["final_proj.weight"] = O.hash_uniform("fp.w", tuple(model.final_proj.weight.shape), -0.03, 0.03)
-            sd["final_proj.bias"] = torch.zeros_like(model.final_proj.bias)
-            sd["label_embs_concat"] = O.hash_uniform("lab", tuple(model.label_embs_concat.shape), 0.0, 1.0)
-            model.load_state_dict(sd)
             self.labels = [torch.randint(0, 504, (B, self.T), generator=torch.Generator().manual_seed(99 + rank))]
             self.final_dim = model.final_dim
         else:
+            torch.manual_seed(20 + 0)  # random init of the architecture (the reference's initialisers), same on every rank
             model = WavLM(WavLMConfig(vars(cfg)))
-            model.load_state_dict(cached_state_dict(model_name, cfg))
         self.model = model.to(dev).train()
         gen = torch.Generator().manual_seed(1337 + rank)
         wav = torch.randn(B, self.L, generator=gen)
@@ -218,43 +218,73 @@ class Workload:
         self.wav_dev = self.wav_host.to(dev)
         self.R = torch.randn(B, self.T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
         self.loss_host = torch.zeros(1).pin_memory()
-        self.fwd_flops = O.forward_flops(self.L, cfg)          # padded shape (what the kernels execute)
-        self.valid_fwd_flops = sum(O.forward_flops(n, cfg) for n in self.lengths) / B   # per utterance at its own length
+        self.fwd_flops = workloads.forward_flops(self.L, vars(cfg))          # padded shape (what the kernels execute)
+        self.valid_fwd_flops = sum(workloads.forward_flops(n, vars(cfg)) for n in self.lengths) / B   # per utterance at its own length
+
+    def _sync_for(self, collective: bool):
+        """Bucketed gradient averaging overlapped with the backward pass (N > 1); created once the engine owns the layout."""
+        if self.world == 1:
+            return None
+        if self.sync is None:
+            from unispeech_b200.parallel import OverlappedGradSync
+            self.sync = OverlappedGradSync(self.model, layers_per_bucket=6)
+        self.sync.active = bool(collective)
+        self.sync.begin()
+        return self.sync
 
     def step(self, e2e: bool, collective: bool = True):
-        from unispeech_b200.parallel import all_reduce_grads
+        """One step; the NVTX range names are the reference trainer's (src/fairseq/trainer.py:781-827, fairseq_cli/train.py:288-290)."""
+        nvtx = torch.cuda.nvtx
         model = self.model
         if model._engine is not None and model._engine.flat is not None:
             if not self.pretrain:  # (the optimizer step of the pre-training workload zeroes the gradients itself)
-                model.grad_buffer().zero_()
+                model.zero_grad_buffer()
             model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
         wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
         if self.pretrain:
             return self.pretrain_step(wav, e2e, collective)
+        nvtx.range_push("forward")
         x, _ = model.extract_features(wav, padding_mask=self.pad_host, mask=True)
         loss = (x.float() * self.R).sum()
+        nvtx.range_pop()
+        sync = self._sync_for(collective)
+        nvtx.range_push("backward")
         loss.backward()
-        if self.world > 1 and collective:
-            all_reduce_grads(model.grad_buffer())  # the one collective of the step (NCCL over NVLink)
+        nvtx.range_pop()
+        if sync is not None:
+            nvtx.range_push("reduce-grads")
+            sync.finish()  # buckets were issued during backward; this sends the last one and joins the NCCL stream
+            nvtx.range_pop()
         if e2e:
             self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
 
     def pretrain_step(self, wav, e2e: bool, collective: bool):
-        """forward -> masked-prediction criterion -> backward -> [allreduce] -> scale / clip / Adam (gradients zeroed by the update)."""
+        """forward -> masked-prediction criterion -> backward (+ overlapped gradient average) -> scale / clip / Adam."""
         from unispeech_b200.optim import FusedAdam
-        from unispeech_b200.parallel import all_reduce_grads
+        nvtx = torch.cuda.nvtx
         model = self.model
+        nvtx.range_push("forward")
         out = model(wav, target_list=self.labels, padding_mask=self.pad_host, mask=True)
         loss, sample_size, _ = model.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.0, loss_weights=[10.0])
+        nvtx.range_pop()
+        sync = self._sync_for(collective)
+        nvtx.range_push("backward")
         loss.backward()
-        if self.world > 1 and collective:
-            all_reduce_grads(model.grad_buffer())
+        nvtx.range_pop()
+        if sync is not None:
+            nvtx.range_push("reduce-grads")
+            sync.finish()
+            nvtx.range_pop()
         if self.opt is None:
             self.opt = FusedAdam(model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
         self.opt.multiply_grads(self.world / max(sample_size, 1))   # trainer.py:796-801 (sample_size is per rank here: equal shards)
+        nvtx.range_push("clip-grads")
         self.opt.clip_grad_norm(1.0)
+        nvtx.range_pop()
+        nvtx.range_push("optimizer")
         self.opt.step(zero_grad=True)
+        nvtx.range_pop()
         if e2e:
             self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
@@ -302,22 +332,66 @@ class Workload:
                 f"{self.cfg.mask_prob}, {drop}, all-False padding mask")
 
     def free(self):
-        self.model = self.R = self.wav_dev = self.opt = None
+        self.model = self.R = self.wav_dev = self.opt = self.sync = None
         torch.cuda.empty_cache()
 
 
 def parity_line(dev, model_name: str):
-    """The other half of BASELINE.json's metric ("...; max-abs hidden diff"): final hidden states of this GPU path against the
-    committed fixture generated from the UNMODIFIED reference (tools/make_golden.py: fp32 CPU, the model's real widths, 2 layers,
-    1 x 0.5 s), same weights and waveform.  The full-depth parity evidence is the GPU test suite; this is the number in the run."""
+    """The other half of BASELINE.json's metric ("...; max-abs hidden diff").  Two numbers, both measured in this run:
+    (1) FULL DEPTH at the benchmark's sequence length: all layers of the model, one utterance of the workload's duration, same
+        hash-generated weights and waveform on both sides, against the reference's own CPU forward (the unmodified modules in
+        oracle/_ref when present, else the oracle port) -- final hidden states and the worst layer;
+    (2) the committed fixture of the unmodified reference (tests/golden, 2 layers, 0.5 s) as a box-independent anchor.
+    The per-layer tables and the gradient parity at real widths are the GPU test suite (tests/test_fullscale_gpu.py)."""
     import numpy as np
+    from oracle import build_ref
     from oracle import wavlm_oracle as O
     from unispeech_b200.wavlm import WavLM, WavLMConfig
     name = {"large": "large2l_halfsec", "base": "base2l_halfsec"}.get(model_name)
     if name is None:
         return None
+    mk = O.large_config if model_name == "large" else O.base_config
+    out = {}
+    # ---- (1) full depth
+    cfg = mk()
+    secs = 20 if model_name == "large" else 15
+    sd = O.deterministic_state_dict(cfg)
+    wav, _ = O.deterministic_waveform(1, secs * SR, seed=3)
+    n = cfg.encoder_layers
+    torch.set_num_threads(min(32, os.cpu_count() or 1))
+    with torch.no_grad():
+        if build_ref.available():
+            mref = build_ref.build_model(cfg, sd)
+            (_, lr), _ = mref.extract_features(wav, ret_layer_results=True, output_layer=n)
+            want_layers = [t[0] for t in lr]
+            want_x = mref.extract_features(wav)[0]
+            against = "unmodified reference modules (oracle/_ref), fp32 CPU"
+            del mref
+        else:
+            r = O.extract_features(sd, wav, cfg, output_layer=n)
+            want_layers = r["layer_results"]
+            want_x = O.extract_features(sd, wav, cfg)["x"]
+            against = "oracle port, fp32 CPU"
+    m = WavLM(WavLMConfig(vars(cfg)))
+    m.load_state_dict(sd)
+    m = m.to(dev).eval()
+    with torch.no_grad():
+        (_, got_lr), _ = m.extract_features(wav.to(dev), ret_layer_results=True, output_layer=n)
+        got_x = m.extract_features(wav.to(dev))[0]
+    worst = max(range(n + 1), key=lambda i: ((got_lr[i][0].float().cpu() - want_layers[i]).abs().max() / want_layers[i].abs().max()).item())
+    dw = (got_lr[worst][0].float().cpu() - want_layers[worst]).abs()
+    d = (got_x.float().cpu() - want_x).abs()
+    out["full_depth"] = {
+        "model": f"WavLM-{model_name}, {n} layers, 1 x {secs} s (T = {want_x.shape[1]})", "against": against,
+        "max_abs_hidden_diff": d.max().item(), "mean_abs_hidden_diff": d.mean().item(),
+        "hidden_abs_max": want_x.abs().max().item(), "hidden_abs_mean": want_x.abs().mean().item(),
+        "worst_layer": worst, "worst_layer_max_abs_diff": dw.max().item(), "worst_layer_abs_max": want_layers[worst].abs().max().item(),
+        "tolerance": "max-abs <= 3 % of the layer's max|h|, mean-abs <= 1.5 % of its mean|h| (tests/test_fullscale_gpu.py)"}
+    del m, sd
+    torch.cuda.empty_cache()
+    # ---- (2) committed fixture
     g = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
-    cfg = (O.large_config if model_name == "large" else O.base_config)(encoder_layers=2)
+    cfg = mk(encoder_layers=2)
     m = WavLM(WavLMConfig(vars(cfg)))
     m.load_state_dict(O.deterministic_state_dict(cfg))
     m = m.to(dev).eval()
@@ -326,9 +400,10 @@ def parity_line(dev, model_name: str):
         x, _ = m.extract_features(wav.to(dev))
     want = torch.from_numpy(g["x_final"]).float()
     d = (x.float().cpu() - want).abs()
-    return {"max_abs_hidden_diff": d.max().item(), "mean_abs_hidden_diff": d.mean().item(), "hidden_abs_max": want.abs().max().item(),
-            "tolerance_max_abs": 0.12, "against": f"tests/golden/{name}.npz (unmodified reference WavLM forward, fp32 CPU; WavLM-{model_name} "
-                                                  "widths, 2 layers, 1 x 0.5 s, same weights and waveform)"}
+    out.update({"max_abs_hidden_diff": d.max().item(), "mean_abs_hidden_diff": d.mean().item(), "hidden_abs_max": want.abs().max().item(),
+                "tolerance_max_abs": 0.12, "against": f"tests/golden/{name}.npz (unmodified reference WavLM forward, fp32 CPU; WavLM-{model_name} "
+                                                      "widths, 2 layers, 1 x 0.5 s, same weights and waveform)"})
+    return out
 
 
 def quick_line(w: Workload, steps: int, warmup: int, e2e: bool = True):
@@ -489,12 +564,13 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and not args.no_cpu_baseline:
-        threads = best_cpu_threads(cfg)
         cb = {"tiny": B, "base": 4, "large": 2}[args.model]
-        v, s = cpu_step(cfg, cb, secs, 1, threads)
-        cpu_baseline = {"value": v, "unit": "audio-s/s", "cores": threads, "kind": "port",
-                        "sample": f"oracle fwd+bwd fp32, {cb} x {secs} s, 1 step ({s:.1f} s); thread count auto-tuned "
-                                  f"(host has {os.cpu_count()} logical CPUs)"}
+        r = cpu_measure(cfg, cb, secs, steps=1, warmup=0)
+        what = "unmodified reference modules (oracle/_ref)" if r["kind"] == "reference" else "oracle port"
+        cpu_baseline = {"value": r["value"], "unit": "audio-s/s", "cores": r["threads"], "kind": r["kind"],
+                        "sample": f"{what} fwd+bwd fp32, {cb} x {secs} s, 1 step ({r['seconds']:.1f} s); fastest of 16 / 32 / all "
+                                  f"intra-op threads on a 2 x 5 s probe (host has {os.cpu_count()} logical CPUs); "
+                                  "`--impl reference` times 3+ steps"}
 
     if rank == 0:
         fwd_flops = w.valid_fwd_flops

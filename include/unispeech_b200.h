@@ -32,6 +32,9 @@ const char* b200s_last_error(void);
 int b200s_check_device(void);
 /* number of kernels launched by this library so far (bench.py reports the per-step count) */
 long long b200s_launch_count(void);
+/* zero `bytes` bytes of device memory on the stream (cudaMemsetAsync): the per-step reset of the flat gradient buffer that the
+ * backward kernels accumulate into (the reference's `optimizer.zero_grad()`, src/fairseq/trainer.py:627) */
+int b200s_memset_zero(void* p, unsigned long long bytes, b200s_stream stream);
 
 /* ---- fused GEMM epilogue description (all tensors optional) ------------------------------------------------
  * value = acc (+ bias[col]);  if gelu: out_pre <- value (gelu = 1) or gelu'(value) (gelu = 2) (optional), value = gelu_erf(value)

@@ -111,12 +111,21 @@ def test_attn_dropout_fwd_bwd(cuda_device, B, T, H, bias, padded, p):
     # 1. the recorded keep bits are exactly the hash decisions
     got_keep = _unpack_mask(words, B, T, H)
     want_keep = torch.from_numpy(d.keep_attn(site, B, H, T, p))
-    assert torch.equal(got_keep, want_keep), (got_keep != want_keep).float().mean().item()
+    if padded:
+        # key tiles that are fully padded at the end of an utterance are not visited (their probabilities are zero whatever the
+        # mask says), so the recorded bits are only specified where the key is valid
+        kvalid = (pad == 0).cpu()[:, None, None, :].expand_as(want_keep)
+        assert torch.equal(got_keep[kvalid], want_keep[kvalid]), (got_keep != want_keep)[kvalid].float().mean().item()
+    else:
+        assert torch.equal(got_keep, want_keep), (got_keep != want_keep).float().mean().item()
     keep = want_keep.to(dev)
     # 2. forward (and the log-sum-exp is the one of the un-dropped softmax)
     ref = _attn_ref_drop(qkv, gate, tab, pad, keep, p, B, T, H, 0.125)
     assert torch.isfinite(out.float()).all()
-    err = (out.float() - ref).abs().max().item()
+    dd = (out.float() - ref).abs()
+    if padded:
+        dd = dd[pad == 0]  # rows of padded query frames are unspecified-but-finite (see b200s_attn_fwd)
+    err = dd.max().item()
     assert err < 0.04, err
     out0 = torch.empty_like(out)
     lse0 = torch.empty_like(lse)
@@ -125,6 +134,8 @@ def test_attn_dropout_fwd_bwd(cuda_device, B, T, H, bias, padded, p):
     assert torch.allclose(lse, lse0, atol=1e-4, rtol=1e-5)
     # 3. backward
     dout = bf(torch.randn(B, T, D, device=dev))
+    if padded:
+        dout[pad.bool()] = 0  # padded query frames carry no gradient in the model
     delta = torch.empty(B, H, T, device=dev)
     dqkv = torch.zeros(B, T, 3 * D, device=dev, dtype=torch.bfloat16)
     dgate = torch.full((B, H, T), 7.0, device=dev) if bias else None

@@ -22,12 +22,47 @@ CASES = {
 }
 
 
+LONG_CASES = {
+    "long_postln_T499": (lambda: O.tiny_config(pre_ln=False), 2, 160000, [160000, 101234]),
+    "long_preln_T1499": (lambda: O.tiny_config(pre_ln=True), 2, 480000, [480000, 160480]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LONG_CASES))
+def test_long_sequence_rows_match_reference(name):
+    """The oracle against the unmodified reference at T = 499 / 1499 frames (tools/make_long_golden.py): ragged batches, every
+    layer, a subsample of the frames.  This is the regime of BASELINE.json's configs: the relative-position buckets take the
+    LOG branch (|delta| >= 80, WavLM/modules.py:417-443; 319 distinct buckets at T = 1499) and attention spans many key tiles."""
+    mk, B, L, lengths = LONG_CASES[name]
+    cfg = mk()
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    sd = O.deterministic_state_dict(cfg)
+    wav, pmask = O.deterministic_waveform(B, L, seed=11, lengths=lengths)
+    with torch.no_grad():
+        res = O.extract_features(sd, wav, cfg, padding_mask=pmask)
+        res_l = O.extract_features(sd, wav, cfg, padding_mask=pmask, output_layer=cfg.encoder_layers)
+    rows = g["rows"]
+    fpm = g["frame_padding_mask"]
+    assert np.array_equal(res["padding_mask"].numpy(), fpm)
+    valid = ~fpm[:, rows]                                    # [B, rows]
+    dx = np.abs(res["x"][:, rows].numpy() - g["x_final"])
+    assert dx[valid].max() < 2e-4, dx[valid].max()
+    lr = np.stack([t[rows].numpy() for t in res_l["layer_results"]])    # [n+1, rows, B, D]
+    assert lr.shape == g["layer_results"].shape
+    dl = np.abs(lr - g["layer_results"])
+    assert dl[:, valid.T].max() < 2e-4, dl[:, valid.T].max()
+    # padded frames too: the reference computes them (garbage in, but deterministic) and so does the restatement
+    assert dl.max() < 1e-3, dl.max()
+
+
 def test_all_fixtures_are_covered():
     names = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, "*.npz")))
     names.remove("mask_indices")  # span-sampler fixture, covered by tests/test_api_cpu.py
     names.remove("train_heads")   # compute_nce / clip_grad_norm_ / Adam fixture, covered by test_training_heads_match_reference_code
     names.remove("utterance_mixing")  # host data-path fixture, covered by tests/test_api_cpu.py
     names.remove("sat_heads")     # UniSpeech-SAT utterance-contrastive fixture, covered by test_sat_utterance_contrastive_branch_...
+    for n in LONG_CASES:          # long-sequence fixtures (subsampled rows), covered by test_long_sequence_rows_match_reference
+        names.remove(n)
     assert names == sorted(CASES)
 
 

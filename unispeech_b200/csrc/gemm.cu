@@ -303,6 +303,15 @@ int b200s_version(void) { return 100; }
 long long b200s_launch_count(void) { return b200::g_launch_count; }
 const char* b200s_last_error(void) { return b200::last_error_buf(); }
 
+// zero `bytes` bytes of device memory on the stream (cudaMemsetAsync: the copy engine's fill, no SM kernel): the per-step reset of
+// the flat gradient buffer the backward kernels accumulate into
+int b200s_memset_zero(void* p, unsigned long long bytes, b200s_stream stream) {
+  B200_CHECK_ARG(p != nullptr || bytes == 0, "memset_zero: null pointer");
+  if (bytes == 0) return 0;
+  B200_CHECK_CUDA(cudaMemsetAsync(p, 0, static_cast<size_t>(bytes), static_cast<cudaStream_t>(stream)));
+  return 0;
+}
+
 int b200s_check_device(void) {
   int dev = 0;
   B200_CHECK_CUDA(cudaGetDevice(&dev));

@@ -219,6 +219,11 @@ def dropout_rows(x, x_bs, x_rs, res, res_bs, res_rs, y, y_bs, y_rs, rows_per_bat
            L.ll(y_rs), i32(rows_per_batch), i32(batches), i32(N), f32(p), u32(key[0]), u32(key[1]), _s())
 
 
+def memset_zero(t):
+    """Zero a contiguous device tensor on the current stream (cudaMemsetAsync)."""
+    _call("b200s_memset_zero", L.ptr(t), C.c_ulonglong(t.numel() * t.element_size()), _s())
+
+
 def sumsq_rows(x, x_bs, x_rs, rows_per_batch, batches, N, out):
     """*out (fp64, device) += sum x^2 over the bf16 rows view."""
     _call("b200s_sumsq_rows", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())

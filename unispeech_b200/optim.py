@@ -90,7 +90,7 @@ class FusedAdam:
         self.eng.prepared_version = None  # the masters changed behind autograd's version counters: re-derive the bf16 operands
 
     def zero_grad(self):
-        self.g.zero_()
+        ops.memset_zero(self.g)
         self._multiply_factor, self._have_norm = 1.0, False
 
     def state_dict(self):

@@ -375,16 +375,17 @@ class TransformerEncoder(nn.Module):
             self.layer_norm_for_extract = nn.LayerNorm(D)
         self.layerdrop = cfg.encoder_layerdrop
         self._owner = None
-        for mod in self.modules():  # init_bert_params (WavLM/modules.py:168-200)
-            if isinstance(mod, nn.Linear) and not any(mod is l for lyr in self.layers for l in
-                                                      (lyr.self_attn.q_proj, lyr.self_attn.k_proj, lyr.self_attn.v_proj,
-                                                       lyr.self_attn.out_proj)):
+        # `self.apply(init_bert_params)` of the reference (WavLM/WavLM.py:560-562, WavLM/modules.py:168-200): EVERY nn.Linear of the
+        # encoder -- q/k/v/out_proj, grep_linear, fc1/fc2 -- is re-drawn from N(0, 0.02) with a zero bias, and the
+        # relative_attention_bias Embedding from N(0, 0.02) (it runs after MultiheadAttention.reset_parameters, so the xavier
+        # values of the constructor do not survive)
+        for mod in self.modules():
+            if isinstance(mod, nn.Linear):
                 mod.weight.data.normal_(mean=0.0, std=0.02)
                 if mod.bias is not None:
                     mod.bias.data.zero_()
-        for lyr in self.layers:
-            for lin in (lyr.self_attn.q_proj, lyr.self_attn.k_proj, lyr.self_attn.v_proj):
-                lin.weight.data.normal_(mean=0.0, std=0.02)
+            elif isinstance(mod, nn.Embedding):
+                mod.weight.data.normal_(mean=0.0, std=0.02)
 
     def _make_bias_state(self, T, device):
         from . import ops
@@ -525,6 +526,12 @@ class WavLM(nn.Module):
         if self._engine is None or self._engine.flat is None:
             raise RuntimeError("run a forward pass on the GPU first")
         return self._engine.flat.flat
+
+    def zero_grad_buffer(self):
+        """Reset every gradient (the flat buffer all `param.grad` alias) on the current stream: the backward kernels ACCUMULATE,
+        so this is the step's `optimizer.zero_grad()` when no `FusedAdam.step(zero_grad=True)` does it."""
+        from . import ops
+        ops.memset_zero(self.grad_buffer())
 
     def _extractor(self, source):
         eng = self._begin(source.device)
