@@ -292,6 +292,39 @@ int b200s_nce_dproj(void* dproj, long long d_rs, const void* proj, long long p_r
 int b200s_nce_dlabel(const float* d_en, const float* label_embs, const float* invn, int C, int Dp, float* d_label_embs,
                      b200s_stream stream);
 
+/* ============================ UniSpeech-SAT utterance-contrastive head (csrc/sat.cu) ============================ */
+/* Utterance-contrastive loss of src/fairseq/models/unispeech_sat/unispeech_sat.py:699-758 (compute_pred_spk, compute_nce with
+ * replace_inf=False :545-557, F.binary_cross_entropy_with_logits(...).mean() :736) without the [N+1, S, Dp] gathered instances:
+ *   logit[s,0] = cos(proj_s, y_s)/temp, logit[s,1+n] = cos(proj_s, y[idx[n*S+s]])/temp; target[s,0] = 1, target[s,1+n] = same[n*S+s].
+ * proj, y: bf16 [S, Dp] rows; idx: int32 [N, S] (host-drawn like sample_instances :487-543); same: uint8 [N, S].
+ * Outputs: g fp32 [S, N+1] = d loss / d logit; *loss_sum (fp64, +=) the mean loss; stats[0] += #{(logit >= 0) == target},
+ * stats[1] += #{target == 1} (contrastive_acc and mean_targets are these / (S (N+1))).  Dp % 4 == 0, Dp <= 1024. */
+int b200s_sat_nce_fwd(const void* proj, long long proj_rs, const void* y, long long y_rs, const int* idx, const uint8_t* same,
+                      int S, int N, int Dp, float logit_temp, float* g, double* loss_sum, int* stats, b200s_stream stream);
+/* Backward: dproj_acc[s,:] += d loss/d proj_s, dy_acc[r,:] += d loss/d y_r (fp32 [S, Dp], vector reductions; pass the SAME buffer
+ * for both when y IS proj, i.e. no quantizer); upstream = DEVICE float, the gradient of the loss scalar. */
+int b200s_sat_nce_bwd(const void* proj, long long proj_rs, const void* y, long long y_rs, const int* idx, int S, int N, int Dp,
+                      float logit_temp, const float* g, const float* upstream, float* dproj_acc, float* dy_acc,
+                      b200s_stream stream);
+/* dst (bf16 rows) = src (fp32 rows); N and the row strides multiples of 4 elements */
+int b200s_f32_to_bf16_rows(const float* src, long long src_rs, void* dst, long long dst_rs, long long rows, int N,
+                           b200s_stream stream);
+/* GumbelVectorQuantizer.forward with hard codes (src/fairseq/modules/gumbel_vector_quantizer.py:141-201; time_first,
+ * combine_groups = False): logits bf16 [S, G*V] = weight_proj(x); codes[s*G+g] = argmax_v logits (eval) or argmax_v (logits +
+ * Gumbel noise from the counter hash with (key0, key1)) (training: the hard sample of F.gumbel_softmax);
+ * q[s, g*dv ..] = vars[g*V + code, :] (bf16; vars fp32 [G*V, dv]); counts[g*V+v] += [v == code], probs[g*V+v] += softmax(logits)_v
+ * (fp32, the caller zeroes them: hard_probs / avg_probs of :152-170 are these / S). */
+int b200s_vq_hard(const void* logits, long long logits_rs, const float* vars, int S, int G, int V, int dv, int* codes, void* q,
+                  long long q_rs, float* counts, float* probs, int gumbel, uint32_t key0, uint32_t key1, b200s_stream stream);
+/* d loss / d logits (bf16 [S, G*V], fully written) = p (c - <c, p>) / S  [c: fp32 [G*V] = d loss / d avg_probs, or NULL]
+ *   + ys (h - <h, ys>) / tau  [h: bf16 [S, G*V] = dq . vars^T, or NULL: straight-through gradient of F.gumbel_softmax(hard=True),
+ *     ys = softmax((logits + the same noise) / tau)]. */
+int b200s_vq_logits_bwd(const void* logits, long long logits_rs, int S, int G, int V, const float* c, const void* h, long long h_rs,
+                        float tau, uint32_t key0, uint32_t key1, void* dlogits, long long dlogits_rs, b200s_stream stream);
+/* dvars[g*V + codes[s*G+g], :] += dq[s, g*dv ..]   (backward of the codebook lookup) */
+int b200s_vq_dvars(const void* dq, long long dq_rs, const int* codes, int S, int G, int V, int dv, float* dvars,
+                   b200s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

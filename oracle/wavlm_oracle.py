@@ -682,9 +682,22 @@ def sat_compute_nce(x: Tensor, pos: Tensor, instances: Tensor, logit_temp: float
     return logits.transpose(0, 1)
 
 
-def gumbel_vq_eval(x: Tensor, weight_proj_w: Tensor, weight_proj_b: Tensor, vars_: Tensor, groups: int, num_vars: int):
-    """Eval-mode GumbelVectorQuantizer.forward (time_first, combine_groups=False, weight_proj_depth=1): hard arg-max code per
-    group, concatenated codebook vectors, plus the two perplexities the criterion logs."""
+def gumbel_noise(seed: int, site: int, n: int) -> Tensor:
+    """Gumbel(0,1) samples 0..n-1 of the product's counter-based generator (csrc/sat.cu gumbel_noise, keys as for dropout):
+    u = (float32(bits) + 0.5) * 2^-32 clamped below 1, g = -log(-log u)."""
+    k0, k1 = HashDropout(seed).key(site)
+    bits = _drop_bits(k0, k1, np.arange(n, dtype=np.uint64))
+    u = (bits.astype(np.float32) + np.float32(0.5)) * np.float32(2.3283064365386963e-10)
+    u = np.minimum(u, np.float32(0.99999994)).astype(np.float64)
+    return torch.from_numpy(-np.log(-np.log(u))).float()
+
+
+def gumbel_vq_eval(x: Tensor, weight_proj_w: Tensor, weight_proj_b: Tensor, vars_: Tensor, groups: int, num_vars: int,
+                   noise: Optional[Tensor] = None, tau: float = 1.0):
+    """GumbelVectorQuantizer.forward (time_first, combine_groups=False, weight_proj_depth=1), gumbel_vector_quantizer.py:141-201.
+    Eval mode (noise None): hard arg-max code per group.  Training mode: `F.gumbel_softmax(x, tau, hard=True)` with the Gumbel
+    noise supplied by the caller ([B*T*G, V]; torch draws it from its Philox stream): one-hot of the soft sample's arg-max in the
+    forward value, the soft sample's gradient in the backward pass.  Plus the two perplexities the criterion logs / penalises."""
     bsz, tsz, fsz = x.shape
     lg = F.linear(x.reshape(-1, fsz), weight_proj_w, weight_proj_b).view(bsz * tsz * groups, -1)
     k = lg.argmax(-1)
@@ -693,7 +706,14 @@ def gumbel_vq_eval(x: Tensor, weight_proj_w: Tensor, weight_proj_b: Tensor, vars
     code_ppl = torch.exp(-torch.sum(hard_probs * torch.log(hard_probs + 1e-7), dim=-1)).sum()
     avg_probs = torch.softmax(lg.view(bsz * tsz, groups, -1).float(), dim=-1).mean(0)
     prob_ppl = torch.exp(-torch.sum(avg_probs * torch.log(avg_probs + 1e-7), dim=-1)).sum()
-    q = (hard.view(bsz * tsz, -1).unsqueeze(-1) * vars_).view(bsz * tsz, groups, num_vars, -1).sum(-2).view(bsz, tsz, -1)
+    if noise is not None:   # F.gumbel_softmax(hard=True): y_hard - y_soft.detach() + y_soft
+        y_soft = torch.softmax((lg.float() + noise) / tau, dim=-1)
+        idx = y_soft.argmax(-1, keepdim=True)
+        y_hard = torch.zeros_like(y_soft).scatter_(-1, idx, 1.0)
+        sel = (y_hard - y_soft.detach() + y_soft).view(bsz * tsz, groups, -1)
+    else:
+        sel = hard
+    q = (sel.view(bsz * tsz, -1).unsqueeze(-1) * vars_).view(bsz * tsz, groups, num_vars, -1).sum(-2).view(bsz, tsz, -1)
     return {"x": q, "code_perplexity": code_ppl, "prob_perplexity": prob_ppl, "num_vars": num_vars * groups}
 
 

@@ -113,8 +113,10 @@ def test_attn_dropout_fwd_bwd(cuda_device, B, T, H, bias, padded, p):
     want_keep = torch.from_numpy(d.keep_attn(site, B, H, T, p))
     if padded:
         # key tiles that are fully padded at the end of an utterance are not visited (their probabilities are zero whatever the
-        # mask says), so the recorded bits are only specified where the key is valid
-        kvalid = (pad == 0).cpu()[:, None, None, :].expand_as(want_keep)
+        # mask says) and blocks of padded query rows are not computed at all: the recorded bits are only specified where both
+        # the key and the query frame are valid
+        ok = (pad == 0).cpu()
+        kvalid = (ok[:, None, None, :] & ok[:, None, :, None]).expand_as(want_keep)
         assert torch.equal(got_keep[kvalid], want_keep[kvalid]), (got_keep != want_keep)[kvalid].float().mean().item()
     else:
         assert torch.equal(got_keep, want_keep), (got_keep != want_keep).float().mean().item()

@@ -94,6 +94,73 @@ def test_head_base_dims_504_classes(cuda_device):
     _run_case(cuda_device, O.base_config(encoder_layers=2), [504], False, 256, 2, 16000, [16000, 12000], 1.0, 0.0, [10.0])
 
 
+def test_reference_criterion_surface_get_logits(cuda_device):
+    """B2 surface: the reference's criterion does `logp_m_list = model.get_logits(net_output, True)`, `targ = model.get_targets(...)`,
+    `F.cross_entropy(logp, targ, reduction="sum")` (src/fairseq/criterions/wavlm_criterion.py:63-87).  Drive THIS model that way
+    (the oracle's `wavlm_criterion` is that code, pinned to the reference source by tests/golden/train_heads.npz) and hold the
+    result to the fp32 oracle and to the fused `criterion` path: same loss, same sample size, same gradients."""
+    from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
+    dev = cuda_device
+    cfg = O.tiny_config(pre_ln=True)
+    num_classes, final_dim = [23, 70], 64
+    D = cfg.encoder_embed_dim
+    pcfg = WavLMPretrainConfig(dict(vars(cfg), final_dim=final_dim, untie_final_proj=True, logit_temp=0.1))
+    sd = O.deterministic_state_dict(cfg)
+    head = _head_state(cfg, D, final_dim * 2, sum(num_classes), final_dim)
+    wav, pmask = O.deterministic_waveform(2, 6400, seed=1, lengths=[6400, 4321])
+    T = O.num_frames(6400, cfg)
+    mi = O.hash_uniform("premask", (2, T)) > 0.35
+    target_list = [(O.hash_uniform(f"tgt{i}", (2, T), 0.0, 1.0) * C).long().clamp(max=C - 1) for i, C in enumerate(num_classes)]
+
+    def run(use_logits):
+        m = WavLMForPretraining(pcfg, num_classes)
+        m.load_state_dict({**sd, **head}, strict=True)
+        m = m.to(dev).train()
+        out = m(wav.to(dev), target_list=target_list, padding_mask=pmask, mask=True, mask_indices=mi)
+        if use_logits:
+            lm, lu = m.get_logits(out, True), m.get_logits(out, False)
+            assert all(t.dtype == torch.float32 for t in lm + lu)
+            assert [t.shape[1] for t in lm] == [c + 1 for c in num_classes]
+            assert all(int(t.sum()) == 0 and t.dtype == torch.long for t in m.get_targets(out, True))
+            loss, ss, log = O.wavlm_criterion(lm, lu, 1.0, 0.5, out["features_pen"], [10.0])   # == WavLMCriterion.get_loss
+        else:
+            loss, ss, log = m.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.5, loss_weights=[10.0])
+        loss.backward()
+        torch.cuda.synchronize()
+        return loss.item(), ss, {k: v.grad.detach().double().cpu() for k, v in m.named_parameters() if v.grad is not None}, log
+
+    l_ref, ss_ref, g_ref, log_ref = run(True)
+    l_fused, ss_fused, g_fused, _ = run(False)
+    # fp32 oracle
+    sdr = {k: v.clone().requires_grad_(True) for k, v in {**sd, **head}.items()}
+    conv = O.conv_feature_extractor(sdr, wav, cfg)
+    ref = O.extract_features(sdr, wav, cfg, padding_mask=pmask, mask_indices=mi)
+    fpm = ref["padding_mask"]
+    args = (sdr["final_proj.weight"], sdr["final_proj.bias"], sdr["label_embs_concat"], num_classes, True, 0.1)
+    lm = O.masked_prediction_logits(ref["x"], torch.logical_and(~fpm, mi), target_list, *args)
+    lu = O.masked_prediction_logits(ref["x"], torch.logical_and(~fpm, ~mi), target_list, *args)
+    want, want_ss, want_log = O.wavlm_criterion(lm, lu, 1.0, 0.5, conv.float().pow(2).mean(), [10.0])
+    want.backward()
+    assert ss_ref == ss_fused == want_ss
+    assert abs(l_ref - want.item()) < 0.02 * abs(want.item()) + 0.5, (l_ref, want.item())
+    assert abs(l_ref - l_fused) < 0.01 * abs(l_fused) + 0.2, (l_ref, l_fused)
+    for i in range(2):
+        assert log_ref[f"count_m_{i}"] == want_log[f"count_m_{i}"]
+    bad = []
+    for k, w_ in g_fused.items():
+        if k.endswith("k_proj.bias") or w_.norm().item() < 1e-7:
+            continue
+        g_ = g_ref[k]
+        cos = ((g_ * w_).sum() / (g_.norm() * w_.norm() + 1e-30)).item()
+        rel = abs(g_.norm().item() - w_.norm().item()) / w_.norm().item()
+        if cos < 0.995 or rel > 0.05:   # both are this model's bf16 kernels: only the logit assembly differs (fp32 vs fused bf16)
+            bad.append((k, round(cos, 4), round(rel, 4)))
+    assert not bad, bad
+    o = sdr["final_proj.weight"].grad.double()
+    g_ = g_ref["final_proj.weight"]
+    assert ((g_ * o).sum() / (g_.norm() * o.norm())).item() > 0.98
+
+
 def test_feature_grad_mult_scales_the_penalty_gradient_too(cuda_device):
     """The released recipes: feature_grad_mult = 0.1 with loss_weights = [10] (features_pen).  The extractor's gradients must be
     0.1 x (main-loss gradient + penalty gradient); an implementation that scales only the projection branch is 10x off on the

@@ -65,9 +65,11 @@ constexpr int kCudaThreads = 512;             // 16 CUDA-core warps: four per sc
 constexpr int kFThreads = kCudaThreads + 32;  // + 1 producer warp (only its first lane works): 17 warps x 120 registers
 constexpr int kProdWarp = kCudaThreads / 32;
 
-// floats of ONE copy of the bias-table slice: (N + 1) * 128 entries + 18, so that the second copy (shifted by one element)
-// starts 18 banks further: the 64-bit loads of a half warp, whose lanes alternate between the copies, touch 32 distinct banks
-__host__ __device__ constexpr int bwd_tab_stride(int N) { return (N + 1) * kAttnTile + 18; }
+// floats of ONE copy of the bias-table slice: (N + 1) * 128 entries + 16, so that the second copy (shifted by one element)
+// starts 16 banks further.  Lane 0 of every warp starts on an ODD table index (j0 - r + N*128 - 1 with j0, r multiples of 32), so
+// within a half warp the 8 odd lanes read 16 consecutive words of copy 1 and the 8 even lanes the SAME 16 word offsets of copy 0:
+// with the copies 16 banks apart the 64-bit loads touch 32 distinct banks (measured: 2 wavefronts per load instead of 4)
+__host__ __device__ constexpr int bwd_tab_stride(int N) { return (N + 1) * kAttnTile + 16; }
 
 }  // namespace
 
@@ -97,7 +99,11 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
   __shared__ uint32_t tmem_base_s;
   __shared__ uint32_t key_mask_s[4];  // bit j of word j>>5: key k0 + j is padded / beyond T
 
-  // ---- padding: which of this CTA's keys are masked, and how many query tiles hold a valid query
+  // ---- padding: which of this CTA's keys are masked, and how many query tiles hold a valid query.  ONE pass over the
+  // utterance's pad bytes (every thread takes a few), one block-wide reduction: the prologue pays a single global-load latency.
+  __shared__ int nq_s;
+  if (tid == 0) nq_s = 1;
+  int NQ = N;  // query tiles to visit
   {
     bool masked = false;
     if (tid < kAttnTile) {
@@ -105,6 +111,11 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       masked = (j >= T) || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + j] != 0);
       const uint32_t bal = __ballot_sync(0xffffffffu, masked);
       if (lane == 0) key_mask_s[warp] = bal;
+    }
+    int last_live = -1;
+    if (p.key_pad != nullptr) {
+      for (int i = tid; i < T; i += kFThreads)
+        if (p.key_pad[static_cast<long long>(b) * T + i] == 0) last_live = i;   // increasing i: the last hit is the largest
     }
     const int n_masked = __syncthreads_count(masked);
     if (n_masked == kAttnTile) {
@@ -119,21 +130,16 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       }
       return;
     }
-  }
-  int NQ = N;  // query tiles to visit
-  if (p.key_pad != nullptr) {
-    NQ = 1;
-    for (int t = 0; t < N; ++t) {
-      bool live = false;
-      if (tid < kAttnTile) {
-        const int i = t * kAttnTile + tid;
-        live = (i < T) && (p.key_pad[static_cast<long long>(b) * T + i] == 0);
-      }
-      if (__syncthreads_count(live) != 0) NQ = t + 1;
+    if (p.key_pad != nullptr) {
+      if (last_live >= 0) atomicMax(&nq_s, last_live / kAttnTile + 1);
+      __syncthreads();
+      NQ = nq_s;
     }
   }
 
-  if (tid == 0) {
+  if (warp == kProdWarp && lane == 0) {
+    // the producer thread initialises the barriers itself and puts K, V and the first Q / dO tiles in flight right away: they
+    // land while the rest of the CTA is still filling the tables (the other warps see the barriers after the __syncthreads below)
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     mbar_init(&kv_full, 1);
@@ -147,6 +153,14 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     mbar_init(&dq_full, 1);
     mbar_init(&acc_done, 1);
     fence_mbar_init();
+    mbar_expect_tx(&kv_full, 32768);
+    tma_load_4d(sK, &tm_qkv, &kv_full, D + h * kHeadDim, k0, b, 0);
+    tma_load_4d(sV, &tm_qkv, &kv_full, 2 * D + h * kHeadDim, k0, b, 0);
+    for (int qi = 0; qi < 2 && qi < NQ; ++qi) {
+      mbar_expect_tx(&qdo_full[qi], 32768);
+      tma_load_4d(sQ + qi * 16384, &tm_qkv, &qdo_full[qi], h * kHeadDim, qi * kAttnTile, b, 0);
+      tma_load_4d(sDO + qi * 16384, &tm_do, &qdo_full[qi], h * kHeadDim, qi * kAttnTile, b, 0);
+    }
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -197,12 +211,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
         umma_commit(&st_full[hf]);
       };
 
-      mbar_expect_tx(&kv_full, 32768);
-      tma_load_4d(sK, &tm_qkv, &kv_full, D + h * kHeadDim, k0, b, 0);
-      tma_load_4d(sV, &tm_qkv, &kv_full, 2 * D + h * kHeadDim, k0, b, 0);
-      load_qdo(0);
-      if (NQ > 1) load_qdo(1);
-      mbar_wait(&kv_full, 0);
+      mbar_wait(&kv_full, 0);  // (K, V and the first two Q / dO tiles were issued in the prologue)
       mbar_wait(&qdo_full[0], 0);
       tc_fence_after();
       issue_st(0, 0);
@@ -263,22 +272,20 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     uint32_t* wtile = reinterpret_cast<uint32_t*>(smem + kFW + hf * kFWBytes);
     const long long bh = static_cast<long long>(b) * p.H + h;
 
-    // per-row scalars of query tile qi (prefetched one tile ahead)
-    float lse2 = INFINITY, dsc = 0.f, gl = 0.f, gos = 0.f;
-    auto load_row = [&](int qi, float& a_lse, float& a_dsc, float& a_gl, float& a_gos) {
+    // per-row scalars of query tile qi: the RAW values are loaded one tile ahead (no arithmetic on them until the next tile starts,
+    // so the loads stay in flight under a whole tile of work); lse = +inf marks out-of-range queries (p = exp2(-inf) = 0)
+    float r_lse = INFINITY, r_delta = 0.f, r_gate = 0.f;
+    auto load_row = [&](int qi, float& a_lse, float& a_delta, float& a_gate) {
       const int i = qi * kAttnTile + r;
+      a_lse = INFINITY; a_delta = 0.f; a_gate = 0.f;
       if (i < T) {
-        const float gt = HAS_BIAS ? ((p.gate != nullptr) ? p.gate[bh * T + i] : 1.0f) : 0.f;
         a_lse = p.lse[bh * T + i];
-        a_dsc = p.delta[bh * T + i] * p.scale;
-        a_gl = gt * kLog2e;
-        a_gos = gt / p.scale;
-      } else {
-        a_lse = INFINITY;  // p = exp2(-inf) = 0 for out-of-range queries
-        a_dsc = 0.f; a_gl = 0.f; a_gos = 0.f;
+        a_delta = p.delta[bh * T + i];
+        if (HAS_BIAS) a_gate = (p.gate != nullptr) ? p.gate[bh * T + i] : 1.0f;
       }
     };
-    load_row(0, lse2, dsc, gl, gos);
+    load_row(0, r_lse, r_delta, r_gate);
+    const float inv_scale = 1.0f / p.scale;
 
     // dQ tile of query tile qi: TMEM -> fp32 reductions into dq_acc[b, q, h*64 + g*16 ..]  (thread = query row, 16 columns)
     auto flush_dq = [&](int qi) {
@@ -323,9 +330,10 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     for (int qi = 0; qi < NQ; ++qi) {
       mbar_wait(&st_full[hf], qi & 1);
       tc_fence_after();
+      const float lse2 = r_lse, dsc = r_delta * p.scale, gl = r_gate * kLog2e, gos = r_gate * inv_scale;
       // next tile's row scalars: in flight under this tile's arithmetic
-      float n_lse = INFINITY, n_dsc = 0.f, n_gl = 0.f, n_gos = 0.f;
-      if (qi + 1 < NQ) load_row(qi + 1, n_lse, n_dsc, n_gl, n_gos);
+      float n_lse = INFINITY, n_delta = 0.f, n_gate = 0.f;
+      if (qi + 1 < NQ) load_row(qi + 1, n_lse, n_delta, n_gate);
       uint32_t keep_bits = 0xffffffffu;
       if (DROP) {  // word (32-query block, key column) holds the bits of this warp's 32 rows: transpose to one word per row
         const long long blk = bh * (4 * N) + ((qi * kAttnTile + r) >> 5);
@@ -399,12 +407,12 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
 
       if (HAS_BIAS && p.dgate != nullptr) {
         const int i = qi * kAttnTile + r;
-        if (i < T) atomicAdd(p.dgate + bh * T + i, dg * (1.0f / p.scale));
+        if (i < T) atomicAdd(p.dgate + bh * T + i, dg * inv_scale);
       }
       fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
       tc_fence_before();
       mbar_arrive_cta(&ready[hf]);
-      lse2 = n_lse; dsc = n_dsc; gl = n_gl; gos = n_gos;
+      r_lse = n_lse; r_delta = n_delta; r_gate = n_gate;
       if (HAS_BIAS) {
         mbar_wait(&ready[hf], qi & 1);  // all 256 threads of this half have staged their rows
         diag_task(qi, ht & 127, ht >> 7);

@@ -96,38 +96,46 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
   __shared__ uint64_t q_full, k_full[2], k_empty[2], v_full[2], v_empty[2], s_full[2], p_ready[2], pv_done[2];
   __shared__ uint32_t tmem_base_s;
 
-  // ---- key padding: additive mask, per-tile flags, number of key tiles that hold any valid key (uniform over the CTA)
-  int n_eff = 1;
-  for (int t = 0; t < N; ++t) {
-    bool masked = false;
-    if (tid < kAttnTile) {
-      const int j = t * kAttnTile + tid;
-      masked = (j >= T) || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + j] != 0);
-      kbias[j] = masked ? -INFINITY : 0.f;
-    }
-    const int cnt = __syncthreads_count(masked);
-    if (tid == 0) tile_flags[t] = (cnt == 0) ? 0 : (cnt == kAttnTile ? 2 : 1);
-    if (cnt != kAttnTile) n_eff = t + 1;
-  }
-  // ---- a CTA whose query rows are all padded (or beyond T) has nothing to compute
-  if (p.key_pad != nullptr) {
+  // ---- key padding: additive mask, per-tile flags, number of key tiles that hold any valid key, and whether any of this CTA's
+  // 256 query rows is live.  ONE pass over the utterance's pad bytes (every thread takes a few), shared-memory counters, one
+  // barrier: the prologue pays a single global-load latency instead of one per key tile.
+  __shared__ int n_eff_s, live_s;
+  for (int t = tid; t < N; t += kFwdThreads) tile_flags[t] = 0;   // masked keys per tile (turned into 0 / 1 / 2 below)
+  if (tid == 0) { n_eff_s = 1; live_s = 0; }
+  __syncthreads();
+  {
+    int last_valid = -1;
     bool live = false;
-    if (tid < 2 * kAttnTile) {
-      const int i = q0 + tid;
-      live = (i < T) && (p.key_pad[static_cast<long long>(b) * T + i] == 0);
+    for (int j = tid; j < N * kAttnTile; j += kFwdThreads) {
+      const bool masked = (j >= T) || (p.key_pad != nullptr && p.key_pad[static_cast<long long>(b) * T + j] != 0);
+      kbias[j] = masked ? -INFINITY : 0.f;
+      if (masked) atomicAdd(&tile_flags[j / kAttnTile], 1);
+      else last_valid = j;                                     // increasing j: the last hit is the largest
+      if (!masked && j >= q0 && j < q0 + 2 * kAttnTile) live = true;
     }
-    if (__syncthreads_count(live) == 0) {
-      if (tid < 2 * kAttnTile && q0 + tid < T) {
-        uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + q0 + tid) * D + h * kHeadDim);
+    if (last_valid >= 0) atomicMax(&n_eff_s, last_valid / kAttnTile + 1);
+    if (live) live_s = 1;
+  }
+  __syncthreads();
+  const int n_eff = n_eff_s;
+  // ---- a CTA whose query rows are all padded (or beyond T) has nothing to compute
+  if (p.key_pad != nullptr && live_s == 0) {
+    if (tid < 2 * kAttnTile && q0 + tid < T) {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (static_cast<long long>(b) * T + q0 + tid) * D + h * kHeadDim);
 #pragma unroll
-        for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
-        if (p.lse != nullptr) p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + tid] = INFINITY;
-      }
-      return;
+      for (int g = 0; g < 8; ++g) dst[g] = make_uint4(0u, 0u, 0u, 0u);
+      if (p.lse != nullptr) p.lse[(static_cast<long long>(b) * p.H + h) * T + q0 + tid] = INFINITY;
     }
+    return;
+  }
+  for (int t = tid; t < N; t += kFwdThreads) {  // counts -> 0 no masked key, 1 some, 2 all (read after the barrier below)
+    const int c = tile_flags[t];
+    tile_flags[t] = (c == 0) ? 0 : (c == kAttnTile ? 2 : 1);
   }
 
-  if (tid == 0) {
+  if (warp == 8 && (tid & 31) == 0) {
+    // the TMA thread initialises the barriers itself and puts Q and the first K / V tiles in flight right away: they land while
+    // the rest of the CTA is still filling the bias-table copies (the other warps see the barriers after the __syncthreads below)
     tma_prefetch_desc(&tm);
     mbar_init(&q_full, 1);
     for (int i = 0; i < 2; ++i) {
@@ -140,6 +148,13 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
       mbar_init(&p_ready[i], kAttnTile);
     }
     fence_mbar_init();
+    mbar_expect_tx(&q_full, 32768);
+    tma_load_4d(sQ, &tm, &q_full, h * kHeadDim, q0, b, 0);
+    tma_load_4d(sQ + 16384, &tm, &q_full, h * kHeadDim, q0 + kAttnTile, b, 0);
+    mbar_expect_tx(&k_full[0], 16384);
+    tma_load_4d(sK, &tm, &k_full[0], D + h * kHeadDim, 0, b, 0);
+    mbar_expect_tx(&v_full[0], 16384);
+    tma_load_4d(sV, &tm, &v_full[0], 2 * D + h * kHeadDim, 0, b, 0);
   }
   __syncwarp();
   if (warp == 0) tmem_alloc(&tmem_base_s, 512);
@@ -161,10 +176,7 @@ __global__ void __launch_bounds__(kFwdThreads, 1) attn_fwd_kernel(const __grid_c
   if (warp == 8) {
     // ------------------------------------------------------------------ TMA producer warp
     if ((tid & 31) == 0) {
-      mbar_expect_tx(&q_full, 32768);
-      tma_load_4d(sQ, &tm, &q_full, h * kHeadDim, q0, b, 0);
-      tma_load_4d(sQ + 16384, &tm, &q_full, h * kHeadDim, q0 + kAttnTile, b, 0);
-      for (int n = 0; n < n_eff; ++n) {
+      for (int n = 1; n < n_eff; ++n) {  // (Q and tile 0 were issued in the prologue)
         const int s = n & 1;
         const uint32_t ph = (n >> 1) & 1;
         mbar_wait(&k_empty[s], ph ^ 1);

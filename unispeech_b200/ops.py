@@ -292,3 +292,32 @@ def nce_dproj(dproj, d_rs, proj, p_rs, S, Dp, pn, rvec):
 
 def nce_dlabel(d_en, label_embs, invn, C, Dp, d_label_embs):
     _call("b200s_nce_dlabel", L.ptr(d_en), L.ptr(label_embs), L.ptr(invn), i32(C), i32(Dp), L.ptr(d_label_embs), _s())
+
+
+# ------------------------------------------------------------------------------------------------- UniSpeech-SAT head
+def sat_nce_fwd(proj, proj_rs, y, y_rs, idx, same, S, N, Dp, logit_temp, g, loss_sum, stats):
+    _call("b200s_sat_nce_fwd", L.ptr(proj), L.ll(proj_rs), L.ptr(y), L.ll(y_rs), L.ptr(idx), L.ptr(same), i32(S), i32(N), i32(Dp),
+          f32(logit_temp), L.ptr(g), L.ptr(loss_sum), L.ptr(stats), _s())
+
+
+def sat_nce_bwd(proj, proj_rs, y, y_rs, idx, S, N, Dp, logit_temp, g, upstream, dproj_acc, dy_acc):
+    _call("b200s_sat_nce_bwd", L.ptr(proj), L.ll(proj_rs), L.ptr(y), L.ll(y_rs), L.ptr(idx), i32(S), i32(N), i32(Dp),
+          f32(logit_temp), L.ptr(g), L.ptr(upstream), L.ptr(dproj_acc), L.ptr(dy_acc), _s())
+
+
+def f32_to_bf16_rows(src, src_rs, dst, dst_rs, rows, N):
+    _call("b200s_f32_to_bf16_rows", L.ptr(src), L.ll(src_rs), L.ptr(dst), L.ll(dst_rs), L.ll(rows), i32(N), _s())
+
+
+def vq_hard(logits, logits_rs, vars_, S, G, V, dv, codes, q, q_rs, counts, probs, gumbel=False, key=(0, 0)):
+    _call("b200s_vq_hard", L.ptr(logits), L.ll(logits_rs), L.ptr(vars_), i32(S), i32(G), i32(V), i32(dv), L.ptr(codes), L.ptr(q),
+          L.ll(q_rs), L.ptr(counts), L.ptr(probs), i32(1 if gumbel else 0), u32(key[0]), u32(key[1]), _s())
+
+
+def vq_logits_bwd(logits, logits_rs, S, G, V, c, h, h_rs, tau, key, dlogits, dlogits_rs):
+    _call("b200s_vq_logits_bwd", L.ptr(logits), L.ll(logits_rs), i32(S), i32(G), i32(V), L.ptr(c), L.ptr(h), L.ll(h_rs), f32(tau),
+          u32(key[0]), u32(key[1]), L.ptr(dlogits), L.ll(dlogits_rs), _s())
+
+
+def vq_dvars(dq, dq_rs, codes, S, G, V, dv, dvars):
+    _call("b200s_vq_dvars", L.ptr(dq), L.ll(dq_rs), L.ptr(codes), i32(S), i32(G), i32(V), i32(dv), L.ptr(dvars), _s())

@@ -41,81 +41,154 @@ def _rows(n, C, dtype, dev):
     return torch.empty(n, C, dtype=dtype, device=dev)
 
 
+def _head_forward(model, x2d, w, b, label_embs, idx):
+    """Shared front of the masked-prediction head: gather the selected frames, final_proj, and per label set the GEMM against the
+    row-normalised label embeddings.  Returns the state both the fused criterion and the materialising logits path build on."""
+    dev = x2d.device
+    S, D = idx.numel(), x2d.shape[1]
+    Dp = model.final_dim
+    Dt = w.shape[0]
+    untie = model.untie_final_proj
+    wp, wpT = torch.empty(Dt, D, dtype=BF, device=dev), torch.empty(D, Dt, dtype=BF, device=dev)
+    ops.prep_linear(w, Dt, D, 1.0, wp, D, wpT, Dt)
+    xs = _rows(S, D, BF, dev)
+    ops.gather_rows(x2d, D, idx, S, D, xs, D)
+    proj = _rows(S, Dt, BF, dev)
+    ops.gemm_rows(xs, 0, D, S, 1, D, wp, Dt, proj, 0, Dt, L.make_epilogue(bias=b))
+    sets, off = [], 0
+    for i, C in enumerate(model.num_classes):
+        Cpad = (C + 63) // 64 * 64
+        E = label_embs[off:off + C]
+        en, en_t = _rows(Cpad, Dp, BF, dev), _rows(Dp, Cpad, BF, dev)
+        invn = torch.empty(C, dtype=torch.float32, device=dev)
+        ops.nce_prep(E, C, Cpad, Dp, en, en_t, invn)
+        proj_i = proj[:, i * Dp:(i + 1) * Dp] if untie else proj
+        zraw = _rows(S, Cpad, BF, dev)
+        ops.gemm_rows(proj_i, 0, Dt, S, 1, Dp, en, Cpad, zraw, 0, Cpad, None)
+        sets.append(dict(off=off, C=C, Cpad=Cpad, en_t=en_t, invn=invn, zraw=zraw))
+        off += C
+    return dict(xs=xs, proj=proj, wpT=wpT, sets=sets, shape=(x2d.shape[0], D, S, Dp, Dt, untie))
+
+
+def _head_backward(model, eng, st, label_embs, idx, Gs, pns, rvecs):
+    """Shared back of the head.  Gs[i] = d loss / d (proj . En^T) (bf16 [S, Cpad]), rvecs[i] = sum_c G_sc cos_sc, pns[i] = 1/|proj_s|:
+    d proj = G En - rvec pn proj,  d En = G^T proj,  then final_proj's weight / bias / input gradients and the scatter back."""
+    rows, D, S, Dp, Dt, untie = st["shape"]
+    dev = st["xs"].device
+    g = eng.g
+    dproj = _rows(S, Dt, BF, dev)
+    for i, se in enumerate(st["sets"]):
+        off, C, Cpad = se["off"], se["C"], se["Cpad"]
+        proj_i = st["proj"][:, i * Dp:(i + 1) * Dp] if untie else st["proj"]
+        first = untie or i == 0
+        tgt = (dproj[:, i * Dp:(i + 1) * Dp] if untie else dproj) if first else _rows(S, Dp, BF, dev)
+        ops.gemm_rows(Gs[i], 0, Cpad, S, 1, Cpad, se["en_t"], Dp, tgt, 0, tgt.stride(0), None)          # G En
+        ops.nce_dproj(tgt, tgt.stride(0), proj_i, Dt, S, Dp, pns[i], rvecs[i])
+        if not first:
+            dproj.add_(tgt)  # tied final_proj shared by several label sets
+        d_en = torch.zeros(Cpad, Dp, dtype=torch.float32, device=dev)
+        ops.gemm_wgrad(Gs[i], 0, Cpad, proj_i, 0, Dt, S, 1, Cpad, Dp, d_en, Dp)                          # G^T proj
+        ops.nce_dlabel(d_en, label_embs[off:off + C], se["invn"], C, Dp, g(model.label_embs_concat)[off:off + C])
+    ops.colsum(dproj, 0, Dt, S, 1, Dt, g(model.final_proj.bias))
+    ops.gemm_wgrad(dproj, 0, Dt, st["xs"], 0, D, S, 1, Dt, D, g(model.final_proj.weight), D)
+    dxs = _rows(S, D, BF, dev)
+    ops.gemm_rows(dproj, 0, Dt, S, 1, Dt, st["wpT"], D, dxs, 0, D, None)
+    dx = torch.zeros(rows, D, dtype=BF, device=dev)
+    ops.scatter_add_rows(dxs, D, idx, S, D, dx, D)
+    return dx
+
+
 class _MaskedPredictionFn(torch.autograd.Function):
     """loss = sum over label sets of weight * CE(cos(final_proj(x[idx]), label_embs) / temp, target).  x: bf16 [B*T, D]."""
 
     @staticmethod
     def forward(ctx, x2d, w, b, label_embs, model, idx, targets, weight, stats):
         ctx.fwd_stream = torch.cuda.current_stream()
-        eng = model._engine
         dev = x2d.device
-        S, D = idx.numel(), x2d.shape[1]
-        Dp, n_sets = model.final_dim, len(model.num_classes)
-        Dt = w.shape[0]
-        untie = model.untie_final_proj
-        wp, wpT = torch.empty(Dt, D, dtype=BF, device=dev), torch.empty(D, Dt, dtype=BF, device=dev)
-        ops.prep_linear(w, Dt, D, 1.0, wp, D, wpT, Dt)
-        xs = _rows(S, D, BF, dev)
-        ops.gather_rows(x2d, D, idx, S, D, xs, D)
-        proj = _rows(S, Dt, BF, dev)
-        ops.gemm_rows(xs, 0, D, S, 1, D, wp, Dt, proj, 0, Dt, L.make_epilogue(bias=b))
+        st = _head_forward(model, x2d, w, b, label_embs, idx)
+        S, Dp, Dt, untie = idx.numel(), model.final_dim, w.shape[0], model.untie_final_proj
         loss_sum = torch.zeros(1, dtype=torch.float64, device=dev)
-        sets, off = [], 0
-        for i, C in enumerate(model.num_classes):
-            Cpad = (C + 63) // 64 * 64
-            E = label_embs[off:off + C]
-            en, en_t = _rows(Cpad, Dp, BF, dev), _rows(Dp, Cpad, BF, dev)
-            invn = torch.empty(C, dtype=torch.float32, device=dev)
-            ops.nce_prep(E, C, Cpad, Dp, en, en_t, invn)
-            proj_i = proj[:, i * Dp:(i + 1) * Dp] if untie else proj
-            zraw = _rows(S, Cpad, BF, dev)
-            ops.gemm_rows(proj_i, 0, Dt, S, 1, Dp, en, Cpad, zraw, 0, Cpad, None)
+        Gs, pns, rvecs = [], [], []
+        for i, se in enumerate(st["sets"]):
+            C, Cpad = se["C"], se["Cpad"]
+            proj_i = st["proj"][:, i * Dp:(i + 1) * Dp] if untie else st["proj"]
             G = _rows(S, Cpad, BF, dev)
             pn = torch.empty(S, dtype=torch.float32, device=dev)
             rvec = torch.empty(S, dtype=torch.float32, device=dev)
             part = torch.zeros(1, dtype=torch.float64, device=dev)
             correct = torch.zeros(1, dtype=torch.int32, device=dev)
-            ops.nce_ce(proj_i, Dt, Dp, zraw, Cpad, targets[i], S, C, Cpad, model.logit_temp, weight, G, Cpad, pn, rvec, part, correct)
+            ops.nce_ce(proj_i, Dt, Dp, se["zraw"], Cpad, targets[i], S, C, Cpad, model.logit_temp, weight, G, Cpad, pn, rvec, part, correct)
             loss_sum += part
             stats.append(dict(loss=part, correct=correct, count=S))
-            sets.append((off, C, Cpad, en_t, invn, G, pn, rvec))
-            off += C
-        ctx.model, ctx.eng, ctx.idx, ctx.sets = model, eng, idx, sets
-        ctx.xs, ctx.proj, ctx.wpT, ctx.shape = xs, proj, wpT, (x2d.shape[0], D, S, Dp, Dt, untie)
+            se["zraw"] = None
+            Gs.append(G); pns.append(pn); rvecs.append(rvec)
+        ctx.model, ctx.eng, ctx.idx, ctx.st, ctx.grads = model, model._engine, idx, st, (Gs, pns, rvecs)
         ctx.save_for_backward(w, b, label_embs)
         return loss_sum.float().reshape(())
 
     @staticmethod
     @_on_forward_stream
     def backward(ctx, dloss):
-        model, eng, idx = ctx.model, ctx.eng, ctx.idx
         w, b, label_embs = ctx.saved_tensors
-        rows, D, S, Dp, Dt, untie = ctx.shape
-        dev = ctx.xs.device
-        g = eng.g
-        dproj = _rows(S, Dt, BF, dev)
+        Gs, pns, rvecs = ctx.grads
         scale_bf, scale_f = dloss.to(BF), dloss.float()
-        for i, (off, C, Cpad, en_t, invn, G, pn, rvec) in enumerate(ctx.sets):
+        for G, rvec in zip(Gs, rvecs):
             G.mul_(scale_bf)     # upstream gradient of the scalar loss (device scalar, no sync): everything below is linear in G
             rvec.mul_(scale_f)
-            proj_i = ctx.proj[:, i * Dp:(i + 1) * Dp] if untie else ctx.proj
-            first = untie or i == 0
-            tgt = (dproj[:, i * Dp:(i + 1) * Dp] if untie else dproj) if first else _rows(S, Dp, BF, dev)
-            ops.gemm_rows(G, 0, Cpad, S, 1, Cpad, en_t, Dp, tgt, 0, tgt.stride(0), None)          # G En
-            ops.nce_dproj(tgt, tgt.stride(0), proj_i, Dt, S, Dp, pn, rvec)
-            if not first:
-                dproj.add_(tgt)  # tied final_proj shared by several label sets
-            d_en = torch.zeros(Cpad, Dp, dtype=torch.float32, device=dev)
-            ops.gemm_wgrad(G, 0, Cpad, proj_i, 0, Dt, S, 1, Cpad, Dp, d_en, Dp)                    # G^T proj
-            ops.nce_dlabel(d_en, label_embs[off:off + C], invn, C, Dp, g(model.label_embs_concat)[off:off + C])
-        ops.colsum(dproj, 0, Dt, S, 1, Dt, g(model.final_proj.bias))
-        ops.gemm_wgrad(dproj, 0, Dt, ctx.xs, 0, D, S, 1, Dt, D, g(model.final_proj.weight), D)
-        dxs = _rows(S, D, BF, dev)
-        ops.gemm_rows(dproj, 0, Dt, S, 1, Dt, ctx.wpT, D, dxs, 0, D, None)
-        dx = torch.zeros(rows, D, dtype=BF, device=dev)
-        ops.scatter_add_rows(dxs, D, idx, S, D, dx, D)
-        ctx.sets = ctx.xs = ctx.proj = None
+        dx = _head_backward(ctx.model, ctx.eng, ctx.st, label_embs, ctx.idx, Gs, pns, rvecs)
+        ctx.st = ctx.grads = None
         return dx, None, None, None, None, None, None, None, None
+
+
+class _LogitsFn(torch.autograd.Function):
+    """Opt-in MATERIALISING path of the head: the `[S, C+1]` float logit lists of the reference (`compute_nce`,
+    src/fairseq/models/wavlm/wavlm.py:426-438: column 0 = the positive, column 1 + c = class c, -inf where the class IS the
+    positive), differentiable, so that the reference's own `WavLMCriterion.get_loss` (wavlm_criterion.py:52-103) can drive this
+    model through `get_logits` / `get_targets`.  Same GEMMs as the fused criterion; the logits are assembled from their outputs."""
+
+    @staticmethod
+    def forward(ctx, x2d, w, b, label_embs, model, idx, targets):
+        ctx.fwd_stream = torch.cuda.current_stream()
+        st = _head_forward(model, x2d, w, b, label_embs, idx)
+        Dp, untie = model.final_dim, model.untie_final_proj
+        outs, pns = [], []
+        for i, se in enumerate(st["sets"]):
+            C = se["C"]
+            proj_i = st["proj"][:, i * Dp:(i + 1) * Dp] if untie else st["proj"]
+            pn = 1.0 / proj_i.float().norm(dim=-1).clamp_min(1e-8)                 # torch.cosine_similarity clamps each norm
+            z = se["zraw"][:, :C].float() * (pn / model.logit_temp).unsqueeze(1)   # cos(proj_s, E_c) / temp
+            t = targets[i].long().unsqueeze(1)
+            pos = z.gather(1, t)
+            outs.append(torch.cat([pos, z.scatter(1, t, float("-inf"))], dim=1))
+            pns.append(pn)
+        ctx.model, ctx.eng, ctx.idx, ctx.st, ctx.pns, ctx.targets = model, model._engine, idx, st, pns, targets
+        ctx.save_for_backward(w, b, label_embs)
+        return tuple(outs)
+
+    @staticmethod
+    @_on_forward_stream
+    def backward(ctx, *dlogits):
+        w, b, label_embs = ctx.saved_tensors
+        model, st = ctx.model, ctx.st
+        dev = st["xs"].device
+        S = ctx.idx.numel()
+        Gs, rvecs = [], []
+        for i, se in enumerate(st["sets"]):
+            C, Cpad = se["C"], se["Cpad"]
+            dl = dlogits[i].float() if dlogits[i] is not None else torch.zeros(S, C + 1, device=dev)
+            t = ctx.targets[i].long().unsqueeze(1)
+            dz = dl[:, 1:].scatter(1, t, 0.0)            # the -inf entry receives no gradient ...
+            dz.scatter_add_(1, t, dl[:, :1])             # ... the positive's gradient lands on its class column
+            zs = (ctx.pns[i] / model.logit_temp).unsqueeze(1)
+            Gf = dz * zs                                 # d / d (proj . En^T)
+            cosv = se["zraw"][:, :C].float() * ctx.pns[i].unsqueeze(1)
+            rvecs.append((Gf * cosv).sum(1).contiguous())
+            G = torch.zeros(S, Cpad, dtype=BF, device=dev)
+            G[:, :C] = Gf.to(BF)
+            Gs.append(G)
+        dx = _head_backward(model, ctx.eng, st, label_embs, ctx.idx, Gs, ctx.pns, rvecs)
+        ctx.st = None
+        return dx, None, None, None, None, None, None
 
 
 class WavLMForPretraining(WavLM):
@@ -168,12 +241,45 @@ class WavLMForPretraining(WavLM):
             names.append("features_pen")
         return extra_losses, names
 
-    def get_logits(self, net_output, is_masked=True):
-        raise NotImplementedError("the [S, C+1] logit lists of the reference are never materialised on this path: use "
-                                  "`model.criterion(net_output, ...)`, which returns the same loss / sample_size / accuracy counts as "
-                                  "WavLMCriterion.get_loss")
+    def _selection(self, net_output, masked: bool):
+        """Host-side frame selection of the criterion: flat indices of the masked (or unmasked) unpadded frames + their labels."""
+        x = net_output["x"]
+        B, T, D = x.shape
+        dev = x.device
+        mi, pm, targets = net_output["mask_indices"], net_output["padding_mask"], net_output["target_list"]
+        assert mi is not None and targets is not None, "forward(..., target_list=..., mask=True) must run first"
+        mi_h = mi.cpu() if mi.device.type != "cpu" else mi
+        pm_h = net_output.get("padding_mask_host")
+        if pm_h is None:
+            pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
+        sel = torch.logical_and(~pm_h, mi_h if masked else ~mi_h)
+        idx_h = torch.nonzero(sel.reshape(-1), as_tuple=False).squeeze(1)
+        idx = idx_h.to(torch.int32).to(dev, non_blocking=True)
+        tg = [t.reshape(-1).to(dev)[idx.long()].to(torch.int32).contiguous() if t.device.type != "cpu"
+              else t.reshape(-1)[idx_h].to(torch.int32).to(dev, non_blocking=True) for t in targets]
+        return idx_h, idx, tg
 
-    get_targets = get_logits
+    def get_logits(self, net_output, is_masked=True):
+        """`[S, C+1]` float logit list of the reference (wavlm.py:599-607), one per label set, positives in column 0.  Opt-in
+        materialising path (the fused `criterion` never builds these); differentiable, cached in `net_output`."""
+        key = "logit_m_list" if is_masked else "logit_u_list"
+        if net_output.get(key) is None:
+            skip = self.skip_masked if is_masked else self.skip_nomask
+            idx_h, idx, tg = self._selection(net_output, is_masked)
+            if skip or idx_h.numel() == 0:
+                net_output[key] = [None for _ in self.num_classes]
+            else:
+                x = net_output["x"]
+                x2d = x.reshape(-1, x.shape[-1])
+                if x2d.dtype != BF or not x2d.is_contiguous():
+                    x2d = x2d.to(BF).contiguous()
+                net_output[key] = list(_LogitsFn.apply(x2d, self.final_proj.weight, self.final_proj.bias, self.label_embs_concat,
+                                                       self, idx, tg))
+        return [lg.float() for lg in net_output[key] if lg is not None]
+
+    def get_targets(self, net_output, is_masked=True):
+        """All-zero class indices: the positive sits in column 0 (wavlm.py:608-610)."""
+        return [lg.new_zeros(lg.size(0), dtype=torch.long) for lg in self.get_logits(net_output, is_masked)]
 
     def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
                 mask_indices=None):
@@ -232,12 +338,17 @@ class WavLMForPretraining(WavLM):
                 log[f"loss_{tag}_{i}"] = st["loss"] / wgt
                 log[f"correct_{tag}_{i}"] = st["correct"]
                 log[f"count_{tag}_{i}"] = st["count"]
-        if loss_weights is not None and net_output.get("features_pen") is not None:
-            coef = loss_weights[0]
-            if coef != 0:
-                p = coef * net_output["features_pen"].float() * sample_size  # wavlm_criterion.py:100-103
-                loss = loss + p
-                log["loss_features_pen"] = p.detach()
+        if loss_weights is not None:  # wavlm_criterion.py:89-103: every extra loss the model reports, weight x value x sample_size
+            extra_losses, names = self.get_extra_losses(net_output)
+            lw = list(loss_weights)
+            if len(lw) == 1 and len(extra_losses) != 1:
+                lw = [lw[0]] * len(extra_losses)
+            assert len(extra_losses) == len(lw), f"{len(extra_losses)}, {len(lw)}"
+            for p, n, coef in zip(extra_losses, names, lw):
+                if coef != 0 and p is not None:
+                    p = coef * p.float() * sample_size
+                    loss = loss + p
+                    log[f"loss_{n}"] = p.detach()
         log.update(ntokens=sample_size, sample_size=sample_size, nsentences=B)
         log["loss"] = loss.detach() if torch.is_tensor(loss) else loss
         return loss, sample_size, log

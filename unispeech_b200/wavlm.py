@@ -587,9 +587,11 @@ class WavLM(nn.Module):
         pad_u8 = fpm.to(torch.uint8).contiguous() if fpm is not None else None
         xv, features = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv)
         xv._b200_xpad = eng._last_xpad
-        x, layer_results = self.encoder(xv, padding_mask=fpm, layer=None if output_layer is None else output_layer - 1)
+        el = getattr(self, "_extract_layer", None)  # UniSpeech-SAT: 0-based `utterance_contrastive_layer - 1` (unispeech_sat.py:640-645)
+        enc = self.encoder(xv, padding_mask=fpm, layer=None if output_layer is None else output_layer - 1, extract_layer=el)
+        x, layer_results = enc[0], enc[1]
         res = {"x": x, "padding_mask": fpm, "features": features, "layer_results": layer_results,
-               "mask_indices": mask_indices, "padding_mask_host": fpm_host}
+               "mask_indices": mask_indices, "padding_mask_host": fpm_host, "spk_x": enc[2] if el is not None else None}
         self._last = res
         feature = res["features"] if ret_conv else res["x"]
         if ret_layer_results:
