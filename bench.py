@@ -174,12 +174,19 @@ class Workload:
     """One model + one synthetic batch per rank, stepped through the public API (extract_features + probe loss + backward
     [+ the gradient allreduce for N > 1])."""
 
-    def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False, pretrain=False):
+    def __init__(self, model_name, dev, rank, world, dropout=0.0, ragged=False, pretrain=False, sat=False):
         from unispeech_b200 import workloads
         from unispeech_b200.wavlm import WavLM, WavLMConfig
         self.name, self.dev, self.world, self.dropout, self.pretrain = model_name, dev, world, dropout, pretrain
-        self.opt, self.sync = None, None
+        self.opt, self.sync, self.sat = None, None, sat
+        pretrain = self.pretrain = pretrain or sat
         cfg, B, secs = model_config(model_name)
+        if sat:
+            # BASELINE.json configs[3]: UniSpeech-SAT Large as shipped (SURVEY.md section 8c): WavLM-Large encoder geometry WITHOUT the
+            # relative-position bias / gate, masked-prediction head (504 labels, final_dim 768, mask_prob 0.8) + utterance-contrastive
+            # loss on layer 12 with 100 cross-sample instances and Gumbel-quantised targets (320 x 2 codes), utterance mixing on the
+            # host in front of every batch
+            cfg.relative_position_embedding, cfg.gru_rel_pos, cfg.mask_prob = False, False, 0.8
         if dropout > 0:  # the reference's WavLMConfig defaults: dropout = attention_dropout = 0.1 (WavLM/WavLM.py:180-181)
             cfg.dropout, cfg.attention_dropout = dropout, dropout
         self.cfg, self.B, self.secs, self.ragged = cfg, B, secs, ragged
@@ -199,7 +206,15 @@ class Workload:
             # at 50 Hz, final_dim 768 (the released Large recipe), WavLMCriterion with features_pen x 10, Adam(0.9, 0.98), clip 1.0
             from unispeech_b200.pretrain import WavLMForPretraining, WavLMPretrainConfig
             torch.manual_seed(20 + 0)  # random init of the architecture (the reference's initialisers), same on every rank
-            model = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=768 if model_name == "large" else 256)), [504])
+            fd = 768 if model_name == "large" else 256
+            if sat:
+                from unispeech_b200.unispeech_sat import UniSpeechSATConfig, UniSpeechSATForPretraining
+                model = UniSpeechSATForPretraining(UniSpeechSATConfig(dict(
+                    vars(cfg), final_dim=fd, utterance_contrastive_layer=cfg.encoder_layers // 2, num_instances=0,
+                    cross_sample_instances=100, quantize_targets=True, latent_vars=320, latent_groups=2, latent_dim=fd,
+                    layer_norm_for_extract=True)), [504])
+            else:
+                model = WavLMForPretraining(WavLMPretrainConfig(dict(vars(cfg), final_dim=fd)), [504])
             self.labels = [torch.randint(0, 504, (B, self.T), generator=torch.Generator().manual_seed(99 + rank))]
             self.final_dim = model.final_dim
         else:
@@ -215,6 +230,7 @@ class Workload:
             wav[b, n:] = 0.0
             self.pad_host[b, n:] = True
         self.wav_host = wav.pin_memory()
+        self.wav_mixed = torch.empty_like(wav).pin_memory() if sat else None
         self.wav_dev = self.wav_host.to(dev)
         self.R = torch.randn(B, self.T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
         self.loss_host = torch.zeros(1).pin_memory()
@@ -240,7 +256,15 @@ class Workload:
             if not self.pretrain:  # (the optimizer step of the pre-training workload zeroes the gradients itself)
                 model.zero_grad_buffer()
             model._engine.prepared_version = None  # parameters change every optimisation step: re-derive the bf16 operands
-        wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
+        if self.sat and e2e:
+            # the data path of the reference mixes utterances on the host for every batch (utterance_mixing_dataset.py:373-438);
+            # in the end-to-end measurement it is inside the timed region, like the host-to-device copy
+            from unispeech_b200.mixing import mix_utterances
+            self.wav_mixed.copy_(self.wav_host)
+            mix_utterances(self.wav_mixed, mixing_prob=0.5, mixing_num=1, mixing_max_len=-1, normalize=self.cfg.normalize)
+            wav = self.wav_mixed.to(self.dev, non_blocking=True)
+        else:
+            wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
         if self.pretrain:
             return self.pretrain_step(wav, e2e, collective)
         nvtx.range_push("forward")
@@ -266,7 +290,8 @@ class Workload:
         model = self.model
         nvtx.range_push("forward")
         out = model(wav, target_list=self.labels, padding_mask=self.pad_host, mask=True)
-        loss, sample_size, _ = model.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.0, loss_weights=[10.0])
+        lw = [10.0, 10.0, 0.0, 0.1] if self.sat else [10.0]   # features_pen, loss_spk_m, loss_spk_u, diversity (prob_perplexity)
+        loss, sample_size, _ = model.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.0, loss_weights=lw)
         nvtx.range_pop()
         sync = self._sync_for(collective)
         nvtx.range_push("backward")
@@ -319,6 +344,13 @@ class Workload:
 
     def describe(self) -> str:
         drop = f"dropout {self.dropout} / attention_dropout {self.dropout}" if self.dropout > 0 else "dropout 0"
+        if self.sat:
+            return (f"UniSpeech-SAT {self.name} full pre-training step (BASELINE configs[3]): fwd (no rel-pos bias, as shipped) + masked-"
+                    f"prediction head (504 classes, final_dim {self.final_dim}) + utterance-contrastive loss on layer "
+                    f"{self.cfg.encoder_layers // 2} (100 cross-sample instances, Gumbel-quantised targets 320 x 2, training mode) + "
+                    f"WavLMCriterion (features_pen x 10, loss_spk_m x 10, diversity x 0.1) + bwd + gradient scale / clip 1.0 / Adam, "
+                    f"batch {self.B} x {self.secs} s per GPU, mask_prob {self.cfg.mask_prob}, {drop}; utterance mixing (p 0.5) on "
+                    f"the host inside the end-to-end timed region")
         if self.pretrain:
             return (f"WavLM-{self.name} full optimisation step: fwd + masked-prediction head (504 classes, final_dim "
                     f"{self.final_dim}) + WavLMCriterion (features_pen x 10) + bwd + gradient scale / clip 1.0 / Adam, batch "
@@ -436,6 +468,8 @@ def main():
                     "section 3 times both arms with dropout 0; the reference's config default 0.1 is reported under `also`)")
     ap.add_argument("--ragged", action="store_true", help="BASELINE.json configs[4]: variable-length batch 4..30 s with padding mask")
     ap.add_argument("--pretrain", action="store_true", help="time the full optimisation step (loss head + criterion + optimizer)")
+    ap.add_argument("--sat", action="store_true", help="BASELINE.json configs[3]: UniSpeech-SAT Large pre-training step (masked "
+                    "prediction + utterance-contrastive loss + Gumbel quantizer + host utterance mixing)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (WavLM-Base, reference dropouts)")
@@ -457,7 +491,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
-    w = Workload(args.model, dev, rank, world, dropout=args.dropout, ragged=args.ragged, pretrain=args.pretrain)
+    w = Workload(args.model, dev, rank, world, dropout=args.dropout, ragged=args.ragged, pretrain=args.pretrain, sat=args.sat)
     cfg, B, secs, T = w.cfg, w.B, w.secs, w.T
 
     for _ in range(args.warmup):
@@ -555,6 +589,10 @@ def main():
                 wp = Workload(args.model, dev, rank, world, dropout=0.0, pretrain=True)
                 also[f"wavlm_{args.model}_pretrain_step"] = quick_line(wp, args.steps, 3, e2e=True)
                 wp.free()
+            if not args.ragged and not args.sat and args.model == "large":
+                ws = Workload("large", dev, rank, world, dropout=0.0, sat=True)
+                also["unispeech_sat_large_pretrain_step"] = quick_line(ws, args.steps, 3, e2e=True)
+                ws.free()
             other = "base" if args.model == "large" else "large"
             wo = Workload(other, dev, rank, world, dropout=0.0)
             also[f"wavlm_{other}"] = quick_line(wo, args.steps, 3, e2e=True)

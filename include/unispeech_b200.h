@@ -325,6 +325,26 @@ int b200s_vq_logits_bwd(const void* logits, long long logits_rs, int S, int G, i
 int b200s_vq_dvars(const void* dq, long long dq_rs, const int* codes, int S, int G, int V, int dv, float* dvars,
                    b200s_stream stream);
 
+/* ============================ on-device data path (csrc/datapath.cu) ============================ */
+/* Span masking of compute_mask_indices (WavLM/WavLM.py:35-159; static span length, overlapping spans) on the device, with the
+ * library's counter-based RNG instead of numpy's (statistical parity): per row count = max(min_masks, floor(mask_prob sz / L + u)),
+ * `count` distinct uniform starts in [0, sz - L), union of the spans, every row trimmed to the batch-minimum number of masked
+ * frames.  valid_len: int32 [B] unpadded frames per row, or NULL (all T).  mask: uint8 [B, T] out; counts: int32 [B] workspace.
+ * T <= 4096. */
+int b200s_span_mask(const int* valid_len, int B, int T, float mask_prob, int mask_length, int min_masks, uint32_t key0,
+                    uint32_t key1, uint8_t* mask, int* counts, b200s_stream stream);
+/* power[b] += sum_t x[b,t]^2 (fp32 waveforms [B, L], batch stride x_bs; fp64 accumulators zeroed by the caller) */
+int b200s_row_power(const float* x, long long x_bs, int B, int L, double* power, b200s_stream stream);
+/* Utterance mixing (src/fairseq/data/audio/utterance_mixing_dataset.py:415-432): plan = DEVICE array of B records
+ * {int32 c (-1: not mixed), int32 len, int32 c_start, int32 s_start, float snr_db} drawn by the caller;
+ * dst[b, s_start + t] += src[c, c_start + t] * sqrt(P_b / (P_c 10^(snr/10))), P = power / L (from b200s_row_power of src). */
+int b200s_mix_apply(const float* src, long long bs, int B, int L, const void* plan, const double* power, float* dst,
+                    b200s_stream stream);
+/* x[b, :n_b] = (x - mean) / sqrt(var + 1e-5) over the row's n_b = valid_len[b] (or L) samples (F.layer_norm(wav, wav.shape),
+ * utterance_mixing_dataset.py:433-435,571-573); stats: fp64 [B, 2] zeroed by the caller; plan != NULL: only rows with c >= 0. */
+int b200s_row_normalize(float* x, long long bs, int B, int L, const int* valid_len, double* stats, const void* plan,
+                        b200s_stream stream);
+
 #ifdef __cplusplus
 }
 #endif

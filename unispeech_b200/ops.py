@@ -321,3 +321,21 @@ def vq_logits_bwd(logits, logits_rs, S, G, V, c, h, h_rs, tau, key, dlogits, dlo
 
 def vq_dvars(dq, dq_rs, codes, S, G, V, dv, dvars):
     _call("b200s_vq_dvars", L.ptr(dq), L.ll(dq_rs), L.ptr(codes), i32(S), i32(G), i32(V), i32(dv), L.ptr(dvars), _s())
+
+
+# ------------------------------------------------------------------------------------------------- on-device data path
+def span_mask(valid_len, B, T, mask_prob, mask_length, min_masks, key, mask, counts):
+    _call("b200s_span_mask", L.ptr(valid_len), i32(B), i32(T), f32(mask_prob), i32(mask_length), i32(min_masks), u32(key[0]),
+          u32(key[1]), L.ptr(mask), L.ptr(counts), _s())
+
+
+def row_power(x, x_bs, B, Ln, power):
+    _call("b200s_row_power", L.ptr(x), L.ll(x_bs), i32(B), i32(Ln), L.ptr(power), _s())
+
+
+def mix_apply(src, bs, B, Ln, plan, power, dst):
+    _call("b200s_mix_apply", L.ptr(src), L.ll(bs), i32(B), i32(Ln), L.ptr(plan), L.ptr(power), L.ptr(dst), _s())
+
+
+def row_normalize(x, bs, B, Ln, valid_len, stats, plan):
+    _call("b200s_row_normalize", L.ptr(x), L.ll(bs), i32(B), i32(Ln), L.ptr(valid_len), L.ptr(stats), L.ptr(plan), _s())
