@@ -27,16 +27,6 @@ def _free_port():
     return p
 
 
-def _grads(model, wav, pmask, dev, sync=None, seed=2):
-    x, fpm = model.extract_features(wav.to(dev), padding_mask=pmask.to(dev), mask=False)
-    R = O.hash_uniform(f"probe:{seed}", tuple(x.shape)).to(dev).masked_fill(fpm.unsqueeze(-1), 0.0)
-    loss = (x.float() * R).sum()
-    if sync is not None:
-        sync.begin()
-    loss.backward()
-    return loss
-
-
 def _worker(rank, world, port, overlapped, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     torch.cuda.set_device(rank)

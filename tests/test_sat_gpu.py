@@ -43,7 +43,7 @@ def test_sat_step_vs_oracle(cuda_device, quant, train):
     from unispeech_b200.unispeech_sat import UniSpeechSATConfig, UniSpeechSATForPretraining
     dev = cuda_device
     cfg = O.tiny_config(pre_ln=True, layer_norm_for_extract=True, relative_position_embedding=False, gru_rel_pos=False)
-    D, Dp, C, G, V, vq_dim = cfg.encoder_embed_dim, 64, 30, 2, 16, 128
+    D, Dp, C, G, V, vq_dim = cfg.encoder_embed_dim, 64, 30, 2, 32, 128
     n_inst, n_cross, layer = 3, 5, 1
     scfg = UniSpeechSATConfig(dict(vars(cfg), final_dim=Dp, logit_temp=0.1, utterance_contrastive_layer=layer, num_instances=n_inst,
                                    cross_sample_instances=n_cross, quantize_targets=quant, latent_vars=V, latent_groups=G,

@@ -3,6 +3,7 @@
 // relative-position table gather/scatter.  One warp per row, 16-byte vector accesses, warp-shuffle reductions.
 #include <algorithm>
 #include <type_traits>
+#include <type_traits>
 
 #include "../../include/unispeech_b200.h"
 #include "common.h"
@@ -284,16 +285,36 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
   const bool want_gb = dgamma != nullptr || dbeta != nullptr;
   const bool want_c = colsum != nullptr;
 
+  // The kernel is latency-bound (a row is loads -> two shuffle reductions -> store, 16 warps per SM): the NEXT row's x vectors and
+  // statistics are requested (raw, still packed as bf16) before the current row is touched, so each warp keeps 1.5 rows of loads
+  // in flight (prefetching dy as well does not fit the 128-register budget at D = 1024 without spilling).
+  using RawVec = typename std::conditional<VEC == 8, uint4, typename std::conditional<VEC == 4, uint2, uint32_t>::type>::type;
+  RawVec nx[NCH];
+  float nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](long long r) {
+    const __nv_bfloat16* xr = x + xv.off(r);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) nx[i] = *reinterpret_cast<const RawVec*>(xr + (i * 32 + lane) * VEC);
+    nmean = mean_in[r];
+    nrstd = rstd_in[r];
+  };
+  if (warp_global < rows) fetch(warp_global);
   for (long long r = warp_global; r < rows; r += nwarps) {
     float xh[N], dz[N];
-    const __nv_bfloat16* xr = x + xv.off(r);
     const __nv_bfloat16* dr = dy + dyv.off(r);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-      VecIO<VEC>::load(xr + (i * 32 + lane) * VEC, xh + i * VEC);
       VecIO<VEC>::load(dr + (i * 32 + lane) * VEC, dz + i * VEC);
+      const uint32_t* u = reinterpret_cast<const uint32_t*>(&nx[i]);
+#pragma unroll
+      for (int k = 0; k < VEC / 2; ++k) {
+        const float2 f = unpack_bf16x2(u[k]);
+        xh[i * VEC + 2 * k] = f.x;
+        xh[i * VEC + 2 * k + 1] = f.y;
+      }
     }
-    const float mean = mean_in[r], rstd = rstd_in[r];
+    const float mean = nmean, rstd = nrstd;
+    if (r + nwarps < rows) fetch(r + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {

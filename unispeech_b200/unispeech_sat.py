@@ -229,6 +229,7 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
             if cfg.quantize_targets:
                 vq_dim = cfg.latent_dim if cfg.latent_dim > 0 else self.final_dim
                 assert (vq_dim // cfg.latent_groups) % 64 == 0, "vq_dim / latent_groups must be a multiple of 64 (GEMM K blocks)"
+                assert (cfg.latent_vars * cfg.latent_groups) % 64 == 0, "latent_vars * latent_groups must be a multiple of 64 (GEMM K blocks)"
                 self.quantizer = GumbelVectorQuantizer(D, cfg.latent_vars, tuple(cfg.latent_temp), cfg.latent_groups, vq_dim)
                 self.project_q = nn.Linear(vq_dim, self.final_dim)
             else:
