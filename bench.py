@@ -233,6 +233,9 @@ class Workload:
         self.wav_mixed = torch.empty_like(wav).pin_memory() if sat else None
         self.wav_dev = self.wav_host.to(dev)
         self.R = torch.randn(B, self.T, cfg.encoder_embed_dim, device=dev, generator=torch.Generator(device=dev).manual_seed(7))
+        if ragged:  # the probe loss reads VALID frames only, like every criterion of the reference (padded frames carry no loss)
+            tl = torch.tensor([workloads.num_frames(n, vars(cfg)) for n in self.lengths], device=dev)
+            self.R.mul_((torch.arange(self.T, device=dev)[None, :] < tl[:, None]).unsqueeze(-1))
         self.loss_host = torch.zeros(1).pin_memory()
         self.fwd_flops = workloads.forward_flops(self.L, vars(cfg))          # padded shape (what the kernels execute)
         self.valid_fwd_flops = sum(workloads.forward_flops(n, vars(cfg)) for n in self.lengths) / B   # per utterance at its own length

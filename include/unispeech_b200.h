@@ -70,6 +70,20 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
 int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs,
                      long long x_rs, int rows, int batches, int N, int K, float* dw, long long dw_ld,
                      b200s_stream stream);
+/* Ragged batches (utterances of different lengths, zero-padded to the longest: BASELINE.json configs[4]).  Same contracts as
+ * b200s_gemm_rows / b200s_gemm_wgrad with batches = utterances and rows = padded frames per utterance, plus a DEVICE int32 array
+ * `valid[batches]` = frames of each utterance that hold real audio (padding is a suffix).  gemm_rows_ragged: an M tile that
+ * starts at or beyond valid[b] is not computed; its output rows (and the saved pre-activation) are written as ZEROS (padded rows
+ * must stay finite).  gemm_wgrad_ragged: 64-row blocks that start at or beyond valid[b] are neither loaded nor multiplied --
+ * exact whenever the loss does not read padded frames (their gradient rows are then zero; the reference computes them anyway,
+ * WavLM/WavLM.py:574-575 zeroes the inputs but every row-wise op still runs on them).  Small shapes that take the single-CTA
+ * kernel ignore `valid` (they compute every row). */
+int b200s_gemm_rows_ragged(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
+                           void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, const int* valid,
+                           b200s_stream stream);
+int b200s_gemm_wgrad_ragged(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
+                            int rows, int batches, int N, int K, float* dw, long long dw_ld, const int* valid,
+                            b200s_stream stream);
 
 /* Grouped positional convolution as an implicit GEMM (TransformerEncoder.pos_conv, WavLM/WavLM.py:514-527,577-579;
  * SamePad WavLM/modules.py:72-83), also used for its input gradient with flipped/transposed taps:
@@ -312,7 +326,7 @@ int b200s_f32_to_bf16_rows(const float* src, long long src_rs, void* dst, long l
 /* GumbelVectorQuantizer.forward with hard codes (src/fairseq/modules/gumbel_vector_quantizer.py:141-201; time_first,
  * combine_groups = False): logits bf16 [S, G*V] = weight_proj(x); codes[s*G+g] = argmax_v logits (eval) or argmax_v (logits +
  * Gumbel noise from the counter hash with (key0, key1)) (training: the hard sample of F.gumbel_softmax);
- * q[s, g*dv ..] = vars[g*V + code, :] (bf16; vars fp32 [G*V, dv]); counts[g*V+v] += [v == code], probs[g*V+v] += softmax(logits)_v
+ * q[s, g*dv ..] = vars[g*V + code, :] (bf16; vars fp32 [G*V, dv]); counts[g*V+v] += [v == argmax of the NOISE-FREE logits], probs[g*V+v] += softmax(logits)_v
  * (fp32, the caller zeroes them: hard_probs / avg_probs of :152-170 are these / S). */
 int b200s_vq_hard(const void* logits, long long logits_rs, const float* vars, int S, int G, int V, int dv, int* codes, void* q,
                   long long q_rs, float* counts, float* probs, int gumbel, uint32_t key0, uint32_t key1, b200s_stream stream);

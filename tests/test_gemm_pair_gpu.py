@@ -162,3 +162,47 @@ def test_gelu_derivative_modes(cuda_device, M, K, N):
     ops.dgelu_mul(dy, 0, N, grad, 0, N, o3, 0, N, M, 1, N, None, pre_is_grad=True)
     torch.cuda.synchronize()
     assert (o3.float() - dy.float() * grad.float()).abs().max().item() < 0.02
+
+
+@pytest.mark.parametrize("B,T,K,N,lengths", [(4, 1419, 1024, 1024, [1419, 205, 500, 999]), (3, 700, 768, 3072, [256, 700, 1]),
+                                             (2, 1000, 4096, 1024, [999, 1000])])
+def test_ragged_gemm_rows_and_wgrad(cuda_device, B, T, K, N, lengths):
+    """Ragged batches (BASELINE.json configs[4]): `b200s_gemm_rows_ragged` computes exactly what the dense call computes on every
+    M tile that holds a valid row and writes ZEROS on the tiles that start beyond an utterance's valid frames (output and saved
+    GELU derivative); `b200s_gemm_wgrad_ragged` equals the weight gradient over the live 64-row blocks."""
+    from unispeech_b200 import _lib as L
+    from unispeech_b200 import ops
+    torch.manual_seed(T + K)
+    dev = cuda_device
+    a = bf(torch.randn(B, T, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) / K ** 0.5)
+    bias = torch.randn(N, device=dev)
+    r1 = bf(torch.randn(B, T, N, device=dev))
+    valid = torch.tensor(lengths, dtype=torch.int32, device=dev)
+    out = torch.full((B, T, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    pre = torch.full((B, T, N), float("nan"), device=dev, dtype=torch.bfloat16)
+    epi = L.make_epilogue(bias=bias, gelu=2, out_pre=pre, pre_bs=T * N, pre_ld=N, res1=r1, res1_bs=T * N, res1_ld=N)
+    ops.gemm_rows(a, T * K, K, T, B, K, w, N, out, T * N, N, epi, valid=valid)
+    dense = torch.empty_like(out)
+    pre_d = torch.empty_like(out)
+    epi_d = L.make_epilogue(bias=bias, gelu=2, out_pre=pre_d, pre_ld=N, res1=r1, res1_ld=N)
+    ops.gemm_rows(a, 0, K, B * T, 1, K, w, N, dense.view(B * T, N), 0, N, epi_d)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all() and torch.isfinite(pre.float()).all()   # padded rows stay finite
+    for b, n in enumerate(lengths):
+        live_rows = min(T, -(-n // 256) * 256)   # tiles of 256 rows per utterance: every tile that starts below n is computed
+        assert (out[b, :live_rows].float() - dense[b, :live_rows].float()).abs().max().item() < 0.03
+        assert (pre[b, :live_rows].float() - pre_d[b, :live_rows].float()).abs().max().item() < 0.03
+        if live_rows < T:
+            assert float(out[b, live_rows:].float().abs().max()) == 0.0 and float(pre[b, live_rows:].float().abs().max()) == 0.0
+    # weight gradient: dw[n, k] = sum over live rows of y[b, t, n] x[b, t, k]; rows of a live 64-block beyond `valid` still count
+    y = bf(torch.randn(B, T, N, device=dev))
+    dw = torch.zeros(N, K, device=dev)
+    ops.gemm_wgrad(y, T * N, N, a, T * K, K, T, B, N, K, dw, K, valid=valid)
+    torch.cuda.synchronize()
+    want = torch.zeros(N, K, device=dev)
+    for b, n in enumerate(lengths):
+        live = min(T, -(-n // 64) * 64)
+        want += y[b, :live].float().t() @ a[b, :live].float()
+    scale = want.abs().max().item()
+    assert (dw - want).abs().max().item() < 0.01 * scale + 0.05, ((dw - want).abs().max().item(), scale)

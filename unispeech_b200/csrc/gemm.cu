@@ -322,8 +322,9 @@ int b200s_check_device(void) {
   return 0;
 }
 
-int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
-                    void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, b200s_stream stream) {
+static int gemm_rows_impl(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
+                          void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, const int* m_valid,
+                          b200s_stream stream) {
   B200_CHECK_ARG(a && w && out, "gemm_rows: null pointer");
   B200_CHECK_ARG(rows > 0 && batches > 0 && K > 0 && N > 0, "gemm_rows: bad sizes");
   B200_CHECK_ARG(K % 64 == 0, "gemm_rows: K=%d must be a multiple of 64", K);
@@ -344,7 +345,8 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
   if (pair_kernel_enabled() && pair_epi_ok && N >= 256 && rows >= 256 && static_cast<long long>(rows) * batches >= 2048) {
     // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows (loaded as one box,
     // or as 64-row quarters multicast between two pairs)
-    const int npair = cluster_pairs_for(ceil_div(rows, 256) * batches);
+    const int npair = m_valid != nullptr ? 1 : cluster_pairs_for(ceil_div(rows, 256) * batches);
+    p.m_valid = m_valid;  // ragged batch: tiles beyond a batch's valid rows are zero-filled instead of computed
     ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, npair == 2 ? 64 : 128, 1, 1}};
     if (make_tmap(&tb, vb2)) return -3;
     p.m_rows = rows;
@@ -390,8 +392,20 @@ int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int
                         : launch_gemm<64, false, false>(ta, tb, p, grid, st);
 }
 
-int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
-                     int rows, int batches, int N, int K, float* dw, long long dw_ld, b200s_stream stream) {
+int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
+                    void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, b200s_stream stream) {
+  return gemm_rows_impl(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi, nullptr, stream);
+}
+
+int b200s_gemm_rows_ragged(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,
+                           void* out, long long out_bs, long long out_ld, const b200s_epilogue* epi, const int* m_valid,
+                           b200s_stream stream) {
+  return gemm_rows_impl(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi, m_valid, stream);
+}
+
+static int gemm_wgrad_impl(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
+                           int rows, int batches, int N, int K, float* dw, long long dw_ld, const int* k_valid,
+                           b200s_stream stream) {
   B200_CHECK_ARG(y && x && dw, "gemm_wgrad: null pointer");
   B200_CHECK_ARG(rows > 0 && batches > 0 && K > 0 && N > 0, "gemm_wgrad: bad sizes");
   B200_CHECK_ARG(N % 8 == 0 && K % 8 == 0, "gemm_wgrad: N=%d, K=%d must be multiples of 8", N, K);
@@ -418,6 +432,7 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
     p.tiles_total = p.m_tiles_per_batch * p.n_tiles;
     p.k_blocks_per_batch = ceil_div(rows, 64);
     p.k_blocks = p.k_blocks_per_batch * batches;
+    p.k_valid = k_valid;  // ragged batch: row blocks beyond a batch's valid rows are neither loaded nor multiplied
     // multicast pays only when the M (output-feature) tile count pairs up without much waste
     const int npair = (p.m_tiles_per_batch % 2 == 0 || p.m_tiles_per_batch >= 8) ? cluster_pairs_for(p.m_tiles_per_batch) : 1;
     int units = 0;
@@ -465,6 +480,17 @@ int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   return block_n == 128 ? launch_gemm<128, true, true>(ta, tb, p, grid, st)
                         : launch_gemm<64, true, true>(ta, tb, p, grid, st);
+}
+
+int b200s_gemm_wgrad(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
+                     int rows, int batches, int N, int K, float* dw, long long dw_ld, b200s_stream stream) {
+  return gemm_wgrad_impl(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld, nullptr, stream);
+}
+
+int b200s_gemm_wgrad_ragged(const void* y, long long y_bs, long long y_rs, const void* x, long long x_bs, long long x_rs,
+                            int rows, int batches, int N, int K, float* dw, long long dw_ld, const int* k_valid,
+                            b200s_stream stream) {
+  return gemm_wgrad_impl(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld, k_valid, stream);
 }
 
 int b200s_posconv_gemm(const void* xpad, long long xpad_bs, int T, int B, int D, int G, int taps, const void* wp,

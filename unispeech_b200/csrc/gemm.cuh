@@ -58,6 +58,12 @@ struct GemmParams {
   EpiTensor in[3];
   int n_in;
   int debug;  // diagnostics only (B200S_GEMM_DEBUG): 1 = no epilogue global traffic, 2 = no MMAs, 4 = no TMA loads
+  // ragged batches (CTA-pair kernel only; null = every row counts).  m_valid[b]: rows of batch b that hold real frames -- an M
+  // tile that starts at or beyond it is not computed, its output rows are written as zeros.  k_valid[b] (weight gradients, K
+  // iterates over (batch, row block)): row blocks that start at or beyond it are not loaded / multiplied (their gradient rows
+  // are zero by construction: nothing downstream of a padded frame reaches the loss).
+  const int* m_valid;
+  const int* k_valid;
 };
 
 template <int BLOCK_N>

@@ -191,6 +191,14 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   // item -> (split, m tile of THIS pair, n tile) and its K-block range; identical in every role of the pair's CTAs.
   // `active` is false for the second pair of a cluster when the M tile count is odd: it still loads and multicasts its part
   // of B and keeps the stage barriers flowing, but issues no MMA and has no epilogue.
+  // `active` is also false for a DEAD tile of a ragged batch (p.m_valid: every row of the tile is padding): no loads, no MMAs, the
+  // epilogue writes zeros (NPAIR = 1 only: the host never combines ragged batches with the multicast cluster).  For ragged
+  // weight gradients (p.k_valid) the K range is trimmed to its first live row block and is empty if none is live.
+  auto k_block_live = [&](int kb) {
+    if (p.k_valid == nullptr) return true;
+    const int kbatch = kb / p.k_blocks_per_batch;
+    return (kb - kbatch * p.k_blocks_per_batch) * 64 < p.k_valid[kbatch];
+  };
   auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end, bool& active) {
     const int split = item / sup_tiles;
     const int tile = item % sup_tiles;
@@ -201,6 +209,13 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
     m0 = (mt % p.m_tiles_per_batch) * p.m_tile_stride;
     kb_begin = split * p.k_blocks_per_split;
     kb_end = min(kb_begin + p.k_blocks_per_split, p.k_blocks);
+    if (NPAIR == 1 && p.m_valid != nullptr && active && m0 >= p.m_valid[mb]) active = false;
+    if (p.k_valid != nullptr) {
+      while (kb_begin < kb_end && !k_block_live(kb_begin)) {  // padding is a suffix of every batch: jump to the next batch
+        const int kbatch = kb_begin / p.k_blocks_per_batch;
+        kb_begin = min(kb_end, (kbatch + 1) * p.k_blocks_per_batch);
+      }
+    }
   };
 
   if (warp == 0) {
@@ -215,6 +230,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         bool active;
         decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
         if (kb_begin >= kb_end) continue;
+        if (NPAIR == 1 && !active) continue;  // dead tile of a ragged batch: nothing to load
         v[0] = 1; v[1] = m0 + 128 * static_cast<int>(rank); v[2] = mb; v[3] = n_tile;
         v[4] = 0; v[5] = 0; v[6] = 0; v[7] = 0;
         int ta[4], tb[4];
@@ -232,9 +248,15 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
           kbatch = kb_begin / p.k_blocks_per_batch;
           kin = kb_begin - kbatch * p.k_blocks_per_batch;
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!k_block_live(kb)) {  // padded row block of a ragged weight gradient: skipped by the MMA issuer too
+            if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) { kin = 0; ++kbatch; }
+            else if (p.k_blocks_per_batch == 0) ++kin;
+            continue;
+          }
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
+          ++it;
           int ka[4], kbv[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
@@ -294,6 +316,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         bool active;
         decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
         if (kb_begin >= kb_end) continue;
+        if (NPAIR == 1 && !active) continue;  // dead tile of a ragged batch: the producer loaded nothing
         if (!active) {  // nothing to compute: just hand the stages (which received the multicast B parts) back
           for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
             mbar_wait(&full_bar[it % kStages], (it / kStages) & 1);
@@ -306,9 +329,11 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         tc_fence_after();
         const uint32_t tmem_acc = tmem_base + a * 256;
         bool first = true;
-        for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!k_block_live(kb)) continue;  // (kb_begin itself is live: decode trimmed the range, so `first` is consumed)
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
+          ++it;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * Cfg::kStageBytes);
@@ -342,16 +367,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
     float* bias_s = reinterpret_cast<float*>(smem + kStages * Cfg::kStageBytes + Cfg::kStagingBytes) + ew * 128;
     const int n_in = (KIND == EK_F32) ? 0 : p.n_in;
 
-    // next non-empty work item of this pair at or after `item` (n_items if none)
-    auto next_item = [&](int item) {
-      for (; item < n_items; item += n_pairs) {
-        int mb, m0, n_tile, kb_begin, kb_end;
-        bool active;
-        decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
-        if (kb_begin < kb_end && active) break;
-      }
-      return item;
-    };
+    // which 32 x 128 block of which tile this warp owns (independent of the ragged validity)
     auto tile_of = [&](int item) {
       int mb, m0, n_tile, kb_begin, kb_end;
       bool active;
@@ -366,6 +382,41 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
       et.cols_valid = max(0, min(128, n_valid));
       et.col0 = col_base + half * 128;
       return et;
+    };
+    // dead tile of a ragged batch: its output rows (and the saved pre-activation / derivative) become zeros -- padded frames must
+    // stay FINITE (a NaN in a padded key row would survive the -inf mask as NaN * 0 in the probabilities x V product)
+    auto zero_tile = [&](int item) {
+      if constexpr (KIND != EK_F32) {
+        const EpiTile zt = tile_of(item);
+        const int chunk = lane & 7;
+#pragma unroll 1
+        for (int t2 = 0; t2 < 2; ++t2) {
+          const EpiTensor& t = (t2 == 0) ? p.out : p.out2;
+          if (t.p == nullptr) continue;
+#pragma unroll 1
+          for (int cc = 0; cc < 2; ++cc) {
+            const int colc = cc * 64 + chunk * 8;
+            if (colc >= zt.cols_valid) continue;
+            __nv_bfloat16* base = static_cast<__nv_bfloat16*>(t.p) + zt.mb * t.bs + zt.row0 * t.ld + zt.col0 + colc;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row = i * 4 + (lane >> 3);
+              if (row < zt.rows_valid) *reinterpret_cast<uint4*>(base + row * t.ld) = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
+        }
+      }
+    };
+    // next non-empty work item of this pair at or after `item` (n_items if none); dead tiles met on the way are zero-filled
+    auto next_item = [&](int item) {
+      for (; item < n_items; item += n_pairs) {
+        int mb, m0, n_tile, kb_begin, kb_end;
+        bool active;
+        decode(item, mb, m0, n_tile, kb_begin, kb_end, active);
+        if (kb_begin < kb_end && active) break;
+        if (NPAIR == 1 && p.m_valid != nullptr && kb_begin < kb_end && !active) zero_tile(item);
+      }
+      return item;
     };
     // Input staging protocol.  `early` (exactly one input, no pre-activation output): the input of sequence element
     // (tile, chunk) #seq lives in buffer seq & 1 and the output is staged through the same buffer once the input is consumed, so

@@ -204,20 +204,24 @@ __global__ void __launch_bounds__(256) vq_hard_kernel(const __nv_bfloat16* __res
   for (long long w = (static_cast<long long>(blockIdx.x) * 256 + threadIdx.x) >> 5; w < static_cast<long long>(S) * G; w += warps) {
     const int s = static_cast<int>(w / G), grp = static_cast<int>(w % G);
     const __nv_bfloat16* row = logits + s * l_rs + grp * V;
-    float mx = -INFINITY, hmx = -INFINITY;  // mx: noise-free maximum (statistics); hmx / arg: maximum that selects the code
-    int arg = 0x7fffffff;
+    // carg: arg-max of the NOISE-FREE logits (the logged hard_probs / code_perplexity use it in both modes,
+    // gumbel_vector_quantizer.py:152-163); arg: arg-max that selects the code (with Gumbel noise in training mode)
+    float mx = -INFINITY, hmx = -INFINITY;
+    int carg = 0x7fffffff, arg = 0x7fffffff;
     for (int v = lane; v < V; v += 32) {
       const float x = __bfloat162float(row[v]);
-      mx = fmaxf(mx, x);
+      if (x > mx) { mx = x; carg = v; }
       const float xs = gumbel ? x + gumbel_noise(k0, k1, static_cast<uint32_t>(w) * static_cast<uint32_t>(V) + v) : x;
       if (xs > hmx) { hmx = xs; arg = v; }
     }
-    mx = warp_max(mx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-      const float om = __shfl_xor_sync(0xffffffffu, hmx, o);
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, carg, o);
+      if (om > mx || (om == mx && oc < carg)) { mx = om; carg = oc; }
+      const float oh = __shfl_xor_sync(0xffffffffu, hmx, o);
       const int oa = __shfl_xor_sync(0xffffffffu, arg, o);
-      if (om > hmx || (om == hmx && oa < arg)) { hmx = om; arg = oa; }
+      if (oh > hmx || (oh == hmx && oa < arg)) { hmx = oh; arg = oa; }
     }
     float sum = 0.f;
     for (int v = lane; v < V; v += 32) sum += __expf(__bfloat162float(row[v]) - mx);
@@ -225,7 +229,7 @@ __global__ void __launch_bounds__(256) vq_hard_kernel(const __nv_bfloat16* __res
     const float rs = 1.0f / sum;
     for (int v = lane; v < V; v += 32) atomicAdd(&s_prob[grp * V + v], __expf(__bfloat162float(row[v]) - mx) * rs);
     if (lane == 0) {
-      atomicAdd(&s_cnt[grp * V + arg], 1.0f);
+      atomicAdd(&s_cnt[grp * V + carg], 1.0f);
       codes[w] = arg;
     }
     const float* src = vars + (static_cast<long long>(grp) * V + arg) * dv;

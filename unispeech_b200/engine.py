@@ -165,6 +165,7 @@ class Engine:
         self._params = None
         self.drop: Optional[DR.DropState] = None  # set per forward pass by WavLM._begin (training-mode dropout)
         self.grad_sync = None  # parallel.OverlappedGradSync: told when a stage of the backward pass has produced its gradients
+        self.ragged_valid = None  # int32 [B] valid frames per utterance of the current forward (ragged batch), else None
 
     def backward_stage_done(self, stage):
         if self.grad_sync is not None:
@@ -269,6 +270,27 @@ class Engine:
 
     def g(self, p):  # gradient view of a parameter
         return self.flat.view(p)
+
+    # ---- row-wise GEMMs of the layer stack: flat over all B*T rows, or -- for a ragged batch -- per utterance with the padded
+    # tail of every utterance skipped (`rag`: int32 [B] valid frames on the device, see WavLM.extract_features)
+    @staticmethod
+    def _mm(a, K, w, N, out, rag, T, B, **epi):
+        if rag is None:
+            ops.gemm_rows(a, 0, K, B * T, 1, K, w, N, out, 0, N, L.make_epilogue(**epi) if epi else None)
+            return
+        kw = dict(epi)
+        for name, ldk, bsk in (("res1", "res1_ld", "res1_bs"), ("res2", "res2_ld", "res2_bs"), ("gelu_aux", "aux_ld", "aux_bs"),
+                               ("out_pre", "pre_ld", "pre_bs")):
+            if kw.get(name) is not None:
+                kw[bsk] = T * kw[ldk]
+        ops.gemm_rows(a, T * K, K, T, B, K, w, N, out, T * N, N, L.make_epilogue(**kw) if kw else None, valid=rag)
+
+    @staticmethod
+    def _wg(y, N, x, K, dw, rag, T, B):
+        if rag is None:
+            ops.gemm_wgrad(y, 0, N, x, 0, K, B * T, 1, N, K, dw, K)
+        else:
+            ops.gemm_wgrad(y, T * N, N, x, T * K, K, T, B, N, K, dw, K, valid=rag)
 
     # ---- LayerNorm whose output feeds a gated attention: the gate (WavLM/modules.py:523-533) is computed in the same pass
     def _uses_gate(self) -> bool:
@@ -572,6 +594,7 @@ class Engine:
             raise NotImplementedError("attention_dropout > 0 is implemented in the fused attention kernels for T <= 2048 frames "
                                       f"(got T={T}); set attention_dropout=0 for longer inputs")
         st = dict(x=x, drop=d)
+        rag = self.ragged_valid if pad_u8 is not None else None   # int32 [B] valid frames (ragged batch) or None
         want_gate = tab is not None and cfg.gru_rel_pos
         gate = self._take_gate(x, idx) if (want_gate and not pre_ln) else None
         if pre_ln:
@@ -586,7 +609,7 @@ class Engine:
         else:
             xn = x
         qkv = e(B, T, 3 * D)
-        ops.gemm_rows(xn, 0, D, M, 1, D, w["qkv"], 3 * D, qkv, 0, 3 * D, L.make_epilogue(bias=w["bqkv"]))
+        self._mm(xn, D, w["qkv"], 3 * D, qkv, rag, T, B, bias=w["bqkv"])
         if want_gate and gate is None:  # the producer of x did not leave a gate behind (first use, layerdrop, foreign input)
             gate = f(B, H, T)
             ops.gate_fwd(xn, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, gate)
@@ -600,10 +623,10 @@ class Engine:
             ops.attn_fwd(qkv, gate, tab, pad_u8, ao, lse, B, T, H, 64 ** -0.5)
         y1 = e(B, T, D)
         if p_h > 0:  # x + dropout1(out_proj(attn)), WavLM/WavLM.py:702-703,726-727
-            ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias))
+            self._mm(ao, D, w["o"], D, y1, rag, T, B, bias=a.out_proj.bias)
             ops.dropout_rows(y1, T * D, D, x, T * D, D, y1, T * D, D, T, B, D, p_h, d.key(DR.layer_site(idx, DR.L_DROPOUT1)))
         else:
-            ops.gemm_rows(ao, 0, D, M, 1, D, w["o"], D, y1, 0, D, L.make_epilogue(bias=a.out_proj.bias, res1=x, res1_ld=D))
+            self._mm(ao, D, w["o"], D, y1, rag, T, B, bias=a.out_proj.bias, res1=x, res1_ld=D)
         if pre_ln:
             x1 = y1
             x1n, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
@@ -617,8 +640,7 @@ class Engine:
             ffn_in = x1
         hg = e(B, T, Fd)
         hp = e(B, T, Fd) if save else None
-        ops.gemm_rows(ffn_in, 0, D, M, 1, D, w["w1"], Fd, hg, 0, Fd,
-                      L.make_epilogue(bias=lyr.fc1.bias, gelu=2, out_pre=hp, pre_ld=Fd))  # hp = gelu'(fc1 output)
+        self._mm(ffn_in, D, w["w1"], Fd, hg, rag, T, B, bias=lyr.fc1.bias, gelu=2, out_pre=hp, pre_ld=Fd)  # hp = gelu'(fc1 output)
         if p_act > 0:  # dropout2 after the activation (WavLM/WavLM.py:711,736); the same mask folded into the stored
             # derivative makes the backward epilogue (dy * hp) the gradient through activation AND dropout
             k_act = d.key(DR.layer_site(idx, DR.L_ACTIVATION))
@@ -627,10 +649,10 @@ class Engine:
                 ops.dropout_rows(hp, T * Fd, Fd, None, 0, 0, hp, T * Fd, Fd, T, B, Fd, p_act, k_act)
         y2 = e(B, T, D)
         if p_h > 0:  # residual + dropout3(fc2(.)), WavLM/WavLM.py:713-714,738-739
-            ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias))
+            self._mm(hg, Fd, w["w2"], D, y2, rag, T, B, bias=lyr.fc2.bias)
             ops.dropout_rows(y2, T * D, D, x1, T * D, D, y2, T * D, D, T, B, D, p_h, d.key(DR.layer_site(idx, DR.L_DROPOUT3)))
         else:
-            ops.gemm_rows(hg, 0, Fd, M, 1, Fd, w["w2"], D, y2, 0, D, L.make_epilogue(bias=lyr.fc2.bias, res1=x1, res1_ld=D))
+            self._mm(hg, Fd, w["w2"], D, y2, rag, T, B, bias=lyr.fc2.bias, res1=x1, res1_ld=D)
         if pre_ln:
             out = y2
         else:
@@ -642,7 +664,7 @@ class Engine:
                 ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
         if save:
             st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8,
-                      dmask=dmask)
+                      dmask=dmask, rag=rag)
         return out, (st if save else None)
 
     def layer_backward(self, idx: int, st, dout: torch.Tensor, dtab):
@@ -660,6 +682,7 @@ class Engine:
         g = self.g
         pre_ln = cfg.layer_norm_first
         tab, pad = st["tab"], st["pad"]
+        rag = st["rag"]
         d = st["drop"]
         p_h = d.p if d is not None else 0.0
         p_a = d.p_attn if d is not None else 0.0
@@ -683,15 +706,14 @@ class Engine:
             if p_h > 0:
                 dz2 = through_dropout(dy2, DR.L_DROPOUT3)
                 ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias))
-        ops.gemm_wgrad(dz2, 0, D, st["hg"], 0, Fd, M, 1, D, Fd, g(lyr.fc2.weight), Fd)
+        self._wg(dz2, D, st["hg"], Fd, g(lyr.fc2.weight), rag, T, B)
         dhp = e(B, T, Fd)
-        ops.gemm_rows(dz2, 0, D, M, 1, D, w["w2T"], Fd, dhp, 0, Fd,
-                      L.make_epilogue(dgelu=2, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias)))
-        ops.gemm_wgrad(dhp, 0, Fd, st["ffn_in"], 0, D, M, 1, Fd, D, g(lyr.fc1.weight), D)
+        self._mm(dz2, D, w["w2T"], Fd, dhp, rag, T, B, dgelu=2, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias))
+        self._wg(dhp, Fd, st["ffn_in"], D, g(lyr.fc1.weight), rag, T, B)
         dx1 = e(B, T, D)
         if pre_ln:
             dffn_in = e(B, T, D)
-            ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dffn_in, 0, D, None)
+            self._mm(dhp, Fd, w["w1T"], D, dffn_in, rag, T, B)
             ln = lyr.final_layer_norm
             # (without dropout1 the out_proj bias gradient is the column sum of dx1: taken inside the LayerNorm backward)
             ops.layer_norm_bwd(dffn_in, T * D, D, st["x1"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, dy2, T * D, D,
@@ -702,7 +724,7 @@ class Engine:
                 dz1 = through_dropout(dy1, DR.L_DROPOUT1)
                 ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
         else:
-            ops.gemm_rows(dhp, 0, Fd, M, 1, Fd, w["w1T"], D, dx1, 0, D, L.make_epilogue(res1=dy2, res1_ld=D))
+            self._mm(dhp, Fd, w["w1T"], D, dx1, rag, T, B, res1=dy2, res1_ld=D)
             dy1 = e(B, T, D)
             ln = lyr.self_attn_layer_norm
             ops.layer_norm_bwd(dx1, T * D, D, st["y1"], T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, None, 0, 0,
@@ -712,9 +734,9 @@ class Engine:
                 dz1 = through_dropout(dy1, DR.L_DROPOUT1)
                 ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
         # ---------------- attention block
-        ops.gemm_wgrad(dz1, 0, D, st["ao"], 0, D, M, 1, D, D, g(a.out_proj.weight), D)
+        self._wg(dz1, D, st["ao"], D, g(a.out_proj.weight), rag, T, B)
         dao = e(B, T, D)
-        ops.gemm_rows(dz1, 0, D, M, 1, D, w["oT"], D, dao, 0, D, None)
+        self._mm(dz1, D, w["oT"], D, dao, rag, T, B)
         dqkv = e(B, T, 3 * D)
         delta = f(B, H, T)
         gate = st["gate"]
@@ -740,16 +762,20 @@ class Engine:
             dxg = e(B, T, D)
             ops.gate_bwd(attn_in, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, dgate, dxg, T * D, D,
                          g(a.grep_linear.weight), g(a.grep_linear.bias), g(a.grep_a))
-        ops.gemm_wgrad(dqkv, 0, 3 * D, attn_in, 0, D, M, 1, 3 * D, D, g(a.q_proj.weight), D)
+        self._wg(dqkv, 3 * D, attn_in, D, g(a.q_proj.weight), rag, T, B)
         dx = e(B, T, D)
         if pre_ln:
             dxn = e(B, T, D)
-            ops.gemm_rows(dqkv, 0, 3 * D, M, 1, 3 * D, w["qkvT"], D, dxn, 0, D,
-                          L.make_epilogue(res1=dxg, res1_ld=D) if dxg is not None else None)
+            if dxg is not None:
+                self._mm(dqkv, 3 * D, w["qkvT"], D, dxn, rag, T, B, res1=dxg, res1_ld=D)
+            else:
+                self._mm(dqkv, 3 * D, w["qkvT"], D, dxn, rag, T, B)
             ln = lyr.self_attn_layer_norm
             ops.layer_norm_bwd(dxn, T * D, D, x, T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, dy1, T * D, D, dx,
                                T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
         else:
-            ops.gemm_rows(dqkv, 0, 3 * D, M, 1, 3 * D, w["qkvT"], D, dx, 0, D,
-                          L.make_epilogue(res1=dy1, res1_ld=D, res2=dxg, res2_ld=D))
+            if dxg is not None:
+                self._mm(dqkv, 3 * D, w["qkvT"], D, dx, rag, T, B, res1=dy1, res1_ld=D, res2=dxg, res2_ld=D)
+            else:
+                self._mm(dqkv, 3 * D, w["qkvT"], D, dx, rag, T, B, res1=dy1, res1_ld=D)
         return dx

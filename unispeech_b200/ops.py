@@ -57,13 +57,22 @@ def _call(name, *args, flops=0.0):
 
 
 # ------------------------------------------------------------------------------------------------- GEMM family
-def gemm_rows(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi: Optional[L.Epilogue] = None):
+def gemm_rows(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi: Optional[L.Epilogue] = None, valid=None):
+    """`valid` (int32 [batches] on the device): ragged batch -- M tiles beyond an utterance's valid frames are zero-filled."""
+    if valid is not None:
+        return _call("b200s_gemm_rows_ragged", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
+                     L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, L.ptr(valid), _s(),
+                     flops=2.0 * rows * batches * K * N)
     _call("b200s_gemm_rows", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
            L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s(),
           flops=2.0 * rows * batches * K * N)
 
 
-def gemm_wgrad(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld):
+def gemm_wgrad(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld, valid=None):
+    """`valid` (int32 [batches] on the device): ragged batch -- row blocks beyond an utterance's valid frames are skipped."""
+    if valid is not None:
+        return _call("b200s_gemm_wgrad_ragged", L.ptr(y), L.ll(y_bs), L.ll(y_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows),
+                     i32(batches), i32(N), i32(K), L.ptr(dw), L.ll(dw_ld), L.ptr(valid), _s(), flops=2.0 * rows * batches * K * N)
     _call("b200s_gemm_wgrad", L.ptr(y), L.ll(y_bs), L.ll(y_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows),
            i32(batches), i32(N), i32(K), L.ptr(dw), L.ll(dw_ld), _s(), flops=2.0 * rows * batches * K * N)
 

@@ -448,6 +448,7 @@ class TransformerEncoder(nn.Module):
         er = None
         pos_bias = self._make_bias_state(T, x.device) if self.relative_position_embedding else None
         pad_u8 = padding_mask.to(torch.uint8).contiguous() if padding_mask is not None else None
+        eng.ragged_valid = getattr(padding_mask, "_b200_valid", None) if padding_mask is not None else None
         for i, layer in enumerate(self.layers):
             dropout_probability = np.random.random()
             if not self.training or (dropout_probability > self.layerdrop):
@@ -462,6 +463,7 @@ class TransformerEncoder(nn.Module):
             if tgt_list is None and i == tgt_layer:
                 r = x
                 break
+        eng.ragged_valid = None  # belongs to this batch only (a layer called on its own later computes every row)
         if r is not None:
             x = r
         if extract_layer is not None:
@@ -583,6 +585,17 @@ class WavLM(nn.Module):
             if fpm is not None and fpm_host is None:
                 fpm_host = fpm.cpu()  # device-resident mask: one sync, exactly like the reference's `.item()` per row
             mask_indices = self.apply_mask(B, T, fpm_host)
+        # ragged batch: frames of every utterance up to its last valid one (host arithmetic when the mask lives on the host; with
+        # a device-only mask two tiny device ops, no synchronisation).  The layer GEMMs skip the padded tail of every utterance.
+        # The tensor travels to the encoder as an attribute of the frame mask, so a stale one can never meet another batch.
+        if fpm is not None:
+            if fpm_host is not None:
+                if bool(fpm_host.any()):
+                    last = ((~fpm_host).to(torch.int32) * torch.arange(1, T + 1, dtype=torch.int32)).amax(1)
+                    fpm._b200_valid = last.to(torch.int32).contiguous().to(source.device, non_blocking=True)
+            else:
+                fpm._b200_valid = ((~fpm).to(torch.int32) * torch.arange(1, T + 1, dtype=torch.int32, device=fpm.device)) \
+                    .amax(1).to(torch.int32).contiguous()
         mask_u8 = mask_indices.to(device=source.device, dtype=torch.uint8).contiguous() if mask_indices is not None else None
         pad_u8 = fpm.to(torch.uint8).contiguous() if fpm is not None else None
         xv, features = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv)
