@@ -566,6 +566,22 @@ def main():
                     "flop_per_launch": gemm_flops / max(n_gemm, 1), "launches_per_step": n_gemm,
                     "us_per_launch": gemm_ms * 1e3 / max(n_gemm, 1), "traffic": traffic, "traffic_source": traffic_src,
                     "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / (ms / args.steps)}
+        # the other kernel families of the same profiled step, each against its own bound (algorithmic work / CUDA-event time)
+        fam = {}
+        att = {k: v for k, v in breakdown.items() if k.startswith("attn_")}
+        for k, v in att.items():
+            if v["ms"] > 0 and v["flops"] > 0:
+                tf = v["flops"] / (v["ms"] * 1e-3) / 1e12
+                fam[k] = {"bound": "tensor (+ SFU: one exp2 per score)", "achieved": tf, "unit": "TFLOP/s (algorithmic)",
+                          "frac": tf / peak, "ms_per_step": v["ms"], "launches": v["calls"]}
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        for k in ("layer_norm_fwd", "layer_norm_gate_fwd", "layer_norm_bwd", "colsum"):
+            v = breakdown.get(k)
+            if v and v["ms"] > 0 and v["bytes"] > 0:
+                gbs = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+                fam[k] = {"bound": "hbm", "achieved": gbs, "unit": "GB/s (algorithmic)", "frac": gbs / hbm_peak,
+                          "ms_per_step": v["ms"], "launches": v["calls"]}
+        roofline["other_families"] = fam
 
     parity = None
     if rank == 0 and not args.no_profile:

@@ -180,3 +180,23 @@ def test_encoder_variants_fairseq_and_sat(cuda_device):
     for (g, _), w in zip(got_lr2, want_lr2):
         cmp("layer_result", g.transpose(0, 1), w.transpose(0, 1), mask=fpm)
     cmp("x2", got_x2, want_x2, mask=fpm)
+
+
+def test_deepcopy_gets_its_own_engine(cuda_device):
+    """EMA / teacher copies: a deep copy must derive its bf16 operands from ITS OWN masters, not from the original's (the engine's
+    descriptor tables hold raw device pointers)."""
+    import copy
+    cfg = O.tiny_config(pre_ln=True)
+    m = build(cfg, cuda_device)
+    wav, _ = O.deterministic_waveform(1, 6400, seed=1)
+    with torch.no_grad():
+        x0, _ = m.extract_features(wav.to(cuda_device))
+        c = copy.deepcopy(m)
+        assert c._engine is None and m._engine is not None
+        assert c.encoder.layers[0]._owner[0] is c
+        c.encoder.layers[0].fc1.weight.mul_(1.5)
+        c.post_extract_proj.bias.add_(0.3)
+        x1, _ = m.extract_features(wav.to(cuda_device))
+        y1, _ = c.extract_features(wav.to(cuda_device))
+    assert torch.equal(x0, x1)                              # the original is untouched by the copy's parameter edits
+    assert (y1.float() - x0.float()).abs().max().item() > 1e-2   # and the copy really uses its own (edited) weights

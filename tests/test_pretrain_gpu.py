@@ -199,7 +199,9 @@ def test_clip_norm_ignores_parameters_the_optimizer_does_not_own(cuda_device):
         assert abs(got - want) < 1e-4 * want, (it, got, want)
         norms.append(got)
         opt.step(zero_grad=True)
-    assert abs(norms[2] - norms[0]) < 1e-3 * norms[0], norms
+    # (identical steps differ by bf16 rounding of atomically reduced gradients, ~1e-3; an accumulating frozen gradient would add
+    # several per cent per step)
+    assert abs(norms[2] - norms[0]) < 1e-2 * norms[0], norms
 
 
 def test_optimisation_steps_reduce_the_loss(cuda_device):

@@ -30,10 +30,11 @@ class Profiler:
     def summary(self):
         torch.cuda.synchronize()
         out = {}
-        for name, flops, e0, e1 in self.records:
-            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "calls": 0})
+        for name, flops, nbytes, e0, e1 in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "flops": 0.0, "bytes": 0.0, "calls": 0})
             d["ms"] += e0.elapsed_time(e1)
             d["flops"] += flops
+            d["bytes"] += nbytes
             d["calls"] += 1
         return out
 
@@ -46,14 +47,15 @@ def set_profiler(p: Optional[Profiler]):
     _profiler = p
 
 
-def _call(name, *args, flops=0.0):
+def _call(name, *args, flops=0.0, nbytes=0.0):
+    """`flops` / `nbytes`: ALGORITHMIC work of the call (logical tensors read / written once), recorded by the step profiler."""
     if _profiler is None:
         return L.call(name, *args)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     L.call(name, *args)
     e1.record()
-    _profiler.records.append((name[len("b200s_"):], flops, e0, e1))
+    _profiler.records.append((name[len("b200s_"):], flops, nbytes, e0, e1))
 
 
 # ------------------------------------------------------------------------------------------------- GEMM family
@@ -91,13 +93,14 @@ def posconv_wgrad(dy, dy_bs, dy_rs, xpad, xpad_bs, T, B, D, G, taps, dwp):
 # ------------------------------------------------------------------------------------------------- row kernels
 def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu=False):
     _call("b200s_layer_norm_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
-           L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s())
+           L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s(),
+          nbytes=2.0 * 2 * rows_per_batch * batches * D)
 
 
 def layer_norm_gate_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate):
     _call("b200s_layer_norm_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
            L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(T), i32(B), i32(D), L.ptr(grep_w), L.ptr(grep_b), L.ptr(grep_a), i32(H),
-           L.ptr(gate), _s())
+           L.ptr(gate), _s(), nbytes=2.0 * 2 * T * B * D)
 
 
 def layer_norm_bwd(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
@@ -105,11 +108,12 @@ def layer_norm_bwd(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dre
     _call("b200s_layer_norm_bwd", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean),
            L.ptr(rstd), L.ptr(gamma), L.ptr(beta), L.ptr(dres), L.ll(dres_bs), L.ll(dres_rs), L.ptr(dx), L.ll(dx_bs),
            L.ll(dx_rs), L.ptr(dgamma), L.ptr(dbeta), L.ptr(colsum), i32(rows_per_batch), i32(batches), i32(D),
-           i32(1 if gelu else 0), _s())
+           i32(1 if gelu else 0), _s(), nbytes=(4.0 if dres is not None else 3.0) * 2 * rows_per_batch * batches * D)
 
 
 def colsum(x, x_bs, x_rs, rows_per_batch, batches, N, out):
-    _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s())
+    _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s(),
+          nbytes=2.0 * rows_per_batch * batches * N)
 
 
 def dgelu_mul(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum_out=None,
@@ -205,17 +209,19 @@ def posconv_unprep(weight_v, weight_g, dwp, D, G, taps, work, dweight_v, dweight
 # ------------------------------------------------------------------------------------------------- attention
 def attn_fwd(qkv, gate, tab, key_pad, out, lse, B, T, H, scale):
     _call("b200s_attn_fwd", L.ptr(qkv), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(out), L.ptr(lse), i32(B), i32(T),
-           i32(H), f32(scale), _s())
+           i32(H), f32(scale), _s(), flops=4.0 * B * H * T * T * 64)
 
 
 def attn_bwd(qkv, out, dout, gate, tab, key_pad, lse, delta, dqkv, dgate, dtab, B, T, H, scale):
     _call("b200s_attn_bwd", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
-           L.ptr(delta), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
+           L.ptr(delta), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s(),
+          flops=10.0 * B * H * T * T * 64)
 
 
 def attn_bwd_fused(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale):
     _call("b200s_attn_bwd_fused", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(lse),
-           L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s())
+           L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale), _s(),
+          flops=10.0 * B * H * T * T * 64)
 
 
 # ------------------------------------------------------------------------------------------------- dropout
@@ -251,14 +257,14 @@ def attn_dropout_mask_words(B, T, H) -> int:
 
 def attn_fwd_dropout(qkv, gate, tab, key_pad, out, lse, B, T, H, scale, p, key, drop_mask):
     _call("b200s_attn_fwd_dropout", L.ptr(qkv), L.ptr(gate), L.ptr(tab), L.ptr(key_pad), L.ptr(out), L.ptr(lse), i32(B), i32(T),
-           i32(H), f32(scale), f32(p), u32(key[0]), u32(key[1]), L.ptr(drop_mask), _s())
+           i32(H), f32(scale), f32(p), u32(key[0]), u32(key[1]), L.ptr(drop_mask), _s(), flops=4.0 * B * H * T * T * 64)
 
 
 def attn_bwd_fused_dropout(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, scale, p,
                            drop_mask):
     _call("b200s_attn_bwd_fused_dropout", L.ptr(qkv), L.ptr(out), L.ptr(dout), L.ptr(gate), L.ptr(tab), L.ptr(key_pad),
            L.ptr(lse), L.ptr(delta), L.ptr(dq_acc), L.ptr(dqkv), L.ptr(dgate), L.ptr(dtab), i32(B), i32(T), i32(H), f32(scale),
-           f32(p), L.ptr(drop_mask), _s())
+           f32(p), L.ptr(drop_mask), _s(), flops=10.0 * B * H * T * T * 64)
 
 
 # ------------------------------------------------------------------------------------------------- optimizer

@@ -500,6 +500,17 @@ class WavLM(nn.Module):
         self._engine: Optional[Engine] = None
         self.dropout_seed: Optional[int] = None  # None: draw a fresh seed per forward; an int pins the dropout masks (tests)
 
+    def __deepcopy__(self, memo):
+        """`copy.deepcopy(model)` (EMA / teacher copies, checkpoint averaging): the engine holds raw device pointers to THIS model's
+        masters (operand-preparation and optimizer descriptor tables), so the copy must not inherit it -- it builds its own on its
+        first forward pass."""
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = None if k == "_engine" else copy.deepcopy(v, memo)
+        return new
+
     # ---- engine plumbing
     def _engine_for(self, device) -> Engine:
         if device.type != "cuda":
