@@ -121,7 +121,7 @@ def test_layer_norm_gate_fwd(cuda_device, H):
     assert (g1 - g2).abs().max().item() < 1e-5
 
 
-@pytest.mark.parametrize("H", [2, 12])
+@pytest.mark.parametrize("H", [2, 12, 16])
 def test_gate_fwd_bwd(cuda_device, H):
     from unispeech_b200 import ops
     dev = cuda_device

@@ -35,6 +35,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default=None)
+    ap.add_argument("--large", action="store_true", help="WavLM-Large 8 x 20 s shapes (7992 rows, D = 1024, F = 4096), layer GEMMs only")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     L.check_device()
@@ -55,6 +56,14 @@ def main():
                            ("conv6", 749, 2)):
         cases.append((name, "conv", T_out, 16, k * 512, 512))
         cases.append((name + "_wgrad", "convw", T_out, 16, k * 512, 512))
+    if args.large:
+        M = 8 * 999
+        cases = []
+        for name, K, N in (("qkv", 1024, 3072), ("out_proj", 1024, 1024), ("fc1", 1024, 4096), ("fc2", 4096, 1024),
+                           ("qkv_dgrad", 3072, 1024)):
+            cases.append((name, "rows", M, 1, K, N))
+        for name, N, K in (("wgrad_qkv", 3072, 1024), ("wgrad_o", 1024, 1024), ("wgrad_fc1", 4096, 1024), ("wgrad_fc2", 1024, 4096)):
+            cases.append((name, "wgrad", M, 1, K, N))
     print(f"{'case':14s} {'ms':>8s} {'TFLOP/s':>9s} {'frac':>6s}")
     for name, kind, rows, batches, K, N in cases:
         if args.only and name not in args.only.split(','):

@@ -10,6 +10,7 @@ from unispeech_b200 import ops
 ap = argparse.ArgumentParser()
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--only", default=None)
+ap.add_argument("--norms", action="store_true", help="LayerNorm / gate / column-sum kernels only (skip dropout and Adam)")
 args = ap.parse_args()
 dev = torch.device("cuda:0")
 try:
@@ -43,6 +44,32 @@ for name, B, T, D, F, nparam in (("base", 16, 749, 768, 3072, 94_381_936), ("lar
         ("dropout_rows [B,T,D] y=res+drop(x)", lambda: ops.dropout_rows(x, T * D, D, res, T * D, D, y, T * D, D, T, B, D, 0.1, (1, 2)), 3 * 2 * B * T * D),
         ("dropout_rows [B,T,F] in place", lambda: ops.dropout_rows(h, T * F, F, None, 0, 0, h, T * F, F, T, B, F, 0.1, (1, 2)), 2 * 2 * B * T * F),
     ]
+    H = D // 64
+    f32 = lambda *sh: torch.randn(*sh, device=dev)
+    gam, bet, mean, rstd = f32(D), f32(D), f32(B * T), f32(B * T).abs() + 0.5
+    dgam, dbet, csum = torch.zeros(D, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    gw, gb, ga_ = f32(8, 64) * 0.1, f32(8) * 0.1, f32(H)
+    gate, dgate = torch.empty(B, H, T, device=dev), f32(B, H, T)
+    dgw, dgb, dga = torch.zeros(8, 64, device=dev), torch.zeros(8, device=dev), torch.zeros(H, device=dev)
+    qkv = torch.randn(B * T, 3 * D, device=dev).to(torch.bfloat16)
+    csum3 = torch.zeros(3 * D, device=dev)
+    E = 2 * B * T * D
+    rows += [
+        ("layer_norm_fwd", lambda: ops.layer_norm_fwd(x, T * D, D, gam, bet, y, T * D, D, mean, rstd, T, B, D), 2 * E),
+        ("layer_norm_gate_fwd", lambda: ops.layer_norm_gate_fwd(x, T * D, D, gam, bet, y, T * D, D, mean, rstd, T, B, D, gw, gb, ga_, H, gate), 2 * E),
+        ("layer_norm_bwd (+dres, colsum)", lambda: ops.layer_norm_bwd(x, T * D, D, res, T * D, D, mean, rstd, gam, bet, res, T * D, D, y, T * D, D, dgam, dbet, csum, T, B, D), 4 * E),
+        ("layer_norm_bwd (plain)", lambda: ops.layer_norm_bwd(x, T * D, D, res, T * D, D, mean, rstd, gam, bet, None, 0, 0, y, T * D, D, dgam, dbet, None, T, B, D), 3 * E),
+        ("gate_bwd", lambda: ops.gate_bwd(x, T * D, D, T, B, H, gw, gb, ga_, dgate, y, T * D, D, dgw, dgb, dga), 2 * E),
+        ("colsum [B*T, D]", lambda: ops.colsum(x, T * D, D, T, B, D, csum), E),
+        ("colsum [B*T, 3D]", lambda: ops.colsum(qkv, 0, 3 * D, B * T, 1, 3 * D, csum3), 3 * E),
+    ]
+    if args.norms:
+        rows = rows[3:]
+        for label, fn, nbytes in rows:
+            ms = timeit(fn, args.reps)
+            gbs = nbytes / (ms * 1e-3) / 1e9
+            print(f"{name:6s} {label:38s} {ms*1e3:9.1f} us  {nbytes/1e6:9.1f} MB  {gbs:8.0f} GB/s  = {gbs/peak:5.2f} of measured HBM peak {peak:.0f}", flush=True)
+        continue
     # Adam over one flat tensor of the model's parameter count (the table has one record per parameter tensor in the model;
     # here a handful of large records: the kernel's cost is per element)
     n = (nparam + 3) // 4 * 4

@@ -1,0 +1,9 @@
+#!/bin/bash
+# Round-2 GPU call E: full GPU suite, ragged bench line (configs[4]), default bench line.
+TAG=${1:-x}
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -q -m gpu -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest exit $?"; tail -8 gpurun_out/pytest_gpu_$TAG.log | cut -c1-220
+timeout 600 python bench.py --ragged --no-also > gpurun_out/bench_ragged_$TAG.json 2> gpurun_out/bench_ragged_$TAG.err; echo "ragged exit $?"; cut -c1-400 gpurun_out/bench_ragged_$TAG.json; tail -2 gpurun_out/bench_ragged_$TAG.err
+timeout 600 python bench.py --no-also > gpurun_out/bench_large_$TAG.json 2> gpurun_out/bench_large_$TAG.err; echo "bench exit $?"; cut -c1-300 gpurun_out/bench_large_$TAG.json; tail -3 gpurun_out/bench_large_$TAG.err
+timeout 300 python tools/bench_rowops.py --norms --only large > gpurun_out/microbench_norms_$TAG.txt 2>&1; cat gpurun_out/microbench_norms_$TAG.txt
+timeout 300 python tools/bench_gemm.py --large > gpurun_out/microbench_gemm_large_$TAG.txt 2>&1; cat gpurun_out/microbench_gemm_large_$TAG.txt

@@ -65,10 +65,12 @@ def build(force: bool = False, verbose: bool = False) -> Path:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    cmd = [nvcc, "-shared", "-o", str(LIB), *map(str, objs), "-cudart", "static"]
+    tmp = BUILD / (LIB.name + ".tmp")  # linked aside and renamed: a reader (or a repo snapshot) never sees a half-written library
+    cmd = [nvcc, "-shared", "-o", str(tmp), *map(str, objs), "-cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp, LIB)
     stamp.write_text(dig)
     return LIB
 

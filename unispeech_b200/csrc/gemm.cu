@@ -346,7 +346,9 @@ static int gemm_rows_impl(const void* a, long long a_bs, long long a_rs, int row
     // persistent CTA-pair kernel: 256 x 256 tiles, each CTA stages 128 A rows and 128 of the 256 B rows (loaded as one box,
     // or as 64-row quarters multicast between two pairs)
     const int npair = m_valid != nullptr ? 1 : cluster_pairs_for(ceil_div(rows, 256) * batches);
-    p.m_valid = m_valid;  // ragged batch: tiles beyond a batch's valid rows are zero-filled instead of computed
+    // ragged batch: tiles beyond a batch's valid rows are zero-filled instead of computed (too many batches for the kernel's
+    // prefix table: computed densely, which is what the padded path has always done)
+    p.m_valid = (batches <= kMaxRagBatches && ceil_div(rows, 256) * batches < 65536) ? m_valid : nullptr;
     ViewSpec vb2{w, {K, N, 1, 1}, {K, 0, 0}, {64, npair == 2 ? 64 : 128, 1, 1}};
     if (make_tmap(&tb, vb2)) return -3;
     p.m_rows = rows;
@@ -432,7 +434,8 @@ static int gemm_wgrad_impl(const void* y, long long y_bs, long long y_rs, const 
     p.tiles_total = p.m_tiles_per_batch * p.n_tiles;
     p.k_blocks_per_batch = ceil_div(rows, 64);
     p.k_blocks = p.k_blocks_per_batch * batches;
-    p.k_valid = k_valid;  // ragged batch: row blocks beyond a batch's valid rows are neither loaded nor multiplied
+    // ragged batch: row blocks beyond a batch's valid rows are neither loaded nor multiplied
+    p.k_valid = (batches <= kMaxRagBatches && p.k_blocks < 65536) ? k_valid : nullptr;
     // multicast pays only when the M (output-feature) tile count pairs up without much waste
     const int npair = (p.m_tiles_per_batch % 2 == 0 || p.m_tiles_per_batch >= 8) ? cluster_pairs_for(p.m_tiles_per_batch) : 1;
     int units = 0;

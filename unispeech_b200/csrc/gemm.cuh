@@ -34,6 +34,9 @@ enum : int {
 // variables the coordinate matrices multiply: {1, m0, mb, n_tile, k0, kbatch, kb, sub}
 constexpr int kCoordVars = 8;
 
+// ragged batches: at most this many batches per launch take the live-unit schedule (the per-batch prefix lives in shared memory)
+constexpr int kMaxRagBatches = 255;
+
 struct GemmParams {
   int m_rows;            // valid rows per batch
   int m_tiles_per_batch; // ceil over m_tile_stride

@@ -42,7 +42,7 @@ struct Gemm2Cfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStagingBytes + kBiasBytes + 1024;
   static constexpr int kThreads = 320;  // TMA warp + MMA warp + 8 epilogue warps
   static constexpr int kTileM = 256, kTileN = 256;
-  static_assert(kSmemBytes + 256 <= 232448, "pair GEMM exceeds the 227 KB shared-memory limit");
+  static_assert(kSmemBytes + 1792 <= 232448, "pair GEMM exceeds the 227 KB shared-memory limit");
 };
 
 // ---------------------------------------------------------------- staged (coalesced) epilogue helpers
@@ -188,33 +188,91 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   const uint32_t tmem_base = tmem_base_smem;
   pdl_wait();  // everything above overlapped the previous kernel's tail; global memory is touched only from here on
 
+  // Ragged batches (p.m_valid: valid rows per batch of an activation GEMM; p.k_valid: the same for the reduction dimension of a
+  // weight gradient).  Padding is a suffix of every batch, so the live units of batch b are its first live_b M tiles (or 64-row K
+  // blocks); rag_pref[b] = live units of batches < b.  Work is then enumerated over LIVE units only -- a static round-robin over
+  // the dense tile grid would leave most of the gain on the table (the dead tiles of a short utterance are consecutive items) --
+  // and the dead M tiles, which only have to be zero-filled, are appended after the live ones.
+  __shared__ uint16_t rag_pref[kMaxRagBatches + 1];
+  const int* rag = p.m_valid != nullptr ? p.m_valid : p.k_valid;
+  const int rag_unit = p.m_valid != nullptr ? p.m_tile_stride : 64;
+  const int rag_per_batch = p.m_valid != nullptr ? p.m_tiles_per_batch : p.k_blocks_per_batch;
+  const int rag_batches = rag == nullptr ? 0 : (p.m_valid != nullptr ? m_tiles_total : p.k_blocks) / rag_per_batch;
+  if (rag != nullptr) {
+    if (warp == 2) {
+      int carry = 0;
+      for (int b0 = 0; b0 < rag_batches; b0 += 32) {
+        const int b = b0 + lane;
+        int incl = 0;
+        if (b < rag_batches) incl = min(rag_per_batch, max(0, (rag[b] + rag_unit - 1) / rag_unit));
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += t;
+        }
+        if (b < rag_batches) rag_pref[b + 1] = static_cast<uint16_t>(carry + incl);
+        carry += __shfl_sync(0xffffffffu, incl, 31);
+      }
+      if (lane == 0) rag_pref[0] = 0;
+    }
+    __syncthreads();
+  }
+  const int rag_live = rag != nullptr ? rag_pref[rag_batches] : 0;
+  // batch holding live unit r (0 <= r < rag_live) / dead unit d (0 <= d < total - rag_live)
+  auto live_batch = [&](int r) {
+    int lo = 0, hi = rag_batches;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (rag_pref[mid] <= r) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+  auto dead_batch = [&](int d) {
+    int lo = 0, hi = rag_batches;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (mid * rag_per_batch - rag_pref[mid] <= d) lo = mid; else hi = mid;
+    }
+    return lo;
+  };
+
   // item -> (split, m tile of THIS pair, n tile) and its K-block range; identical in every role of the pair's CTAs.
   // `active` is false for the second pair of a cluster when the M tile count is odd: it still loads and multicasts its part
   // of B and keeps the stage barriers flowing, but issues no MMA and has no epilogue.
   // `active` is also false for a DEAD tile of a ragged batch (p.m_valid: every row of the tile is padding): no loads, no MMAs, the
-  // epilogue writes zeros (NPAIR = 1 only: the host never combines ragged batches with the multicast cluster).  For ragged
-  // weight gradients (p.k_valid) the K range is trimmed to its first live row block and is empty if none is live.
-  auto k_block_live = [&](int kb) {
-    if (p.k_valid == nullptr) return true;
-    const int kbatch = kb / p.k_blocks_per_batch;
-    return (kb - kbatch * p.k_blocks_per_batch) * 64 < p.k_valid[kbatch];
-  };
+  // epilogue writes zeros (NPAIR = 1 only: the host never combines ragged activations with the multicast cluster).  For ragged
+  // weight gradients (p.k_valid) [kb_begin, kb_end) is a range of LIVE K-block ranks, split evenly.
   auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end, bool& active) {
     const int split = item / sup_tiles;
     const int tile = item % sup_tiles;
     n_tile = tile % p.n_tiles;
-    const int mt = (tile / p.n_tiles) * NPAIR + cp;
-    active = mt < m_tiles_total;
-    mb = mt / p.m_tiles_per_batch;
-    m0 = (mt % p.m_tiles_per_batch) * p.m_tile_stride;
-    kb_begin = split * p.k_blocks_per_split;
-    kb_end = min(kb_begin + p.k_blocks_per_split, p.k_blocks);
-    if (NPAIR == 1 && p.m_valid != nullptr && active && m0 >= p.m_valid[mb]) active = false;
-    if (p.k_valid != nullptr) {
-      while (kb_begin < kb_end && !k_block_live(kb_begin)) {  // padding is a suffix of every batch: jump to the next batch
-        const int kbatch = kb_begin / p.k_blocks_per_batch;
-        kb_begin = min(kb_end, (kbatch + 1) * p.k_blocks_per_batch);
+    if (NPAIR == 1 && p.m_valid != nullptr) {
+      const int tr = tile / p.n_tiles;
+      int mt_in;
+      if (tr < rag_live) {
+        mb = live_batch(tr);
+        mt_in = tr - rag_pref[mb];
+        active = true;
+      } else {
+        const int d = tr - rag_live;
+        mb = dead_batch(d);
+        mt_in = (rag_pref[mb + 1] - rag_pref[mb]) + d - (mb * rag_per_batch - rag_pref[mb]);
+        active = false;
       }
+      m0 = mt_in * p.m_tile_stride;
+    } else {
+      const int mt = (tile / p.n_tiles) * NPAIR + cp;
+      active = mt < m_tiles_total;
+      mb = mt / p.m_tiles_per_batch;
+      m0 = (mt % p.m_tiles_per_batch) * p.m_tile_stride;
+    }
+    if (p.k_valid != nullptr) {
+      const int per = (rag_live + p.splits - 1) / p.splits;
+      kb_begin = split * per;
+      kb_end = min(kb_begin + per, rag_live);
+    } else {
+      kb_begin = split * p.k_blocks_per_split;
+      kb_end = min(kb_begin + p.k_blocks_per_split, p.k_blocks);
     }
   };
 
@@ -243,17 +301,28 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         }
         const uint32_t tx_bytes = (active ? 2 * Cfg::kABytes : 0) + 2 * Cfg::kBBytes;
         const uint16_t mc_mask = static_cast<uint16_t>((1u << rank) | (1u << (rank + 2)));
-        int kbatch = 0, kin = kb_begin;  // kb = kbatch * k_blocks_per_batch + kin
-        if (p.k_blocks_per_batch > 0) {
+        // K position: kb = kbatch * k_blocks_per_batch + kin; `klive` = K blocks of the current batch that are walked
+        int kbatch = 0, kin = kb_begin, klive = p.k_blocks_per_batch;
+        if (p.k_valid != nullptr) {
+          kbatch = live_batch(kb_begin);
+          kin = kb_begin - rag_pref[kbatch];
+          klive = rag_pref[kbatch + 1] - rag_pref[kbatch];
+        } else if (p.k_blocks_per_batch > 0) {
           kbatch = kb_begin / p.k_blocks_per_batch;
           kin = kb_begin - kbatch * p.k_blocks_per_batch;
         }
-        for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!k_block_live(kb)) {  // padded row block of a ragged weight gradient: skipped by the MMA issuer too
-            if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) { kin = 0; ++kbatch; }
-            else if (p.k_blocks_per_batch == 0) ++kin;
-            continue;
+        auto advance = [&](int r) {
+          ++kin;
+          if (p.k_blocks_per_batch > 0 && kin == klive) {
+            kin = 0;
+            ++kbatch;
+            if (p.k_valid != nullptr && r + 1 < kb_end) {
+              while ((klive = rag_pref[kbatch + 1] - rag_pref[kbatch]) == 0) ++kbatch;  // utterances without a live block
+            }
           }
+        };
+        for (int r = kb_begin; r < kb_end; ++r) {
+          const int kb = p.k_valid != nullptr ? kbatch * p.k_blocks_per_batch + kin : r;
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           ++it;
@@ -268,8 +337,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
           uint8_t* sb = sa + Cfg::kABytes;
           if (NPAIR == 1 && (p.debug & 4)) {  // diagnostics: barriers flow, no loads
             if (rank == 0) mbar_arrive(&full_bar[s]);
-            if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) { kin = 0; ++kbatch; }
-            else if (p.k_blocks_per_batch == 0) ++kin;
+            advance(r);
             continue;
           }
           if (rank == 0) mbar_expect_tx(&full_bar[s], tx_bytes);  // bytes landing in both CTAs of this pair
@@ -297,12 +365,7 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
             // of the same pair rank in the other pair; each destination signals its own pair leader's full barrier
             tma_load_4d_2cta_mc(sb + cp * 8192, &tmB, &full_bar[s], kbv[0], kbv[1], kbv[2], kbv[3], mc_mask);
           }
-          if (p.k_blocks_per_batch > 0 && ++kin == p.k_blocks_per_batch) {
-            kin = 0;
-            ++kbatch;
-          } else if (p.k_blocks_per_batch == 0) {
-            ++kin;
-          }
+          advance(r);
         }
       }
     }
@@ -330,7 +393,6 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
         const uint32_t tmem_acc = tmem_base + a * 256;
         bool first = true;
         for (int kb = kb_begin; kb < kb_end; ++kb) {
-          if (!k_block_live(kb)) continue;  // (kb_begin itself is live: decode trimmed the range, so `first` is consumed)
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           ++it;

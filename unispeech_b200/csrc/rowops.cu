@@ -60,8 +60,20 @@ struct VecIO<2> {
 struct RowView {
   long long bs, rs;
   int rows_per_batch;
+  // element offset of row r (r < 2^32: every caller's row count is batches x frames); 32-bit division -- the 64-bit one is a
+  // ~100-instruction subroutine, which showed in kernels that touch a handful of rows per thread
   __device__ __forceinline__ long long off(long long r) const {
-    return (r / rows_per_batch) * bs + (r % rows_per_batch) * rs;
+    const unsigned ur = static_cast<unsigned>(r);
+    const unsigned b = ur / static_cast<unsigned>(rows_per_batch);
+    const unsigned t = ur - b * static_cast<unsigned>(rows_per_batch);
+    return static_cast<long long>(b) * bs + static_cast<long long>(t) * rs;
+  }
+  __device__ __forceinline__ void split(long long r, unsigned& b, unsigned& t) const {
+    b = static_cast<unsigned>(r) / static_cast<unsigned>(rows_per_batch);
+    t = static_cast<unsigned>(r) - b * static_cast<unsigned>(rows_per_batch);
+  }
+  __device__ __forceinline__ long long at(unsigned b, unsigned t) const {
+    return static_cast<long long>(b) * bs + static_cast<long long>(t) * rs;
   }
 };
 
@@ -187,6 +199,154 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __r
       }
     }
   }
+}
+
+// Wide rows (D = 256 * NW: 512 / 768 / 1024): the row is spread over the NW warps of the block, one 16-byte vector per thread, R rows
+// per iteration with all their loads issued up front; mean and variance (two-pass, as above) cross the warps through shared
+// memory with one block barrier each.  The gate of a head is an 8-lane affair exactly as in the warp-per-row kernel, but all
+// heads of a row are evaluated in parallel (thread t owns columns 8t..8t+7 = head t / 8).
+template <int NW, int R, bool GATE, bool GELU>
+__global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat16* __restrict__ x, RowView xv,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             __nv_bfloat16* __restrict__ y, RowView yv,
+                                                             float* __restrict__ mean_out, float* __restrict__ rstd_out,
+                                                             long long rows, float eps, GateArgs ga) {
+  pdl_grid_sync();
+  constexpr int D = 256 * NW;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int c0 = threadIdx.x * 8;
+  float g[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    g[j] = gamma[c0 + j];
+    b[j] = beta[c0 + j];
+  }
+  float wa[GATE ? 8 : 1], wb[GATE ? 8 : 1], gba = 0.f, gbb = 0.f, a_h = 0.f;
+  if constexpr (GATE) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = (lane & 7) * 8 + j;
+      wa[j] = ga.grep_w[c] + ga.grep_w[64 + c] + ga.grep_w[128 + c] + ga.grep_w[192 + c];
+      wb[j] = ga.grep_w[256 + c] + ga.grep_w[320 + c] + ga.grep_w[384 + c] + ga.grep_w[448 + c];
+    }
+    gba = ga.grep_b[0] + ga.grep_b[1] + ga.grep_b[2] + ga.grep_b[3];
+    gbb = ga.grep_b[4] + ga.grep_b[5] + ga.grep_b[6] + ga.grep_b[7];
+    a_h = ga.grep_a[threadIdx.x >> 3];
+  }
+  __shared__ float red[2][NW][R];
+  for (long long r0 = static_cast<long long>(blockIdx.x) * R; r0 < rows; r0 += static_cast<long long>(gridDim.x) * R) {
+    uint4 raw[R];
+    unsigned rb[R], rt[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = r0 + i;
+      xv.split(r < rows ? r : 0, rb[i], rt[i]);
+      raw[i] = r < rows ? *reinterpret_cast<const uint4*>(x + xv.at(rb[i], rt[i]) + c0) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    float v[R][8], s[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint32_t u[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+      s[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = unpack_bf16x2(u[k]);
+        v[i][2 * k] = f.x;
+        v[i][2 * k + 1] = f.y;
+        s[i] += f.x + f.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) s[i] = warp_sum(s[i]);
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) red[0][warp][i] = s[i];
+    }
+    __syncthreads();
+    float mean[R], rstd[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += red[0][w][i];
+      mean[i] = t * (1.0f / D);
+      float q = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v[i][j] - mean[i];
+        q = fmaf(d, d, q);
+      }
+      s[i] = warp_sum(q);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) red[1][warp][i] = s[i];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) t += red[1][w][i];
+      rstd[i] = rsqrtf(t * (1.0f / D) + eps);
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = r0 + i;
+      uint32_t ou[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float o0 = (v[i][2 * k] - mean[i]) * rstd[i] * g[2 * k] + b[2 * k];
+        float o1 = (v[i][2 * k + 1] - mean[i]) * rstd[i] * g[2 * k + 1] + b[2 * k + 1];
+        if (GELU) {
+          o0 = gelu_f(o0);
+          o1 = gelu_f(o1);
+        }
+        ou[k] = pack_bf16x2(o0, o1);
+      }
+      if (r < rows) {
+        *reinterpret_cast<uint4*>(y + yv.at(rb[i], rt[i]) + c0) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+        if (threadIdx.x == 0) {
+          if (mean_out) mean_out[r] = mean[i];
+          if (rstd_out) rstd_out[r] = rstd[i];
+        }
+      }
+      if constexpr (GATE) {
+        float sa = 0.f, sb = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 yb = unpack_bf16x2(ou[k]);  // what the attention kernel will read
+          sa = fmaf(yb.x, wa[2 * k], sa);
+          sa = fmaf(yb.y, wa[2 * k + 1], sa);
+          sb = fmaf(yb.x, wb[2 * k], sb);
+          sb = fmaf(yb.y, wb[2 * k + 1], sb);
+        }
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          sa += __shfl_xor_sync(0xffffffffu, sa, o);
+          sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        }
+        if ((lane & 7) == 0 && r < rows) {
+          const long long bidx = rb[i], t = rt[i];  // (the gate variant's views have T rows per batch)
+          const float g1 = 1.0f / (1.0f + __expf(-(sa + gba)));
+          const float g2 = 1.0f / (1.0f + __expf(-(sb + gbb)));
+          ga.gate[(bidx * ga.H + (threadIdx.x >> 3)) * ga.T + t] = g1 * (g2 * a_h - 1.0f) + 2.0f;
+        }
+      }
+    }
+  }
+}
+
+template <bool GATE, bool GELU, typename... Args>
+static int launch_ln_fwd_wide(int D, long long rows, cudaStream_t st, Args... args) {
+  constexpr int R = 4;
+  const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), 8LL * sm_count()));
+  if (D == 512) B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<2, R, GATE, GELU>, dim3(grid), dim3(64), 0, st, args...));
+  else if (D == 768) B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<3, R, GATE, GELU>, dim3(grid), dim3(96), 0, st, args...));
+  else B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<4, R, GATE, GELU>, dim3(grid), dim3(128), 0, st, args...));
+  B200_CHECK_LAUNCH();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------ LayerNorm backward
@@ -380,6 +540,144 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
     if (dbeta != nullptr) atomicAdd(dbeta + c, sb);
     if (colsum != nullptr) atomicAdd(colsum + c, sc);
   }
+}
+
+// Wide rows (D = 256 * NW, NW = 2..4: the encoder widths 512 / 768 / 1024): a row is spread over the NW warps of the block, one
+// 16-byte vector per thread, and the block walks R rows per iteration.  A thread owns 8 COLUMNS for the whole kernel, so the
+// parameter-gradient partials (d gamma, d beta, column sums of dx) are 24 registers instead of a shared-memory read-modify-write
+// per row and element (the warp-per-row kernel above moved 16 KB through shared memory per 6 KB row and ran at 20 % of the HBM
+// peak); the two row sums cross the warps through one double-buffered shared exchange and ONE block barrier per R rows.  All
+// loads of the R rows (dy, x, dres, statistics) are issued before the first use.
+template <int NW, int R>
+__global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
+                                                             const __nv_bfloat16* __restrict__ x, RowView xv,
+                                                             const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
+                                                             const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                             const __nv_bfloat16* __restrict__ dres, RowView dresv,
+                                                             __nv_bfloat16* __restrict__ dx, RowView dxv,
+                                                             float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                             float* __restrict__ colsum, long long rows, int gelu, int vec_atomics) {
+  pdl_grid_sync();
+  constexpr int D = 256 * NW;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int c0 = threadIdx.x * 8;
+  float g[8], bt[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    g[j] = gamma[c0 + j];
+    bt[j] = gelu ? beta[c0 + j] : 0.f;
+  }
+  float ag[8], ab[8], ac[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) ag[j] = ab[j] = ac[j] = 0.f;
+  __shared__ float red[2][NW][2 * R];
+  const bool want_c = colsum != nullptr;
+  int it = 0;
+  for (long long r0 = static_cast<long long>(blockIdx.x) * R; r0 < rows; r0 += static_cast<long long>(gridDim.x) * R, ++it) {
+    uint4 xr[R], dr[R], rr[R];
+    float mean[R], rstd[R];
+    long long dxo[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const long long r = r0 + i;
+      if (r < rows) {
+        unsigned rb, rt;  // every view of one call has the same rows-per-batch: one division per row
+        xv.split(r, rb, rt);
+        xr[i] = *reinterpret_cast<const uint4*>(x + xv.at(rb, rt) + c0);
+        dr[i] = *reinterpret_cast<const uint4*>(dy + dyv.at(rb, rt) + c0);
+        if (dres != nullptr) rr[i] = *reinterpret_cast<const uint4*>(dres + dresv.at(rb, rt) + c0);
+        dxo[i] = dxv.at(rb, rt);
+        mean[i] = mean_in[r];
+        rstd[i] = rstd_in[r];
+      } else {  // past the end: contributes zeros everywhere, never stored
+        xr[i] = dr[i] = rr[i] = make_uint4(0u, 0u, 0u, 0u);
+        mean[i] = rstd[i] = 0.f;
+        dxo[i] = 0;
+      }
+      if (dres == nullptr) rr[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
+    float xh[R][8], dz[R][8], s1[R], s2[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const uint32_t xu[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
+      const uint32_t du[4] = {dr[i].x, dr[i].y, dr[i].z, dr[i].w};
+      s1[i] = s2[i] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 xf = unpack_bf16x2(xu[k]), df = unpack_bf16x2(du[k]);
+        const float xv2[2] = {xf.x, xf.y}, dv2[2] = {df.x, df.y};
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int j = 2 * k + h;
+          const float xn = (xv2[h] - mean[i]) * rstd[i];
+          float d = dv2[h];
+          if (gelu) d *= gelu_grad_f(g[j] * xn + bt[j]);
+          ag[j] = fmaf(d, xn, ag[j]);
+          ab[j] += d;
+          const float dxh = d * g[j];
+          xh[i][j] = xn;
+          dz[i][j] = dxh;
+          s1[i] += dxh;
+          s2[i] = fmaf(dxh, xn, s2[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      s1[i] = warp_sum(s1[i]);
+      s2[i] = warp_sum(s2[i]);
+    }
+    float* mine = red[it & 1][warp];
+    if (lane == 0) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        mine[2 * i] = s1[i];
+        mine[2 * i + 1] = s2[i];
+      }
+    }
+    __syncthreads();  // (the buffer of iteration it - 1 is re-written only after every warp has passed this barrier once more)
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+      for (int w = 0; w < NW; ++w) {
+        t1 += red[it & 1][w][2 * i];
+        t2 += red[it & 1][w][2 * i + 1];
+      }
+      t1 *= (1.0f / D);
+      t2 *= (1.0f / D);
+      const long long r = r0 + i;
+      const uint32_t ru[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
+      uint32_t ou[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 rf = unpack_bf16x2(ru[k]);
+        const float o0 = rf.x + rstd[i] * (dz[i][2 * k] - t1 - xh[i][2 * k] * t2);
+        const float o1 = rf.y + rstd[i] * (dz[i][2 * k + 1] - t1 - xh[i][2 * k + 1] * t2);
+        ou[k] = pack_bf16x2(o0, o1);
+        if (want_c) {  // the column sum is taken over dx AS STORED (what the producer's weight-gradient GEMM reads)
+          const float2 of = unpack_bf16x2(ou[k]);
+          ac[2 * k] += of.x;
+          ac[2 * k + 1] += of.y;
+        }
+      }
+      if (r < rows) *reinterpret_cast<uint4*>(dx + dxo[i] + c0) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
+    }
+  }
+  auto flush = [&](float* dst, const float* v) {
+    if (dst == nullptr) return;
+    if (vec_atomics) {
+      atomicAdd(reinterpret_cast<float4*>(dst + c0), make_float4(v[0], v[1], v[2], v[3]));
+      atomicAdd(reinterpret_cast<float4*>(dst + c0 + 4), make_float4(v[4], v[5], v[6], v[7]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) atomicAdd(dst + c0 + j, v[j]);
+    }
+  };
+  flush(dgamma, ag);
+  flush(dbeta, ab);
+  flush(colsum, ac);
 }
 
 template <typename F>
@@ -681,6 +979,7 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __re
 // One warp per row; EIGHT lanes per head (8 columns = one 16-byte vector each), so a warp covers four heads per iteration and
 // the two dot products of a head are 3-step shuffle reductions over 8 lanes (the earlier one-head-per-warp mapping spent its
 // time in 5-step, 32-lane reductions: 62 us per WavLM-Large layer for 32 MB of traffic).
+template <int NG>  // head groups of four per row: ceil(H / 4), all of a row's loads are issued before the first use
 __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int H, int T,
                                                        long long rows, const float* __restrict__ grep_w,
                                                        const float* __restrict__ grep_b, const float* __restrict__ grep_a,
@@ -717,18 +1016,32 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
     const __nv_bfloat16* xr = x + xv.off(r);
     __nv_bfloat16* dr = dxg + dxv.off(r);
     const long long b = r / T, t = r % T;
-    for (int h0 = 0; h0 < H; h0 += 4) {
-      const int h = h0 + hs;
+    uint4 raw[NG];
+    float dgs[NG], as[NG];
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      const int h = gi * 4 + hs;
+      const bool live = h < H;
+      raw[gi] = live ? *reinterpret_cast<const uint4*>(xr + h * 64 + q * 8) : make_uint4(0u, 0u, 0u, 0u);
+      dgs[gi] = live ? dgate[(b * H + h) * T + t] : 0.f;
+      as[gi] = live ? grep_a[h] : 0.f;
+    }
+#pragma unroll
+    for (int gi = 0; gi < NG; ++gi) {
+      const int h = gi * 4 + hs;
       const bool live = h < H;
       float f[8];
-      if (live) {
-        VecIO<8>::load(xr + h * 64 + q * 8, f);
-      } else {
+      {
+        const uint32_t u[4] = {raw[gi].x, raw[gi].y, raw[gi].z, raw[gi].w};
 #pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] = 0.f;
+        for (int k = 0; k < 4; ++k) {
+          const float2 t2 = unpack_bf16x2(u[k]);
+          f[2 * k] = t2.x;
+          f[2 * k + 1] = t2.y;
+        }
       }
-      const float dg = live ? dgate[(b * H + h) * T + t] : 0.f;
-      const float a = live ? grep_a[h] : 0.f;
+      const float dg = dgs[gi];
+      const float a = as[gi];
       float pa = 0.f, pb = 0.f;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -832,6 +1145,12 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
   RowView xv{x_bs, x_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GateArgs no_gate{nullptr, nullptr, nullptr, nullptr, 0, 1};
+  if (D == 512 || D == 768 || D == 1024) {
+    const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
+    __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
+    return gelu ? launch_ln_fwd_wide<false, true>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate)
+                : launch_ln_fwd_wide<false, false>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate);
+  }
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
     if (gelu) {
       B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value, false, true>, dim3(ln_fwd_grid(rows)),
@@ -863,6 +1182,10 @@ int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, con
   RowView xv{x_bs, x_rs, T}, yv{y_bs, y_rs, T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GateArgs ga{grep_w, grep_b, grep_a, gate, H, T};
+  if (D == 512 || D == 768 || D == 1024) {
+    return launch_ln_fwd_wide<true, false>(D, rows, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
+                                           static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, ga);
+  }
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
     if constexpr (decltype(vec)::value == 8) {
       B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<8, decltype(nch)::value, true, false>, dim3(ln_fwd_grid(rows)), dim3(256), 0, st,
@@ -888,6 +1211,25 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   RowView dyv{dy_bs, dy_rs, rows_per_batch}, xv{x_bs, x_rs, rows_per_batch}, rv{dres_bs, dres_rs, rows_per_batch},
       dxv{dx_bs, dx_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (D == 512 || D == 768 || D == 1024) {
+    constexpr int R = 4;
+    const auto aligned16 = [](const float* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const int vec_atomics = aligned16(dgamma) && aligned16(dbeta) && aligned16(colsum);
+    const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), 4LL * sm_count()));
+    auto go = [&](auto nw) {
+      constexpr int NW = decltype(nw)::value;
+      B200_CHECK_CUDA(launch_pdl(ln_bwd_wide_kernel<NW, R>, dim3(grid), dim3(32 * NW), 0, st, static_cast<const __nv_bfloat16*>(dy),
+                                 dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
+                                 static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv, dgamma, dbeta,
+                                 colsum, rows, gelu, vec_atomics));
+      return 0;
+    };
+    int rcw = D == 512 ? go(std::integral_constant<int, 2>{}) : D == 768 ? go(std::integral_constant<int, 3>{})
+                                                                          : go(std::integral_constant<int, 4>{});
+    if (rcw) return rcw;
+    B200_CHECK_LAUNCH();
+    return 0;
+  }
   long long blocks = ceil_div_ll(rows, 8 * 4);  // >=4 rows per warp so the column partial sums amortise
   const long long cap = static_cast<long long>(sm_count()) * 2;
   if (blocks > cap) blocks = cap;
@@ -1065,9 +1407,17 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   RowView xv{x_bs, x_rs, T}, dv{dx_bs, dx_rs, T};
   long long blocks = std::min<long long>(ceil_div_ll(rows, 8 * 2), 4LL * sm_count());  // (2 x SMs measured 60 % slower: the row loop is latency-bound)
   if (blocks < 1) blocks = 1;
-  B200_CHECK_CUDA(launch_pdl(gate_bwd_kernel, dim3(static_cast<int>(blocks)), dim3(256), 8 * H * sizeof(float), static_cast<cudaStream_t>(stream), 
-      static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w, grep_b, grep_a, dgate,
-      static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a));
+  B200_CHECK_ARG(H >= 1 && H <= 16, "gate_bwd: H=%d heads (supported: 1..16)", H);
+  auto go = [&](auto ng) {
+    B200_CHECK_CUDA(launch_pdl(gate_bwd_kernel<decltype(ng)::value>, dim3(static_cast<int>(blocks)), dim3(256), 8 * H * sizeof(float),
+                               static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w,
+                               grep_b, grep_a, dgate, static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a));
+    return 0;
+  };
+  const int ng = (H + 3) / 4;
+  const int rcg = ng == 1 ? go(std::integral_constant<int, 1>{}) : ng == 2 ? go(std::integral_constant<int, 2>{})
+                : ng == 3 ? go(std::integral_constant<int, 3>{}) : go(std::integral_constant<int, 4>{});
+  if (rcg) return rcg;
   B200_CHECK_LAUNCH();
   return 0;
 }
