@@ -63,6 +63,17 @@ for name, B, T, D, F, nparam in (("base", 16, 749, 768, 3072, 94_381_936), ("lar
         ("colsum [B*T, D]", lambda: ops.colsum(x, T * D, D, T, B, D, csum), E),
         ("colsum [B*T, 3D]", lambda: ops.colsum(qkv, 0, 3 * D, B * T, 1, 3 * D, csum3), 3 * E),
     ]
+    # one LayerNorm (+GELU) of the `layer_norm` conv stack: conv layer 1 of the large workload (rows = B x 31999 at 20 s, 512 channels)
+    Tc, Cc = (16000 * (20 if name == "large" else 15) // 320 * 32) - 1, 512
+    xc = torch.randn(B, Tc, Cc, device=dev).to(torch.bfloat16)
+    yc, dc = torch.empty_like(xc), torch.randn(B, Tc, Cc, device=dev).to(torch.bfloat16)
+    gc, bc, mc, rc = f32(Cc), f32(Cc), f32(B * Tc), f32(B * Tc).abs() + 0.5
+    dgc, dbc = torch.zeros(Cc, device=dev), torch.zeros(Cc, device=dev)
+    Ec = 2 * B * Tc * Cc
+    rows += [
+        (f"conv-stack LN+GELU fwd [{B}x{Tc}, 512]", lambda: ops.layer_norm_fwd(xc, Tc * Cc, Cc, gc, bc, yc, Tc * Cc, Cc, mc, rc, Tc, B, Cc, True), 2 * Ec),
+        (f"conv-stack LN+GELU bwd [{B}x{Tc}, 512]", lambda: ops.layer_norm_bwd(dc, Tc * Cc, Cc, xc, Tc * Cc, Cc, mc, rc, gc, bc, None, 0, 0, yc, Tc * Cc, Cc, dgc, dbc, None, Tc, B, Cc, True), 3 * Ec),
+    ]
     if args.norms:
         rows = rows[3:]
         for label, fn, nbytes in rows:

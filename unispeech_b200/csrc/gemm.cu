@@ -200,7 +200,7 @@ static int launch_gemm_pair_n(const CUtensorMap& ta, const CUtensorMap& tb, cons
   B200_CHECK_CUDA((pair_kernel_setup<A_MN, B_MN, KIND, NPAIR>(&max_units)));
   const int m_tiles_total = p.tiles_total / p.n_tiles;
   const int items = ceil_div(m_tiles_total, NPAIR) * p.n_tiles * p.splits;
-  const int pairs = std::max(1, std::min(items, max_units));
+  const int pairs = p.stream_k ? std::max(1, max_units) : std::max(1, std::min(items, max_units));  // stream-K: every pair has a range
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(2 * NPAIR * pairs, 1, 1);
@@ -225,6 +225,16 @@ static int launch_gemm_pair(const CUtensorMap& ta, const CUtensorMap& tb, const 
                             cudaStream_t stream) {
   return npair == 2 ? launch_gemm_pair_n<A_MN, B_MN, KIND, 2>(ta, tb, p, stream)
                     : launch_gemm_pair_n<A_MN, B_MN, KIND, 1>(ta, tb, p, stream);
+}
+
+// stream-K schedule of the weight-gradient GEMMs (B200S_WGRAD_STREAMK=0: whole (split, tile) items, the round-1 schedule)
+static bool wgrad_stream_k() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_WGRAD_STREAMK");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v == 1;
 }
 
 // 0/1 switch for the CTA-pair kernel (B200S_GEMM_PAIR=0 forces the single-CTA kernel; used by the A/B micro-benchmarks)
@@ -444,9 +454,21 @@ static int gemm_wgrad_impl(const void* y, long long y_bs, long long y_rs, const 
     // about one work item per cluster: the fp32 reduction epilogue of a split is the expensive part, the main loop is cheap
     const int pairs = std::max(1, units);
     int splits = std::max(1, pairs / (ceil_div(p.m_tiles_per_batch, npair) * p.n_tiles));
+    if (const char* e = getenv("B200S_WGRAD_SPLITS")) {  // micro-benchmark knob
+      if (atoi(e) > 0) splits = atoi(e);
+    }
     if (splits > p.k_blocks) splits = p.k_blocks;
     p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
     p.splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
+    const int tiles = p.m_tiles_per_batch * p.n_tiles;
+    if (npair == 1 && wgrad_stream_k() && tiles * p.k_blocks >= 2 * pairs) {
+      // stream-K: equal K-block ranges per pair; a range of `per` blocks touches at most ceil(per / kbt) + 1 tiles (kbt = K blocks
+      // per tile; for a ragged batch only the live ones count, which makes `per` smaller, never larger)
+      const int per = ceil_div(tiles * p.k_blocks, pairs);
+      p.stream_k = 1;
+      p.splits = std::min(tiles, ceil_div(per, std::max(1, p.k_blocks)) + 1);
+      if (p.k_valid != nullptr) p.splits = std::min(tiles, p.splits + 1);  // live blocks per tile unknown on the host: one spare segment
+    }
     // A coords: (m0 [+128*rank] + sub, k0, kbatch, 0)   B coords: (n_tile*256 + sub (=128*rank + 64*i), k0, kbatch, 0)
     p.ca[0][1] = 1; p.ca[0][7] = 1; p.ca[1][4] = 1; p.ca[2][5] = 1;
     p.cb[0][3] = 256; p.cb[0][7] = 1; p.cb[1][4] = 1; p.cb[2][5] = 1;

@@ -67,6 +67,9 @@ struct GemmParams {
   // are zero by construction: nothing downstream of a padded frame reaches the loss).
   const int* m_valid;
   const int* k_valid;
+  // weight gradients (fp32 kind, one pair per cluster): the (tile, K block) space is cut into one contiguous range per CTA pair
+  // (stream-K) instead of whole (split, tile) items; `splits` then holds the largest number of tiles a range can touch
+  int stream_k;
 };
 
 template <int BLOCK_N>

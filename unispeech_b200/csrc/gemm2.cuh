@@ -153,7 +153,8 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   const int n_pairs = gridDim.x / (2 * NPAIR);
   const int m_tiles_total = p.tiles_total / p.n_tiles;
   const int sup_tiles = ((m_tiles_total + NPAIR - 1) / NPAIR) * p.n_tiles;  // work items per K split
-  const int n_items = sup_tiles * p.splits;
+  // (stream-K: item = pair + seg * n_pairs is the seg-th tile segment of that pair's range, see decode)
+  const int n_items = (NPAIR == 1 && KIND == EK_F32 && p.stream_k) ? n_pairs * p.splits : sup_tiles * p.splits;
   constexpr uint16_t kAllCtas = static_cast<uint16_t>((1u << (2 * NPAIR)) - 1u);
 
   extern __shared__ uint8_t smem_raw[];
@@ -243,6 +244,27 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
   // epilogue writes zeros (NPAIR = 1 only: the host never combines ragged activations with the multicast cluster).  For ragged
   // weight gradients (p.k_valid) [kb_begin, kb_end) is a range of LIVE K-block ranks, split evenly.
   auto decode = [&](int item, int& mb, int& m0, int& n_tile, int& kb_begin, int& kb_end, bool& active) {
+    if (NPAIR == 1 && KIND == EK_F32 && p.stream_k) {
+      // stream-K: this pair owns units [u0, u1) of the tile-major (tile, K block) space -- every pair gets the same number of K
+      // blocks (64 tiles on 74 pairs would otherwise leave 10 pairs idle); the range is walked one tile segment per item.
+      // K blocks are LIVE ranks for ragged batches.
+      const int kbt = p.k_valid != nullptr ? rag_live : p.k_blocks;
+      const int total = sup_tiles * kbt;
+      const int per = (total + n_pairs - 1) / n_pairs;
+      const int seg = item / n_pairs;
+      const int u0 = min(total, (item - seg * n_pairs) * per), u1 = min(total, u0 + per);
+      const int t0 = kbt > 0 ? u0 / kbt : 0;
+      const int tile = min(t0 + seg, sup_tiles - 1);
+      kb_begin = seg == 0 ? u0 - t0 * kbt : 0;
+      kb_end = (t0 + seg < sup_tiles) ? min(kbt, u1 - (t0 + seg) * kbt) : 0;   // <= kb_begin: empty segment, skipped by every role
+      if (kb_end < kb_begin) kb_end = kb_begin;
+      n_tile = tile % p.n_tiles;
+      const int mt = tile / p.n_tiles;
+      active = true;
+      mb = mt / p.m_tiles_per_batch;
+      m0 = (mt % p.m_tiles_per_batch) * p.m_tile_stride;
+      return;
+    }
     const int split = item / sup_tiles;
     const int tile = item % sup_tiles;
     n_tile = tile % p.n_tiles;
@@ -563,16 +585,12 @@ __global__ void __launch_bounds__(320, 1) gemm_bf16_pair_kernel(const __grid_con
                 const uint4 w = lds128(stg0 + stg_off(row, chunk));
                 if (col_ok && row < et.rows_valid) {
                   float* o = base + row * p.out.ld;
-                  if (p.flags & EPI_ATOMIC) {
-                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(__uint_as_float(w.x)),
-                                 "f"(__uint_as_float(w.y)), "f"(__uint_as_float(w.z)), "f"(__uint_as_float(w.w))
-                                 : "memory");
-                  } else {
-                    float4 o4 = *reinterpret_cast<float4*>(o);
-                    o4.x += __uint_as_float(w.x); o4.y += __uint_as_float(w.y);
-                    o4.z += __uint_as_float(w.z); o4.w += __uint_as_float(w.w);
-                    *reinterpret_cast<float4*>(o) = o4;
-                  }
+                  // fire-and-forget vector reduction for the single-writer case too: a read-modify-write here is 32 DEPENDENT
+                  // global round trips per warp and tile (the compiler cannot move a row's load above the previous row's
+                  // store), which left the weight-gradient GEMMs at half the speed of the forward ones
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o), "f"(__uint_as_float(w.x)),
+                               "f"(__uint_as_float(w.y)), "f"(__uint_as_float(w.z)), "f"(__uint_as_float(w.w))
+                               : "memory");
                 }
               }
               __syncwarp();

@@ -341,10 +341,17 @@ __global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat1
 template <bool GATE, bool GELU, typename... Args>
 static int launch_ln_fwd_wide(int D, long long rows, cudaStream_t st, Args... args) {
   constexpr int R = 4;
-  const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), 8LL * sm_count()));
-  if (D == 512) B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<2, R, GATE, GELU>, dim3(grid), dim3(64), 0, st, args...));
-  else if (D == 768) B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<3, R, GATE, GELU>, dim3(grid), dim3(96), 0, st, args...));
-  else B200_CHECK_CUDA(launch_pdl(ln_fwd_wide_kernel<4, R, GATE, GELU>, dim3(grid), dim3(128), 0, st, args...));
+  auto go = [&](auto nw) {
+    constexpr int NW = decltype(nw)::value;
+    auto kern = ln_fwd_wide_kernel<NW, R, GATE, GELU>;
+    static const int cap = resident_grid(kern, 32 * NW);
+    const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), cap));
+    B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(32 * NW), 0, st, args...));
+    return 0;
+  };
+  const int rc = D == 512 ? go(std::integral_constant<int, 2>{}) : D == 768 ? go(std::integral_constant<int, 3>{})
+                                                                           : go(std::integral_constant<int, 4>{});
+  if (rc) return rc;
   B200_CHECK_LAUNCH();
   return 0;
 }
@@ -547,26 +554,28 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
 // parameter-gradient partials (d gamma, d beta, column sums of dx) are 24 registers instead of a shared-memory read-modify-write
 // per row and element (the warp-per-row kernel above moved 16 KB through shared memory per 6 KB row and ran at 20 % of the HBM
 // peak); the two row sums cross the warps through one double-buffered shared exchange and ONE block barrier per R rows.  All
-// loads of the R rows (dy, x, dres, statistics) are issued before the first use.
-template <int NW, int R>
-__global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
+// loads of the R rows (dy, x, dres, statistics) are issued before the first use.  Across the barrier a row is kept as the RAW
+// packed vectors (12 registers) and x-hat / d x-hat are re-derived afterwards (two FMAs) -- except in the GELU variant, whose
+// derivative is too expensive to evaluate twice.
+template <int NW, int R, bool GELU>
+__global__ void __launch_bounds__(32 * NW, 16 / NW) ln_bwd_wide_kernel(const __nv_bfloat16* __restrict__ dy, RowView dyv,
                                                              const __nv_bfloat16* __restrict__ x, RowView xv,
                                                              const float* __restrict__ mean_in, const float* __restrict__ rstd_in,
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              const __nv_bfloat16* __restrict__ dres, RowView dresv,
                                                              __nv_bfloat16* __restrict__ dx, RowView dxv,
                                                              float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                             float* __restrict__ colsum, long long rows, int gelu, int vec_atomics) {
+                                                             float* __restrict__ colsum, long long rows, int vec_atomics) {
   pdl_grid_sync();
   constexpr int D = 256 * NW;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int c0 = threadIdx.x * 8;
-  float g[8], bt[8];
+  float g[8], bt[GELU ? 8 : 1];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     g[j] = gamma[c0 + j];
-    bt[j] = gelu ? beta[c0 + j] : 0.f;
+    if (GELU) bt[j] = beta[c0 + j];
   }
   float ag[8], ab[8], ac[8];
 #pragma unroll
@@ -581,6 +590,7 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const long long r = r0 + i;
+      rr[i] = make_uint4(0u, 0u, 0u, 0u);
       if (r < rows) {
         unsigned rb, rt;  // every view of one call has the same rows-per-batch: one division per row
         xv.split(r, rb, rt);
@@ -591,13 +601,12 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
         mean[i] = mean_in[r];
         rstd[i] = rstd_in[r];
       } else {  // past the end: contributes zeros everywhere, never stored
-        xr[i] = dr[i] = rr[i] = make_uint4(0u, 0u, 0u, 0u);
+        xr[i] = dr[i] = make_uint4(0u, 0u, 0u, 0u);
         mean[i] = rstd[i] = 0.f;
         dxo[i] = 0;
       }
-      if (dres == nullptr) rr[i] = make_uint4(0u, 0u, 0u, 0u);
     }
-    float xh[R][8], dz[R][8], s1[R], s2[R];
+    float dz[GELU ? R : 1][8], s1[R], s2[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const uint32_t xu[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
@@ -612,12 +621,11 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
           const int j = 2 * k + h;
           const float xn = (xv2[h] - mean[i]) * rstd[i];
           float d = dv2[h];
-          if (gelu) d *= gelu_grad_f(g[j] * xn + bt[j]);
+          if (GELU) d *= gelu_grad_f(g[j] * xn + bt[j]);
           ag[j] = fmaf(d, xn, ag[j]);
           ab[j] += d;
           const float dxh = d * g[j];
-          xh[i][j] = xn;
-          dz[i][j] = dxh;
+          if (GELU) dz[i][j] = dxh;
           s1[i] += dxh;
           s2[i] = fmaf(dxh, xn, s2[i]);
         }
@@ -637,6 +645,15 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
       }
     }
     __syncthreads();  // (the buffer of iteration it - 1 is re-written only after every warp has passed this barrier once more)
+    if (!GELU) {
+      // make the packed vectors opaque so that x-hat and d x-hat are RE-DERIVED below instead of being carried across the
+      // barrier in 16 registers per row (common-subexpression elimination would otherwise keep them)
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        asm volatile("" : "+r"(xr[i].x), "+r"(xr[i].y), "+r"(xr[i].z), "+r"(xr[i].w));
+        asm volatile("" : "+r"(dr[i].x), "+r"(dr[i].y), "+r"(dr[i].z), "+r"(dr[i].w));
+      }
+    }
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       float t1 = 0.f, t2 = 0.f;
@@ -648,13 +665,18 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
       t1 *= (1.0f / D);
       t2 *= (1.0f / D);
       const long long r = r0 + i;
+      const uint32_t xu[4] = {xr[i].x, xr[i].y, xr[i].z, xr[i].w};
+      const uint32_t du[4] = {dr[i].x, dr[i].y, dr[i].z, dr[i].w};
       const uint32_t ru[4] = {rr[i].x, rr[i].y, rr[i].z, rr[i].w};
       uint32_t ou[4];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 rf = unpack_bf16x2(ru[k]);
-        const float o0 = rf.x + rstd[i] * (dz[i][2 * k] - t1 - xh[i][2 * k] * t2);
-        const float o1 = rf.y + rstd[i] * (dz[i][2 * k + 1] - t1 - xh[i][2 * k + 1] * t2);
+        const float2 xf = unpack_bf16x2(xu[k]), df = unpack_bf16x2(du[k]), rf = unpack_bf16x2(ru[k]);
+        const float xn0 = (xf.x - mean[i]) * rstd[i], xn1 = (xf.y - mean[i]) * rstd[i];
+        const float z0 = GELU ? dz[GELU ? i : 0][2 * k] : df.x * g[2 * k];
+        const float z1 = GELU ? dz[GELU ? i : 0][2 * k + 1] : df.y * g[2 * k + 1];
+        const float o0 = rf.x + rstd[i] * (z0 - t1 - xn0 * t2);
+        const float o1 = rf.y + rstd[i] * (z1 - t1 - xn1 * t2);
         ou[k] = pack_bf16x2(o0, o1);
         if (want_c) {  // the column sum is taken over dx AS STORED (what the producer's weight-gradient GEMM reads)
           const float2 of = unpack_bf16x2(ou[k]);
@@ -680,6 +702,14 @@ __global__ void __launch_bounds__(32 * NW) ln_bwd_wide_kernel(const __nv_bfloat1
   flush(colsum, ac);
 }
 
+// blocks of `threads` threads of kernel `k` that fit the chip at once (a grid-stride kernel gains nothing from more)
+template <typename K>
+static int resident_grid(K k, int threads) {
+  int per_sm = 1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+  return per_sm * sm_count();
+}
+
 template <typename F>
 static int dispatch_width(int D, F&& f) {
   switch (D) {
@@ -693,6 +723,30 @@ static int dispatch_width(int D, F&& f) {
       set_last_error("row kernels support widths 64/128/256/512/768/1024, got %d", D);
       return -1;
   }
+}
+
+// Which LayerNorm kernels run at the wide widths (512 / 768 / 1024).  Measured on B200 (tools/bench_rowops.py --norms, WavLM-Large
+// shapes, profiles/r02_microbench_norms.txt): the block-per-row-group kernels win only for the gate-fused forward (14.7 vs 17.5 us);
+// the plain forward ties (9.6 us) and the backward LOSES (21 vs 15-18 us; conv-stack shape 315 vs 230 us) -- one block barrier per
+// row group stalls all of a block's warps on the same loads, while 16 independent warp-per-row chains per SM overlap better.
+// B200S_LN_WIDE=0 / 1 forces the warp-per-row / wide kernels everywhere (A/B runs).
+static int ln_wide_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_LN_WIDE");
+    v = (e && e[0] == '0') ? 0 : (e && e[0] == '1') ? 1 : 2;
+  }
+  return v;
+}
+static bool ln_wide_enabled(bool gate_fwd) { return ln_wide_mode() == 1 || (ln_wide_mode() == 2 && gate_fwd); }
+
+static int ln_wide_rows() {  // rows per iteration of the wide backward kernel (B200S_LN_R=2|4, micro-benchmark knob)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("B200S_LN_R");
+    v = (e && e[0] == '2') ? 2 : 4;
+  }
+  return v;
 }
 
 // one row per warp and iteration, 8 warps per block, four resident blocks per SM
@@ -1145,7 +1199,7 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
   RowView xv{x_bs, x_rs, rows_per_batch}, yv{y_bs, y_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GateArgs no_gate{nullptr, nullptr, nullptr, nullptr, 0, 1};
-  if (D == 512 || D == 768 || D == 1024) {
+  if (ln_wide_enabled(false) && (D == 512 || D == 768 || D == 1024)) {
     const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
     return gelu ? launch_ln_fwd_wide<false, true>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate)
@@ -1182,7 +1236,7 @@ int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, con
   RowView xv{x_bs, x_rs, T}, yv{y_bs, y_rs, T};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const GateArgs ga{grep_w, grep_b, grep_a, gate, H, T};
-  if (D == 512 || D == 768 || D == 1024) {
+  if (ln_wide_enabled(true) && (D == 512 || D == 768 || D == 1024)) {
     return launch_ln_fwd_wide<true, false>(D, rows, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
                                            static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, ga);
   }
@@ -1211,21 +1265,32 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   RowView dyv{dy_bs, dy_rs, rows_per_batch}, xv{x_bs, x_rs, rows_per_batch}, rv{dres_bs, dres_rs, rows_per_batch},
       dxv{dx_bs, dx_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (D == 512 || D == 768 || D == 1024) {
-    constexpr int R = 4;
+  if (ln_wide_enabled(false) && (D == 512 || D == 768 || D == 1024)) {
     const auto aligned16 = [](const float* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const int vec_atomics = aligned16(dgamma) && aligned16(dbeta) && aligned16(colsum);
-    const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), 4LL * sm_count()));
-    auto go = [&](auto nw) {
-      constexpr int NW = decltype(nw)::value;
-      B200_CHECK_CUDA(launch_pdl(ln_bwd_wide_kernel<NW, R>, dim3(grid), dim3(32 * NW), 0, st, static_cast<const __nv_bfloat16*>(dy),
-                                 dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
+    auto go = [&](auto nw, auto rr, auto ge) {
+      constexpr int NW = decltype(nw)::value, R = decltype(rr)::value;
+      auto kern = ln_bwd_wide_kernel<NW, R, decltype(ge)::value>;
+      static const int cap = resident_grid(kern, 32 * NW);
+      const int grid = static_cast<int>(std::min<long long>(ceil_div_ll(rows, R), cap));
+      B200_CHECK_CUDA(launch_pdl(kern, dim3(grid), dim3(32 * NW), 0, st, static_cast<const __nv_bfloat16*>(dy), dyv,
+                                 static_cast<const __nv_bfloat16*>(x), xv, mean, rstd, gamma, beta,
                                  static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv, dgamma, dbeta,
-                                 colsum, rows, gelu, vec_atomics));
+                                 colsum, rows, vec_atomics));
       return 0;
     };
-    int rcw = D == 512 ? go(std::integral_constant<int, 2>{}) : D == 768 ? go(std::integral_constant<int, 3>{})
-                                                                          : go(std::integral_constant<int, 4>{});
+    using I2 = std::integral_constant<int, 2>;
+    using I3 = std::integral_constant<int, 3>;
+    using I4 = std::integral_constant<int, 4>;
+    const int r_sel = ln_wide_rows();
+    int rcw;
+    if (gelu) {
+      rcw = D == 512 ? go(I2{}, I2{}, std::true_type{}) : D == 768 ? go(I3{}, I2{}, std::true_type{}) : go(I4{}, I2{}, std::true_type{});
+    } else if (r_sel == 2) {
+      rcw = D == 512 ? go(I2{}, I2{}, std::false_type{}) : D == 768 ? go(I3{}, I2{}, std::false_type{}) : go(I4{}, I2{}, std::false_type{});
+    } else {
+      rcw = D == 512 ? go(I2{}, I4{}, std::false_type{}) : D == 768 ? go(I3{}, I4{}, std::false_type{}) : go(I4{}, I4{}, std::false_type{});
+    }
     if (rcw) return rcw;
     B200_CHECK_LAUNCH();
     return 0;

@@ -154,6 +154,21 @@ class ConvGeom:
             self.Tg.append(_even((t_in + s - 1) // s + lead + 1))
 
 
+def conv_valid_rows(last: torch.Tensor, conv_layers, T_list) -> torch.Tensor:
+    """Rows of every conv layer's output that the first `last[b]` output frames of the LAST layer depend on: int32 [n_layers, B]
+    (row l contiguous).  V_L = last;  V_l = s_{l+1} * (V_{l+1} - 1) + k_{l+1}  (0 stays 0), clamped to the layer's frame count.
+    Works on host or device tensors; anything beyond V_l[b] is padding that no valid frame ever reads (the reference's own
+    length formula, WavLM.py:311-321, makes the receptive field of a valid frame end inside the valid samples)."""
+    v = last.to(torch.int32)
+    out = [None] * len(conv_layers)
+    out[-1] = v.clamp(max=int(T_list[-1]))
+    for l in range(len(conv_layers) - 2, -1, -1):
+        _, k, s = conv_layers[l + 1]
+        nxt = out[l + 1]
+        out[l] = torch.where(nxt > 0, s * (nxt - 1) + k, torch.zeros_like(nxt)).clamp(max=int(T_list[l]))
+    return torch.stack(out).to(torch.int32).contiguous()
+
+
 class Engine:
     def __init__(self, model):
         self.m = model
@@ -164,6 +179,7 @@ class Engine:
         self.flat: Optional[FlatGrads] = None
         self._params = None
         self.drop: Optional[DR.DropState] = None  # set per forward pass by WavLM._begin (training-mode dropout)
+        self.conv_valid_last = None  # ragged batch: int32 [B] valid frames of the extractor output (set per call by WavLM._extractor)
         self.grad_sync = None  # parallel.OverlappedGradSync: told when a stage of the backward pass has produced its gradients
         self.ragged_valid = None  # int32 [B] valid frames per utterance of the current forward (ragged batch), else None
 
@@ -328,6 +344,13 @@ class Engine:
         ln_mode = cfg.extractor_mode == "layer_norm"
         dev = wav.device
         st = dict(geo=geo, wav=wav, a=[], y=[], mean=[], rstd=[])
+        # ragged batch: per layer, the rows any valid output frame depends on; the conv GEMMs zero-fill whole tiles beyond them
+        # (layer 0 and the LayerNorms still walk every row: finite values, never read by a valid frame)
+        cv = None
+        if self.conv_valid_last is not None:
+            cv = conv_valid_rows(self.conv_valid_last, convs, geo.T).to(dev, non_blocking=True)
+        st["cv"] = cv
+        vrow = (lambda i: cv[i]) if cv is not None else (lambda i: None)
         blk0 = m.feature_extractor.conv_layers[0]
         _, k0, s0 = convs[0]
         a0 = torch.empty(B, geo.Tp[0], C, dtype=BF, device=dev)
@@ -354,7 +377,7 @@ class Engine:
             out = torch.empty(B, Tpi, C, dtype=BF, device=dev)
             if ln_mode:
                 y = torch.empty(B, Tpi, C, dtype=BF, device=dev)
-                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, y, Tpi * C, C, None)
+                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, y, Tpi * C, C, None, valid=vrow(i))
                 ln = m.feature_extractor.conv_layers[i][2][1]
                 mean = torch.empty(B * Ti, dtype=torch.float32, device=dev)
                 rstd = torch.empty(B * Ti, dtype=torch.float32, device=dev)
@@ -363,7 +386,7 @@ class Engine:
             else:
                 y = torch.empty(B, Tpi, C, dtype=BF, device=dev) if save else None
                 epi = L.make_epilogue(gelu=2, out_pre=y, pre_bs=Tpi * C, pre_ld=C)  # y = gelu'(conv output), used by backward
-                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, out, Tpi * C, C, epi)
+                ops.gemm_rows(a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, k * C, self.wf[i], C, out, Tpi * C, C, epi, valid=vrow(i))
                 st["y"].append(y); st["mean"].append(None); st["rstd"].append(None)
             st["a"].append(out)
             if not save:
@@ -384,6 +407,7 @@ class Engine:
         n = len(convs)
         dA = dfeat  # gradient w.r.t. a[i], no-lead layout [B, Tp_i, C]
         gpad = None
+        cv = st.get("cv")
         for i in range(n - 1, 0, -1):
             _, k, s = convs[i]
             Ti, Tpi, lead, Tg = geo.T[i], geo.Tp[i], geo.lead[i], geo.Tg[i]
@@ -402,7 +426,8 @@ class Engine:
             # ---- weight gradient: dW[co, (j,ci)] = sum dY[b,t,co] * a_{i-1}[b, s*t + j, ci]
             a_prev = st["a"][i - 1]
             dwk = torch.zeros(C, k * C, dtype=torch.float32, device=dev)
-            ops.gemm_wgrad(gv, Tg * C, C, a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, C, k * C, dwk, k * C)
+            ops.gemm_wgrad(gv, Tg * C, C, a_prev, geo.Tp[i - 1] * C, s * C, Ti, B, C, k * C, dwk, k * C,
+                           valid=cv[i] if cv is not None else None)
             w = m.feature_extractor.conv_layers[i][0].weight
             ops.unprep_conv_wgrad(dwk, C, C, k, self.g(w))
             # ---- input gradient, one GEMM per phase rho of the stride
@@ -426,8 +451,10 @@ class Engine:
                 if fuse_dgelu:
                     y_prev = st["y"][i - 1]
                     epi = L.make_epilogue(dgelu=2, gelu_aux=y_prev.view(-1)[rho * C:], aux_bs=Tp_in * C, aux_ld=s * C)
+                # rows u' of phase rho are input frames s*u' + rho: beyond the utterance's valid input frames the gradient is zero
+                pv = ((cv[i - 1] - rho + (s - 1)).clamp(min=0) // s).to(torch.int32) if cv is not None else None
                 ops.gemm_rows(a_view, Tg * C, C, n_u, B, nm * C, self.wd[i][rho], C, dst.view(-1)[dst_off + rho * C:], dst_bs,
-                              s * C, epi)
+                              s * C, epi, valid=pv)
             if fuse_dgelu:
                 gpad = gnext
                 dA = None

@@ -546,16 +546,23 @@ class WavLM(nn.Module):
         from . import ops
         ops.memset_zero(self.grad_buffer())
 
-    def _extractor(self, source):
+    def _extractor(self, source, valid_last=None):
+        """`valid_last` (int32 [B], host or device): frames of the extractor output up to every utterance's last valid one.  The
+        conv GEMMs then skip whole tiles of padding (engine.conv_valid_rows) -- not when the feature penalty is wanted: the
+        reference takes `features.pow(2).mean()` over the padded frames too, so they must hold the reference's values."""
         eng = self._begin(source.device)
         wav = source.float().contiguous()
         w0 = self.feature_extractor.conv_layers[0][0].weight
         want_pen = bool(getattr(self, "_want_features_pen", False))
-        if self.feature_grad_mult > 0:
-            feats, st, pen = _ConvFn.apply(w0, eng, wav, want_pen)
-        else:
-            with torch.no_grad():
+        eng.conv_valid_last = None if want_pen else valid_last
+        try:
+            if self.feature_grad_mult > 0:
                 feats, st, pen = _ConvFn.apply(w0, eng, wav, want_pen)
+            else:
+                with torch.no_grad():
+                    feats, st, pen = _ConvFn.apply(w0, eng, wav, want_pen)
+        finally:
+            eng.conv_valid_last = None
         self._last_pen = pen
         return feats, st["geo"].T[-1]
 
@@ -581,9 +588,8 @@ class WavLM(nn.Module):
                          ret_layer_results=False, mask_indices=None):
         """Same contract as the reference.  `mask_indices` (bool [B,T], optional) lets a caller inject the masked frames instead
         of sampling them (used by the parity tests; the reference's sampler is host numpy RNG)."""
-        feats, T = self._extractor(source)
-        self._last_conv = feats  # conv features [B, Tp, C] (valid rows T): `features_pen` of the pre-training criterion reads them
-        eng = self._engine
+        from .engine import ConvGeom
+        T = ConvGeom(self.conv_cfg, source.shape[1]).T[-1]
         B = source.shape[0]
         # `padding_mask` may live on the host (as it does in the reference's collater): the frame mask and the span sampler
         # then run on the host without a device sync, and only the small uint8 masks are uploaded.
@@ -603,10 +609,18 @@ class WavLM(nn.Module):
             if fpm_host is not None:
                 if bool(fpm_host.any()):
                     last = ((~fpm_host).to(torch.int32) * torch.arange(1, T + 1, dtype=torch.int32)).amax(1)
-                    fpm._b200_valid = last.to(torch.int32).contiguous().to(source.device, non_blocking=True)
+                    fpm._b200_valid_host = last.to(torch.int32).contiguous()
+                    fpm._b200_valid = fpm._b200_valid_host.to(source.device, non_blocking=True)
             else:
                 fpm._b200_valid = ((~fpm).to(torch.int32) * torch.arange(1, T + 1, dtype=torch.int32, device=fpm.device)) \
                     .amax(1).to(torch.int32).contiguous()
+        valid_last = None
+        if fpm is not None and getattr(fpm, "_b200_valid", None) is not None:
+            valid_last = fpm._b200_valid_host if fpm_host is not None else fpm._b200_valid
+        feats, T2 = self._extractor(source, valid_last)
+        assert T2 == T
+        self._last_conv = feats  # conv features [B, Tp, C] (valid rows T): `features_pen` of the pre-training criterion reads them
+        eng = self._engine
         mask_u8 = mask_indices.to(device=source.device, dtype=torch.uint8).contiguous() if mask_indices is not None else None
         pad_u8 = fpm.to(torch.uint8).contiguous() if fpm is not None else None
         xv, features = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv)
