@@ -159,6 +159,29 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
                          long long dx_bs, long long dx_rs, float* dgamma, float* dbeta, float* colsum,
                          int rows_per_batch, int batches, int D, int gelu, b200s_stream stream);
 
+/* Ragged-batch forms of the row kernels (BASELINE configs[4]; the reference pads and computes every frame, WavLM.py:574-575).
+ * valid[b] (int32, device): rows of batch b that hold real frames.  Rows at or beyond it are PADDING: the forward kernels write
+ * zeros (mean = rstd = 0, gate = 1) without reading x, the backward kernels write a zero gradient row (nothing downstream of a
+ * padded frame reaches the loss), the column sum skips them.  valid == NULL: identical to the plain entry point. */
+int b200s_layer_norm_fwd_ragged(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta,
+                                void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch,
+                                int batches, int D, int gelu, const int* valid, b200s_stream stream);
+int b200s_layer_norm_gate_fwd_ragged(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta,
+                                     void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                                     const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                                     const int* valid, b200s_stream stream);
+int b200s_layer_norm_bwd_ragged(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs,
+                                long long x_rs, const float* mean, const float* rstd, const float* gamma,
+                                const float* beta, const void* dres, long long dres_bs, long long dres_rs, void* dx,
+                                long long dx_bs, long long dx_rs, float* dgamma, float* dbeta, float* colsum,
+                                int rows_per_batch, int batches, int D, int gelu, const int* valid, b200s_stream stream);
+int b200s_colsum_ragged(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                        const int* valid, b200s_stream stream);
+int b200s_gate_bwd_ragged(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                          const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                          long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, const int* valid,
+                          b200s_stream stream);
+
 /* out[c] (+=) sum_rows x[r,c]  -- nn.Linear bias gradients */
 int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
                  b200s_stream stream);

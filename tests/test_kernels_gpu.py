@@ -117,7 +117,13 @@ def test_layer_norm_gate_fwd(cuda_device, H):
     torch.cuda.synchronize()
     ref = F.layer_norm(x.float(), (D,), gamma, beta)
     assert (y1.float() - ref).abs().max().item() < 0.03
-    assert torch.equal(y1, y2) and torch.equal(m1, m2) and torch.equal(r1, r2)
+    # (at the wide widths the fused kernel spreads a row over the block: its reduction order differs from the warp-per-row
+    # kernel's, so the statistics agree to fp32 rounding and y to one bf16 step, not bit for bit)
+    assert (m1 - m2).abs().max().item() < 1e-5 and (r1 - r2).abs().max().item() < 1e-4 * r1.abs().max().item()
+    assert (y1.float() - y2.float()).abs().max().item() <= 0.0625
+    # the gate must be that of the STORED y of the same kernel: recompute it from y2 with the stand-alone gate kernel
+    ops.gate_fwd(y2, T * D, D, T, B, H, gw, gb, ga, g1)
+    torch.cuda.synchronize()
     assert (g1 - g2).abs().max().item() < 1e-5
 
 
@@ -419,3 +425,83 @@ def test_prep_linear_batched_shapes(cuda_device):
         want = src.to(torch.bfloat16)
         assert torch.equal(dst, want), (N, K)
         assert torch.equal(dstT, want.t().contiguous()), (N, K)
+
+
+@pytest.mark.parametrize("D,gelu", [(128, False), (512, True), (1024, False)])
+def test_ragged_row_kernels(cuda_device, D, gelu):
+    """`valid` forms (BASELINE configs[4]): rows below valid[b] are bit-identical to the dense kernels, padded rows come out as
+    zeros, and the parameter-gradient sums equal the dense sums of a gradient that is zero on the padded rows."""
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(7 + D)
+    B, T = 3, 61
+    valid = torch.tensor([61, 17, 0], dtype=torch.int32, device=dev)
+    live = (torch.arange(T, device=dev)[None, :] < valid[:, None])            # [B, T]
+    x = bf(torch.randn(B, T, D, device=dev) * 1.5 + 0.2)
+    gamma, beta = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev) * 0.1
+    y0, y1 = torch.empty_like(x), torch.full_like(x, float("nan"))
+    m0, r0, m1, r1 = (torch.full((B * T,), float("nan"), device=dev) for _ in range(4))
+    ops.layer_norm_fwd(x, T * D, D, gamma, beta, y0, T * D, D, m0, r0, T, B, D, gelu)
+    ops.layer_norm_fwd(x, T * D, D, gamma, beta, y1, T * D, D, m1, r1, T, B, D, gelu, valid=valid)
+    torch.cuda.synchronize()
+    assert torch.equal(y1[live], y0[live]) and y1[~live].abs().max().item() == 0
+    assert torch.equal(m1.view(B, T)[live], m0.view(B, T)[live]) and torch.equal(r1.view(B, T)[live], r0.view(B, T)[live])
+    # backward
+    dy = bf(torch.randn(B, T, D, device=dev)) * live.unsqueeze(-1)
+    dres = bf(torch.randn(B, T, D, device=dev)) * live.unsqueeze(-1)
+    outs = []
+    for v in (None, valid):
+        dx = torch.full_like(x, float("nan"))
+        dg, db, cs = torch.zeros(D, device=dev), torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+        # dense run: statistics of the padded rows come from the dense forward; their dy is zero, so they add nothing
+        ops.layer_norm_bwd(dy, T * D, D, x, T * D, D, m0, r0, gamma, beta, dres, T * D, D, dx, T * D, D, dg, db, cs, T, B, D,
+                           gelu, valid=v)
+        outs.append((dx, dg, db, cs))
+    torch.cuda.synchronize()
+    (dx0, dg0, db0, cs0), (dx1, dg1, db1, cs1) = outs
+    assert torch.equal(dx1[live], dx0[live]) and dx1[~live].abs().max().item() == 0
+    for a_, b_ in ((dg0, dg1), (db0, db1), (cs0, cs1)):
+        assert (a_ - b_).abs().max().item() <= 1e-3 * max(1.0, a_.abs().max().item())
+    c0, c1 = torch.zeros(D, device=dev), torch.zeros(D, device=dev)
+    ops.colsum(dy, T * D, D, T, B, D, c0)
+    ops.colsum(bf(torch.randn(B, T, D, device=dev)).masked_scatter_(live.unsqueeze(-1).expand(B, T, D), dy[live]), T * D, D, T, B, D,
+               c1, valid=valid)   # garbage on the padded rows must not be counted
+    torch.cuda.synchronize()
+    assert (c0 - c1).abs().max().item() <= 1e-3 * max(1.0, c0.abs().max().item())
+
+
+@pytest.mark.parametrize("H", [12, 16])
+def test_ragged_gate_kernels(cuda_device, H):
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(50 + H)
+    B, T, D = 3, 53, H * 64
+    valid = torch.tensor([53, 9, 0], dtype=torch.int32, device=dev)
+    live = (torch.arange(T, device=dev)[None, :] < valid[:, None])
+    x = bf(torch.randn(B, T, D, device=dev))
+    gamma, beta = torch.rand(D, device=dev) + 0.5, torch.randn(D, device=dev) * 0.1
+    gw, gb, ga = torch.randn(8, 64, device=dev) * 0.2, torch.randn(8, device=dev) * 0.1, torch.rand(1, H, 1, 1, device=dev) + 0.5
+    res = []
+    for v in (None, valid):
+        y = torch.full_like(x, float("nan"))
+        mean, rstd = torch.empty(B * T, device=dev), torch.empty(B * T, device=dev)
+        gate = torch.full((B, H, T), float("nan"), device=dev)
+        ops.layer_norm_gate_fwd(x, T * D, D, gamma, beta, y, T * D, D, mean, rstd, T, B, D, gw, gb, ga, H, gate, valid=v)
+        res.append((y, gate))
+    torch.cuda.synchronize()
+    (y0, g0), (y1, g1) = res
+    lg = live[:, None, :].expand(B, H, T)
+    assert torch.equal(y1[live], y0[live]) and y1[~live].abs().max().item() == 0
+    assert torch.equal(g1[lg], g0[lg]) and bool((g1[~lg] == 1.0).all())
+    dgate = torch.randn(B, H, T, device=dev) * lg
+    outs = []
+    for v in (None, valid):
+        dxg = torch.full_like(x, float("nan"))
+        dgw, dgb, dga = torch.zeros_like(gw), torch.zeros_like(gb), torch.zeros(H, device=dev)
+        ops.gate_bwd(x, T * D, D, T, B, H, gw, gb, ga, dgate, dxg, T * D, D, dgw, dgb, dga, valid=v)
+        outs.append((dxg, dgw, dgb, dga))
+    torch.cuda.synchronize()
+    (d0, w0, b0, a0), (d1, w1, b1, a1) = outs
+    assert torch.equal(d1[live], d0[live]) and d1[~live].abs().max().item() == 0
+    for p_, q_ in ((w0, w1), (b0, b1), (a0, a1)):
+        assert (p_ - q_).abs().max().item() <= 1e-3 * max(1.0, p_.abs().max().item())

@@ -34,6 +34,9 @@ for name, B, T, H in (("base", 16, 749, 12), ("large", 8, 999, 16)):
         "bwd_fused": lambda: ops.attn_bwd_fused(qkv, out, dout, gate, tab, pad, lse, delta, dq_acc, dqkv, dgate, dtab, B, T, H, 0.125),
         "bwd_2kernel": lambda: ops.attn_bwd(qkv, out, dout, gate, tab, pad, lse, delta, dqkv, dgate, dtab, B, T, H, 0.125),
     }
+    # the same kernels without the gated relative-position bias (HuBERT / wav2vec2 encoders): what the bias path costs
+    fns["fwd_nobias"] = lambda: ops.attn_fwd(qkv, None, None, pad, out, lse, B, T, H, 0.125)
+    fns["bwd_fused_nobias"] = lambda: ops.attn_bwd_fused(qkv, out, dout, None, None, pad, lse, delta, dq_acc, dqkv, None, None, B, T, H, 0.125)
     if args.dropout > 0:
         words = torch.empty(ops.attn_dropout_mask_words(B, T, H), dtype=torch.int32, device=dev)
         fns["fwd_dropout"] = lambda: ops.attn_fwd_dropout(qkv, gate, tab, pad, out, lse, B, T, H, 0.125, args.dropout, (123, 456), words)

@@ -461,7 +461,10 @@ static int gemm_wgrad_impl(const void* y, long long y_bs, long long y_rs, const 
     p.k_blocks_per_split = ceil_div(p.k_blocks, splits);
     p.splits = ceil_div(p.k_blocks, p.k_blocks_per_split);
     const int tiles = p.m_tiles_per_batch * p.n_tiles;
-    if (npair == 1 && wgrad_stream_k() && tiles * p.k_blocks >= 2 * pairs) {
+    // (few tiles, e.g. the 1024 x 1024 out_proj gradient with 16: whole (split, tile) items already balance and a range per pair
+    // only adds partial-tile epilogues -- measured 23.6 vs 22.9 us; from ~half a wave of tiles on, stream-K wins: 47 vs 64 us for
+    // the 3072 x 1024 qkv gradient, 60 vs 64 us for the FFN ones, profiles/r02_microbench_gemm_large.txt)
+    if (npair == 1 && wgrad_stream_k() && 2 * tiles >= pairs && tiles * p.k_blocks >= 2 * pairs) {
       // stream-K: equal K-block ranges per pair; a range of `per` blocks touches at most ceil(per / kbt) + 1 tiles (kbt = K blocks
       // per tile; for a ragged batch only the live ones count, which makes `per` smaller, never larger)
       const int per = ceil_div(tiles * p.k_blocks, pairs);

@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __r
                                                      const float* __restrict__ gamma, const float* __restrict__ beta,
                                                      __nv_bfloat16* __restrict__ y, RowView yv,
                                                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                     long long rows, float eps, GateArgs ga) {
+                                                     long long rows, float eps, GateArgs ga, const int* __restrict__ valid) {
   pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
   constexpr int N = NCH * VEC;
@@ -141,6 +141,25 @@ __global__ void __launch_bounds__(256, 4) ln_fwd_kernel(const __nv_bfloat16* __r
   }
   for (long long r = warp_global; r < rows; r += nwarps) {
     float v[N];
+    if (valid != nullptr) {  // ragged batch: a padded frame is written as zeros (finite), nothing is read
+      unsigned rb, rt;
+      xv.split(r, rb, rt);
+      if (static_cast<int>(rt) >= valid[rb]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[i] = 0.f;
+        __nv_bfloat16* yz = y + yv.at(rb, rt);
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(yz + (i * 32 + lane) * VEC, v + i * VEC);
+        if (lane == 0) {
+          if (mean_out) mean_out[r] = 0.f;
+          if (rstd_out) rstd_out[r] = 0.f;
+        }
+        if constexpr (GATE) {
+          if (lane < ga.H) ga.gate[(static_cast<long long>(rb) * ga.H + lane) * ga.T + rt] = 1.0f;
+        }
+        continue;
+      }
+    }
     const __nv_bfloat16* xr = x + xv.off(r);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) VecIO<VEC>::load(xr + (i * 32 + lane) * VEC, v + i * VEC);
@@ -210,7 +229,8 @@ __global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat1
                                                              const float* __restrict__ gamma, const float* __restrict__ beta,
                                                              __nv_bfloat16* __restrict__ y, RowView yv,
                                                              float* __restrict__ mean_out, float* __restrict__ rstd_out,
-                                                             long long rows, float eps, GateArgs ga) {
+                                                             long long rows, float eps, GateArgs ga,
+                                                             const int* __restrict__ valid) {
   pdl_grid_sync();
   constexpr int D = 256 * NW;
   const int lane = threadIdx.x & 31;
@@ -238,11 +258,13 @@ __global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat1
   for (long long r0 = static_cast<long long>(blockIdx.x) * R; r0 < rows; r0 += static_cast<long long>(gridDim.x) * R) {
     uint4 raw[R];
     unsigned rb[R], rt[R];
+    bool dead[R];  // ragged batch: padded frame -> zeros out, nothing read
 #pragma unroll
     for (int i = 0; i < R; ++i) {
       const long long r = r0 + i;
       xv.split(r < rows ? r : 0, rb[i], rt[i]);
-      raw[i] = r < rows ? *reinterpret_cast<const uint4*>(x + xv.at(rb[i], rt[i]) + c0) : make_uint4(0u, 0u, 0u, 0u);
+      dead[i] = valid != nullptr && r < rows && static_cast<int>(rt[i]) >= valid[rb[i]];
+      raw[i] = (r < rows && !dead[i]) ? *reinterpret_cast<const uint4*>(x + xv.at(rb[i], rt[i]) + c0) : make_uint4(0u, 0u, 0u, 0u);
     }
     float v[R][8], s[R];
 #pragma unroll
@@ -303,13 +325,13 @@ __global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat1
           o0 = gelu_f(o0);
           o1 = gelu_f(o1);
         }
-        ou[k] = pack_bf16x2(o0, o1);
+        ou[k] = dead[i] ? 0u : pack_bf16x2(o0, o1);
       }
       if (r < rows) {
         *reinterpret_cast<uint4*>(y + yv.at(rb[i], rt[i]) + c0) = make_uint4(ou[0], ou[1], ou[2], ou[3]);
         if (threadIdx.x == 0) {
-          if (mean_out) mean_out[r] = mean[i];
-          if (rstd_out) rstd_out[r] = rstd[i];
+          if (mean_out) mean_out[r] = dead[i] ? 0.f : mean[i];
+          if (rstd_out) rstd_out[r] = dead[i] ? 0.f : rstd[i];
         }
       }
       if constexpr (GATE) {
@@ -331,7 +353,7 @@ __global__ void __launch_bounds__(32 * NW) ln_fwd_wide_kernel(const __nv_bfloat1
           const long long bidx = rb[i], t = rt[i];  // (the gate variant's views have T rows per batch)
           const float g1 = 1.0f / (1.0f + __expf(-(sa + gba)));
           const float g2 = 1.0f / (1.0f + __expf(-(sb + gbb)));
-          ga.gate[(bidx * ga.H + (threadIdx.x >> 3)) * ga.T + t] = g1 * (g2 * a_h - 1.0f) + 2.0f;
+          ga.gate[(bidx * ga.H + (threadIdx.x >> 3)) * ga.T + t] = dead[i] ? 1.0f : g1 * (g2 * a_h - 1.0f) + 2.0f;
         }
       }
     }
@@ -425,7 +447,8 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
                                                         const __nv_bfloat16* __restrict__ dres, RowView dresv,
                                                         __nv_bfloat16* __restrict__ dx, RowView dxv,
                                                         float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                        float* __restrict__ colsum, long long rows, int gelu) {
+                                                        float* __restrict__ colsum, long long rows, int gelu,
+                                                        const int* __restrict__ valid) {
   pdl_grid_sync();
   constexpr int D = 32 * VEC * NCH;
   constexpr int N = NCH * VEC;
@@ -465,9 +488,25 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
     nmean = mean_in[r];
     nrstd = rstd_in[r];
   };
-  if (warp_global < rows) fetch(warp_global);
+  // ragged batch: the gradient of a padded frame is zero by construction -- its dx row is written as zeros, nothing is read
+  auto dead = [&](long long r) {
+    if (valid == nullptr) return false;
+    unsigned rb, rt;
+    xv.split(r, rb, rt);
+    return static_cast<int>(rt) >= valid[rb];
+  };
+  if (warp_global < rows && !dead(warp_global)) fetch(warp_global);
   for (long long r = warp_global; r < rows; r += nwarps) {
     float xh[N], dz[N];
+    if (dead(r)) {
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) dz[i] = 0.f;
+      __nv_bfloat16* oz = dx + dxv.off(r);
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) VecIO<VEC>::store(oz + (i * 32 + lane) * VEC, dz);
+      if (r + nwarps < rows && !dead(r + nwarps)) fetch(r + nwarps);
+      continue;
+    }
     const __nv_bfloat16* dr = dy + dyv.off(r);
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
@@ -481,7 +520,7 @@ __global__ void __launch_bounds__(256, 2) ln_bwd_kernel(const __nv_bfloat16* __r
       }
     }
     const float mean = nmean, rstd = nrstd;
-    if (r + nwarps < rows) fetch(r + nwarps);
+    if (r + nwarps < rows && !dead(r + nwarps)) fetch(r + nwarps);
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int ch = 0; ch < NCH; ++ch) {
@@ -769,7 +808,7 @@ static int row_grid(long long rows, int warps_per_block) {
 // ------------------------------------------------------------------------------------------------ column sums
 // colsum[c] += sum_rows x[r, c]   (bias gradients); x bf16 [rows, N] with batch/row strides.
 __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __restrict__ x, RowView xv, int N,
-                                                     long long rows, float* __restrict__ out) {
+                                                     long long rows, float* __restrict__ out, const int* __restrict__ valid) {
   pdl_grid_sync();
   // block: a strip of 256 columns (32 lanes x 8 columns, 16-byte loads) x 8 row lanes; rows strided over blockIdx.y
   const int lane = threadIdx.x & 31;
@@ -783,6 +822,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __nv_bfloat16* __rest
 #pragma unroll 4
     for (long long r = static_cast<long long>(blockIdx.y) * 8 + rl; r < rows; r += step) {
       float v[8];
+      if (valid != nullptr) {  // ragged batch: padded frames hold zeros
+        unsigned rb, rt;
+        xv.split(r, rb, rt);
+        if (static_cast<int>(rt) >= valid[rb]) continue;
+      }
       VecIO<8>::load(x + xv.off(r) + c, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) a[i] += v[i];
@@ -1013,7 +1057,8 @@ __global__ void __launch_bounds__(256) gate_fwd_kernel(const __nv_bfloat16* __re
   }
   for (long long r = warp_global; r < rows; r += nwarps) {
     const __nv_bfloat16* xr = x + xv.off(r);
-    const long long b = r / T, t = r % T;
+    const unsigned ub = static_cast<unsigned>(r) / static_cast<unsigned>(T);
+    const long long b = ub, t = static_cast<unsigned>(r) - ub * static_cast<unsigned>(T);
 #pragma unroll 4
     for (int h = 0; h < H; ++h) {
       const float2 f = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(xr + h * 64 + lane * 2));
@@ -1039,7 +1084,8 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
                                                        const float* __restrict__ grep_b, const float* __restrict__ grep_a,
                                                        const float* __restrict__ dgate, __nv_bfloat16* __restrict__ dxg,
                                                        RowView dxv, float* __restrict__ dgrep_w,
-                                                       float* __restrict__ dgrep_b, float* __restrict__ dgrep_a) {
+                                                       float* __restrict__ dgrep_b, float* __restrict__ dgrep_a,
+                                                       const int* __restrict__ valid) {
   pdl_grid_sync();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -1069,7 +1115,16 @@ __global__ void __launch_bounds__(256) gate_bwd_kernel(const __nv_bfloat16* __re
   for (long long r = warp_global; r < rows; r += nwarps) {
     const __nv_bfloat16* xr = x + xv.off(r);
     __nv_bfloat16* dr = dxg + dxv.off(r);
-    const long long b = r / T, t = r % T;
+    const unsigned ub = static_cast<unsigned>(r) / static_cast<unsigned>(T);
+    const long long b = ub, t = static_cast<unsigned>(r) - ub * static_cast<unsigned>(T);
+    if (valid != nullptr && t >= valid[b]) {  // ragged batch: padded frame, zero gradient row, nothing read
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) {
+        const int h = gi * 4 + hs;
+        if (h < H) *reinterpret_cast<uint4*>(dr + h * 64 + q * 8) = make_uint4(0u, 0u, 0u, 0u);
+      }
+      continue;
+    }
     uint4 raw[NG];
     float dgs[NG], as[NG];
 #pragma unroll
@@ -1190,9 +1245,11 @@ using namespace b200;
 
 extern "C" {
 
-int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
-                         long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch, int batches,
-                         int D, int gelu, b200s_stream stream) {
+}  // extern "C"
+
+static int layer_norm_fwd_impl(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                               long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch, int batches,
+                               int D, int gelu, const int* valid, b200s_stream stream) {
   B200_CHECK_ARG(x && gamma && beta && y, "layer_norm_fwd: null pointer");
   const long long rows = static_cast<long long>(rows_per_batch) * batches;
   if (rows == 0) return 0;
@@ -1202,18 +1259,18 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
   if (ln_wide_enabled(false) && (D == 512 || D == 768 || D == 1024)) {
     const __nv_bfloat16* xp = static_cast<const __nv_bfloat16*>(x);
     __nv_bfloat16* yp = static_cast<__nv_bfloat16*>(y);
-    return gelu ? launch_ln_fwd_wide<false, true>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate)
-                : launch_ln_fwd_wide<false, false>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate);
+    return gelu ? launch_ln_fwd_wide<false, true>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate, valid)
+                : launch_ln_fwd_wide<false, false>(D, rows, st, xp, xv, gamma, beta, yp, yv, mean, rstd, rows, 1e-5f, no_gate, valid);
   }
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
     if (gelu) {
       B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value, false, true>, dim3(ln_fwd_grid(rows)),
                                  dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
-                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate));
+                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate, valid));
     } else {
       B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<decltype(vec)::value, decltype(nch)::value, false, false>, dim3(ln_fwd_grid(rows)),
                                  dim3(256), 0, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
-                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate));
+                                 static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, no_gate, valid));
     }
     return 0;
   });
@@ -1224,10 +1281,10 @@ int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const fl
 
 // LayerNorm forward that also writes the gru_rel_pos gate of the attention consuming y (replaces b200s_gate_fwd + one pass
 // over y).  D = H * 64 in {768, 1024}; x/y contiguous-row views as in b200s_layer_norm_fwd; gate: fp32 [B, H, T].
-int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
-                              long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
-                              const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
-                              b200s_stream stream) {
+static int layer_norm_gate_fwd_impl(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                                    long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                                    const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                                    const int* valid, b200s_stream stream) {
   B200_CHECK_ARG(x && gamma && beta && y && grep_w && grep_b && grep_a && gate, "layer_norm_gate_fwd: null pointer");
   B200_CHECK_ARG(D == H * 64 && (D == 256 || D == 512 || D == 768 || D == 1024),
                  "layer_norm_gate_fwd: D=%d must be H*64 and one of 256/512/768/1024", D);
@@ -1238,13 +1295,13 @@ int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, con
   const GateArgs ga{grep_w, grep_b, grep_a, gate, H, T};
   if (ln_wide_enabled(true) && (D == 512 || D == 768 || D == 1024)) {
     return launch_ln_fwd_wide<true, false>(D, rows, st, static_cast<const __nv_bfloat16*>(x), xv, gamma, beta,
-                                           static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, ga);
+                                           static_cast<__nv_bfloat16*>(y), yv, mean, rstd, rows, 1e-5f, ga, valid);
   }
   int rc = dispatch_width(D, [&](auto vec, auto nch) {
     if constexpr (decltype(vec)::value == 8) {
       B200_CHECK_CUDA(launch_pdl(ln_fwd_kernel<8, decltype(nch)::value, true, false>, dim3(ln_fwd_grid(rows)), dim3(256), 0, st,
                                  static_cast<const __nv_bfloat16*>(x), xv, gamma, beta, static_cast<__nv_bfloat16*>(y), yv, mean,
-                                 rstd, rows, 1e-5f, ga));
+                                 rstd, rows, 1e-5f, ga, valid));
     }
     return 0;
   });
@@ -1253,11 +1310,11 @@ int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, con
   return 0;
 }
 
-int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs, long long x_rs,
-                         const float* mean, const float* rstd, const float* gamma, const float* beta, const void* dres,
-                         long long dres_bs, long long dres_rs, void* dx, long long dx_bs, long long dx_rs, float* dgamma,
-                         float* dbeta, float* colsum, int rows_per_batch, int batches, int D, int gelu,
-                         b200s_stream stream) {
+static int layer_norm_bwd_impl(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs, long long x_rs,
+                               const float* mean, const float* rstd, const float* gamma, const float* beta, const void* dres,
+                               long long dres_bs, long long dres_rs, void* dx, long long dx_bs, long long dx_rs, float* dgamma,
+                               float* dbeta, float* colsum, int rows_per_batch, int batches, int D, int gelu,
+                               const int* valid, b200s_stream stream) {
   B200_CHECK_ARG(dy && x && mean && rstd && gamma && dx, "layer_norm_bwd: null pointer");
   B200_CHECK_ARG(!gelu || beta, "layer_norm_bwd: gelu mode needs beta");
   const long long rows = static_cast<long long>(rows_per_batch) * batches;
@@ -1265,7 +1322,7 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   RowView dyv{dy_bs, dy_rs, rows_per_batch}, xv{x_bs, x_rs, rows_per_batch}, rv{dres_bs, dres_rs, rows_per_batch},
       dxv{dx_bs, dx_rs, rows_per_batch};
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (ln_wide_enabled(false) && (D == 512 || D == 768 || D == 1024)) {
+  if (valid == nullptr && ln_wide_enabled(false) && (D == 512 || D == 768 || D == 1024)) {  // (the wide kernel has no ragged form)
     const auto aligned16 = [](const float* p) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const int vec_atomics = aligned16(dgamma) && aligned16(dbeta) && aligned16(colsum);
     auto go = [&](auto nw, auto rr, auto ge) {
@@ -1306,7 +1363,7 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
     B200_CHECK_CUDA(launch_pdl(kern, dim3(static_cast<int>(blocks)), dim3(256), smem, st,
                                static_cast<const __nv_bfloat16*>(dy), dyv, static_cast<const __nv_bfloat16*>(x), xv, mean, rstd,
                                gamma, beta, static_cast<const __nv_bfloat16*>(dres), rv, static_cast<__nv_bfloat16*>(dx), dxv,
-                               dgamma, dbeta, colsum, rows, gelu));
+                               dgamma, dbeta, colsum, rows, gelu, valid));
     return 0;
   });
   if (rc) return rc;
@@ -1314,8 +1371,8 @@ int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const
   return 0;
 }
 
-int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
-                 b200s_stream stream) {
+static int colsum_impl(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                       const int* valid, b200s_stream stream) {
   B200_CHECK_ARG(x && out, "colsum: null pointer");
   B200_CHECK_ARG(N % 8 == 0, "colsum: N must be a multiple of 8");
   const long long rows = static_cast<long long>(rows_per_batch) * batches;
@@ -1324,10 +1381,61 @@ int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_bat
   const int gx = ceil_div(N, 256);
   int gy = static_cast<int>(std::min<long long>(ceil_div_ll(rows, 32), std::max(1, 4 * sm_count() / gx)));
   dim3 grid(gx, std::max(1, gy));
-  B200_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), xv, N, rows,
-                                                                    out));
+  B200_CHECK_CUDA(launch_pdl(colsum_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const __nv_bfloat16*>(x), xv, N, rows, out, valid));
   B200_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" {
+
+int b200s_layer_norm_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                         long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch, int batches,
+                         int D, int gelu, b200s_stream stream) {
+  return layer_norm_fwd_impl(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu, nullptr, stream);
+}
+int b200s_layer_norm_fwd_ragged(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                                long long y_bs, long long y_rs, float* mean, float* rstd, int rows_per_batch, int batches,
+                                int D, int gelu, const int* valid, b200s_stream stream) {
+  return layer_norm_fwd_impl(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu, valid, stream);
+}
+int b200s_layer_norm_gate_fwd(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta, void* y,
+                              long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                              const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                              b200s_stream stream) {
+  return layer_norm_gate_fwd_impl(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate,
+                                  nullptr, stream);
+}
+int b200s_layer_norm_gate_fwd_ragged(const void* x, long long x_bs, long long x_rs, const float* gamma, const float* beta,
+                                     void* y, long long y_bs, long long y_rs, float* mean, float* rstd, int T, int B, int D,
+                                     const float* grep_w, const float* grep_b, const float* grep_a, int H, float* gate,
+                                     const int* valid, b200s_stream stream) {
+  return layer_norm_gate_fwd_impl(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate,
+                                  valid, stream);
+}
+int b200s_layer_norm_bwd(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs, long long x_rs,
+                         const float* mean, const float* rstd, const float* gamma, const float* beta, const void* dres,
+                         long long dres_bs, long long dres_rs, void* dx, long long dx_bs, long long dx_rs, float* dgamma,
+                         float* dbeta, float* colsum, int rows_per_batch, int batches, int D, int gelu,
+                         b200s_stream stream) {
+  return layer_norm_bwd_impl(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
+                             dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu, nullptr, stream);
+}
+int b200s_layer_norm_bwd_ragged(const void* dy, long long dy_bs, long long dy_rs, const void* x, long long x_bs, long long x_rs,
+                                const float* mean, const float* rstd, const float* gamma, const float* beta, const void* dres,
+                                long long dres_bs, long long dres_rs, void* dx, long long dx_bs, long long dx_rs, float* dgamma,
+                                float* dbeta, float* colsum, int rows_per_batch, int batches, int D, int gelu,
+                                const int* valid, b200s_stream stream) {
+  return layer_norm_bwd_impl(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
+                             dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu, valid, stream);
+}
+int b200s_colsum(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                 b200s_stream stream) {
+  return colsum_impl(x, x_bs, x_rs, rows_per_batch, batches, N, out, nullptr, stream);
+}
+int b200s_colsum_ragged(const void* x, long long x_bs, long long x_rs, int rows_per_batch, int batches, int N, float* out,
+                        const int* valid, b200s_stream stream) {
+  return colsum_impl(x, x_bs, x_rs, rows_per_batch, batches, N, out, valid, stream);
 }
 
 int b200s_dgelu_mul_ex(const void* dy, long long dy_bs, long long dy_rs, const void* pre, long long pre_bs, long long pre_rs,
@@ -1463,9 +1571,11 @@ int b200s_gate_fwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   return 0;
 }
 
-int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
-                   const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
-                   long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, b200s_stream stream) {
+}  // extern "C"
+
+static int gate_bwd_impl(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                         const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                         long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, const int* valid, b200s_stream stream) {
   B200_CHECK_ARG(x && grep_w && grep_b && grep_a && dgate && dxg && dgrep_w && dgrep_b && dgrep_a,
                  "gate_bwd: null pointer");
   const long long rows = static_cast<long long>(T) * B;
@@ -1476,7 +1586,7 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   auto go = [&](auto ng) {
     B200_CHECK_CUDA(launch_pdl(gate_bwd_kernel<decltype(ng)::value>, dim3(static_cast<int>(blocks)), dim3(256), 8 * H * sizeof(float),
                                static_cast<cudaStream_t>(stream), static_cast<const __nv_bfloat16*>(x), xv, H, T, rows, grep_w,
-                               grep_b, grep_a, dgate, static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a));
+                               grep_b, grep_a, dgate, static_cast<__nv_bfloat16*>(dxg), dv, dgrep_w, dgrep_b, dgrep_a, valid));
     return 0;
   };
   const int ng = (H + 3) / 4;
@@ -1485,6 +1595,22 @@ int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, 
   if (rcg) return rcg;
   B200_CHECK_LAUNCH();
   return 0;
+}
+
+extern "C" {
+
+int b200s_gate_bwd(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                   const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                   long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, b200s_stream stream) {
+  return gate_bwd_impl(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, dgate, dxg, dx_bs, dx_rs, dgrep_w, dgrep_b, dgrep_a, nullptr,
+                       stream);
+}
+int b200s_gate_bwd_ragged(const void* x, long long x_bs, long long x_rs, int T, int B, int H, const float* grep_w,
+                          const float* grep_b, const float* grep_a, const float* dgate, void* dxg, long long dx_bs,
+                          long long dx_rs, float* dgrep_w, float* dgrep_b, float* dgrep_a, const int* valid,
+                          b200s_stream stream) {
+  return gate_bwd_impl(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, dgate, dxg, dx_bs, dx_rs, dgrep_w, dgrep_b, dgrep_a, valid,
+                       stream);
 }
 
 int b200s_relpos_table_fwd(const float* emb, const int* lut, int n, int H, float* tab, b200s_stream stream) {

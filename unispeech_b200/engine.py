@@ -312,17 +312,17 @@ class Engine:
     def _uses_gate(self) -> bool:
         return bool(getattr(self.cfg, "relative_position_embedding", False) and getattr(self.cfg, "gru_rel_pos", False))
 
-    def _ln_with_gate(self, x, ln, y, mean, rstd, T, B, D, consumer_idx):
+    def _ln_with_gate(self, x, ln, y, mean, rstd, T, B, D, consumer_idx, rag=None):
         """y = ln(x) and the gate of encoder.layers[consumer_idx].self_attn; remembered until that layer consumes y."""
         a = self.m.encoder.layers[consumer_idx].self_attn
         H = self.cfg.encoder_attention_heads
         if D not in (256, 512, 768, 1024):  # the fused kernel needs 8 columns per lane; narrow models take two passes
-            ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, y, T * D, D, mean, rstd, T, B, D)
+            ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, y, T * D, D, mean, rstd, T, B, D, valid=rag)
             self._pending_gate = None
             return None
         gate = torch.empty(B, H, T, dtype=torch.float32, device=x.device)
         ops.layer_norm_gate_fwd(x, T * D, D, ln.weight, ln.bias, y, T * D, D, mean, rstd, T, B, D, a.grep_linear.weight,
-                                a.grep_linear.bias, a.grep_a, H, gate)
+                                a.grep_linear.bias, a.grep_a, H, gate, valid=rag)
         self._pending_gate = (y.data_ptr(), consumer_idx, gate)
         return gate
 
@@ -381,7 +381,7 @@ class Engine:
                 ln = m.feature_extractor.conv_layers[i][2][1]
                 mean = torch.empty(B * Ti, dtype=torch.float32, device=dev)
                 rstd = torch.empty(B * Ti, dtype=torch.float32, device=dev)
-                ops.layer_norm_fwd(y, Tpi * C, C, ln.weight, ln.bias, out, Tpi * C, C, mean, rstd, Ti, B, C, gelu=True)
+                ops.layer_norm_fwd(y, Tpi * C, C, ln.weight, ln.bias, out, Tpi * C, C, mean, rstd, Ti, B, C, gelu=True, valid=vrow(i))
                 st["y"].append(y); st["mean"].append(mean); st["rstd"].append(rstd)
             else:
                 y = torch.empty(B, Tpi, C, dtype=BF, device=dev) if save else None
@@ -419,7 +419,7 @@ class Engine:
                     ln = m.feature_extractor.conv_layers[i][2][1]
                     ops.layer_norm_bwd(dA, Tpi * C, C, st["y"][i], Tpi * C, C, st["mean"][i], st["rstd"][i], ln.weight,
                                        ln.bias, None, 0, 0, gv, Tg * C, C, self.g(ln.weight), self.g(ln.bias), None, Ti, B, C,
-                                       gelu=True)
+                                       gelu=True, valid=cv[i] if cv is not None else None)
                 else:
                     ops.dgelu_mul(dA, Tpi * C, C, st["y"][i], Tpi * C, C, gv, Tg * C, C, Ti, B, C, None, pre_is_grad=True)
             gv = gpad[:, lead:]
@@ -462,7 +462,7 @@ class Engine:
                 ln = m.feature_extractor.conv_layers[i - 1][2][1]
                 ops.layer_norm_bwd(dAp, Tp_in * C, C, st["y"][i - 1], Tp_in * C, C, st["mean"][i - 1], st["rstd"][i - 1],
                                    ln.weight, ln.bias, None, 0, 0, gnext[:, lead_p:], Tg_p * C, C, self.g(ln.weight),
-                                   self.g(ln.bias), None, T_in, B, C, gelu=True)
+                                   self.g(ln.bias), None, T_in, B, C, gelu=True, valid=cv[i - 1] if cv is not None else None)
                 gpad = gnext
                 dA = None
             else:
@@ -628,10 +628,10 @@ class Engine:
             xn, st["mean1"], st["rstd1"] = e(B, T, D), f(M), f(M)
             ln = lyr.self_attn_layer_norm
             if want_gate:
-                gate = self._ln_with_gate(x, ln, xn, st["mean1"], st["rstd1"], T, B, D, idx)
+                gate = self._ln_with_gate(x, ln, xn, st["mean1"], st["rstd1"], T, B, D, idx, rag=rag)
                 self._pending_gate = None
             else:
-                ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, xn, T * D, D, st["mean1"], st["rstd1"], T, B, D)
+                ops.layer_norm_fwd(x, T * D, D, ln.weight, ln.bias, xn, T * D, D, st["mean1"], st["rstd1"], T, B, D, valid=rag)
             st["xn"] = xn
         else:
             xn = x
@@ -658,12 +658,12 @@ class Engine:
             x1 = y1
             x1n, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
             ln = lyr.final_layer_norm
-            ops.layer_norm_fwd(x1, T * D, D, ln.weight, ln.bias, x1n, T * D, D, st["mean2"], st["rstd2"], T, B, D)
+            ops.layer_norm_fwd(x1, T * D, D, ln.weight, ln.bias, x1n, T * D, D, st["mean2"], st["rstd2"], T, B, D, valid=rag)
             ffn_in = x1n
         else:
             x1, st["mean1"], st["rstd1"] = e(B, T, D), f(M), f(M)
             ln = lyr.self_attn_layer_norm
-            ops.layer_norm_fwd(y1, T * D, D, ln.weight, ln.bias, x1, T * D, D, st["mean1"], st["rstd1"], T, B, D)
+            ops.layer_norm_fwd(y1, T * D, D, ln.weight, ln.bias, x1, T * D, D, st["mean1"], st["rstd1"], T, B, D, valid=rag)
             ffn_in = x1
         hg = e(B, T, Fd)
         hp = e(B, T, Fd) if save else None
@@ -686,9 +686,9 @@ class Engine:
             out, st["mean2"], st["rstd2"] = e(B, T, D), f(M), f(M)
             ln = lyr.final_layer_norm
             if want_gate and idx + 1 < len(m.encoder.layers):  # `out` is the next layer's input: leave its gate behind
-                self._ln_with_gate(y2, ln, out, st["mean2"], st["rstd2"], T, B, D, idx + 1)
+                self._ln_with_gate(y2, ln, out, st["mean2"], st["rstd2"], T, B, D, idx + 1, rag=rag)
             else:
-                ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D)
+                ops.layer_norm_fwd(y2, T * D, D, ln.weight, ln.bias, out, T * D, D, st["mean2"], st["rstd2"], T, B, D, valid=rag)
         if save:
             st.update(qkv=qkv, gate=gate, ao=ao, lse=lse, y1=y1, x1=x1, ffn_in=ffn_in, hp=hp, hg=hg, y2=y2, tab=tab, pad=pad_u8,
                       dmask=dmask, rag=rag)
@@ -723,16 +723,16 @@ class Engine:
         if pre_ln:
             dy2 = dout                                           # x2 = x1 + fc2(...)
             dz2 = through_dropout(dy2, DR.L_DROPOUT3) if p_h > 0 else dy2
-            ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias))
+            ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias), valid=rag)
         else:
             dy2 = e(B, T, D)
             ln = lyr.final_layer_norm
             ops.layer_norm_bwd(dout, T * D, D, st["y2"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, None, 0, 0,
-                               dy2, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(lyr.fc2.bias), T, B, D)
+                               dy2, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(lyr.fc2.bias), T, B, D, valid=rag)
             dz2 = dy2
             if p_h > 0:
                 dz2 = through_dropout(dy2, DR.L_DROPOUT3)
-                ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias))
+                ops.colsum(dz2, T * D, D, T, B, D, g(lyr.fc2.bias), valid=rag)
         self._wg(dz2, D, st["hg"], Fd, g(lyr.fc2.weight), rag, T, B)
         dhp = e(B, T, Fd)
         self._mm(dz2, D, w["w2T"], Fd, dhp, rag, T, B, dgelu=2, gelu_aux=st["hp"], aux_ld=Fd, colsum=g(lyr.fc1.bias))
@@ -744,22 +744,22 @@ class Engine:
             ln = lyr.final_layer_norm
             # (without dropout1 the out_proj bias gradient is the column sum of dx1: taken inside the LayerNorm backward)
             ops.layer_norm_bwd(dffn_in, T * D, D, st["x1"], T * D, D, st["mean2"], st["rstd2"], ln.weight, ln.bias, dy2, T * D, D,
-                               dx1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D)
+                               dx1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D, valid=rag)
             dy1 = dx1                                            # x1 = x + out_proj(attn)
             dz1 = dy1
             if p_h > 0:
                 dz1 = through_dropout(dy1, DR.L_DROPOUT1)
-                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
+                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias), valid=rag)
         else:
             self._mm(dhp, Fd, w["w1T"], D, dx1, rag, T, B, res1=dy2, res1_ld=D)
             dy1 = e(B, T, D)
             ln = lyr.self_attn_layer_norm
             ops.layer_norm_bwd(dx1, T * D, D, st["y1"], T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, None, 0, 0,
-                               dy1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D)
+                               dy1, T * D, D, g(ln.weight), g(ln.bias), None if p_h > 0 else g(a.out_proj.bias), T, B, D, valid=rag)
             dz1 = dy1
             if p_h > 0:
                 dz1 = through_dropout(dy1, DR.L_DROPOUT1)
-                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias))
+                ops.colsum(dz1, T * D, D, T, B, D, g(a.out_proj.bias), valid=rag)
         # ---------------- attention block
         self._wg(dz1, D, st["ao"], D, g(a.out_proj.weight), rag, T, B)
         dao = e(B, T, D)
@@ -782,13 +782,13 @@ class Engine:
         else:
             ops.attn_bwd(st["qkv"], st["ao"], dao, gate, tab, pad, st["lse"], delta, dqkv, dgate,
                          dtab if tab is not None else None, B, T, H, 64 ** -0.5)
-        ops.colsum(dqkv, 0, 3 * D, M, 1, 3 * D, g(a.q_proj.bias).view(-1))  # q,k,v bias grads are adjacent in the flat buffer
+        ops.colsum(dqkv, T * 3 * D, 3 * D, T, B, 3 * D, g(a.q_proj.bias).view(-1), valid=rag)  # q,k,v bias grads are adjacent in the flat buffer
         attn_in = st["xn"] if pre_ln else x
         dxg = None
         if gate is not None:
             dxg = e(B, T, D)
             ops.gate_bwd(attn_in, T * D, D, T, B, H, a.grep_linear.weight, a.grep_linear.bias, a.grep_a, dgate, dxg, T * D, D,
-                         g(a.grep_linear.weight), g(a.grep_linear.bias), g(a.grep_a))
+                         g(a.grep_linear.weight), g(a.grep_linear.bias), g(a.grep_a), valid=rag)
         self._wg(dqkv, 3 * D, attn_in, D, g(a.q_proj.weight), rag, T, B)
         dx = e(B, T, D)
         if pre_ln:
@@ -799,7 +799,7 @@ class Engine:
                 self._mm(dqkv, 3 * D, w["qkvT"], D, dxn, rag, T, B)
             ln = lyr.self_attn_layer_norm
             ops.layer_norm_bwd(dxn, T * D, D, x, T * D, D, st["mean1"], st["rstd1"], ln.weight, ln.bias, dy1, T * D, D, dx,
-                               T * D, D, g(ln.weight), g(ln.bias), None, T, B, D)
+                               T * D, D, g(ln.weight), g(ln.bias), None, T, B, D, valid=rag)
         else:
             if dxg is not None:
                 self._mm(dqkv, 3 * D, w["qkvT"], D, dx, rag, T, B, res1=dy1, res1_ld=D, res2=dxg, res2_ld=D)

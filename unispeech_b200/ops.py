@@ -91,29 +91,52 @@ def posconv_wgrad(dy, dy_bs, dy_rs, xpad, xpad_bs, T, B, D, G, taps, dwp):
 
 
 # ------------------------------------------------------------------------------------------------- row kernels
-def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu=False):
-    _call("b200s_layer_norm_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
-           L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s(),
-          nbytes=2.0 * 2 * rows_per_batch * batches * D)
+def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu=False, valid=None):
+    """`valid` (int32 [batches], device): ragged batch, rows at or beyond valid[b] are padding (written as zeros, not read)."""
+    nb = 2.0 * 2 * rows_per_batch * batches * D
+    if valid is None:
+        _call("b200s_layer_norm_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
+              L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0), _s(),
+              nbytes=nb)
+    else:
+        _call("b200s_layer_norm_fwd_ragged", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
+              L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0),
+              L.ptr(valid), _s(), nbytes=nb)
 
 
-def layer_norm_gate_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate):
-    _call("b200s_layer_norm_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
-           L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(T), i32(B), i32(D), L.ptr(grep_w), L.ptr(grep_b), L.ptr(grep_a), i32(H),
-           L.ptr(gate), _s(), nbytes=2.0 * 2 * T * B * D)
+def layer_norm_gate_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, T, B, D, grep_w, grep_b, grep_a, H, gate,
+                        valid=None):
+    nb = 2.0 * 2 * T * B * D
+    if valid is None:
+        _call("b200s_layer_norm_gate_fwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y), L.ll(y_bs),
+              L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(T), i32(B), i32(D), L.ptr(grep_w), L.ptr(grep_b), L.ptr(grep_a), i32(H),
+              L.ptr(gate), _s(), nbytes=nb)
+    else:
+        _call("b200s_layer_norm_gate_fwd_ragged", L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(gamma), L.ptr(beta), L.ptr(y),
+              L.ll(y_bs), L.ll(y_rs), L.ptr(mean), L.ptr(rstd), i32(T), i32(B), i32(D), L.ptr(grep_w), L.ptr(grep_b),
+              L.ptr(grep_a), i32(H), L.ptr(gate), L.ptr(valid), _s(), nbytes=nb)
 
 
 def layer_norm_bwd(dy, dy_bs, dy_rs, x, x_bs, x_rs, mean, rstd, gamma, beta, dres, dres_bs, dres_rs, dx, dx_bs, dx_rs,
-                   dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu=False):
-    _call("b200s_layer_norm_bwd", L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean),
-           L.ptr(rstd), L.ptr(gamma), L.ptr(beta), L.ptr(dres), L.ll(dres_bs), L.ll(dres_rs), L.ptr(dx), L.ll(dx_bs),
-           L.ll(dx_rs), L.ptr(dgamma), L.ptr(dbeta), L.ptr(colsum), i32(rows_per_batch), i32(batches), i32(D),
-           i32(1 if gelu else 0), _s(), nbytes=(4.0 if dres is not None else 3.0) * 2 * rows_per_batch * batches * D)
+                   dgamma, dbeta, colsum, rows_per_batch, batches, D, gelu=False, valid=None):
+    nb = (4.0 if dres is not None else 3.0) * 2 * rows_per_batch * batches * D
+    head = (L.ptr(dy), L.ll(dy_bs), L.ll(dy_rs), L.ptr(x), L.ll(x_bs), L.ll(x_rs), L.ptr(mean), L.ptr(rstd), L.ptr(gamma),
+            L.ptr(beta), L.ptr(dres), L.ll(dres_bs), L.ll(dres_rs), L.ptr(dx), L.ll(dx_bs), L.ll(dx_rs), L.ptr(dgamma),
+            L.ptr(dbeta), L.ptr(colsum), i32(rows_per_batch), i32(batches), i32(D), i32(1 if gelu else 0))
+    if valid is None:
+        _call("b200s_layer_norm_bwd", *head, _s(), nbytes=nb)
+    else:
+        _call("b200s_layer_norm_bwd_ragged", *head, L.ptr(valid), _s(), nbytes=nb)
 
 
-def colsum(x, x_bs, x_rs, rows_per_batch, batches, N, out):
-    _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s(),
-          nbytes=2.0 * rows_per_batch * batches * N)
+def colsum(x, x_bs, x_rs, rows_per_batch, batches, N, out, valid=None):
+    nb = 2.0 * rows_per_batch * batches * N
+    if valid is None:
+        _call("b200s_colsum", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out), _s(),
+              nbytes=nb)
+    else:
+        _call("b200s_colsum_ragged", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(rows_per_batch), i32(batches), i32(N), L.ptr(out),
+              L.ptr(valid), _s(), nbytes=nb)
 
 
 def dgelu_mul(dy, dy_bs, dy_rs, pre, pre_bs, pre_rs, out, out_bs, out_rs, rows_per_batch, batches, N, colsum_out=None,
@@ -138,10 +161,14 @@ def gate_fwd(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, gate):
            L.ptr(grep_a), L.ptr(gate), _s())
 
 
-def gate_bwd(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, dgate, dxg, dx_bs, dx_rs, dgrep_w, dgrep_b, dgrep_a):
-    _call("b200s_gate_bwd", L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b),
-           L.ptr(grep_a), L.ptr(dgate), L.ptr(dxg), L.ll(dx_bs), L.ll(dx_rs), L.ptr(dgrep_w), L.ptr(dgrep_b),
-           L.ptr(dgrep_a), _s())
+def gate_bwd(x, x_bs, x_rs, T, B, H, grep_w, grep_b, grep_a, dgate, dxg, dx_bs, dx_rs, dgrep_w, dgrep_b, dgrep_a, valid=None):
+    head = (L.ptr(x), L.ll(x_bs), L.ll(x_rs), i32(T), i32(B), i32(H), L.ptr(grep_w), L.ptr(grep_b), L.ptr(grep_a), L.ptr(dgate),
+            L.ptr(dxg), L.ll(dx_bs), L.ll(dx_rs), L.ptr(dgrep_w), L.ptr(dgrep_b), L.ptr(dgrep_a))
+    nb = 2.0 * 2 * T * B * H * 64
+    if valid is None:
+        _call("b200s_gate_bwd", *head, _s(), nbytes=nb)
+    else:
+        _call("b200s_gate_bwd_ragged", *head, L.ptr(valid), _s(), nbytes=nb)
 
 
 def relpos_table_fwd(emb, lut, n, H, tab):

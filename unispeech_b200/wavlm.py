@@ -548,8 +548,9 @@ class WavLM(nn.Module):
 
     def _extractor(self, source, valid_last=None):
         """`valid_last` (int32 [B], host or device): frames of the extractor output up to every utterance's last valid one.  The
-        conv GEMMs then skip whole tiles of padding (engine.conv_valid_rows) -- not when the feature penalty is wanted: the
-        reference takes `features.pow(2).mean()` over the padded frames too, so they must hold the reference's values."""
+        conv stack then skips the padding beyond them (engine.conv_valid_rows) -- not when the feature penalty is wanted (the
+        reference takes `features.pow(2).mean()` over the padded frames too, so they must hold the reference's values), and
+        not when the caller asks for the conv features themselves (`ret_conv`: extract_features passes no `valid_last` then)."""
         eng = self._begin(source.device)
         wav = source.float().contiguous()
         w0 = self.feature_extractor.conv_layers[0][0].weight
@@ -617,7 +618,7 @@ class WavLM(nn.Module):
         valid_last = None
         if fpm is not None and getattr(fpm, "_b200_valid", None) is not None:
             valid_last = fpm._b200_valid_host if fpm_host is not None else fpm._b200_valid
-        feats, T2 = self._extractor(source, valid_last)
+        feats, T2 = self._extractor(source, None if ret_conv else valid_last)
         assert T2 == T
         self._last_conv = feats  # conv features [B, Tp, C] (valid rows T): `features_pen` of the pre-training criterion reads them
         eng = self._engine
