@@ -240,6 +240,13 @@ class Workload:
         self.fwd_flops = workloads.forward_flops(self.L, vars(cfg))          # padded shape (what the kernels execute)
         self.valid_fwd_flops = sum(workloads.forward_flops(n, vars(cfg)) for n in self.lengths) / B   # per utterance at its own length
 
+    def _mark(self, name):
+        """(--phases) a CUDA event at a phase boundary of the step, on the current stream."""
+        if getattr(self, "phases", None) is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.phases.append((name, ev))
+
     def _sync_for(self, collective: bool):
         """Bucketed gradient averaging overlapped with the backward pass (N > 1); created once the engine owns the layout."""
         if self.world == 1:
@@ -270,18 +277,22 @@ class Workload:
             wav = self.wav_host.to(self.dev, non_blocking=True) if e2e else self.wav_dev
         if self.pretrain:
             return self.pretrain_step(wav, e2e, collective)
+        self._mark("start")
         nvtx.range_push("forward")
         x, _ = model.extract_features(wav, padding_mask=self.pad_host, mask=True)
         loss = (x.float() * self.R).sum()
         nvtx.range_pop()
+        self._mark("forward")
         sync = self._sync_for(collective)
         nvtx.range_push("backward")
         loss.backward()
         nvtx.range_pop()
+        self._mark("backward")
         if sync is not None:
             nvtx.range_push("reduce-grads")
             sync.finish()  # buckets were issued during backward; this sends the last one and joins the NCCL stream
             nvtx.range_pop()
+        self._mark("reduce-grads")
         if e2e:
             self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
@@ -291,28 +302,34 @@ class Workload:
         from unispeech_b200.optim import FusedAdam
         nvtx = torch.cuda.nvtx
         model = self.model
+        self._mark("start")
         nvtx.range_push("forward")
         out = model(wav, target_list=self.labels, padding_mask=self.pad_host, mask=True)
         lw = [10.0, 10.0, 0.0, 0.1] if self.sat else [10.0]   # features_pen, loss_spk_m, loss_spk_u, diversity (prob_perplexity)
         loss, sample_size, _ = model.criterion(out, pred_masked_weight=1.0, pred_nomask_weight=0.0, loss_weights=lw)
         nvtx.range_pop()
+        self._mark("forward")
         sync = self._sync_for(collective)
         nvtx.range_push("backward")
         loss.backward()
         nvtx.range_pop()
+        self._mark("backward")
         if sync is not None:
             nvtx.range_push("reduce-grads")
             sync.finish()
             nvtx.range_pop()
+        self._mark("reduce-grads")
         if self.opt is None:
             self.opt = FusedAdam(model, lr=1e-5, betas=(0.9, 0.98), eps=1e-6, weight_decay=0.01)
         self.opt.multiply_grads(self.world / max(sample_size, 1))   # trainer.py:796-801 (sample_size is per rank here: equal shards)
         nvtx.range_push("clip-grads")
         self.opt.clip_grad_norm(1.0)
         nvtx.range_pop()
+        self._mark("clip-grads")
         nvtx.range_push("optimizer")
         self.opt.step(zero_grad=True)
         nvtx.range_pop()
+        self._mark("optimizer")
         if e2e:
             self.loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
         return loss
@@ -459,6 +476,50 @@ def quick_line(w: Workload, steps: int, warmup: int, e2e: bool = True):
     return out
 
 
+def graph_probe(args):
+    """The fixed-length fwd+bwd workload captured as ONE CUDA graph (unispeech_b200.graphed.GraphedForwardBackward): device time per
+    replayed step, the same with the batch coming from pinned host memory, and what the HOST spends per step (span-mask sampling +
+    two small copies + one graph launch).  Runs in its own process: a failed capture must not take the bench line with it."""
+    from unispeech_b200 import _lib
+    from unispeech_b200.graphed import GraphedForwardBackward
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    _lib.check_device()
+    w = Workload(args.model, dev, 0, 1, dropout=0.0)
+    g = GraphedForwardBackward(w.model, lambda x: (x.float() * w.R).sum(), w.B, w.L, dev)
+    g.wav.copy_(w.wav_dev)
+    g.capture(warmup=3)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def run(n, e2e):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            loss = g.step(w.wav_host if e2e else None)
+            if e2e:
+                loss_host.copy_(loss.reshape(1), non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    run(3, False)
+    ms = run(args.steps, False)
+    run(2, True)
+    ms_e = run(args.steps, True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        g.step(None)
+    host_ms = (time.perf_counter() - t0) * 1e3 / 4
+    torch.cuda.synchronize()
+    audio = w.audio_seconds(args.steps)
+    print(json.dumps({"workload": w.describe() + "; forward + loss + backward replayed as one CUDA graph, span mask re-sampled on the "
+                      "host every step", "value": audio / (ms * 1e-3), "unit": "audio-s/s", "ms_per_step": ms / args.steps,
+                      "e2e": {"value": audio / (ms_e * 1e-3), "unit": "audio-s/s", "ms_per_step": ms_e / args.steps},
+                      "host_ms_per_step": host_ms, "loss_finite": bool(torch.isfinite(g.loss).item())}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -477,10 +538,16 @@ def main():
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-also", action="store_true", help="skip the secondary measurements (WavLM-Base, reference dropouts)")
     ap.add_argument("--ncu-step", action="store_true", help="profile exactly one step (cudaProfilerStart/Stop) and exit")
+    ap.add_argument("--phases", action="store_true", help="add `phases_ms` (device time between the NVTX phase boundaries of a step, "
+                    "rank 0, mean of 3 extra steps) to the line")
+    ap.add_argument("--graph-probe", action="store_true", help="(internal) measure the whole step as one CUDA graph "
+                    "(unispeech_b200/graphed.py) and print a small JSON object; the default run calls this in a child process")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     args.warmup = max(args.warmup, 3)
+    if args.graph_probe:
+        return graph_probe(args)
 
     import torch.distributed as dist
     from unispeech_b200 import _lib, ops
@@ -528,6 +595,19 @@ def main():
         w.step(False)
     host_ms = (time.perf_counter() - t0) * 1e3 / 2
     torch.cuda.synchronize()
+
+    phases_ms = None
+    if args.phases:
+        w.phases = []
+        for _ in range(3):
+            w.step(False)
+        torch.cuda.synchronize()
+        acc = {}
+        for (n0_, e0_), (n1_, e1_) in zip(w.phases[:-1], w.phases[1:]):
+            if n1_ != "start":
+                acc.setdefault(n1_, []).append(e0_.elapsed_time(e1_))
+        phases_ms = {k: round(sum(v) / len(v), 3) for k, v in acc.items()}
+        w.phases = None
 
     audio_s = w.audio_seconds(args.steps)
     value = audio_s / (ms * 1e-3)
@@ -629,6 +709,21 @@ def main():
                                   f"intra-op threads on a 2 x 5 s probe (host has {os.cpu_count()} logical CPUs); "
                                   "`--impl reference` times 3+ steps"}
 
+    # ---- the same step replayed as one CUDA graph (N = 1, fixed-length fwd+bwd workload): host cost per step with the launches
+    # taken off the host; measured in a child process
+    graph = None
+    if world == 1 and not (args.no_also or args.ragged or args.pretrain or args.sat) and args.dropout == 0.0 and args.model != "tiny":
+        import subprocess
+        try:
+            if w is not None:
+                w.free()
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--graph-probe", "--model", args.model, "--steps",
+                                str(args.steps)], capture_output=True, text=True, timeout=420)
+            last = [l for l in r.stdout.strip().splitlines() if l.startswith("{")]
+            graph = json.loads(last[-1]) if (r.returncode == 0 and last) else {"error": (r.stderr or r.stdout)[-400:]}
+        except Exception as exc:  # never at the expense of the measured line
+            graph = {"error": f"{type(exc).__name__}: {exc}"}
+
     if rank == 0:
         fwd_flops = w.valid_fwd_flops
         line = {
@@ -646,10 +741,14 @@ def main():
         }
         if parity is not None:
             line["parity"] = parity
+        if phases_ms is not None:
+            line["phases_ms"] = phases_ms
         if args.ragged:
             line["padded_equivalent_value"] = w.padded_audio_seconds(args.steps) / (ms * 1e-3)
         if also is not None:
             line["also"] = also
+        if graph is not None:
+            line["cuda_graph_step"] = graph
         if breakdown is not None:
             line["breakdown_ms"] = {k: round(v["ms"], 3) for k, v in sorted(breakdown.items(), key=lambda kv: -kv[1]["ms"])}
         print(json.dumps(line))
