@@ -557,7 +557,15 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    nccl_ctas = None
     if world > 1:
+        from unispeech_b200.parallel import configure_overlap
+        _lib.check_device()
+        nccl_ctas = configure_overlap(int(os.environ.get("B200S_NCCL_CTAS", "4")))   # NCCL_MAX_CTAS + SMs the persistent GEMMs leave free
+        # the host side of a step (span-mask sampling, instance draws) is torch / numpy CPU work: torchrun pins every rank to ONE
+        # OpenMP thread unless told otherwise
+        if os.environ.get("OMP_NUM_THREADS", "1") == "1":
+            torch.set_num_threads(max(1, min(8, (os.cpu_count() or 8) // max(1, world))))
         dist.init_process_group("nccl", device_id=dev)
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
 
@@ -730,7 +738,9 @@ def main():
             "metric": "audio-sec/sec fwd+bwd", "value": value, "unit": "audio-s/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": w.describe(), "global_batch": world * B,
+            "config": {"workload": w.describe() + (f"; gradient exchange: bucketed NCCL all-reduce (AVG, fp32) overlapped with backward, "
+                                                   f"NCCL_MAX_CTAS={nccl_ctas}, the persistent GEMMs leave that many SMs free" if world > 1 else ""),
+                       "global_batch": world * B,
                        "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", 
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops * B / (sum(w.lengths) / SR) / 1e9},
             "e2e": {"value": e2e_value, "unit": "audio-s/s", "h2d_bytes_per_step": w.wav_host.numel() * 4,

@@ -136,6 +136,12 @@ int b200s_attn_bwd_fused_dropout(const void* qkv, const void* out, const void* d
                                  float drop_p, const uint32_t* drop_mask, b200s_stream stream);
 long long b200s_attn_dropout_mask_words(int B, int T, int H);
 
+/* SMs the persistent CTA-pair GEMM kernels leave free (0 = none, the default).  Data-parallel runs overlap the NCCL gradient exchange
+ * with the backward pass; its CTAs (bounded by NCCL_MAX_CTAS) then find free SMs instead of displacing clusters of a grid that was
+ * sized for the whole chip (legacy_distributed_data_parallel.py:76-165 runs the exchange strictly after backward, so the reference
+ * has no counterpart). */
+int b200s_reserve_sms(int sms);
+
 /* ============================ row kernels (csrc/rowops.cu) ============================ */
 
 /* y = LayerNorm(x) * gamma + beta [then exact GELU]; saves mean / rstd (fp32 [rows]).  nn.LayerNorm / Fp32LayerNorm

@@ -3,6 +3,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 
 #include "../../include/unispeech_b200.h"
@@ -143,6 +144,8 @@ static int cluster_pairs_for(int m_tiles_total) {
   return (e && e[0] == '1' && m_tiles_total >= 2) ? 2 : 1;
 }
 
+static std::atomic<int> g_reserved_sms{0};
+
 // opt the kernel into its shared-memory size (once) and report how many clusters can be resident at once (a 4-CTA cluster
 // does not fit every GPC remainder, so fewer than sm_count / 4 are)
 template <bool A_MN, bool B_MN, int KIND, int NPAIR>
@@ -174,6 +177,11 @@ static cudaError_t pair_kernel_setup(int* units) {
     }
   });
   *units = max_units;
+  // SMs set aside for a concurrent collective (b200s_reserve_sms): a persistent kernel that asks for every SM while NCCL holds a
+  // few would leave its last clusters waiting for the others to finish -- up to twice the kernel's time for a statically
+  // scheduled grid
+  const int keep = g_reserved_sms.load(std::memory_order_relaxed);
+  if (keep > 0) *units = std::max(1, std::min(max_units, (sm_count() - keep) / (2 * NPAIR)));
   return attr_err;
 }
 
@@ -402,6 +410,14 @@ static int gemm_rows_impl(const void* a, long long a_bs, long long a_rs, int row
   B200_CHECK_ARG(grid.y <= 65535, "gemm_rows: too many M tiles (%u)", grid.y);
   return block_n == 128 ? launch_gemm<128, false, false>(ta, tb, p, grid, st)
                         : launch_gemm<64, false, false>(ta, tb, p, grid, st);
+}
+
+/* SMs the persistent GEMM kernels leave free for a concurrently running collective (data-parallel runs: NCCL's CTAs, bounded by
+ * NCCL_MAX_CTAS).  0 = use every SM (default). */
+int b200s_reserve_sms(int sms) {
+  B200_CHECK_ARG(sms >= 0 && sms < sm_count(), "reserve_sms: %d out of range", sms);
+  g_reserved_sms.store(sms, std::memory_order_relaxed);
+  return 0;
 }
 
 int b200s_gemm_rows(const void* a, long long a_bs, long long a_rs, int rows, int batches, int K, const void* w, int N,

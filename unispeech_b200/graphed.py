@@ -86,7 +86,10 @@ class GraphedForwardBackward:
         torch.cuda.current_stream(self.device).wait_stream(side)
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on the SAME side stream as the warm-up: autograd remembers the stream a leaf's gradient accumulator was created
+        # on, and a backward pass captured on another stream would have to wait on that (uncaptured) stream
+        # (cudaErrorStreamCaptureIsolation)
+        with torch.cuda.graph(self.graph, stream=side):
             self._body()
         return self
 

@@ -91,6 +91,11 @@ def posconv_wgrad(dy, dy_bs, dy_rs, xpad, xpad_bs, T, B, D, G, taps, dwp):
 
 
 # ------------------------------------------------------------------------------------------------- row kernels
+def reserve_sms(n: int):
+    """SMs the persistent GEMM kernels leave free for a concurrent collective (see parallel.configure_overlap)."""
+    _call("b200s_reserve_sms", i32(n))
+
+
 def layer_norm_fwd(x, x_bs, x_rs, gamma, beta, y, y_bs, y_rs, mean, rstd, rows_per_batch, batches, D, gelu=False, valid=None):
     """`valid` (int32 [batches], device): ragged batch, rows at or beyond valid[b] are padding (written as zeros, not read)."""
     nb = 2.0 * 2 * rows_per_batch * batches * D

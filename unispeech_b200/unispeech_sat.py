@@ -268,26 +268,12 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
         if hasattr(self.encoder, "layer_norm_for_extract"):
             self.encoder.layer_norm_for_extract = None
 
-    def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
-                mask_indices=None):
-        out = super().forward(source, target_list=target_list, padding_mask=padding_mask, mask=mask, features_only=features_only,
-                              output_layer=output_layer, mask_indices=mask_indices)
-        if features_only or not self.utterance_contrastive_loss:
-            return out
-        res = self._last
-        spk_x = res["spk_x"]                      # [B, T, D]: output of layer `utterance_contrastive_layer` (normalised for pre-LN)
-        B, T, D = spk_x.shape
-        dev = spk_x.device
-        mi, pm = res["mask_indices"], res["padding_mask"]
-        assert mi is not None, "the utterance-contrastive loss needs mask=True"
-        mi_h = mi.cpu() if mi.device.type != "cpu" else mi
-        pm_h = res.get("padding_mask_host")
-        if pm_h is None:
-            pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
-        out["loss_spk_u"] = None
-        if self.skip_masked:
-            out.update(loss_spk_m=None, mean_targets=None, contrastive_acc=None)
-            return out
+    def _draw_instances(self, mi_h: torch.Tensor, pm_h: torch.Tensor, dev):
+        """Host side of the utterance-contrastive loss: the selected (masked, unpadded) frames and the sampled instances
+        (unispeech_sat.py:487-533, 742), uploaded from pinned memory.  Needs nothing from the encoder, so `forward` runs it
+        BEFORE the encoder kernels are enqueued: the ~0.5 M host random draws then overlap the GPU's backlog instead of leaving
+        the GPU idle between the encoder and the loss head (measured: 5 ms of the forward pass with one host thread per rank)."""
+        B, T = mi_h.shape
         masked = ~pm_h & mi_h
         counts = masked.sum(1)
         num = int(counts[0])
@@ -300,15 +286,52 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
         inst = sample_instances(B, num, self.n_instances, self.cross_sample_instances)     # [B, N * num] host RNG
         inst_ns = inst.view(B, N, num).permute(1, 0, 2).reshape(N, S)                       # instances.view(B, N, num, C).permute(1,0,2,3)
         same = (inst_ns // num) == (torch.arange(S) // num).unsqueeze(0)                    # instance from the positive's utterance
+        up = lambda t, dt: t.to(dt).contiguous().pin_memory().to(dev, non_blocking=True)
+        return dict(rows=up(rows_h, torch.int32), inst=up(inst_ns, torch.int32), same=up(same, torch.uint8), S=S, N=N, mi=mi_h)
+
+    def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
+                mask_indices=None):
+        pre = None
+        want_spk = not features_only and self.utterance_contrastive_loss and not self.skip_masked
+        if want_spk and mask and (padding_mask is None or padding_mask.device.type == "cpu") and \
+                (mask_indices is None or mask_indices.device.type == "cpu"):
+            # everything the loss head needs from the host is known before the encoder runs: draw it now (see _draw_instances)
+            from .engine import ConvGeom
+            B = source.shape[0]
+            T = ConvGeom(self.conv_cfg, source.shape[1]).T[-1]
+            pm_h = self.forward_padding_mask(T, padding_mask) if padding_mask is not None else torch.zeros(B, T, dtype=torch.bool)
+            if mask_indices is None:
+                mask_indices = self.apply_mask(B, T, pm_h if padding_mask is not None else None)
+            if mask_indices is not None:
+                pre = self._draw_instances(mask_indices.bool(), pm_h, source.device)
+        out = super().forward(source, target_list=target_list, padding_mask=padding_mask, mask=mask, features_only=features_only,
+                              output_layer=output_layer, mask_indices=mask_indices)
+        if features_only or not self.utterance_contrastive_loss:
+            return out
+        res = self._last
+        spk_x = res["spk_x"]                      # [B, T, D]: output of layer `utterance_contrastive_layer` (normalised for pre-LN)
+        B, T, D = spk_x.shape
+        dev = spk_x.device
+        out["loss_spk_u"] = None
+        if self.skip_masked:
+            out.update(loss_spk_m=None, mean_targets=None, contrastive_acc=None)
+            return out
+        if pre is None:   # device-resident masks: the frame selection needs them on the host first
+            mi, pm = res["mask_indices"], res["padding_mask"]
+            assert mi is not None, "the utterance-contrastive loss needs mask=True"
+            mi_h = mi.cpu() if mi.device.type != "cpu" else mi
+            pm_h = res.get("padding_mask_host")
+            if pm_h is None:
+                pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
+            pre = self._draw_instances(mi_h.bool(), pm_h, dev)
+        S, N = pre["S"], pre["N"]
         spk2d = spk_x.reshape(B * T, D)
         if spk2d.dtype != BF or not spk2d.is_contiguous():
             spk2d = spk2d.to(BF).contiguous()
         seed = self.noise_seed if self.noise_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         stats: Dict = {}
-        outs = _SpkNceFn.apply(spk2d, self.spk_proj.weight, self, rows_h.to(torch.int32).to(dev, non_blocking=True),
-                               inst_ns.to(torch.int32).contiguous().to(dev, non_blocking=True),
-                               same.to(torch.uint8).contiguous().to(dev, non_blocking=True), S, N, DR.site_key(seed, _SITE_GUMBEL),
-                               stats)
+        outs = _SpkNceFn.apply(spk2d, self.spk_proj.weight, self, pre["rows"], pre["inst"], pre["same"], S, N,
+                               DR.site_key(seed, _SITE_GUMBEL), stats)
         out["loss_spk_m"] = outs[0]
         out["mean_targets"] = stats["mean_targets"]
         out["contrastive_acc"] = stats["contrastive_acc"]
