@@ -49,7 +49,9 @@ def test_graphed_step_matches_eager(cuda_device):
         ref.backward()
         torch.cuda.synchronize()
         want = m.grad_buffer().detach()
-        assert abs(got_loss - float(ref)) <= 2e-3 * max(1.0, abs(float(ref))), (step, got_loss, float(ref))
+        dev_mask_equal = bool(torch.equal(g.mask_dev.cpu(), mask))
+        assert abs(got_loss - float(ref)) <= 2e-3 * max(1.0, abs(float(ref))), (step, got_loss, float(ref), dev_mask_equal,
+                                                                                int(mask.sum()), [int(s_.sum()) for s_ in seen])
         scale = want.abs().max().item()
         assert (got - want).abs().max().item() <= 2e-2 * scale, (step, (got - want).abs().max().item(), scale)
     assert not torch.equal(seen[0], seen[1])   # a new span mask every replay

@@ -65,26 +65,39 @@ class GumbelVectorQuantizer(nn.Module):
         self.curr_temp = max(self.max_temp * self.temp_decay ** num_updates, self.min_temp)
 
 
-def sample_instances(bsz: int, num: int, n_instances: int, cross_sample_instances: int) -> torch.Tensor:
-    """Flat row indices [bsz, (n + c) * num] into y.view(-1, C) drawn exactly like unispeech_sat.py:487-533 (host RNG)."""
+def sample_instances(bsz: int, num: int, n_instances: int, cross_sample_instances: int, generator=None) -> torch.Tensor:
+    """Flat row indices [bsz, (n + c) * num] into y.view(-1, C) drawn exactly like unispeech_sat.py:487-533 (host RNG: the same
+    `torch.randint` calls in the same order; `idx[idx >= tszs] += 1` is written as `idx += (idx >= tszs)`, which is the same
+    update without the boolean gather / scatter -- half of the reference formulation's host time)."""
     cross_high, high = num * bsz, num
     assert high > 1, (bsz, num)
     if n_instances > 0:
         tszs = torch.arange(num).unsqueeze(-1).expand(-1, n_instances).flatten()
-        instance_idxs = torch.randint(low=0, high=high - 1, size=(bsz, n_instances * num))
-        instance_idxs[instance_idxs >= tszs] += 1
+        instance_idxs = torch.randint(low=0, high=high - 1, size=(bsz, n_instances * num), generator=generator)
+        instance_idxs += (instance_idxs >= tszs)
     if cross_sample_instances > 0:
         tszs = torch.arange(num).unsqueeze(-1).expand(-1, cross_sample_instances).flatten()
-        cross_instance_idxs = torch.randint(low=0, high=cross_high - 1, size=(bsz, cross_sample_instances * num))
-        cross_instance_idxs[cross_instance_idxs >= tszs] += 1
+        cross_instance_idxs = torch.randint(low=0, high=cross_high - 1, size=(bsz, cross_sample_instances * num), generator=generator)
+        cross_instance_idxs += (cross_instance_idxs >= tszs)
     if n_instances > 0:
-        for i in range(1, bsz):
-            instance_idxs[i] += i * high
+        instance_idxs += (torch.arange(bsz) * high).unsqueeze(1)
     else:
         instance_idxs = cross_instance_idxs
     if cross_sample_instances > 0 and n_instances > 0:
         instance_idxs = torch.cat([instance_idxs, cross_instance_idxs], dim=1)
     return instance_idxs
+
+
+_DRAW_POOL = None
+
+
+def _draw_pool():
+    """One helper thread for the host side of the loss head (torch CPU ops release the GIL)."""
+    global _DRAW_POOL
+    if _DRAW_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _DRAW_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="b200s-draw")
+    return _DRAW_POOL
 
 
 class _SpkNceFn(torch.autograd.Function):
@@ -268,11 +281,14 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
         if hasattr(self.encoder, "layer_norm_for_extract"):
             self.encoder.layer_norm_for_extract = None
 
-    def _draw_instances(self, mi_h: torch.Tensor, pm_h: torch.Tensor, dev):
+    def _draw_instances(self, mi_h: torch.Tensor, pm_h: torch.Tensor, generator=None, device=None):
         """Host side of the utterance-contrastive loss: the selected (masked, unpadded) frames and the sampled instances
-        (unispeech_sat.py:487-533, 742), uploaded from pinned memory.  Needs nothing from the encoder, so `forward` runs it
-        BEFORE the encoder kernels are enqueued: the ~0.5 M host random draws then overlap the GPU's backlog instead of leaving
-        the GPU idle between the encoder and the loss head (measured: 5 ms of the forward pass with one host thread per rank)."""
+        (unispeech_sat.py:487-533, 742) as pinned host tensors.  Needs nothing from the encoder: `forward` runs it on a helper
+        thread WHILE the main thread enqueues the encoder kernels -- the ~0.5 M host random draws take 4-15 ms, and a step whose
+        ~6400 launches already cost the host as much as they cost the GPU cannot afford them on the launching thread (measured:
+        +5 ms per step)."""
+        if device is not None and device.type == "cuda":
+            torch.cuda.set_device(device)   # (helper thread: pinned allocations must not touch another rank's GPU)
         B, T = mi_h.shape
         masked = ~pm_h & mi_h
         counts = masked.sum(1)
@@ -283,15 +299,16 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
         S = B * num
         rows_h = torch.nonzero(masked.reshape(-1), as_tuple=False).squeeze(1)
         N = self.n_instances + self.cross_sample_instances
-        inst = sample_instances(B, num, self.n_instances, self.cross_sample_instances)     # [B, N * num] host RNG
-        inst_ns = inst.view(B, N, num).permute(1, 0, 2).reshape(N, S)                       # instances.view(B, N, num, C).permute(1,0,2,3)
-        same = (inst_ns // num) == (torch.arange(S) // num).unsqueeze(0)                    # instance from the positive's utterance
-        up = lambda t, dt: t.to(dt).contiguous().pin_memory().to(dev, non_blocking=True)
-        return dict(rows=up(rows_h, torch.int32), inst=up(inst_ns, torch.int32), same=up(same, torch.uint8), S=S, N=N, mi=mi_h)
+        inst = sample_instances(B, num, self.n_instances, self.cross_sample_instances, generator)   # [B, N * num] host RNG
+        inst_ns = inst.to(torch.int32).view(B, N, num).permute(1, 0, 2).reshape(N, S)    # instances.view(B, N, num, C).permute(1,0,2,3)
+        utt = torch.div(torch.arange(S, dtype=torch.int32), num, rounding_mode="floor")
+        same = torch.div(inst_ns, num, rounding_mode="floor") == utt.unsqueeze(0)        # instance from the positive's utterance
+        pin = lambda t, dt: t.to(dt).contiguous().pin_memory()
+        return dict(rows=pin(rows_h, torch.int32), inst=pin(inst_ns, torch.int32), same=pin(same, torch.uint8), S=S, N=N)
 
     def forward(self, source, target_list=None, padding_mask=None, mask=True, features_only=False, output_layer=None,
                 mask_indices=None):
-        pre = None
+        pre, fut, gen = None, None, None
         want_spk = not features_only and self.utterance_contrastive_loss and not self.skip_masked
         if want_spk and mask and (padding_mask is None or padding_mask.device.type == "cpu") and \
                 (mask_indices is None or mask_indices.device.type == "cpu"):
@@ -303,9 +320,16 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
             if mask_indices is None:
                 mask_indices = self.apply_mask(B, T, pm_h if padding_mask is not None else None)
             if mask_indices is not None:
-                pre = self._draw_instances(mask_indices.bool(), pm_h, source.device)
+                # The helper thread draws from a COPY of the global CPU generator (the values the global one would have produced);
+                # the global state is moved to where that copy ended once the thread has been joined.
+                gen = torch.Generator()
+                gen.set_state(torch.get_rng_state())
+                fut = _draw_pool().submit(self._draw_instances, mask_indices.bool(), pm_h, gen, source.device)
         out = super().forward(source, target_list=target_list, padding_mask=padding_mask, mask=mask, features_only=features_only,
                               output_layer=output_layer, mask_indices=mask_indices)
+        if fut is not None:
+            pre = fut.result()
+            torch.set_rng_state(gen.get_state())
         if features_only or not self.utterance_contrastive_loss:
             return out
         res = self._last
@@ -323,14 +347,15 @@ class UniSpeechSATForPretraining(WavLMForPretraining):
             pm_h = res.get("padding_mask_host")
             if pm_h is None:
                 pm_h = torch.zeros(B, T, dtype=torch.bool) if pm is None else (pm.cpu() if pm.device.type != "cpu" else pm)
-            pre = self._draw_instances(mi_h.bool(), pm_h, dev)
+            pre = self._draw_instances(mi_h.bool(), pm_h, None, dev)
         S, N = pre["S"], pre["N"]
+        up = lambda t: t.to(dev, non_blocking=True)
         spk2d = spk_x.reshape(B * T, D)
         if spk2d.dtype != BF or not spk2d.is_contiguous():
             spk2d = spk2d.to(BF).contiguous()
         seed = self.noise_seed if self.noise_seed is not None else int(torch.randint(0, 2 ** 62, (1,)).item())
         stats: Dict = {}
-        outs = _SpkNceFn.apply(spk2d, self.spk_proj.weight, self, pre["rows"], pre["inst"], pre["same"], S, N,
+        outs = _SpkNceFn.apply(spk2d, self.spk_proj.weight, self, up(pre["rows"]), up(pre["inst"]), up(pre["same"]), S, N,
                                DR.site_key(seed, _SITE_GUMBEL), stats)
         out["loss_spk_m"] = outs[0]
         out["mean_targets"] = stats["mean_targets"]
