@@ -561,7 +561,7 @@ def main():
     if world > 1:
         from unispeech_b200.parallel import configure_overlap
         _lib.check_device()
-        nccl_ctas = configure_overlap(int(os.environ.get("B200S_NCCL_CTAS", "4")))   # NCCL_MAX_CTAS + SMs the persistent GEMMs leave free
+        nccl_ctas = configure_overlap(int(os.environ.get("B200S_NCCL_CTAS", "0")))   # optional: NCCL_MAX_CTAS + SMs the persistent GEMMs leave free
         # the host side of a step (span-mask sampling, instance draws) is torch / numpy CPU work: torchrun pins every rank to ONE
         # OpenMP thread unless told otherwise
         if os.environ.get("OMP_NUM_THREADS", "1") == "1":
@@ -739,7 +739,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": w.describe() + (f"; gradient exchange: bucketed NCCL all-reduce (AVG, fp32) overlapped with backward, "
-                                                   f"NCCL_MAX_CTAS={nccl_ctas}, the persistent GEMMs leave that many SMs free" if world > 1 else ""),
+                                                   + (f"NCCL_MAX_CTAS={nccl_ctas}, the persistent GEMMs leave that many SMs free" if nccl_ctas else "NCCL defaults")
+                                                   if world > 1 else ""),
                        "global_batch": world * B,
                        "frames": T, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (no flush needed)", 
                        "algorithmic_gflop_per_audio_s": 3 * fwd_flops * B / (sum(w.lengths) / SR) / 1e9},

@@ -48,9 +48,15 @@ def test_graphed_step_matches_eager(cuda_device):
         ref = loss_fn(x)
         ref.backward()
         torch.cuda.synchronize()
-        want = m.grad_buffer().detach()
+        want = m.grad_buffer().detach().clone()
         dev_mask_equal = bool(torch.equal(g.mask_dev.cpu(), mask))
-        assert abs(got_loss - float(ref)) <= 2e-3 * max(1.0, abs(float(ref))), (step, got_loss, float(ref), dev_mask_equal,
+        g.graph.replay()                       # (diagnostics: the same mask replayed again, and the eager step run again)
+        torch.cuda.synchronize()
+        replay2 = float(g.loss)
+        m.zero_grad_buffer()
+        x2, _ = m.extract_features(wav.to(dev), padding_mask=None, mask=True, mask_indices=mask)
+        eager2 = float(loss_fn(x2))
+        assert abs(got_loss - float(ref)) <= 2e-3 * max(1.0, abs(float(ref))), (step, got_loss, replay2, float(ref), eager2, dev_mask_equal,
                                                                                 int(mask.sum()), [int(s_.sum()) for s_ in seen])
         scale = want.abs().max().item()
         assert (got - want).abs().max().item() <= 2e-2 * scale, (step, (got - want).abs().max().item(), scale)

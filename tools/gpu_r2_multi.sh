@@ -26,3 +26,4 @@ fi
 one large
 one sat --sat
 one ragged --ragged
+if [ "$N" = "8" ]; then B200S_NCCL_CTAS=4 one large_ctas4; fi
