@@ -277,7 +277,9 @@ int b200s_prep_linear_batched(const void* descs, int n_descs, int total_tiles, b
 int b200s_prep_conv_fwd(const float* src, int Co, int Ci, int k, void* dst, b200s_stream stream);
 int b200s_prep_conv_dgrad(const float* src, int Co, int Ci, int k, int s, int rho, void* dst, b200s_stream stream);
 int b200s_unprep_conv_wgrad(const float* dwk, int Co, int Ci, int k, float* dw, b200s_stream stream);
-/* weight_norm(dim=2) of pos_conv (WavLM/WavLM.py:526) -> padded per-group operands; and its backward */
+/* weight_norm(dim=2) of pos_conv (WavLM/WavLM.py:526) -> padded per-group operands; and its backward.  Workspaces (8-byte aligned,
+ * zeroed inside): norm2 = 2 * taps floats, work = 4 * taps floats -- the per-tap sums are accumulated in fp64 so that the norm, and
+ * with it every bf16 pos_conv weight, is the same value on every run (the forward pass is bit-reproducible). */
 int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int G, int taps, float* norm2,
                        void* wp_fwd, void* wp_dgrad, b200s_stream stream);
 int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const float* dwp, int D, int G, int taps,

@@ -243,7 +243,7 @@ def test_prep_kernels(cuda_device):
     Cg = D // G
     v = torch.randn(D, Cg, taps, device=dev)
     g = torch.rand(1, 1, taps, device=dev) + 0.5
-    norm2 = torch.zeros(taps, device=dev)
+    norm2 = torch.zeros(2 * taps, device=dev)   # fp64[taps]
     wf = torch.empty(G, 64, taps, 64, device=dev, dtype=torch.bfloat16)
     wd = torch.empty_like(wf)
     ops.posconv_prep(v, g, D, G, taps, norm2, wf, wd)
@@ -260,7 +260,7 @@ def test_prep_kernels(cuda_device):
     dwp[:, :, :, :Cg] = dwn.view(G, Cg, Cg, taps).permute(0, 1, 3, 2)
     wn.backward(dwn)
     dv, dg = torch.zeros_like(v), torch.zeros_like(g)
-    work = torch.zeros(2 * taps, device=dev)
+    work = torch.zeros(4 * taps, device=dev)   # fp64[2 * taps]
     ops.posconv_unprep(v, g, dwp, D, G, taps, work, dv, dg)
     torch.cuda.synchronize()
     assert (dv - vr.grad).abs().max().item() < 1e-3 * max(1, vr.grad.abs().max().item())

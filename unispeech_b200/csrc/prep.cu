@@ -159,9 +159,12 @@ __global__ void unprep_conv_wgrad_kernel(const float* __restrict__ dwk, int Co, 
 }
 
 // ---- pos_conv weight norm -----------------------------------------------------------------------------------------
-// norm2[j] = sum_{co,ci} v[co,ci,j]^2  (and optionally dot[j] = sum dw*v for the backward)
+// norm2[j] = sum_{co,ci} v[co,ci,j]^2  (and optionally dot[j] = sum dw*v for the backward).  The block partials are combined with
+// fp64 atomics: their order varies from launch to launch, but an fp64 sum of a few hundred fp32 partials rounds to the same fp32
+// value whatever the order (fp32 atomics did not: the weight norm, hence a few bf16 pos_conv weights, hence the whole forward pass
+// differed in the last bit between two runs on the same input -- found by tests/test_graph_gpu.py).
 __global__ void posconv_tap_reduce_kernel(const float* __restrict__ v, const float* __restrict__ dwp, int D, int Cg, int taps,
-                                          float* __restrict__ norm2, float* __restrict__ dot) {
+                                          double* __restrict__ norm2, double* __restrict__ dot) {
   pdl_grid_sync();
   // thread -> tap (coalesced over the contiguous tap axis), blocks stride over (co, ci) rows
   const int j = threadIdx.x;
@@ -177,13 +180,13 @@ __global__ void posconv_tap_reduce_kernel(const float* __restrict__ v, const flo
       d += dwp[((static_cast<long long>(g) * Cg + cog) * taps + j) * 64 + ci] * x;
     }
   }
-  atomicAdd(norm2 + j, a);
-  if (dwp) atomicAdd(dot + j, d);
+  atomicAdd(norm2 + j, static_cast<double>(a));
+  if (dwp) atomicAdd(dot + j, static_cast<double>(d));
 }
 // wp_fwd[(g*64+co), j*64+ci] = w[g*Cg+co, ci, j];   wp_dg[(g*64+ci), j'*64+co] = w[g*Cg+co, ci, taps-1-j']
 // with w = gvec[j] * v / sqrt(norm2[j]); zero padding elsewhere.
 __global__ void posconv_prep_kernel(const float* __restrict__ v, const float* __restrict__ gvec,
-                                    const float* __restrict__ norm2, int G, int Cg, int taps,
+                                    const double* __restrict__ norm2, int G, int Cg, int taps,
                                     __nv_bfloat16* __restrict__ wp_fwd, __nv_bfloat16* __restrict__ wp_dg) {
   pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -196,31 +199,31 @@ __global__ void posconv_prep_kernel(const float* __restrict__ v, const float* __
   float wf = 0.f, wd = 0.f;
   if (r < Cg && c < Cg) {
     // forward: row co=r, col ci=c, tap j
-    wf = v[((static_cast<long long>(g) * Cg + r) * Cg + c) * taps + j] * gvec[j] * rsqrtf(norm2[j]);
+    wf = v[((static_cast<long long>(g) * Cg + r) * Cg + c) * taps + j] * gvec[j] * rsqrtf(static_cast<float>(norm2[j]));
     // dgrad: row ci=r, col co=c, tap jj = taps-1-j
     const int jj = taps - 1 - j;
-    wd = v[((static_cast<long long>(g) * Cg + c) * Cg + r) * taps + jj] * gvec[jj] * rsqrtf(norm2[jj]);
+    wd = v[((static_cast<long long>(g) * Cg + c) * Cg + r) * taps + jj] * gvec[jj] * rsqrtf(static_cast<float>(norm2[jj]));
   }
   wp_fwd[i] = __float2bfloat16_rn(wf);
   wp_dg[i] = __float2bfloat16_rn(wd);
 }
 // backward of weight_norm: dg[j] += dot[j]/norm_j;  dv = g/norm * dw - g*dot/norm^3 * v
 __global__ void posconv_unprep_kernel(const float* __restrict__ v, const float* __restrict__ gvec,
-                                      const float* __restrict__ norm2, const float* __restrict__ dot,
+                                      const double* __restrict__ norm2, const double* __restrict__ dot,
                                       const float* __restrict__ dwp, int D, int Cg, int taps, float* __restrict__ dv,
                                       float* __restrict__ dg) {
   pdl_grid_sync();
   const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = static_cast<long long>(D) * Cg * taps;
-  if (i < taps) dg[i] += dot[i] * rsqrtf(norm2[i]);
+  if (i < taps) dg[i] += static_cast<float>(dot[i]) * rsqrtf(static_cast<float>(norm2[i]));
   if (i >= n) return;
   const int j = i % taps;
   const int ci = (i / taps) % Cg;
   const int co = i / (static_cast<long long>(taps) * Cg);
   const int g = co / Cg, cog = co % Cg;
-  const float inv = rsqrtf(norm2[j]);
+  const float inv = rsqrtf(static_cast<float>(norm2[j]));
   const float dw = dwp[((static_cast<long long>(g) * Cg + cog) * taps + j) * 64 + ci];
-  dv[i] += gvec[j] * inv * dw - gvec[j] * dot[j] * inv * inv * inv * v[i];
+  dv[i] += gvec[j] * inv * dw - gvec[j] * static_cast<float>(dot[j]) * inv * inv * inv * v[i];
 }
 
 }  // namespace b200
@@ -288,37 +291,41 @@ int b200s_unprep_conv_wgrad(const float* dwk, int Co, int Ci, int k, float* dw, 
   return 0;
 }
 
-// norm2: fp32 [taps] workspace (zeroed here)
+// norm2: workspace of 2 * taps floats, 8-byte aligned (holds fp64[taps]; zeroed here)
 int b200s_posconv_prep(const float* weight_v, const float* weight_g, int D, int G, int taps, float* norm2, void* wp_fwd,
                        void* wp_dgrad, b200s_stream stream) {
   B200_CHECK_ARG(weight_v && weight_g && norm2 && wp_fwd && wp_dgrad, "posconv_prep: null pointer");
   B200_CHECK_ARG(taps <= 1024 && D % G == 0 && D / G <= 64, "posconv_prep: bad sizes");
   const int Cg = D / G;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  B200_CHECK_CUDA(cudaMemsetAsync(norm2, 0, sizeof(float) * taps, st));
-  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v, nullptr, D, Cg, taps, norm2,
-                                                                               nullptr));
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(norm2) & 7u) == 0, "posconv_prep: workspace must be 8-byte aligned");
+  double* n2 = reinterpret_cast<double*>(norm2);
+  B200_CHECK_CUDA(cudaMemsetAsync(n2, 0, sizeof(double) * taps, st));
+  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v,
+                             static_cast<const float*>(nullptr), D, Cg, taps, n2, static_cast<double*>(nullptr)));
   B200_CHECK_LAUNCH();
   const long long n = static_cast<long long>(G) * 64 * taps * 64;
   B200_CHECK_CUDA(launch_pdl(posconv_prep_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, st, 
-      weight_v, weight_g, norm2, G, Cg, taps, static_cast<__nv_bfloat16*>(wp_fwd),
+      weight_v, weight_g, static_cast<const double*>(n2), G, Cg, taps, static_cast<__nv_bfloat16*>(wp_fwd),
       static_cast<__nv_bfloat16*>(wp_dgrad)));
   B200_CHECK_LAUNCH();
   return 0;
 }
 
-// dwp: fp32 [G, Cg, taps, 64] from b200s_posconv_wgrad.  work: fp32 [2*taps] workspace (zeroed here).
+// dwp: fp32 [G, Cg, taps, 64] from b200s_posconv_wgrad.  work: workspace of 4 * taps floats, 8-byte aligned (fp64[2 * taps]; zeroed here).
 int b200s_posconv_unprep(const float* weight_v, const float* weight_g, const float* dwp, int D, int G, int taps,
                          float* work, float* dweight_v, float* dweight_g, b200s_stream stream) {
   B200_CHECK_ARG(weight_v && weight_g && dwp && work && dweight_v && dweight_g, "posconv_unprep: null pointer");
   const int Cg = D / G;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  B200_CHECK_CUDA(cudaMemsetAsync(work, 0, sizeof(float) * 2 * taps, st));
-  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v, dwp, D, Cg, taps, work,
-                                                                               work + taps));
+  B200_CHECK_ARG((reinterpret_cast<uintptr_t>(work) & 7u) == 0, "posconv_unprep: workspace must be 8-byte aligned");
+  double* w2 = reinterpret_cast<double*>(work);
+  B200_CHECK_CUDA(cudaMemsetAsync(w2, 0, sizeof(double) * 2 * taps, st));
+  B200_CHECK_CUDA(launch_pdl(posconv_tap_reduce_kernel, dim3(4 * sm_count()), dim3(((taps + 31) / 32) * 32), 0, st, weight_v, dwp, D, Cg, taps, w2,
+                             w2 + taps));
   B200_CHECK_LAUNCH();
   const long long n = static_cast<long long>(D) * Cg * taps;
-  B200_CHECK_CUDA(launch_pdl(posconv_unprep_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, st, weight_v, weight_g, work, work + taps,
+  B200_CHECK_CUDA(launch_pdl(posconv_unprep_kernel, dim3(static_cast<unsigned>(ceil_div_ll(n, 256))), dim3(256), 0, st, weight_v, weight_g, static_cast<const double*>(w2), static_cast<const double*>(w2 + taps),
                                                                                    dwp, D, Cg, taps, dweight_v, dweight_g));
   B200_CHECK_LAUNCH();
   return 0;

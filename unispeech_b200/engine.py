@@ -210,7 +210,7 @@ class Engine:
         self.wp, self.wpT = e(D, C), e(C, D)
         G, taps = cfg.conv_pos_groups, cfg.conv_pos
         self.pc_fwd, self.pc_dg = e(G, 64, taps, 64), e(G, 64, taps, 64)
-        self.pc_norm2 = torch.zeros(taps, dtype=torch.float32, device=device)
+        self.pc_norm2 = torch.zeros(2 * taps, dtype=torch.float32, device=device)   # holds fp64[taps] (deterministic tap norms)
         self.lw = []
         for lyr in m.encoder.layers:
             # q/k/v masters become views of ONE fused [3D, D] / [3D] fp32 tensor (same values, same state_dict keys): the fused
@@ -590,7 +590,7 @@ class Engine:
                       pre_is_grad=True)
         dwp = torch.zeros(G, Cg, taps, 64, dtype=torch.float32, device=dev)
         ops.posconv_wgrad(dpre[:, half:], Tpad * D, D, xpad, Tpad * D, T, B, D, G, taps, dwp)
-        work = torch.empty(2 * taps, dtype=torch.float32, device=dev)
+        work = torch.empty(4 * taps, dtype=torch.float32, device=dev)   # fp64[2 * taps]
         ops.posconv_unprep(pc.weight_v, pc.weight_g, dwp, D, G, taps, work, self.g(pc.weight_v), self.g(pc.weight_g))
         # input gradient: correlation with the flipped, transposed taps; frame t reads dpre rows t-63 .. t+64
         dxm = torch.empty(B, T, D, dtype=BF, device=dev)
