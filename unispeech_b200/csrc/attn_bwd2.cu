@@ -37,6 +37,9 @@ __device__ __forceinline__ float ex2f(float x) {
 __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ uint32_t bit_transpose32(uint32_t x, int lane) {  // see warp_bit_transpose in attn_fwd.cu
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) {
@@ -54,17 +57,10 @@ constexpr int kFQ = 32768;         // Q tiles, 2 stages x 16 KB
 constexpr int kFDO = 65536;        // dO tiles, 2 stages x 16 KB
 constexpr int kFP = 98304;         // P  : [128 queries][128 keys] as two 64-key blocks, 32 KB
 constexpr int kFDS = 131072;       // dS : same layout, 32 KB
-// gate*dS for the diagonal sums of the bias gradient, as the A operand of ONE extra tensor-core product per tile: the 128 x 128 tile
-// is cut into 128 blocks of 8 queries x 16 keys; block (a, b) is row m = 8 a + b of a K-major [128 blocks][128] bf16 matrix whose
-// column is (r, s) = (query % 8, key % 16).  Every block has the same 23 diagonals d' = s - r + 7, so
-//     D[m][d'] = sum_{r,s} Wblk[m][r*16+s] * L[d'][r*16+s],   L = constant 0/1 matrix (N = 32 rows, 23 used)
-// is a 128 x 32 x 128 MMA, and a thread's 16 consecutive keys of one query are 32 CONTIGUOUS bytes of a row (two 16-byte stores).
-// (Round 1/2a staged the tile row-major and summed the diagonals with scalar shared loads: 120 instructions per thread and tile and
-// two block-wide barriers; now 4 stores, and 23 shared atomics in one warpgroup.)
-constexpr int kFW = 163840;        // Wblk: 2 K-blocks (64 columns each) x 128 rows x 128 B = 32 KB, SWIZZLE_128B like every operand
-constexpr int kFLT = kFW + 32768;  // L: 2 K-blocks x 32 rows x 128 B = 8 KB
-constexpr int kFTab = kFLT + 8192;  // 204800: tab copies [2][tab_stride], dtab_acc[(N+1)*128]
-constexpr int kDiagN = 32;         // MMA N of the diagonal product (23 diagonals used)
+constexpr int kFW = 163840;        // gate*dS staging for the diagonal sums: one [128 queries][66] bf16 tile per key half
+constexpr int kWStride2 = 66;      // bf16 per staged row (33 words: conflict-free row writes and diagonal reads)
+constexpr int kFWBytes = 128 * kWStride2 * 2;   // 16896
+constexpr int kFTab = kFW + 2 * kFWBytes;        // 197632: tab copies [2][tab_stride], dtab_acc[(N+1)*128]
 constexpr int kCudaThreads = 512;             // 16 CUDA-core warps: four per scheduler hide the TMEM / SFU / LDS latencies
 constexpr int kFThreads = kCudaThreads + 32;  // + 1 producer warp (only its first lane works): 17 warps x 120 registers
 constexpr int kProdWarp = kCudaThreads / 32;
@@ -180,22 +176,13 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       tab_s[c * tab_stride + k] = (gi >= 0 && gi < 2 * T - 1) ? tab_h[gi] : 0.f;
     }
     for (int l = tid; l < len; l += kFThreads) dtab_acc[l] = 0.f;
-    // L[n][r*16 + s] = (s - r + 7 == n), bf16, K-major with the 128-byte swizzle (row n, 16-byte chunk c -> c ^ (n & 7))
-    for (int l = tid; l < kDiagN * 128; l += kFThreads) {
-      const int n = l >> 7, kk = l & 127;
-      const int rr = kk >> 4, ss = kk & 15;
-      const int kin = kk & 63;
-      uint8_t* dst = smem + kFLT + (kk >> 6) * (kDiagN * 128) + n * 128 + (((kin >> 3) ^ (n & 7)) << 4) + (kin & 7) * 2;
-      *reinterpret_cast<uint16_t*>(dst) = (ss - rr + 7 == n) ? static_cast<uint16_t>(0x3F80) : static_cast<uint16_t>(0);
-    }
-    fence_proxy_async_smem();  // read by the tensor core (async proxy)
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_s;
   // TMEM columns: stage hf at hf*128: S [0,64), dP [64,128); dV 256; dK 320; dQ 384
-  constexpr uint32_t kColDV = 256, kColDK = 320, kColDQ = 384, kColDG = 448;  // (diagonal sums: 32 columns)
+  constexpr uint32_t kColDV = 256, kColDK = 320, kColDQ = 384;
 
   if (warp >= kProdWarp) {
     if (warp == kProdWarp && lane == 0) {
@@ -203,7 +190,6 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       constexpr uint32_t idesc_st = make_idesc_bf16(128, 64, 0, 0);   // K-major A (Q / dO), K-major B (K / V half)
       constexpr uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);  // MN-major A (P / dS read transposed), MN-major B (dO / Q)
       constexpr uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);   // K-major A (dS), MN-major B (K)
-      constexpr uint32_t idesc_dg = make_idesc_bf16(128, kDiagN, 0, 0);  // K-major A (Wblk), K-major B (L)
       auto load_qdo = [&](int qi) {
         const int s = qi & 1;
         mbar_expect_tx(&qdo_full[s], 32768);
@@ -259,13 +245,6 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
         for (int k = 0; k < 8; ++k)  // dQ_i = dS K    (K = 128 keys: two 64-key blocks, 16 per step)
           umma_bf16(tmem + kColDQ, make_smem_desc_sw128(ads + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
                     make_smem_desc_sw128(bk + k * 2048, 8192, 1024), idesc_dq, k > 0 ? 1u : 0u);
-        if (HAS_BIAS) {
-          const uint32_t aw = smem_u32(smem + kFW), bl = smem_u32(smem + kFLT);
-#pragma unroll
-          for (int k = 0; k < 8; ++k)  // D = Wblk L^T   (K = 128 = (query % 8, key % 16), 16 per step)
-            umma_bf16(tmem + kColDG, make_smem_desc_sw128(aw + (k >> 2) * 16384 + (k & 3) * 32, 16, 1024),
-                      make_smem_desc_sw128(bl + (k >> 2) * (kDiagN * 128) + (k & 3) * 32, 16, 1024), idesc_dg, k > 0 ? 1u : 0u);
-        }
         umma_commit(&dq_full);
         umma_commit(&mma_done);
         umma_commit(&qdo_free[st]);
@@ -282,6 +261,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     const int hf = g >> 1;                // key half of this warpgroup
     const int j0 = hf * 64 + (g & 1) * 32;  // first of this thread's 32 key columns (inside the 128-key tile)
     const int r = (warp & 3) * 32 + lane;  // query row inside the tile == TMEM lane
+    const int ht = tid & 255;             // thread index inside the half (diagonal-sum tasks)
     const float sc = p.scale * kLog2e;
     const uint32_t lane_addr = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const uint32_t kmask = key_mask_s[j0 >> 5];  // bit jj: key column j0 + jj is masked
@@ -289,9 +269,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
     // bias entries of (row r, keys j0 + jj) in query tile qi: slice[tstart - qi*128 + jj]
     const int tstart = j0 - r + N * kAttnTile - 1;
     const float* tab_row = tab_s + (tstart & 1) * tab_stride + (tstart & ~1);  // 8-byte aligned in the copy of matching parity
-    uint8_t* sW = smem + kFW;
-    const int wrow_m = (r >> 3) * 8 + (j0 >> 4);  // block row of (this query, key sub-chunk 0); + sub for the second one
-    const int wchunk = ((r & 7) >> 2) * 8 + (r & 3) * 2;  // 16-byte chunk of this query's 16 keys inside the block row
+    uint32_t* wtile = reinterpret_cast<uint32_t*>(smem + kFW + hf * kFWBytes);
     const long long bh = static_cast<long long>(b) * p.H + h;
 
     // per-row scalars of query tile qi: the RAW values are loaded one tile ahead (no arithmetic on them until the next tile starts,
@@ -326,20 +304,29 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
                        "f"(__uint_as_float(t0[v * 4 + 3]))
                        : "memory");  // the staged dS already carries the softmax scale
       }
-      if (HAS_BIAS && g == 0) {
-        // diagonal sums of the tile: TMEM lane r = block (a, b) = (r / 8, r % 8), column n = diagonal s - r' + 7 inside the block;
-        // element (query 8a + r', key 16b + s) of query tile qi -> l = 16b - 8a + (n - 7) - qi*128 + N*128 - 1
-        uint32_t t1[32];
-        tmem_ld_32x32b_x32(tmem + lane_addr + kColDG, t1);
-        tmem_ld_wait();
-        const int base = 16 * (r & 7) - 8 * (r >> 3) - 7 - qi * kAttnTile + N * kAttnTile - 1;
-#pragma unroll
-        for (int n = 0; n < 23; ++n) {
-          const float v = __uint_as_float(t1[n]);
-          if (v != 0.f) atomicAdd(&dtab_acc[base + n], v);
-        }
-      }
     };
+    // diagonal sums of the staged gate*dS tile of (query tile qi, this half).  Task (e, s): elements (i = (jj - e) & 127, jj)
+    // for jj = 16 s .. 16 s + 15: diagonal jj - i = e (not wrapped, jj >= e) or e - 128 (wrapped).  The wrap point is a per-task
+    // constant, so every load is base + immediate.
+    auto diag_task = [&](int qi, int e, int s) {
+      const int w0 = e - 16 * s;  // columns jj = 16 s + c with c < w0 are on the wrapped diagonal
+      const uint32_t base_nw = smem_u32(wtile) + static_cast<uint32_t>((16 * s - e) * kWStride2 + 16 * s) * 2u;
+      const uint32_t base_w = base_nw + static_cast<uint32_t>(kAttnTile * kWStride2 * 2);
+      float acc_all = 0.f, acc_nw = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const bool wrapped = c < w0;
+        uint32_t v16;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v16) : "r"((wrapped ? base_w : base_nw) + c * (kWStride2 + 1) * 2));
+        const float v = __uint_as_float(v16 << 16);
+        acc_all += v;
+        if (!wrapped) acc_nw += v;
+      }
+      const int l_nw = hf * 64 - qi * kAttnTile + e + N * kAttnTile - 1;
+      if (w0 < 16) atomicAdd(&dtab_acc[l_nw], acc_nw);
+      if (w0 > 0) atomicAdd(&dtab_acc[l_nw - kAttnTile], acc_all - acc_nw);
+    };
+
     for (int qi = 0; qi < NQ; ++qi) {
       mbar_wait(&st_full[hf], qi & 1);
       tc_fence_after();
@@ -355,6 +342,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       }
       float dg = 0.f;
       const float* trow = tab_row - qi * kAttnTile;
+      uint32_t* wrow = wtile + r * (kWStride2 / 2) + (g & 1) * 16;
 
       // 16 key columns at a time: probabilities / dS / gate*dS packed to bf16 in registers, then staged.  The first stores of a
       // tile wait for the accumulation MMAs of the previous tile (which read the P / dS tiles); by then half of this tile's
@@ -411,8 +399,7 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
           }
           if (HAS_BIAS) {
 #pragma unroll
-            for (int c = 0; c < 2; ++c)
-              store_sw128_chunk(sW, wrow_m + sub, wchunk + c, make_uint4(ww[c * 4], ww[c * 4 + 1], ww[c * 4 + 2], ww[c * 4 + 3]));
+            for (int j = 0; j < 8; ++j) wrow[sub * 8 + j] = ww[j];
           }
         }
       };
@@ -426,6 +413,12 @@ __global__ void __launch_bounds__(kFThreads, 1) attn_bwd_fused_kernel(const __gr
       tc_fence_before();
       mbar_arrive_cta(&ready[hf]);
       r_lse = n_lse; r_delta = n_delta; r_gate = n_gate;
+      if (HAS_BIAS) {
+        mbar_wait(&ready[hf], qi & 1);  // all 256 threads of this half have staged their rows
+        diag_task(qi, ht & 127, ht >> 7);
+        diag_task(qi, ht & 127, (ht >> 7) + 2);
+        named_bar_sync(1 + hf, kCudaThreads / 2);  // the staging tile of this half may be overwritten
+      }
     }
     // ---- tail: last dQ tile, then the dK / dV accumulators
     flush_dq(NQ - 1);

@@ -617,7 +617,7 @@ class Engine:
         p_h = d.p if d is not None else 0.0
         p_a = d.p_attn if d is not None else 0.0
         p_act = d.p_act if d is not None else 0.0
-        t_fused = 1920 if tab is not None else 2048   # longest input of the fused attention backward (its shared-memory tables grow with T)
+        t_fused = 2048   # longest input of the fused attention backward (its shared-memory tables grow with T)
         if p_a > 0 and T > t_fused:
             raise NotImplementedError(f"attention_dropout > 0 is implemented in the fused attention kernels for T <= {t_fused} frames "
                                       f"(got T={T}); set attention_dropout=0 for longer inputs")
@@ -769,7 +769,7 @@ class Engine:
         delta = f(B, H, T)
         gate = st["gate"]
         dgate = f(B, H, T) if tab is not None else None
-        if T <= (1920 if tab is not None else 2048):  # (shared memory of the fused kernel: the bias tables grow with T)
+        if T <= 2048:
             key = (B, T, D)
             if getattr(self, "_dq_acc_key", None) != key:  # fp32 dQ accumulator: zero on entry, re-zeroed by the kernel
                 self._dq_acc = torch.zeros(B, T, D, dtype=torch.float32, device=dev)
