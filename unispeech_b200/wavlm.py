@@ -79,6 +79,8 @@ def _check_supported(cfg):
         bad.append("conv_bias")
     if cfg.mask_channel_prob > 0:
         bad.append("mask_channel_prob > 0")
+    if eval(cfg.conv_feature_layers)[-1][0] == cfg.encoder_embed_dim:
+        bad.append("conv feature width == encoder_embed_dim (the reference then has no post_extract_proj; the projection kernels assume one)")
     return bad
 
 
@@ -521,6 +523,11 @@ class WavLM(nn.Module):
         return self._engine
 
     def _begin(self, device) -> Engine:
+        if device.type != "cuda":
+            raise RuntimeError("the B200 hot path runs on a CUDA device (there is no CPU fallback)")
+        if device.index is not None and device.index != torch.cuda.current_device():
+            # kernels are launched on the CURRENT device's current stream (_lib.stream_ptr)
+            raise RuntimeError(f"make cuda:{device.index} the current device (torch.cuda.set_device) before calling the model")
         eng = self._engine_for(device)
         # training-mode dropout: one seed per forward pass (torch CPU generator, or `self.dropout_seed` when a caller pins it)
         eng.drop = DropState.for_model(self.cfg, self.training, self.dropout_seed)
