@@ -511,7 +511,7 @@ def encoder(sd, x: Tensor, padding_mask: Optional[Tensor], cfg, tgt_layer=None, 
 
 def extract_features(sd, source: Tensor, cfg, padding_mask: Optional[Tensor] = None,
                      mask_indices: Optional[Tensor] = None, output_layer: Optional[int] = None,
-                     drop: Optional["HashDropout"] = None):
+                     drop: Optional["HashDropout"] = None, predict_layers: Optional[List[int]] = None):
     """WavLM.extract_features, WavLM/WavLM.py:323-375.  `mask_indices` [B,T] bool replaces the host-RNG
     compute_mask_indices call of apply_mask (:271-309): masked frames are set to mask_emb."""
     feats = conv_feature_extractor(sd, source, cfg)  # :333-339 (feature_grad_mult handled by callers)
@@ -527,7 +527,10 @@ def extract_features(sd, source: Tensor, cfg, padding_mask: Optional[Tensor] = N
     x = feats
     if mask_indices is not None:
         x = torch.where(mask_indices.unsqueeze(-1), sd["mask_emb"].to(x.dtype), x)  # x[mask_indices] = mask_emb
-    x, layer_results = encoder(sd, x, padding_mask, cfg, None if output_layer is None else output_layer - 1, drop=drop)
+    # `predict_layers` (1-based list): ILS-HuBERT's `layer=self.predict_layers` (src/fairseq/models/hubert/ils_hubert.py:167-171)
+    tgt = list(predict_layers) if (predict_layers is not None and output_layer is None) else \
+        (None if output_layer is None else output_layer - 1)
+    x, layer_results = encoder(sd, x, padding_mask, cfg, tgt, drop=drop)
     return {"x": x, "padding_mask": padding_mask, "features": feats, "layer_results": layer_results}
 
 

@@ -70,12 +70,15 @@ def _head_forward(model, x2d, w, b, label_embs, idx):
     return dict(xs=xs, proj=proj, wpT=wpT, sets=sets, shape=(x2d.shape[0], D, S, Dp, Dt, untie))
 
 
-def _head_backward(model, eng, st, label_embs, idx, Gs, pns, rvecs):
+def _head_backward(model, eng, st, label_embs, idx, Gs, pns, rvecs, grads=None):
     """Shared back of the head.  Gs[i] = d loss / d (proj . En^T) (bf16 [S, Cpad]), rvecs[i] = sum_c G_sc cos_sc, pns[i] = 1/|proj_s|:
-    d proj = G En - rvec pn proj,  d En = G^T proj,  then final_proj's weight / bias / input gradients and the scatter back."""
+    d proj = G En - rvec pn proj,  d En = G^T proj,  then final_proj's weight / bias / input gradients and the scatter back.
+    `grads` = (d label_embs [sum C, Dp], d final_proj.weight, d final_proj.bias) fp32 views to accumulate into; default: the
+    flat-buffer views of `model.label_embs_concat` / `model.final_proj` (models with one head per layer pass their own)."""
     rows, D, S, Dp, Dt, untie = st["shape"]
     dev = st["xs"].device
     g = eng.g
+    g_emb, g_w, g_b = grads if grads is not None else (g(model.label_embs_concat), g(model.final_proj.weight), g(model.final_proj.bias))
     dproj = _rows(S, Dt, BF, dev)
     for i, se in enumerate(st["sets"]):
         off, C, Cpad = se["off"], se["C"], se["Cpad"]
@@ -88,9 +91,9 @@ def _head_backward(model, eng, st, label_embs, idx, Gs, pns, rvecs):
             dproj.add_(tgt)  # tied final_proj shared by several label sets
         d_en = torch.zeros(Cpad, Dp, dtype=torch.float32, device=dev)
         ops.gemm_wgrad(Gs[i], 0, Cpad, proj_i, 0, Dt, S, 1, Cpad, Dp, d_en, Dp)                          # G^T proj
-        ops.nce_dlabel(d_en, label_embs[off:off + C], se["invn"], C, Dp, g(model.label_embs_concat)[off:off + C])
-    ops.colsum(dproj, 0, Dt, S, 1, Dt, g(model.final_proj.bias))
-    ops.gemm_wgrad(dproj, 0, Dt, st["xs"], 0, D, S, 1, Dt, D, g(model.final_proj.weight), D)
+        ops.nce_dlabel(d_en, label_embs[off:off + C], se["invn"], C, Dp, g_emb[off:off + C])
+    ops.colsum(dproj, 0, Dt, S, 1, Dt, g_b)
+    ops.gemm_wgrad(dproj, 0, Dt, st["xs"], 0, D, S, 1, Dt, D, g_w, D)
     dxs = _rows(S, D, BF, dev)
     ops.gemm_rows(dproj, 0, Dt, S, 1, Dt, st["wpT"], D, dxs, 0, D, None)
     dx = torch.zeros(rows, D, dtype=BF, device=dev)
@@ -102,8 +105,9 @@ class _MaskedPredictionFn(torch.autograd.Function):
     """loss = sum over label sets of weight * CE(cos(final_proj(x[idx]), label_embs) / temp, target).  x: bf16 [B*T, D]."""
 
     @staticmethod
-    def forward(ctx, x2d, w, b, label_embs, model, idx, targets, weight, stats):
+    def forward(ctx, x2d, w, b, label_embs, model, idx, targets, weight, stats, grads=None):
         ctx.fwd_stream = torch.cuda.current_stream()
+        ctx.grad_views = grads
         dev = x2d.device
         st = _head_forward(model, x2d, w, b, label_embs, idx)
         S, Dp, Dt, untie = idx.numel(), model.final_dim, w.shape[0], model.untie_final_proj
@@ -135,9 +139,9 @@ class _MaskedPredictionFn(torch.autograd.Function):
         for G, rvec in zip(Gs, rvecs):
             G.mul_(scale_bf)     # upstream gradient of the scalar loss (device scalar, no sync): everything below is linear in G
             rvec.mul_(scale_f)
-        dx = _head_backward(ctx.model, ctx.eng, ctx.st, label_embs, ctx.idx, Gs, pns, rvecs)
+        dx = _head_backward(ctx.model, ctx.eng, ctx.st, label_embs, ctx.idx, Gs, pns, rvecs, ctx.grad_views)
         ctx.st = ctx.grads = None
-        return dx, None, None, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None, None, None
 
 
 class _LogitsFn(torch.autograd.Function):
@@ -147,8 +151,9 @@ class _LogitsFn(torch.autograd.Function):
     model through `get_logits` / `get_targets`.  Same GEMMs as the fused criterion; the logits are assembled from their outputs."""
 
     @staticmethod
-    def forward(ctx, x2d, w, b, label_embs, model, idx, targets):
+    def forward(ctx, x2d, w, b, label_embs, model, idx, targets, grads=None):
         ctx.fwd_stream = torch.cuda.current_stream()
+        ctx.grad_views = grads
         st = _head_forward(model, x2d, w, b, label_embs, idx)
         Dp, untie = model.final_dim, model.untie_final_proj
         outs, pns = [], []
@@ -186,9 +191,9 @@ class _LogitsFn(torch.autograd.Function):
             G = torch.zeros(S, Cpad, dtype=BF, device=dev)
             G[:, :C] = Gf.to(BF)
             Gs.append(G)
-        dx = _head_backward(model, ctx.eng, st, label_embs, ctx.idx, Gs, ctx.pns, rvecs)
+        dx = _head_backward(model, ctx.eng, st, label_embs, ctx.idx, Gs, ctx.pns, rvecs, ctx.grad_views)
         ctx.st = None
-        return dx, None, None, None, None, None, None
+        return dx, None, None, None, None, None, None, None
 
 
 class WavLMForPretraining(WavLM):

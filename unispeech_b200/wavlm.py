@@ -634,7 +634,9 @@ class WavLM(nn.Module):
         xv, features = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv)
         xv._b200_xpad = eng._last_xpad
         el = getattr(self, "_extract_layer", None)  # UniSpeech-SAT: 0-based `utterance_contrastive_layer - 1` (unispeech_sat.py:640-645)
-        enc = self.encoder(xv, padding_mask=fpm, layer=None if output_layer is None else output_layer - 1, extract_layer=el)
+        pl = getattr(self, "_predict_layers", None)  # ILS-HuBERT: 1-based layers whose outputs feed intermediate heads (ils_hubert.py:167-171)
+        lay = (list(pl) if (pl is not None and output_layer is None) else None) if output_layer is None else output_layer - 1
+        enc = self.encoder(xv, padding_mask=fpm, layer=lay, extract_layer=el)
         x, layer_results = enc[0], enc[1]
         res = {"x": x, "padding_mask": fpm, "features": features, "layer_results": layer_results,
                "mask_indices": mask_indices, "padding_mask_host": fpm_host, "spk_x": enc[2] if el is not None else None}
