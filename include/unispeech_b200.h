@@ -348,6 +348,12 @@ int b200s_sat_nce_fwd(const void* proj, long long proj_rs, const void* y, long l
                       int S, int N, int Dp, float logit_temp, float* g, double* loss_sum, int* stats, b200s_stream stream);
 /* Backward: dproj_acc[s,:] += d loss/d proj_s, dy_acc[r,:] += d loss/d y_r (fp32 [S, Dp], vector reductions; pass the SAME buffer
  * for both when y IS proj, i.e. no quantizer); upstream = DEVICE float, the gradient of the loss scalar. */
+/* wav2vec 2.0 InfoNCE (src/fairseq/models/wav2vec/wav2vec2.py:533-553 compute_preds; criterions/wav2vec_criterion.py:57-62,103-118) on
+ * the same operands: logit[s,0] = cos(x_s, y_s)/temp, logit[s,1+n] = cos(x_s, y[idx[n*S+s]])/temp, a negative equal to the positive
+ * is masked with -inf; *loss_sum += sum_s cross_entropy(logit[s,:], 0); g fp32 [S, N+1] = softmax - onehot(0) (consumed by
+ * b200s_sat_nce_bwd); stats[0] += correct (argmax == 0, not also argmin == 0), stats[1] += S.  Dp % 4 == 0, Dp <= 1024. */
+int b200s_w2v_nce_fwd(const void* proj, long long proj_rs, const void* y, long long y_rs, const int* idx, int S, int N, int Dp,
+                      float logit_temp, float* g, double* loss_sum, int* stats, b200s_stream stream);
 int b200s_sat_nce_bwd(const void* proj, long long proj_rs, const void* y, long long y_rs, const int* idx, int S, int N, int Dp,
                       float logit_temp, const float* g, const float* upstream, float* dproj_acc, float* dy_acc,
                       b200s_stream stream);

@@ -752,3 +752,97 @@ def sat_utterance_contrastive_loss(spk_x: Tensor, padding_mask: Tensor, mask_ind
     logits = sat_compute_nce(proj_flat, y_flat, samples, logit_temp, replace_inf=False)
     loss = F.binary_cross_entropy_with_logits(logits, targets.type_as(logits), reduction="none").mean()
     return loss, targets.float().mean(), ((logits >= 0.0) == targets).float().mean(), q
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# wav2vec 2.0 contrastive head
+#   sample_negatives   src/fairseq/models/wav2vec/wav2vec2.py:474-531   (the draws of sat_sample_instances, frame-major layout)
+#   compute_preds      :533-553          forward tail :621-723          get_logits / get_targets / get_extra_losses :741-767
+#   Wav2vecCriterion.get_loss (infonce)  src/fairseq/criterions/wav2vec_criterion.py:44-118
+# Pinned by tests/golden/w2v_heads.npz (tools/make_w2v_golden.py executes the reference's source text).
+# ----------------------------------------------------------------------------------------------------------------
+def w2v_sample_negatives(y: Tensor, num: int, n_negatives: int, cross_sample_negatives: int, padding_count: int = 0):
+    """wav2vec2.py:474-531: the same torch.randint draws as the UniSpeech-SAT sampler, but the flat index list of an utterance is
+    read as [num, N] (frame-major: `negs.view(bsz, num, N, fsz).permute(2, 0, 1, 3)`), not [N, num].  Returns (negs N x B x T x C,
+    flat indices [B, N * num])."""
+    bsz, tsz, fsz = y.shape
+    yf = y.reshape(-1, fsz)
+    cross_high, high = tsz * bsz, tsz - padding_count
+    assert high > 1
+    with torch.no_grad():
+        if n_negatives > 0:
+            tszs = torch.arange(num).unsqueeze(-1).expand(-1, n_negatives).flatten()
+            neg_idxs = torch.randint(low=0, high=high - 1, size=(bsz, n_negatives * num))
+            neg_idxs[neg_idxs >= tszs] += 1
+        if cross_sample_negatives > 0:
+            tszs = torch.arange(num).unsqueeze(-1).expand(-1, cross_sample_negatives).flatten()
+            cross_neg_idxs = torch.randint(low=0, high=cross_high - 1, size=(bsz, cross_sample_negatives * num))
+            cross_neg_idxs[cross_neg_idxs >= tszs] += 1
+    if n_negatives > 0:
+        for i in range(1, bsz):
+            neg_idxs[i] += i * high
+    else:
+        neg_idxs = cross_neg_idxs
+    if cross_sample_negatives > 0 and n_negatives > 0:
+        neg_idxs = torch.cat([neg_idxs, cross_neg_idxs], dim=1)
+    negs = yf[neg_idxs.view(-1)].view(bsz, num, n_negatives + cross_sample_negatives, fsz).permute(2, 0, 1, 3)
+    return negs, neg_idxs
+
+
+def w2v_compute_preds(x: Tensor, y: Tensor, negatives: Tensor, logit_temp: float) -> Tensor:
+    """[N+1, B, T] logits: cosine similarity of x with the positive y and the negatives, / temp; a negative that equals the
+    positive is set to -inf (wav2vec2.py:533-553)."""
+    neg_is_pos = (y == negatives).all(-1)
+    targets = torch.cat([y.unsqueeze(0), negatives], dim=0)
+    logits = torch.cosine_similarity(x.float(), targets.float(), dim=-1).type_as(x) / logit_temp
+    if neg_is_pos.any():
+        logits[1:][neg_is_pos] = float("-inf")
+    return logits
+
+
+def w2v_contrastive_loss(x_enc: Tensor, unmasked_features: Tensor, mask_indices: Tensor, final_proj, project_q, n_negatives: int,
+                         cross_sample_negatives: int, logit_temp: float, quantizer=None, noise: Optional[Tensor] = None,
+                         tau: float = 1.0):
+    """Masked branch of Wav2Vec2Model.forward (:621-723) + the infonce criterion.  `x_enc` [B,T,D] encoder output,
+    `unmasked_features` [B,T,C] LayerNorm'ed conv features, `mask_indices` bool [B,T] with the same count per utterance;
+    `final_proj` / `project_q` = (w, b); `quantizer` = dict(weight_proj_w, weight_proj_b, vars_, groups, num_vars) or None.
+    Returns dict(loss (sum CE), sample_size, correct, count, logits [S, N+1], q)."""
+    B = x_enc.size(0)
+    y = unmasked_features[mask_indices].view(B, -1, unmasked_features.size(-1))
+    q = None
+    if quantizer is not None:
+        q = gumbel_vq_eval(y, noise=noise, tau=tau, **quantizer)
+        y = F.linear(q["x"], project_q[0], project_q[1])
+    else:
+        y = F.linear(y, project_q[0], project_q[1])
+    negs, _ = w2v_sample_negatives(y, y.size(1), n_negatives, cross_sample_negatives)   # N x B x T x C
+    x = x_enc[mask_indices].view(B, -1, x_enc.size(-1))
+    x = F.linear(x, final_proj[0], final_proj[1])
+    logits = w2v_compute_preds(x, y, negs, logit_temp)                  # [N+1, B, T]
+    lg = logits.transpose(0, 2).reshape(-1, logits.size(0)).float()     # get_logits, :741-745
+    tgt = lg.new_zeros(lg.size(0), dtype=torch.long)
+    loss = F.cross_entropy(lg, tgt, reduction="sum")
+    mx, mn = lg.argmax(-1) == 0, lg.argmin(-1) == 0
+    return {"loss": loss, "sample_size": tgt.numel(), "correct": int(mx.long().sum() - (mx & mn).long().sum()), "count": mx.numel(),
+            "logits": lg, "q": q}
+
+
+def w2v_criterion(head: dict, features_pen: Optional[Tensor], loss_weights: Optional[List[float]]):
+    """Wav2vecCriterion.get_loss with infonce (:44-87): loss + sum_i w_i * extra_i * sample_size, extras = [(num_vars - prob_ppl) /
+    num_vars, features_pen] (get_extra_losses, wav2vec2.py:752-767)."""
+    loss, ssz = head["loss"], head["sample_size"]
+    extras = []
+    if head["q"] is not None:
+        nv = head["q"]["num_vars"]
+        extras.append((nv - head["q"]["prob_perplexity"]) / nv)
+    if features_pen is not None:
+        extras.append(features_pen)
+    if loss_weights is not None:
+        lw = list(loss_weights)
+        if len(lw) == 1 and len(extras) != 1:
+            lw = [lw[0]] * len(extras)
+        assert len(lw) == len(extras)
+        for p_, c in zip(extras, lw):
+            if c != 0 and p_ is not None:
+                loss = loss + c * p_.float() * ssz
+    return loss, ssz

@@ -61,6 +61,7 @@ def test_all_fixtures_are_covered():
     names.remove("train_heads")   # compute_nce / clip_grad_norm_ / Adam fixture, covered by test_training_heads_match_reference_code
     names.remove("utterance_mixing")  # host data-path fixture, covered by tests/test_api_cpu.py
     names.remove("sat_heads")     # UniSpeech-SAT utterance-contrastive fixture, covered by test_sat_utterance_contrastive_branch_...
+    names.remove("w2v_heads")     # wav2vec 2.0 contrastive-head fixture, covered by tests/test_w2v_oracle_cpu.py
     for n in LONG_CASES:          # long-sequence fixtures (subsampled rows), covered by test_long_sequence_rows_match_reference
         names.remove(n)
     assert names == sorted(CASES)

@@ -1,0 +1,91 @@
+"""wav2vec 2.0 contrastive head (unispeech_b200/wav2vec2.py) against the oracle (pinned to the reference's source text by
+tests/test_w2v_oracle_cpu.py): loss, accuracy counts, perplexities and gradients of every parameter group, eval-mode quantizer
+(hard arg-max) and training-mode quantizer (Gumbel hard sample, noise from the library's counter-based generator)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import wavlm_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a * b).sum() / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("pre_ln,quantize,training,n_neg,cross", [(False, True, False, 10, 0), (True, True, True, 6, 4),
+                                                                   (True, False, False, 8, 0)])
+def test_wav2vec2_head_matches_oracle(cuda_device, pre_ln, quantize, training, n_neg, cross):
+    from unispeech_b200.wav2vec2 import _SITE_GUMBEL_W2V, Wav2Vec2Config, Wav2Vec2Model
+    dev = cuda_device
+    base = O.tiny_config(pre_ln=pre_ln, encoder_layers=2, relative_position_embedding=False, gru_rel_pos=False)
+    G, V, vq = 2, 32, 128
+    cfg = Wav2Vec2Config(dict(vars(base), final_dim=64, quantize_targets=quantize, latent_vars=V, latent_groups=G, latent_dim=vq,
+                              latent_temp=(2.0, 0.5, 0.999), num_negatives=n_neg, cross_sample_negatives=cross, logit_temp=0.1,
+                              feature_grad_mult=1.0))
+    torch.manual_seed(11)
+    m = Wav2Vec2Model(cfg)
+    m.load_state_dict(O.deterministic_state_dict(base), strict=False)
+    with torch.no_grad():   # moderate head weights: keeps the quantizer's arg-max away from ties between the bf16 and fp32 paths
+        m.final_proj.weight.mul_(1.0)
+        if quantize:
+            m.quantizer.weight_proj.weight.mul_(0.5)
+    m = m.to(dev)
+    m.train(training)
+    m.noise_seed = 77
+    sd = {k: v.detach().cpu().float().requires_grad_(True) for k, v in m.state_dict(keep_vars=True).items()}
+    B, L = 3, 16000
+    wav, _ = O.deterministic_waveform(B, L, seed=4)
+    T = O.num_frames(L, base)
+    # the same number of masked frames in every utterance
+    mask = torch.zeros(B, T, dtype=torch.bool)
+    rng = np.random.RandomState(3)
+    for b in range(B):
+        mask[b, torch.from_numpy(rng.choice(T, 20, replace=False))] = True
+    # ---- GPU
+    torch.manual_seed(5)
+    out = m(wav.to(dev), padding_mask=None, mask=True, mask_indices=mask)
+    lw = [0.1, 10.0] if quantize else [10.0]
+    loss, ssz, log = m.criterion(out, loss_weights=lw)
+    loss.backward()
+    torch.cuda.synchronize()
+    # ---- oracle
+    conv = O.conv_feature_extractor(sd, wav, base)
+    pen = conv.float().pow(2).mean()
+    feats = conv.transpose(1, 2)
+    unm = F.layer_norm(feats, (feats.shape[-1],), sd["layer_norm.weight"], sd["layer_norm.bias"], 1e-5)
+    r = O.extract_features(sd, wav, base, mask_indices=mask)
+    qd, noise, tau = None, None, 1.0
+    S = B * 20
+    if quantize:
+        qd = dict(weight_proj_w=sd["quantizer.weight_proj.weight"], weight_proj_b=sd["quantizer.weight_proj.bias"],
+                  vars_=sd["quantizer.vars"], groups=G, num_vars=V)
+        if training:
+            noise = O.gumbel_noise(77, _SITE_GUMBEL_W2V, S * G * V).view(S * G, V)
+            tau = m.quantizer.curr_temp
+    torch.manual_seed(5)
+    head = O.w2v_contrastive_loss(r["x"], unm, mask, (sd["final_proj.weight"], sd["final_proj.bias"]),
+                                  (sd["project_q.weight"], sd["project_q.bias"]), n_neg, cross, 0.1, quantizer=qd, noise=noise, tau=tau)
+    want, want_ssz = O.w2v_criterion(head, pen, lw)
+    want.backward()
+    assert ssz == want_ssz == S and int(out["count"]) == head["count"]
+    assert abs(float(out["loss_nce"]) - float(head["loss"])) <= 0.03 * abs(float(head["loss"])), (float(out["loss_nce"]), float(head["loss"]))
+    assert abs(float(loss) - float(want)) <= 0.03 * abs(float(want)), (float(loss), float(want))
+    assert abs(int(out["correct"]) - head["correct"]) <= max(2, S // 10)
+    if quantize:
+        assert abs(float(out["prob_perplexity"]) - float(head["q"]["prob_perplexity"])) <= 0.02 * float(head["q"]["prob_perplexity"])
+        assert abs(float(out["code_perplexity"]) - float(head["q"]["code_perplexity"])) <= 0.1 * float(head["q"]["code_perplexity"])
+    names = ["final_proj.weight", "final_proj.bias", "project_q.weight", "encoder.layers.1.fc2.weight", "post_extract_proj.weight",
+             "feature_extractor.conv_layers.2.0.weight", "layer_norm.weight"]
+    if quantize:
+        names += ["quantizer.weight_proj.weight", "quantizer.vars"]
+    params = dict(m.named_parameters())
+    for n in names:
+        got, ref = params[n].grad.detach().cpu(), sd[n].grad
+        assert ref is not None and got.shape == ref.shape, n
+        c = _cos(got, ref)
+        lo = 0.97 if n in ("quantizer.weight_proj.weight", "feature_extractor.conv_layers.2.0.weight", "layer_norm.weight") else 0.99
+        assert c > lo, (n, c)

@@ -91,6 +91,73 @@ __global__ void __launch_bounds__(256) sat_nce_fwd_kernel(const __nv_bfloat16* _
   }
 }
 
+// wav2vec 2.0 InfoNCE on the same operands (src/fairseq/models/wav2vec/wav2vec2.py:533-553 compute_preds, criterions/
+// wav2vec_criterion.py:57-62, 103-118): logit[s,0] = cos(x_s, y_s)/temp, logit[s,1+n] = cos(x_s, y[idx[n*S+s]])/temp, a negative that
+// EQUALS the positive (all Dp entries: frequent with quantised targets) is masked with -inf; loss += sum_s (logsumexp_n - logit[s,0]);
+// g[s,n] = softmax_n - [n == 0] (sum reduction: the criterion's sample_size divides later); stats[0] += #{argmax == 0 and not also
+// argmin == 0}, stats[1] += S.  One warp per frame; the logits of a frame are parked in its g row between the two passes.
+__global__ void __launch_bounds__(256) w2v_nce_fwd_kernel(const __nv_bfloat16* __restrict__ proj, long long p_rs,
+                                                          const __nv_bfloat16* __restrict__ y, long long y_rs,
+                                                          const int* __restrict__ idx, int S, int N, int Dp, float inv_temp,
+                                                          float* __restrict__ g, double* __restrict__ loss_sum,
+                                                          int* __restrict__ stats) {
+  pdl_grid_sync();
+  const int lane = threadIdx.x & 31;
+  const int s = (blockIdx.x * 256 + threadIdx.x) >> 5;
+  if (s >= S) return;
+  float pv[kMaxPerLane], py[kMaxPerLane];
+  float pp = 0.f;
+  for_each_quad(Dp, lane, [&](int k, int c) {
+    load4(proj + s * p_rs + c, pv + 4 * k);
+    load4(y + s * y_rs + c, py + 4 * k);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) pp = fmaf(pv[4 * k + e], pv[4 * k + e], pp);
+  });
+  const float pn = fmaxf(sqrtf(warp_sum(pp)), 1e-8f);
+  float* grow = g + static_cast<long long>(s) * (N + 1);
+  float zmax = -INFINITY, z0 = 0.f, zmin_others = INFINITY, zmax_others = -INFINITY;
+  for (int n = 0; n <= N; ++n) {
+    const long long r = (n == 0) ? s : idx[static_cast<long long>(n - 1) * S + s];
+    float dot = 0.f, yy = 0.f;
+    bool eq = true;
+    for_each_quad(Dp, lane, [&](int k, int c) {
+      float yv[4];
+      load4(y + r * y_rs + c, yv);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        dot = fmaf(pv[4 * k + e], yv[e], dot);
+        yy = fmaf(yv[e], yv[e], yy);
+        eq = eq && (yv[e] == py[4 * k + e]);
+      }
+    });
+    dot = warp_sum(dot);
+    yy = warp_sum(yy);
+    eq = __all_sync(0xffffffffu, eq);
+    float z = dot / (pn * fmaxf(sqrtf(yy), 1e-8f)) * inv_temp;
+    if (n == 0) {
+      z0 = z;
+    } else {
+      if (eq) z = -INFINITY;  // neg_is_pos
+      zmin_others = fminf(zmin_others, z);
+      zmax_others = fmaxf(zmax_others, z);
+    }
+    zmax = fmaxf(zmax, z);
+    if (lane == 0) grow[n] = z;
+  }
+  __syncwarp();
+  float esum = 0.f;
+  for (int n = lane; n <= N; n += 32) esum += __expf(grow[n] - zmax);
+  esum = warp_sum(esum);
+  const float inv = 1.0f / esum;
+  for (int n = lane; n <= N; n += 32) grow[n] = __expf(grow[n] - zmax) * inv - (n == 0 ? 1.f : 0.f);
+  if (lane == 0) {
+    atomicAdd(loss_sum, static_cast<double>(logf(esum) + zmax - z0));
+    const bool is_max = (N == 0) || (z0 >= zmax_others), is_min = (N == 0) || (z0 <= zmin_others);
+    atomicAdd(stats, (is_max && !is_min) ? 1 : 0);
+    atomicAdd(stats + 1, 1);
+  }
+}
+
 // Backward: dacc[r, :] (fp32 [S, Dp], += with vector reductions) receives d loss / d y_r; d loss / d proj_s goes to dacc[s, :]
 // when proj IS y (no quantizer: `y = proj_x`, unispeech_sat.py:707-709), else to dproj_acc[s, :].  up = upstream gradient of the
 // loss scalar (DEVICE float).
@@ -334,6 +401,21 @@ int b200s_sat_nce_fwd(const void* proj, long long proj_rs, const void* y, long l
   B200_CHECK_CUDA(launch_pdl(sat_nce_fwd_kernel, dim3(ceil_div(S, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
                              static_cast<const __nv_bfloat16*>(proj), proj_rs, static_cast<const __nv_bfloat16*>(y), y_rs, idx,
                              same, S, N, Dp, 1.0f / logit_temp, g, loss_sum, stats));
+  B200_CHECK_LAUNCH();
+  return 0;
+}
+
+int b200s_w2v_nce_fwd(const void* proj, long long proj_rs, const void* y, long long y_rs, const int* idx, int S, int N, int Dp,
+                      float logit_temp, float* g, double* loss_sum, int* stats, b200s_stream stream) {
+  B200_CHECK_ARG(proj && y && g && loss_sum && stats, "w2v_nce_fwd: null pointer");
+  B200_CHECK_ARG(N == 0 || idx, "w2v_nce_fwd: negatives need their indices");
+  B200_CHECK_ARG(Dp > 0 && Dp % 4 == 0 && Dp <= 1024, "w2v_nce_fwd: Dp=%d must be a multiple of 4, <= 1024", Dp);
+  B200_CHECK_ARG(proj_rs % 4 == 0 && y_rs % 4 == 0, "w2v_nce_fwd: row strides must be multiples of 4 elements");
+  B200_CHECK_ARG(logit_temp > 0.f, "w2v_nce_fwd: logit_temp must be positive");
+  if (S == 0) return 0;
+  B200_CHECK_CUDA(launch_pdl(w2v_nce_fwd_kernel, dim3(ceil_div(S, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                             static_cast<const __nv_bfloat16*>(proj), proj_rs, static_cast<const __nv_bfloat16*>(y), y_rs, idx, S, N,
+                             Dp, 1.0f / logit_temp, g, loss_sum, stats));
   B200_CHECK_LAUNCH();
   return 0;
 }

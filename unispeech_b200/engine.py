@@ -510,8 +510,9 @@ class Engine:
         ops.frame_mask_fwd(xv, Tpad * D, D, T, B, D, mask_u8, pad_u8, m.mask_emb)
         return dict(fn=fn, mean=mean, rstd=rstd, xpad=xpad, feats=feats if save else None, features=features, drop=d)
 
-    def project_backward(self, st, dxm, T, mask_u8, pad_u8):
-        """dxm: gradient w.r.t. the masked projection output, bf16 [B,T,D] (modified in place). Returns d(features) [B,Tp,C]."""
+    def project_backward(self, st, dxm, T, mask_u8, pad_u8, dfn_extra=None):
+        """dxm: gradient w.r.t. the masked projection output, bf16 [B,T,D] (modified in place). Returns d(features) [B,Tp,C].
+        `dfn_extra` (bf16 [B,T,C]): gradient arriving at the LayerNorm output from a second consumer (wav2vec 2.0 quantizer)."""
         m, cfg = self.m, self.cfg
         B = dxm.shape[0]
         D = cfg.encoder_embed_dim
@@ -525,7 +526,8 @@ class Engine:
         ops.colsum(dxm, T * D, D, T, B, D, self.g(m.post_extract_proj.bias))
         ops.gemm_wgrad(dxm, T * D, D, st["fn"], T * C, C, T, B, D, C, self.g(m.post_extract_proj.weight), C)
         dfn = torch.empty(B, T, C, dtype=BF, device=dev)
-        ops.gemm_rows(dxm, T * D, D, T, B, D, self.wpT, C, dfn, T * C, C, None)
+        ops.gemm_rows(dxm, T * D, D, T, B, D, self.wpT, C, dfn, T * C, C,
+                      L.make_epilogue(res1=dfn_extra, res1_bs=T * C, res1_ld=C) if dfn_extra is not None else None)
         dfeat = torch.empty(B, Tp, C, dtype=BF, device=dev)  # rows < T written below; the pad row is never read
         ops.layer_norm_bwd(dfn, T * C, C, feats, Tp * C, C, st["mean"], st["rstd"], m.layer_norm.weight, m.layer_norm.bias,
                            None, 0, 0, dfeat, Tp * C, C, self.g(m.layer_norm.weight), self.g(m.layer_norm.bias), None, T, B, C)

@@ -347,6 +347,11 @@ def sat_nce_fwd(proj, proj_rs, y, y_rs, idx, same, S, N, Dp, logit_temp, g, loss
           f32(logit_temp), L.ptr(g), L.ptr(loss_sum), L.ptr(stats), _s())
 
 
+def w2v_nce_fwd(proj, proj_rs, y, y_rs, idx, S, N, Dp, logit_temp, g, loss_sum, stats):
+    _call("b200s_w2v_nce_fwd", L.ptr(proj), L.ll(proj_rs), L.ptr(y), L.ll(y_rs), L.ptr(idx), i32(S), i32(N), i32(Dp),
+          f32(logit_temp), L.ptr(g), L.ptr(loss_sum), L.ptr(stats), _s())
+
+
 def sat_nce_bwd(proj, proj_rs, y, y_rs, idx, S, N, Dp, logit_temp, g, upstream, dproj_acc, dy_acc):
     _call("b200s_sat_nce_bwd", L.ptr(proj), L.ll(proj_rs), L.ptr(y), L.ll(y_rs), L.ptr(idx), i32(S), i32(N), i32(Dp),
           f32(logit_temp), L.ptr(g), L.ptr(upstream), L.ptr(dproj_acc), L.ptr(dy_acc), _s())

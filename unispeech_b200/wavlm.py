@@ -141,8 +141,13 @@ class _ConvFn(torch.autograd.Function):
 
 
 class _ProjFn(torch.autograd.Function):
+    """LayerNorm(features) -> post_extract_proj -> dropout_input -> mask_emb / zero padded frames.  Outputs: the view of the padded
+    pos_conv input buffer, `features` (projected, WavLM's ret_conv value) and -- `want_fn`, wav2vec 2.0 -- the LayerNorm output
+    `unmasked_features` (src/fairseq/models/wav2vec/wav2vec2.py:578-580) whose gradient (quantizer branch) is added to the
+    projection's in the backward pass."""
+
     @staticmethod
-    def forward(ctx, feats, anchor, eng: Engine, T, mask_u8, pad_u8, want_features):
+    def forward(ctx, feats, anchor, eng: Engine, T, mask_u8, pad_u8, want_features, want_fn=False):
         ctx.fwd_stream = torch.cuda.current_stream()
         save = bool(ctx.needs_input_grad[0] or ctx.needs_input_grad[1])
         st = eng.project_forward(feats, T, mask_u8, pad_u8, save, want_features)
@@ -150,15 +155,18 @@ class _ProjFn(torch.autograd.Function):
         half = eng.cfg.conv_pos // 2
         eng._last_xpad = st["xpad"]  # the padded pos_conv input buffer the returned view lives in
         xv = st["xpad"][:, half:half + T]
-        return xv, st["features"]
+        return xv, st["features"], (st["fn"] if want_fn else None)
 
     @staticmethod
     @_on_forward_stream
-    def backward(ctx, dxv, _dfeatures):
-        dfeat = ctx.eng.project_backward(ctx.st, dxv.contiguous(), ctx.T, ctx.mask, ctx.pad)
+    def backward(ctx, dxv, _dfeatures, dfn_extra=None):
+        if dfn_extra is not None:
+            dfn_extra = dfn_extra if (dfn_extra.dtype == torch.bfloat16 and dfn_extra.is_contiguous()) else \
+                dfn_extra.to(torch.bfloat16).contiguous()
+        dfeat = ctx.eng.project_backward(ctx.st, dxv.contiguous(), ctx.T, ctx.mask, ctx.pad, dfn_extra)
         ctx.st = None  # (GradMultiply is applied where the gradient enters the extractor: _ConvFn.backward)
         ctx.eng.backward_stage_done("stem")
-        return dfeat, None, None, None, None, None, None
+        return dfeat, None, None, None, None, None, None, None
 
 
 class _StemFn(torch.autograd.Function):
@@ -631,7 +639,8 @@ class WavLM(nn.Module):
         eng = self._engine
         mask_u8 = mask_indices.to(device=source.device, dtype=torch.uint8).contiguous() if mask_indices is not None else None
         pad_u8 = fpm.to(torch.uint8).contiguous() if fpm is not None else None
-        xv, features = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv)
+        want_fn = bool(getattr(self, "_want_unmasked_features", False))
+        xv, features, unmasked = _ProjFn.apply(feats, self.post_extract_proj.weight, eng, T, mask_u8, pad_u8, ret_conv, want_fn)
         xv._b200_xpad = eng._last_xpad
         el = getattr(self, "_extract_layer", None)  # UniSpeech-SAT: 0-based `utterance_contrastive_layer - 1` (unispeech_sat.py:640-645)
         pl = getattr(self, "_predict_layers", None)  # ILS-HuBERT: 1-based layers whose outputs feed intermediate heads (ils_hubert.py:167-171)
@@ -639,7 +648,8 @@ class WavLM(nn.Module):
         enc = self.encoder(xv, padding_mask=fpm, layer=lay, extract_layer=el)
         x, layer_results = enc[0], enc[1]
         res = {"x": x, "padding_mask": fpm, "features": features, "layer_results": layer_results,
-               "mask_indices": mask_indices, "padding_mask_host": fpm_host, "spk_x": enc[2] if el is not None else None}
+               "mask_indices": mask_indices, "padding_mask_host": fpm_host, "spk_x": enc[2] if el is not None else None,
+               "unmasked_features": unmasked}
         self._last = res
         feature = res["features"] if ret_conv else res["x"]
         if ret_layer_results:
