@@ -62,6 +62,7 @@ def test_all_fixtures_are_covered():
     names.remove("utterance_mixing")  # host data-path fixture, covered by tests/test_api_cpu.py
     names.remove("sat_heads")     # UniSpeech-SAT utterance-contrastive fixture, covered by test_sat_utterance_contrastive_branch_...
     names.remove("w2v_heads")     # wav2vec 2.0 contrastive-head fixture, covered by tests/test_w2v_oracle_cpu.py
+    names.remove("vox_real_large2l")  # real-speech ragged fixture, covered by tests/test_vox_real.py
     for n in LONG_CASES:          # long-sequence fixtures (subsampled rows), covered by test_long_sequence_rows_match_reference
         names.remove(n)
     assert names == sorted(CASES)
