@@ -206,3 +206,31 @@ def test_ragged_gemm_rows_and_wgrad(cuda_device, B, T, K, N, lengths):
         want += y[b, :live].float().t() @ a[b, :live].float()
     scale = want.abs().max().item()
     assert (dw - want).abs().max().item() < 0.01 * scale + 0.05, ((dw - want).abs().max().item(), scale)
+
+
+def test_reserved_sms_do_not_change_results(cuda_device):
+    """`b200s_reserve_sms` (room for a concurrent collective's CTAs): fewer CTA pairs walk the same tiles -- rows GEMM bit-identical,
+    stream-K weight gradient equal to fp32 summation order."""
+    from unispeech_b200 import ops
+    dev = cuda_device
+    torch.manual_seed(12)
+    M, K, N = 6000, 1024, 1024
+    a = bf(torch.randn(M, K, device=dev))
+    w = bf(torch.randn(N, K, device=dev) / K ** 0.5)
+    y = bf(torch.randn(M, N, device=dev))
+    res = []
+    try:
+        for keep in (0, 6):
+            ops.reserve_sms(keep)
+            out = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+            ops.gemm_rows(a, 0, K, M, 1, K, w, N, out, 0, N, None)
+            dw = torch.zeros(N, K, device=dev)
+            ops.gemm_wgrad(y, 0, N, a, 0, K, M, 1, N, K, dw, K)
+            torch.cuda.synchronize()
+            res.append((out, dw))
+    finally:
+        ops.reserve_sms(0)
+    assert torch.equal(res[0][0], res[1][0])
+    ref = y.float().t() @ a.float()
+    for _, dw in res:
+        assert (dw - ref).abs().max().item() <= 2e-3 * ref.abs().max().item()
