@@ -23,6 +23,7 @@ if [ "$N" = "2" ]; then
     grep '^{' gpurun_out/bench_n1_same_box_${extra#--}_$TAG.out | tail -1 | python -c "import json,sys; d=json.loads(sys.stdin.read()); print('N=1 same box [$extra]: value %.1f ms/step %.2f phases %s' % (d['value'], d['ms_per_step'], d.get('phases_ms')))"
   done
 fi
+if [ "$N" = "4" ]; then timeout 300 python -m pytest tests/test_w2v_gpu.py -q -p no:cacheprovider 2>&1 | tail -3; fi
 one large
 one sat --sat
 one ragged --ragged
