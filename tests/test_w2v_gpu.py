@@ -83,13 +83,16 @@ def test_wav2vec2_head_matches_oracle(cuda_device, pre_ln, quantize, training, n
     if quantize:
         names += ["quantizer.weight_proj.weight", "quantizer.vars"]
     params = dict(m.named_parameters())
+    # (a single arg-max code that differs between the bf16 logits here and the fp32 logits of the checker moves the few distinct
+    # target rows: the parameters downstream of the quantizer get the looser bound)
+    loose = ("quantizer.weight_proj.weight", "quantizer.vars", "project_q.weight", "feature_extractor.conv_layers.2.0.weight",
+             "layer_norm.weight")
+    report, bad = [], []
     for n in names:
         got, ref = params[n].grad.detach().cpu(), sd[n].grad
         assert ref is not None and got.shape == ref.shape, n
         c = _cos(got, ref)
-        # (a single arg-max code that differs between the bf16 logits here and the fp32 logits of the checker moves the few distinct
-        # target rows: the parameters downstream of the quantizer get the looser bound)
-        loose = ("quantizer.weight_proj.weight", "quantizer.vars", "project_q.weight", "feature_extractor.conv_layers.2.0.weight",
-                 "layer_norm.weight")
-        lo = 0.97 if n in loose else 0.99
-        assert c > lo, (n, c)
+        report.append((n, round(c, 5), round(float(got.norm()), 4), round(float(ref.norm()), 4)))
+        if c <= (0.97 if n in loose else 0.99):
+            bad.append(n)
+    assert not bad, (bad, report)
