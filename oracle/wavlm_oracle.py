@@ -714,10 +714,12 @@ def gumbel_vq_eval(x: Tensor, weight_proj_w: Tensor, weight_proj_b: Tensor, vars
         idx = y_soft.argmax(-1, keepdim=True)
         y_hard = torch.zeros_like(y_soft).scatter_(-1, idx, 1.0)
         sel = (y_hard - y_soft.detach() + y_soft).view(bsz * tsz, groups, -1)
+        k = idx.view(-1)
     else:
         sel = hard
     q = (sel.view(bsz * tsz, -1).unsqueeze(-1) * vars_).view(bsz * tsz, groups, num_vars, -1).sum(-2).view(bsz, tsz, -1)
-    return {"x": q, "code_perplexity": code_ppl, "prob_perplexity": prob_ppl, "num_vars": num_vars * groups}
+    return {"x": q, "code_perplexity": code_ppl, "prob_perplexity": prob_ppl, "num_vars": num_vars * groups,
+            "codes": k.view(bsz * tsz, groups)}   # the selected code per (frame, group)
 
 
 def sat_utterance_contrastive_loss(spk_x: Tensor, padding_mask: Tensor, mask_indices: Tensor, spk_proj_w: Tensor, spk_proj_b: Tensor,

@@ -87,12 +87,18 @@ def test_wav2vec2_head_matches_oracle(cuda_device, pre_ln, quantize, training, n
     # target rows: the parameters downstream of the quantizer get the looser bound)
     loose = ("quantizer.weight_proj.weight", "quantizer.vars", "project_q.weight", "feature_extractor.conv_layers.2.0.weight",
              "layer_norm.weight")
-    report, bad = [], []
+    flips = 0
+    if quantize:   # codes picked from bf16 logits here, from fp32 logits by the checker: near-ties can differ
+        flips = int((out["codes"].cpu().long() != head["q"]["codes"].long()).sum())
+        assert flips <= max(2, S // 20), flips
+    report, bad = [("code flips", flips)], []
     for n in names:
         got, ref = params[n].grad.detach().cpu(), sd[n].grad
         assert ref is not None and got.shape == ref.shape, n
         c = _cos(got, ref)
         report.append((n, round(c, 5), round(float(got.norm()), 4), round(float(ref.norm()), 4)))
-        if c <= (0.97 if n in loose else 0.99):
+        # logits are cosines / 0.1 over a handful of negatives: a bf16 error of 4e-3 in a cosine is 4e-2 in a logit, i.e. a few per
+        # cent in the softmax weights that every gradient of this head is built from -- hence 0.97, not the 0.99 of the encoder tests
+        if c <= ((0.95 if n in loose else 0.97) if flips == 0 else 0.93):
             bad.append(n)
     assert not bad, (bad, report)

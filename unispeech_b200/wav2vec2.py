@@ -97,6 +97,7 @@ class _W2vNceFn(torch.autograd.Function):
             stats_out["code_perplexity"] = torch.exp(-torch.sum(hard_probs * torch.log(hard_probs + 1e-7), dim=-1)).sum()
             stats_out["num_vars"] = V * G
             stats_out["temp"] = qz.curr_temp
+            stats_out["codes"] = codes.view(S, G)   # selected code per (frame, group): `targets` of the reference's produce_targets
             st["quant"] = dict(G=G, V=V, dv=dv, logits=logits, codes=codes, q=q, wqT=wqT, avg_probs=avg_probs, training=training,
                                tau=float(qz.curr_temp))
         else:
@@ -275,7 +276,7 @@ class Wav2Vec2Model(WavLM):
                "padding_mask": res["padding_mask"], "features_pen": self._last_pen, "mask_indices": mi}
         if self.quantizer is not None:
             out.update(prob_perplexity=outs[1], code_perplexity=stats["code_perplexity"], num_vars=stats["num_vars"],
-                       temp=stats["temp"])
+                       temp=stats["temp"], codes=stats["codes"])
         return out
 
     def criterion(self, net_output: Dict, loss_weights: Optional[List[float]] = None):
