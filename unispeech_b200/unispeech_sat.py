@@ -13,7 +13,6 @@ the CPU checker restates this generator, as for dropout).
 """
 from __future__ import annotations
 
-import math
 from typing import Dict, List, Optional
 
 import torch

@@ -23,7 +23,7 @@ import torch.nn as nn
 from . import _lib as L
 from . import dropout as DR
 from . import ops
-from .engine import BF, ConvGeom
+from .engine import BF
 from .pretrain import _rows
 from .unispeech_sat import GumbelVectorQuantizer, sample_instances
 from .wavlm import WavLM, WavLMConfig, _on_forward_stream
