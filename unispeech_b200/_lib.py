@@ -43,9 +43,48 @@ def load():
             "(there is no CPU or PyTorch fallback for the hot path)"
         )
     lib = C.CDLL(str(_LIB_PATH))
-    lib.b200s_last_error.restype = C.c_char_p
+    _bind_prototypes(lib)
     _lib = lib
     return lib
+
+
+_CTYPES = {"int": C.c_int, "long long": C.c_longlong, "unsigned long long": C.c_ulonglong, "size_t": C.c_size_t,
+           "uint32_t": C.c_uint32, "float": C.c_float, "double": C.c_double, "b200s_stream": C.c_void_p, "unsigned": C.c_uint,
+           "unsigned int": C.c_uint, "uint8_t": C.c_uint8, "int64_t": C.c_int64}
+_RESTYPES = {"int": C.c_int, "long long": C.c_longlong, "uint32_t": C.c_uint32, "const char*": C.c_char_p, "void": None,
+             "double": C.c_double, "float": C.c_float}
+
+
+def _bind_prototypes(lib):
+    """Declare `argtypes` / `restype` of every entry point ONCE, from the prototypes of include/unispeech_b200.h.  The wrappers
+    then pass plain Python ints / floats (raw device pointers, strides, sizes): building a ctypes object per argument was ~2.5 us
+    of the ~5 us a launch cost the host, 15-20 arguments per call, ~6400 calls per WavLM-Large step."""
+    import re
+    hdr = Path(__file__).resolve().parent.parent / "include" / "unispeech_b200.h"
+    src = hdr.read_text()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"\b(int|long long|uint32_t|const char\s*\*|void|double|float)\s+(b200s_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S)
+    if len(protos) < 40:
+        raise RuntimeError(f"could not read the C prototypes from {hdr}")
+    for ret, name, params in protos:
+        args = []
+        if params.strip() not in ("", "void"):
+            for prm in params.split(","):
+                prm = " ".join(prm.split())
+                if "*" in prm:
+                    args.append(C.c_void_p)
+                    continue
+                t = re.sub(r"\b\w+$", "", prm).strip() if re.search(r"\s\w+$", prm) else prm
+                t = t.replace("const ", "").strip()
+                if t not in _CTYPES:
+                    raise RuntimeError(f"{hdr}: unknown parameter type {prm!r} in {name}")
+                args.append(_CTYPES[t])
+        fn = getattr(lib, name, None)
+        if fn is None:
+            raise RuntimeError(f"{_LIB_PATH} does not export {name} (stale build? run `python -m unispeech_b200.build`)")
+        fn.argtypes = args
+        fn.restype = _RESTYPES[" ".join(ret.split()).replace(" *", "*")]
 
 
 def _check(rc: int):
@@ -61,26 +100,28 @@ def check_device():
 _raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
 
 
-def stream_ptr() -> C.c_void_p:
-    """Raw cudaStream_t of torch's current stream.  `torch.cuda.current_stream()` costs ~13 us per call (device-index and
-    availability checks) and is needed once per kernel launch, so the raw C accessor is used when present."""
+def stream_ptr() -> int:
+    """Raw cudaStream_t of torch's current stream (an int: every entry point has its argtypes declared).
+    `torch.cuda.current_stream()` costs ~13 us per call (device-index and availability checks) and is needed once per kernel
+    launch, so the raw C accessor is used when present."""
     if _raw_stream is not None:
-        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return _raw_stream(torch.cuda.current_device())
+    return torch.cuda.current_stream().cuda_stream
 
 
-def ptr(t: Optional[torch.Tensor]) -> C.c_void_p:
-    if t is None:
-        return C.c_void_p(0)
-    return C.c_void_p(t.data_ptr())
+def ptr(t: Optional[torch.Tensor]) -> int:
+    """Raw device (or host) address of a tensor's first element, 0 for None."""
+    return 0 if t is None else t.data_ptr()
 
 
-def ll(v) -> C.c_longlong:
-    return C.c_longlong(int(v))
+def ll(v) -> int:
+    return int(v)
 
 
 def call(name: str, *args):
     fn = getattr(load(), name)
+    if fn.argtypes is None:   # a symbol without a prototype in the header would get 32-bit ints for its pointers
+        raise RuntimeError(f"{name} has no prototype in include/unispeech_b200.h")
     _check(fn(*args))
 
 

@@ -13,8 +13,8 @@ import torch
 
 from . import _lib as L
 
-i32 = C.c_int
-f32 = C.c_float
+i32 = int      # (argtypes are declared once in _lib: plain Python numbers go straight to the C call)
+f32 = float
 
 
 def _s():
@@ -63,10 +63,10 @@ def gemm_rows(a, a_bs, a_rs, rows, batches, K, w, N, out, out_bs, out_ld, epi: O
     """`valid` (int32 [batches] on the device): ragged batch -- M tiles beyond an utterance's valid frames are zero-filled."""
     if valid is not None:
         return _call("b200s_gemm_rows_ragged", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
-                     L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, L.ptr(valid), _s(),
+                     L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.addressof(epi) if epi is not None else None, L.ptr(valid), _s(),
                      flops=2.0 * rows * batches * K * N)
     _call("b200s_gemm_rows", L.ptr(a), L.ll(a_bs), L.ll(a_rs), i32(rows), i32(batches), i32(K), L.ptr(w), i32(N),
-           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s(),
+           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.addressof(epi) if epi is not None else None, _s(),
           flops=2.0 * rows * batches * K * N)
 
 
@@ -81,7 +81,7 @@ def gemm_wgrad(y, y_bs, y_rs, x, x_bs, x_rs, rows, batches, N, K, dw, dw_ld, val
 
 def posconv_gemm(xpad, xpad_bs, T, B, D, G, taps, wp, out, out_bs, out_ld, epi=None):
     _call("b200s_posconv_gemm", L.ptr(xpad), L.ll(xpad_bs), i32(T), i32(B), i32(D), i32(G), i32(taps), L.ptr(wp),
-           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.byref(epi) if epi is not None else None, _s(),
+           L.ptr(out), L.ll(out_bs), L.ll(out_ld), C.addressof(epi) if epi is not None else None, _s(),
           flops=2.0 * T * B * D * (D // G) * taps)
 
 
@@ -257,7 +257,8 @@ def attn_bwd_fused(qkv, out, dout, gate, tab, key_pad, lse, delta, dq_acc, dqkv,
 
 
 # ------------------------------------------------------------------------------------------------- dropout
-u32 = C.c_uint32
+def u32(v) -> int:
+    return int(v) & 0xFFFFFFFF
 
 
 def dropout_rows(x, x_bs, x_rs, res, res_bs, res_rs, y, y_bs, y_rs, rows_per_batch, batches, N, p, key):
@@ -268,7 +269,7 @@ def dropout_rows(x, x_bs, x_rs, res, res_bs, res_rs, y, y_bs, y_rs, rows_per_bat
 
 def memset_zero(t):
     """Zero a contiguous device tensor on the current stream (cudaMemsetAsync)."""
-    _call("b200s_memset_zero", L.ptr(t), C.c_ulonglong(t.numel() * t.element_size()), _s())
+    _call("b200s_memset_zero", L.ptr(t), int(t.numel() * t.element_size()), _s())
 
 
 def sumsq_rows(x, x_bs, x_rs, rows_per_batch, batches, N, out):
