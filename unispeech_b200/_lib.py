@@ -118,11 +118,24 @@ def ll(v) -> int:
     return int(v)
 
 
-def call(name: str, *args):
+_fn_cache = {}
+
+
+def _resolve(name: str):
     fn = getattr(load(), name)
     if fn.argtypes is None:   # a symbol without a prototype in the header would get 32-bit ints for its pointers
         raise RuntimeError(f"{name} has no prototype in include/unispeech_b200.h")
-    _check(fn(*args))
+    _fn_cache[name] = fn
+    return fn
+
+
+def call(name: str, *args):
+    fn = _fn_cache.get(name)
+    if fn is None:
+        fn = _resolve(name)
+    rc = fn(*args)
+    if rc:
+        _check(rc)
 
 
 def make_epilogue(bias=None, res1=None, res1_bs=0, res1_ld=0, res2=None, res2_bs=0, res2_ld=0,
