@@ -50,6 +50,7 @@ class GraphedForwardBackward:
         self.mask_host = torch.zeros(self.B, self.T, dtype=torch.bool).pin_memory()
         self.loss = torch.zeros((), dtype=torch.float32, device=self.device)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.capture_host_ms: Optional[float] = None
 
     # ---- the step body (identical in the eager warm-up and inside the capture)
     def _body(self):
@@ -89,8 +90,13 @@ class GraphedForwardBackward:
         # capture on the SAME side stream as the warm-up: autograd remembers the stream a leaf's gradient accumulator was created
         # on, and a backward pass captured on another stream would have to wait on that (uncaptured) stream
         # (cudaErrorStreamCaptureIsolation)
+        import time
+        t0 = time.perf_counter()
         with torch.cuda.graph(self.graph, stream=side):
             self._body()
+        # host time of enqueueing ONE step with nothing executing (stream capture records the launches): the eager path's cost
+        # without the launch queue's back-pressure, which a wall-clock measurement of un-synchronised eager steps includes
+        self.capture_host_ms = (time.perf_counter() - t0) * 1e3
         return self
 
     def step(self, wav_host: Optional[torch.Tensor] = None) -> torch.Tensor:
